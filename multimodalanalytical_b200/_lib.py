@@ -1,0 +1,143 @@
+"""Build + load the C-ABI CUDA library (`lib/libmma_b200.so`, declared in include/mma_b200.h).
+
+The library is compiled in-tree with nvcc for sm_100a only and loaded with ctypes; every entry point takes
+raw device pointers, sizes and a cudaStream_t and returns an int status (0 = ok).  There is no CPU or
+PyTorch fallback: if the library is missing or a launch fails, the caller gets an exception.
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
+SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "trainops.cu", "decode.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
+
+MMA_BF16, MMA_F32 = 0, 1
+EPI_STORE, EPI_GELU, EPI_RESID, EPI_DGELU, EPI_GLU_MUL, EPI_DGLU, EPI_ACCUM, EPI_RELU, EPI_DRELU = range(9)
+
+
+class Epi(C.Structure):
+    """Mirror of `struct Epi` (csrc/common.cuh, include/mma_b200.h)."""
+
+    _fields_ = [
+        ("kind", C.c_int), ("out_f32", C.c_int), ("aux_f32", C.c_int), ("resid_f32", C.c_int),
+        ("out", C.c_void_p), ("out2", C.c_void_p), ("bias", C.c_void_p), ("resid", C.c_void_p),
+        ("aux", C.c_void_p), ("aux2", C.c_void_p),
+        ("ldo", C.c_longlong), ("ldo2", C.c_longlong), ("ldr", C.c_longlong), ("lda", C.c_longlong),
+        ("lda2", C.c_longlong),
+        ("p_drop", C.c_float), ("alpha", C.c_float), ("seed", C.c_ulonglong), ("site", C.c_uint),
+        ("accumulate", C.c_int), ("drop_ld", C.c_longlong),
+    ]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale():
+    if not os.path.exists(LIBPATH):
+        return True
+    t = os.path.getmtime(LIBPATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu -> lib/libmma_b200.so (sm_100a, -lineinfo).  Cross-compiles without a GPU."""
+    if not force and not _stale():
+        return LIBPATH
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose and r.stderr:
+            print(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    tmp = LIBPATH + ".tmp"
+    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIBPATH)
+    return LIBPATH
+
+
+_lock = threading.Lock()
+_lib = None
+
+_vp, _i, _ll, _f, _ull, _u = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_uint
+_SIGS = {
+    "mma_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, C.POINTER(Epi), _i, _i, _vp],
+    "mma_gemm_simt": [_vp, _i, _ll, _ll, _vp, _i, _ll, _ll, _i, _i, _i, C.POINTER(Epi), _vp],
+    "mma_gather_rows": [_vp, _vp, _vp, _vp, _i, _i, _vp],
+    "mma_scatter_add_rows": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
+    "mma_ln_fwd": [_vp, _i, _ll, _vp, _vp, _f, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp],
+    "mma_ln_bwd": [_vp, _i, _ll, _i, _i, _i, _vp, _i, _ll, _vp, _f, _vp, _ll, _vp, _ll, _vp, _i, _ll, _f, _ull, _u,
+                   _vp, _vp, _i, _i, _vp],
+    "mma_colsum": [_vp, _i, _ll, _vp, _i, _i, _vp],
+    "mma_cast_f32_bf16": [_vp, _vp, _ll, _vp],
+    "mma_cast_bf16_f32": [_vp, _vp, _ll, _vp],
+    "mma_attn_fwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _ull, _u, _i,
+                     _vp],
+    "mma_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i,
+                     _i, _i, _i, _i, _f, _f, _ull, _u, _i, _vp],
+    "mma_ce_fwd": [_vp, _ll, _vp, _i, _i, _f, _ll, _vp, _vp, _vp, _vp],
+    "mma_ce_bwd": [_vp, _ll, _vp, _vp, _vp, _f, _i, _i, _f, _ll, _vp, _i, _ll, _vp],
+    "mma_grad_norm": [_vp, _ll, _vp, _vp, _vp],
+    "mma_adam_step": [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _vp],
+    "mma_decode_embed": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp],
+    "mma_decode_self_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
+    "mma_decode_cross_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp],
+    "mma_beam_step": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                      _vp, _vp],
+    "mma_greedy_step": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "mma_advance": [_vp, _vp],
+}
+EXPORTS = tuple(_SIGS)
+
+
+def load():
+    """ctypes handle to the library; builds it if the in-tree .so is missing or stale."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            path = build()
+            lib = C.CDLL(path)
+            for name, sig in _SIGS.items():
+                fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+                fn.argtypes = sig
+                fn.restype = C.c_int
+            _lib = lib
+    return _lib
+
+
+class KernelError(RuntimeError):
+    pass
+
+
+_ERRS = {-1: "bad argument", -2: "kernel launch failed", -3: "unsupported shape/type", -4: "driver / tensor-map error"}
+
+
+def check(rc, what):
+    if rc != 0:
+        raise KernelError(f"{what}: {_ERRS.get(rc, 'error')} (status {rc})")

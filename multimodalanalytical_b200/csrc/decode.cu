@@ -1,0 +1,490 @@
+// KV-cached decoding kernels (prediction path).
+//
+// The reference decodes with use_cache=False (wrapper.py:450): every step re-runs the decoder over the whole
+// prefix.  Here each step processes one token per live row:
+//   * decode_embed      target-token embedding + LayerNorm + positional row `cur_len-1`
+//   * decode_attn       single-query attention.  self mode: appends this step's K/V to the cache and attends
+//                       over the row's history through an ancestor table (beam reordering never copies the
+//                       cache); cross mode: attends over the encoder memory K/V computed once per spectrum and
+//                       shared by the K beams of that spectrum (no xK expansion).
+//   * beam_step         log-softmax -> forced EOS -> + running score -> top-2K of K*V -> live beams / finished
+//                       pool / early-stop heuristic, restating transformers' `_beam_search` (see oracle), one CTA
+//                       per spectrum; emits next tokens + parent rows and rewrites the ancestor table.
+//   * greedy_step       argmax decoding (n_beams == 1), transformers' `_sample` semantics.
+// All kernels read the current length from device memory so one CUDA graph replays for every step.
+#include "common.cuh"
+
+namespace dec {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict__ tok, const float* __restrict__ table,
+                                                           const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps,
+                                                           const float* __restrict__ pos, const int* __restrict__ cur_len,
+                                                           float* __restrict__ out, int rows, int d) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int t = *cur_len - 1;
+  const float* src = table + (long long)tok[r] * d;
+  float mean = 0.f, rstd = 1.f;
+  if (gamma) {
+    float s = 0.f;
+    for (int c = lane; c < d; c += 32) s += src[c];
+    mean = warp_sum(s) / d;
+    float q = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      const float e = src[c] - mean;
+      q += e * e;
+    }
+    rstd = rsqrtf(warp_sum(q) / d + eps);
+  }
+  const float* p = pos + (long long)t * d;
+  float* o = out + (long long)r * d;
+  for (int c = lane; c < d; c += 32) {
+    float v = src[c];
+    if (gamma) v = (v - mean) * rstd * gamma[c] + beta[c];
+    o[c] = v + p[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct AttnArgs {
+  const void* q; long long ldq;      // [R, ldq], head h at h*DH
+  const void* knew; const void* vnew; long long ldkv;   // self: this step's K/V rows [R, ldkv]
+  void* kc; void* vc;                // self: cache [Lmax][R][d];  cross: memory K / V [B][S][ldm] (head offset applied)
+  long long ldm;                     // cross: row pitch of memory K/V
+  const int* anc;                    // self: [R][Lmax] ancestor rows (nullptr: identity)
+  const unsigned char* kmask;        // cross: [B][S]
+  const int* cur_len;
+  void* o; long long ldo;
+  int R, H, d, Lmax, S, beams, cross;
+  float scale;
+};
+
+template <typename T, int DH>
+__global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
+  constexpr int CPL = (DH + 31) / 32;
+  __shared__ float qsh[4][DH];
+  __shared__ float psh[4][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * 4 + warp;
+  if (gw >= a.R * a.H) return;
+  const int r = gw / a.H, h = gw % a.H;
+  const int t = *a.cur_len - 1;
+  const T* q = reinterpret_cast<const T*>(a.q) + (long long)r * a.ldq + h * DH;
+  for (int c = lane; c < DH; c += 32) qsh[warp][c] = to_f(q[c]) * a.scale;
+  int nkeys;
+  const T *Kb, *Vb;
+  long long pitch;
+  const int* anc = nullptr;
+  const unsigned char* km = nullptr;
+  if (!a.cross) {
+    // append this step's K/V for (r, h) at position t, then attend over t+1 positions
+    T* kc = reinterpret_cast<T*>(a.kc) + ((long long)t * a.R + r) * a.d + h * DH;
+    T* vc = reinterpret_cast<T*>(a.vc) + ((long long)t * a.R + r) * a.d + h * DH;
+    const T* kn = reinterpret_cast<const T*>(a.knew) + (long long)r * a.ldkv + h * DH;
+    const T* vn = reinterpret_cast<const T*>(a.vnew) + (long long)r * a.ldkv + h * DH;
+    for (int c = lane; c < DH; c += 32) {
+      kc[c] = kn[c];
+      vc[c] = vn[c];
+    }
+    nkeys = t + 1;
+    Kb = reinterpret_cast<const T*>(a.kc) + h * DH;
+    Vb = reinterpret_cast<const T*>(a.vc) + h * DH;
+    pitch = (long long)a.R * a.d;  // per position
+    anc = a.anc ? a.anc + (long long)r * a.Lmax : nullptr;
+  } else {
+    const int b = r / a.beams;
+    nkeys = a.S;
+    Kb = reinterpret_cast<const T*>(a.kc) + (long long)b * a.S * a.ldm + h * DH;
+    Vb = reinterpret_cast<const T*>(a.vc) + (long long)b * a.S * a.ldm + h * DH;
+    pitch = a.ldm;
+    km = a.kmask ? a.kmask + (long long)b * a.S : nullptr;
+  }
+  __syncwarp();
+  float m = -INFINITY, l = 0.f, o[CPL];
+#pragma unroll
+  for (int cc = 0; cc < CPL; ++cc) o[cc] = 0.f;
+  for (int j0 = 0; j0 < nkeys; j0 += 32) {
+    const int j = j0 + lane;
+    bool valid = j < nkeys && (!km || km[j]);
+    long long off = 0;
+    if (j < nkeys) {
+      if (!a.cross) {
+        const int src = (j == t || !anc) ? r : anc[j];
+        off = (long long)j * pitch + (long long)src * a.d;
+      } else {
+        off = (long long)j * pitch;
+      }
+    }
+    float s = -INFINITY;
+    if (valid) {
+      const T* kr = Kb + off;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < DH; ++c) acc = fmaf(qsh[warp][c], to_f(kr[c]), acc);
+      s = acc;
+    }
+    const float mt = warp_max(s);
+    const float mn = fmaxf(m, mt);
+    float p = 0.f, corr = 1.f;
+    if (mn != -INFINITY) {
+      p = valid ? __expf(s - mn) : 0.f;
+      corr = m == -INFINITY ? 0.f : __expf(m - mn);
+    }
+    l = l * corr + warp_sum(p);
+    m = mn;
+    __syncwarp();
+    psh[warp][lane] = p;
+    __syncwarp();
+#pragma unroll
+    for (int cc = 0; cc < CPL; ++cc) o[cc] *= corr;
+    const int cnt = min(32, nkeys - j0);
+    for (int jj = 0; jj < cnt; ++jj) {
+      const float pj = psh[warp][jj];
+      const long long offj = __shfl_sync(0xffffffffu, off, jj);
+      if (pj != 0.f) {
+#pragma unroll
+        for (int cc = 0; cc < CPL; ++cc) {
+          const int c = lane + cc * 32;
+          if (c < DH) o[cc] = fmaf(pj, to_f(Vb[offj + c]), o[cc]);
+        }
+      }
+    }
+  }
+  T* out = reinterpret_cast<T*>(a.o) + (long long)r * a.ldo + h * DH;
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+  for (int cc = 0; cc < CPL; ++cc) {
+    const int c = lane + cc * 32;
+    if (c < DH) out[c] = from_f<T>(o[cc] * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// beam step
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+struct BeamArgs {
+  const float* logits; long long ldl;   // [B*K, ldl] fp32, last-position logits
+  const float* extra_bias;              // optional [B*K, V] additive processor output (log-prob domain)
+  int B, K, V, L;
+  int pad_id, eos_id;
+  const int* cur_len;
+  int* run_seq;      // [2][B][K][L]
+  int* fin_seq;      // [2][B][K][L]
+  float* run_score;  // [B][K]
+  float* fin_score;  // [B][K]
+  unsigned char* fin_flag;   // [B][K]
+  int* fin_len;      // [B][K]
+  unsigned char* improvable; // [B]
+  unsigned char* all_hit;    // [B]
+  int* anc;          // [2][B*K][L]
+  int* next_tok;     // [B*K]
+  int* parent_row;   // [B*K]
+};
+
+constexpr int MAXK = 64;  // beams (2K candidates <= 128)
+
+__global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
+  extern __shared__ uint32_t cand[];  // [K*V] ordered keys of accumulated log-probs
+  __shared__ float s_lse[MAXK];
+  __shared__ unsigned long long s_red[8];
+  __shared__ float c_score[2 * MAXK];
+  __shared__ int c_idx[2 * MAXK];
+  __shared__ int n_run_src[MAXK];     // candidate slot feeding running beam k
+  __shared__ int n_fin_src[MAXK];     // merged slot feeding finished slot k (<K: old finished, >=K: candidate)
+  __shared__ float n_fin_score[MAXK];
+  __shared__ unsigned char n_fin_flag[MAXK];
+  __shared__ int n_fin_len[MAXK];
+  __shared__ float n_run_score[MAXK];
+
+  const int b = blockIdx.x;
+  const int K = a.K, V = a.V, L = a.L;
+  const int cur = *a.cur_len;
+  const int rd = cur & 1, wr = rd ^ 1;
+  const float NEG = -1.0e9f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const bool force_eos = cur == L - 1;
+
+  // 1. log-softmax statistics per beam row (one warp per row)
+  for (int k = warp; k < K; k += nwarp) {
+    const float* x = a.logits + (long long)(b * K + k) * a.ldl;
+    float mx = -INFINITY;
+    for (int c = lane; c < V; c += 32) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += expf(x[c] - mx);
+    s = warp_sum(s);
+    if (lane == 0) s_lse[k] = mx + logf(s);
+  }
+  __syncthreads();
+  // 2. accumulated scores of the K*V continuations
+  for (int i = threadIdx.x; i < K * V; i += blockDim.x) {
+    const int k = i / V, c = i % V;
+    float lp = a.logits[(long long)(b * K + k) * a.ldl + c] - s_lse[k];
+    if (force_eos) lp = c == a.eos_id ? 0.f : -INFINITY;
+    if (a.extra_bias) lp += a.extra_bias[(long long)(b * K + k) * V + c];
+    cand[i] = f2ord(lp + a.run_score[b * K + k]);
+  }
+  __syncthreads();
+  // 3. top-2K, descending, ties -> lowest flat index
+  const int keep = 2 * K;
+  for (int sel = 0; sel < keep; ++sel) {
+    unsigned long long best = 0ull;
+    for (int i = threadIdx.x; i < K * V; i += blockDim.x) {
+      const uint32_t o = cand[i];
+      if (o) {
+        const unsigned long long key = ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+        best = key > best ? key : best;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) s_red[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long bb = 0ull;
+      for (int w = 0; w < nwarp; ++w) bb = s_red[w] > bb ? s_red[w] : bb;
+      if (bb) {
+        const int idx = (int)(0xffffffffu - (uint32_t)(bb & 0xffffffffull));
+        c_idx[sel] = idx;
+        c_score[sel] = ord2f((uint32_t)(bb >> 32));
+        cand[idx] = 0u;  // taken
+      } else {  // fewer than 2K candidates (K*V < 2K): pad with -inf on slot 0
+        c_idx[sel] = 0;
+        c_score[sel] = -INFINITY;
+      }
+    }
+    __syncthreads();
+  }
+  // 4. serial bookkeeping (tiny): live beams, finished pool, early-stop heuristic
+  if (threadIdx.x == 0) {
+    const bool improvable = a.improvable[b] != 0;
+    bool hits[2 * MAXK];
+    bool used[3 * MAXK];
+    float live[2 * MAXK];
+    bool allh = true;
+    for (int c = 0; c < keep; ++c) {
+      const int tok = c_idx[c] % V;
+      hits[c] = (tok == a.eos_id) || (cur + 1 >= L);
+      allh = allh && hits[c];
+      live[c] = c_score[c] + (hits[c] ? 1.0f : 0.0f) * NEG;
+      used[c] = false;
+    }
+    for (int k = 0; k < K; ++k) {  // top-K of live, ties -> lowest slot
+      int bi = -1;
+      for (int c = 0; c < keep; ++c)
+        if (!used[c] && (bi < 0 || live[c] > live[bi])) bi = c;
+      used[bi] = true;
+      n_run_src[k] = bi;
+      n_run_score[k] = live[bi];
+    }
+    // finished pool: old K slots followed by the 2K candidates
+    float ms[3 * MAXK];
+    const float glen = (float)(cur + 1 - 1);  // generated length incl. this token (prompt length 1)
+    for (int k = 0; k < K; ++k) ms[k] = a.fin_score[b * K + k];
+    for (int c = 0; c < keep; ++c) {
+      const bool just = hits[c] && c < K;
+      float fs = c_score[c] / glen;
+      fs = fs + (improvable ? 0.0f : 1.0f) * NEG;
+      fs = fs + (just ? 0.0f : 1.0f) * NEG;
+      ms[K + c] = fs;
+    }
+    for (int i = 0; i < K + keep; ++i) used[i] = false;
+    bool any_unfinished = false;
+    float worst = INFINITY;
+    for (int k = 0; k < K; ++k) {
+      int bi = -1;
+      for (int i = 0; i < K + keep; ++i)
+        if (!used[i] && (bi < 0 || ms[i] > ms[bi])) bi = i;
+      used[bi] = true;
+      n_fin_src[k] = bi;
+      n_fin_score[k] = ms[bi];
+      if (bi < K) {
+        n_fin_flag[k] = a.fin_flag[b * K + bi];
+        n_fin_len[k] = a.fin_len[b * K + bi];
+      } else {
+        const int c = bi - K;
+        n_fin_flag[k] = (hits[c] && c < K) ? 1 : 0;
+        n_fin_len[k] = cur + 1 - 1;
+      }
+      if (!n_fin_flag[k]) any_unfinished = true;
+      worst = fminf(worst, ms[bi]);
+    }
+    // early-stop heuristic with cur_len already advanced: best live sum / (cur_len+1 - prompt)
+    const float best_possible = n_run_score[0] / (float)(cur + 1 - 1);
+    bool can = false;
+    for (int k = 0; k < K; ++k) {
+      const float w = n_fin_flag[k] ? worst : NEG;
+      can = can || (best_possible > w);
+    }
+    (void)any_unfinished;
+    a.improvable[b] = (improvable && can) ? 1 : 0;
+    a.all_hit[b] = allh ? 1 : 0;
+  }
+  __syncthreads();
+  // 5. parallel state rewrite (ping-pong buffers)
+  const long long seq_stride = (long long)a.B * K * L;
+  const int* rs_old = a.run_seq + rd * seq_stride + (long long)b * K * L;
+  int* rs_new = a.run_seq + wr * seq_stride + (long long)b * K * L;
+  const int* fs_old = a.fin_seq + rd * seq_stride + (long long)b * K * L;
+  int* fs_new = a.fin_seq + wr * seq_stride + (long long)b * K * L;
+  const long long anc_stride = (long long)a.B * K * L;
+  const int* an_old = a.anc + rd * anc_stride + (long long)b * K * L;
+  int* an_new = a.anc + wr * anc_stride + (long long)b * K * L;
+  for (int i = threadIdx.x; i < K * L; i += blockDim.x) {
+    const int k = i / L, p = i % L;
+    {  // running beams
+      const int c = n_run_src[k];
+      const int beam = c_idx[c] / V, tok = c_idx[c] % V;
+      rs_new[i] = p == cur ? tok : rs_old[beam * L + p];
+      // ancestors: positions < cur-1 inherit, position cur-1 is the parent's own row
+      an_new[i] = p == cur - 1 ? b * K + beam : an_old[beam * L + p];
+    }
+    {  // finished pool
+      const int s = n_fin_src[k];
+      int v;
+      if (s < K) v = fs_old[s * L + p];
+      else {
+        const int c = s - K;
+        const int beam = c_idx[c] / V, tok = c_idx[c] % V;
+        v = p == cur ? tok : rs_old[beam * L + p];
+      }
+      fs_new[i] = v;
+    }
+  }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int c = n_run_src[k];
+    a.run_score[b * K + k] = n_run_score[k];
+    a.next_tok[b * K + k] = c_idx[c] % V;
+    a.parent_row[b * K + k] = b * K + c_idx[c] / V;
+    a.fin_score[b * K + k] = n_fin_score[k];
+    a.fin_flag[b * K + k] = n_fin_flag[k];
+    a.fin_len[b * K + k] = n_fin_len[k];
+  }
+}
+
+// greedy: one warp per row.  seq [R][L]; unfinished [R]
+__global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restrict__ logits, long long ldl,
+                                                          const float* __restrict__ extra_bias, int R, int V, int L,
+                                                          int pad_id, int eos_id, const int* __restrict__ cur_len,
+                                                          int* __restrict__ seq, unsigned char* __restrict__ unfinished,
+                                                          int* __restrict__ next_tok) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int cur = *cur_len;
+  const float* x = logits + (long long)r * ldl;
+  unsigned long long best = 0ull;
+  for (int c = lane; c < V; c += 32) {
+    float v = x[c];
+    if (extra_bias) v += extra_bias[(long long)r * V + c];
+    if (cur == L - 1) v = c == eos_id ? 0.f : -INFINITY;
+    const unsigned long long key = ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)c);
+    best = key > best ? key : best;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
+    best = other > best ? other : best;
+  }
+  if (lane == 0) {
+    int tok = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
+    const bool unf = unfinished[r] != 0;
+    if (!unf) tok = pad_id;
+    seq[(long long)r * L + cur] = tok;
+    next_tok[r] = tok;
+    unfinished[r] = (unf && tok != eos_id) ? 1 : 0;
+  }
+}
+
+__global__ void advance_kernel(int* cur_len) { *cur_len += 1; }
+
+template <typename T>
+static int launch_attn(const AttnArgs& a, int dh, cudaStream_t s) {
+  const int blocks = (a.R * a.H + 3) / 4;
+  switch (dh) {
+    case 16: decode_attn_kernel<T, 16><<<blocks, 128, 0, s>>>(a); break;
+    case 32: decode_attn_kernel<T, 32><<<blocks, 128, 0, s>>>(a); break;
+    case 64: decode_attn_kernel<T, 64><<<blocks, 128, 0, s>>>(a); break;
+    case 128: decode_attn_kernel<T, 128><<<blocks, 128, 0, s>>>(a); break;
+    default: return MMA_ERR_UNSUPPORTED;
+  }
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+}  // namespace dec
+
+using namespace dec;
+
+extern "C" int mma_decode_embed(const int* tok, const float* table, const float* gamma, const float* beta, float eps,
+                                const float* pos, const int* cur_len, float* out, int rows, int d,
+                                cudaStream_t stream) {
+  if (rows <= 0) return MMA_ERR_ARG;
+  decode_embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(tok, table, gamma, beta, eps, pos, cur_len, out, rows, d);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_decode_self_attn(const void* q, long long ldq, const void* knew, const void* vnew, long long ldkv,
+                                    void* kcache, void* vcache, const int* anc, const int* cur_len, void* o,
+                                    long long ldo, int R, int H, int dh, int Lmax, float scale, int type,
+                                    cudaStream_t stream) {
+  AttnArgs a{};
+  a.q = q; a.ldq = ldq; a.knew = knew; a.vnew = vnew; a.ldkv = ldkv; a.kc = kcache; a.vc = vcache; a.anc = anc;
+  a.cur_len = cur_len; a.o = o; a.ldo = ldo; a.R = R; a.H = H; a.d = H * dh; a.Lmax = Lmax; a.scale = scale;
+  a.cross = 0; a.beams = 1;
+  return type == MMA_F32 ? launch_attn<float>(a, dh, stream) : launch_attn<bf16>(a, dh, stream);
+}
+
+extern "C" int mma_decode_cross_attn(const void* q, long long ldq, const void* kmem, const void* vmem, long long ldm,
+                                     const unsigned char* kmask, const int* cur_len, void* o, long long ldo, int R,
+                                     int H, int dh, int S, int beams, float scale, int type, cudaStream_t stream) {
+  AttnArgs a{};
+  a.q = q; a.ldq = ldq; a.kc = const_cast<void*>(kmem); a.vc = const_cast<void*>(vmem); a.ldm = ldm; a.kmask = kmask;
+  a.cur_len = cur_len; a.o = o; a.ldo = ldo; a.R = R; a.H = H; a.d = H * dh; a.S = S; a.beams = beams;
+  a.scale = scale; a.cross = 1;
+  return type == MMA_F32 ? launch_attn<float>(a, dh, stream) : launch_attn<bf16>(a, dh, stream);
+}
+
+extern "C" int mma_beam_step(const float* logits, long long ldl, const float* extra_bias, int B, int K, int V, int L,
+                             int pad_id, int eos_id, const int* cur_len, int* run_seq, int* fin_seq, float* run_score,
+                             float* fin_score, unsigned char* fin_flag, int* fin_len, unsigned char* improvable,
+                             unsigned char* all_hit, int* anc, int* next_tok, int* parent_row, cudaStream_t stream) {
+  if (K > MAXK || K < 1 || B < 1) return MMA_ERR_ARG;
+  BeamArgs a{logits, ldl, extra_bias, B, K, V, L, pad_id, eos_id, cur_len, run_seq, fin_seq, run_score, fin_score,
+             fin_flag, fin_len, improvable, all_hit, anc, next_tok, parent_row};
+  const size_t smem = sizeof(uint32_t) * (size_t)K * V;
+  if (smem > 200 * 1024) return MMA_ERR_UNSUPPORTED;
+  if (smem > 40 * 1024) cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  beam_step_kernel<<<B, 256, smem, stream>>>(a);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_greedy_step(const float* logits, long long ldl, const float* extra_bias, int R, int V, int L,
+                               int pad_id, int eos_id, const int* cur_len, int* seq, unsigned char* unfinished,
+                               int* next_tok, cudaStream_t stream) {
+  if (R < 1) return MMA_ERR_ARG;
+  greedy_step_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, ldl, extra_bias, R, V, L, pad_id, eos_id, cur_len, seq,
+                                                      unfinished, next_tok);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_advance(int* cur_len, cudaStream_t stream) {
+  advance_kernel<<<1, 1, 0, stream>>>(cur_len);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}

@@ -1,0 +1,416 @@
+// tcgen05 / TMEM / TMA bf16 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A_op[M,K] * B_op[N,K]^T )      fp32 accumulate in TMEM
+//
+// Each operand is either K-major (memory [rows, K] row-major: activations, nn.Linear weights) or
+// MN-major (memory [K, rows] row-major).  That covers the three GEMMs of a linear layer with no
+// transposed copies:   fwd  y = x W^T        (A K-major, B K-major)
+//                      dgrad dx = dy W       (A K-major, B MN-major)
+//                      wgrad dW = dy^T x     (A MN-major, B MN-major; split over the row dimension)
+//
+// Structure: persistent CTAs (one per SM), 192 threads = TMA producer warp, MMA issuer warp (one
+// elected thread issues tcgen05.mma), four epilogue warps.  STAGES-deep smem ring fed by TMA
+// (128B swizzle), two TMEM accumulator stages so the epilogue of tile i overlaps the mainloop of
+// tile i+1.  The epilogue (bias / GELU / GLU / residual / dropout / split-K accumulate) is shared
+// with the SIMT fp32 GEMM (common.cuh).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug must trap (error returned to the host), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, 128B swizzle (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t tile_addr, int k16) {
+  uint32_t addr, lbo, sbo;
+  if (!MN_MAJOR) {
+    // rows of 128 B (64 bf16 of K), 8-row swizzle atoms 1024 B apart; K advances 32 B inside the row
+    addr = tile_addr + (uint32_t)k16 * 32u;
+    lbo = 16;
+    sbo = 1024;
+  } else {
+    // 64-element MN atoms: BK rows (k) of 128 B each; atoms BK*128 B apart; 8-k groups 1024 B apart
+    addr = tile_addr + (uint32_t)k16 * 2048u;
+    lbo = BK * 128;
+    sbo = 1024;
+  }
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+struct Cfg {
+  static constexpr int STAGES = BN <= 128 ? 6 : 4;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+               int splits, Epi ep) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * C::B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&full[i]), 1);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull[i]), 1);
+      mbar_init(smem_u32(&tempty[i]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_kb = (K + BK - 1) / BK;
+  const int total = tiles_m * tiles_n * splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA producer =================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int split = tile % splits;
+        const int t2 = tile / splits;
+        const int n0 = (t2 % tiles_n) * BN;
+        const int m0 = (t2 / tiles_n) * BM;
+        const int kb0 = (int)((long long)split * num_kb / splits);
+        const int kb1 = (int)((long long)(split + 1) * num_kb / splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full[stage]);
+          mbar_expect_tx(fb, C::A_BYTES + C::B_BYTES);
+          const uint32_t a_dst = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_dst = smem_u32(sB + stage * C::B_BYTES);
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, fb, kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BM / 64; ++a) tma_load_2d(a_dst + a * (BK * 128), &tmA, fb, m0 + a * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, fb, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BN / 64; ++a) tma_load_2d(b_dst + a * (BK * 128), &tmB, fb, n0 + a * 64, kb * BK);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer (single thread) =================
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13),
+      // a_major bit15, b_major bit16, N>>3 [17,23), M>>4 [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int split = tile % splits;
+        const int kb0 = (int)((long long)split * num_kb / splits);
+        const int kb1 = (int)((long long)(split + 1) * num_kb / splits);
+        mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            tc_mma_bf16(d_tmem, make_smem_desc<A_MN>(a_addr, k), make_smem_desc<B_MN>(b_addr, k), idesc,
+                        (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&empty[stage]));  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(smem_u32(&tfull[acc]));  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (TMEM -> registers -> global) =================
+    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int t2 = tile / splits;
+      const int n0 = (t2 % tiles_n) * BN;
+      const int m0 = (t2 / tiles_n) * BM;
+      mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+      tc_fence_after();
+      const long long row = (long long)m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        if (row < M && n0 + c0 < N) epilogue_store<32>(ep, row, n0 + c0, N, v);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps (cached) + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  unsigned long long d0, d1, ld;
+  unsigned int b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ k.d0;
+    h = h * 1000003u ^ k.d1;
+    h = h * 1000003u ^ k.ld;
+    h = h * 1000003u ^ ((size_t)k.b0 << 16 | k.b1);
+    return h;
+  }
+};
+
+// 2-D bf16 tensor map: inner extent d0 (contiguous), outer extent d1, row pitch ld elements.
+static int make_map(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1,
+                    unsigned long long ld, unsigned int b0, unsigned int b1) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, d0, d1, ld, b0, b1};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return MMA_OK;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return MMA_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return MMA_ERR_ARG;
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return MMA_ERR_DRIVER;
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 65536) cache.clear();
+  cache.emplace(key, *out);
+  return MMA_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int splits, const Epi& ep,
+                  int max_ctas, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess)
+      return MMA_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int total = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
+  int grid = total < num_sms() ? total : num_sms();
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  kern<<<grid, NUM_THREADS, C::SMEM, stream>>>(tmA, tmB, M, N, K, splits, ep);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+}  // namespace tc
+
+// C[M,N] = epi(A_op * B_op^T).  a_mn / b_mn: 0 = operand memory is [rows, K] (K-major), 1 = [K, rows].
+// lda / ldb: row pitch of the operand's memory in elements.  splits > 1 splits the K loop across CTAs
+// (requires ep->kind == EPI_ACCUM with accumulate == 2).  max_ctas <= 0: one CTA per SM.
+extern "C" int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M,
+                             int N, int K, const Epi* ep, int splits, int max_ctas, cudaStream_t stream) {
+  using namespace tc;
+  if (M <= 0 || N <= 0 || K <= 0 || !ep) return MMA_ERR_ARG;
+  const int num_kb = (K + BK - 1) / BK;
+  if (splits < 1) splits = 1;
+  if (splits > num_kb) splits = num_kb;
+  if (splits > 1 && !(ep->kind == EPI_ACCUM && ep->accumulate == 2)) return MMA_ERR_ARG;
+  const int BN = 128;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_map(&tmA, A, (unsigned long long)K, (unsigned long long)M, lda, BK, BM);
+  else rc = make_map(&tmA, A, (unsigned long long)M, (unsigned long long)K, lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tmB, B, (unsigned long long)K, (unsigned long long)N, ldb, BK, BN);
+  else rc = make_map(&tmB, B, (unsigned long long)N, (unsigned long long)K, ldb, 64, BK);
+  if (rc) return rc;
+  if (!a_mn && !b_mn) return launch<128, false, false>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
+  if (!a_mn && b_mn) return launch<128, false, true>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
+  if (a_mn && b_mn) return launch<128, true, true>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
+  return launch<128, true, false>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
+}

@@ -1,0 +1,389 @@
+// Memory-bound row kernels: embedding gather / scatter-add, LayerNorm forward / backward (fused with the
+// positional-encoding add + multimodal concat on the way out, and with the residual-gradient add +
+// dropout-masked low-precision copy on the way back), column sums (bias gradients), casts.
+// One warp per row, float4-vectorised lanes, warp-shuffle reductions; fp32 statistics throughout.
+#include "common.cuh"
+
+namespace rowops {
+
+constexpr int MAXI = 8;  // a lane owns float4 columns lane*4 + 128*i, i < MAXI  ->  d <= 1024
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ float4 ld(const bf16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+  }
+  static __device__ __forceinline__ void st(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a);
+    u.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+__device__ __forceinline__ float4 ld4_any(const void* p, long long i, int f32) {
+  return f32 ? Vec4<float>::ld(reinterpret_cast<const float*>(p) + i) : Vec4<bf16>::ld(reinterpret_cast<const bf16*>(p) + i);
+}
+__device__ __forceinline__ void st4_any(void* p, long long i, int f32, float4 v) {
+  if (f32) Vec4<float>::st(reinterpret_cast<float*>(p) + i, v);
+  else Vec4<bf16>::st(reinterpret_cast<bf16*>(p) + i, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather: out[r,:] = table[ids[r],:] * (scale ? scale[r] : 1)          (nn.Embedding, XVal scaling)
+// ---------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const long long* __restrict__ ids, const float* __restrict__ scale,
+                                   const float* __restrict__ table, float* __restrict__ out, int rows, int d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* src = table + ids[warp] * (long long)d;
+  const float s = scale ? scale[warp] : 1.f;
+  float* dst = out + (long long)warp * d;
+  if ((d & 3) == 0) {
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 v = *reinterpret_cast<const float4*>(src + c);
+      v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+      *reinterpret_cast<float4*>(dst + c) = v;
+    }
+  } else {
+    for (int c = lane; c < d; c += 32) dst[c] = src[c] * s;
+  }
+}
+
+// dtable[ids[r],:] += g[r,:] * scale[r]   (skipping the padding row, as nn.Embedding(padding_idx) does)
+__global__ void scatter_add_rows_kernel(const long long* __restrict__ ids, const float* __restrict__ scale,
+                                        const float* __restrict__ g, float* __restrict__ dtable, int rows, int d,
+                                        long long pad_idx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const long long id = ids[warp];
+  if (id == pad_idx) return;
+  const float s = scale ? scale[warp] : 1.f;
+  const float* src = g + (long long)warp * d;
+  float* dst = dtable + id * (long long)d;
+  for (int c = lane; c < d; c += 32) atomicAdd(dst + c, src[c] * s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm forward.  Output row r lands at (r / group) * out_group_stride + out_offset + r % group, which
+// is how each modality writes its slice of the concatenated [B, S_total, d] sequence; `add` (pos-enc
+// table, row = out_offset + r % group) is added after the affine.  gamma == nullptr: no norm.
+// ---------------------------------------------------------------------------------------------
+struct LnFwdArgs {
+  const void* x; int x_f32; long long ldx;
+  const float* gamma; const float* beta; float eps;
+  void* y; int y_f32; long long ldy;
+  void* y2; int y2_f32; long long ldy2;
+  const float* add; long long ld_add;
+  int rows, d, group, out_group_stride, out_offset;
+};
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.rows) return;
+  const long long r = warp;
+  const long long orow = (r / a.group) * (long long)a.out_group_stride + a.out_offset + (r % a.group);
+  const int d = a.d;
+  float4 xv[MAXI];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < d) {
+      xv[i] = ld4_any(a.x, r * a.ldx + c, a.x_f32);
+      sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+    }
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (a.gamma) {
+    mean = warp_sum(sum) / d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < d) {
+        const float dx = xv[i].x - mean, dy = xv[i].y - mean, dz = xv[i].z - mean, dw = xv[i].w - mean;
+        sq += dx * dx + dy * dy + dz * dz + dw * dw;
+      }
+    }
+    rstd = rsqrtf(warp_sum(sq) / d + a.eps);
+  }
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < d) {
+      float4 o = xv[i];
+      if (a.gamma) {
+        const float4 g = *reinterpret_cast<const float4*>(a.gamma + c);
+        const float4 b = *reinterpret_cast<const float4*>(a.beta + c);
+        o.x = (o.x - mean) * rstd * g.x + b.x;
+        o.y = (o.y - mean) * rstd * g.y + b.y;
+        o.z = (o.z - mean) * rstd * g.z + b.z;
+        o.w = (o.w - mean) * rstd * g.w + b.w;
+      }
+      if (a.add) {
+        const float4 p = *reinterpret_cast<const float4*>(a.add + (long long)(a.out_offset + (r % a.group)) * a.ld_add + c);
+        o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+      }
+      st4_any(a.y, orow * a.ldy + c, a.y_f32, o);
+      if (a.y2) st4_any(a.y2, orow * a.ldy2 + c, a.y2_f32, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward (statistics recomputed from x).
+//   g   = dy * gamma;  xhat = (x - mean) * rstd
+//   dx  = [dres +] rstd * (g - mean(g) - xhat * mean(g * xhat))
+//   dgamma += sum_rows dy * xhat;  dbeta += sum_rows dy        (block-reduced, then atomics)
+// dy rows may be remapped exactly like ln_fwd's output rows (embedding backward reads its slice of the
+// [B, S_total, d] gradient).  dxb (optional) = low-precision copy of dx with the dropout mask of the
+// residual branch that produced x applied: it is the dy operand of that branch's dgrad/wgrad GEMMs.
+// ---------------------------------------------------------------------------------------------
+struct LnBwdArgs {
+  const void* dy; int dy_f32; long long lddy;
+  int group, in_group_stride, in_offset;
+  const void* x; int x_f32; long long ldx;
+  const float* gamma; float eps;
+  const float* dres; long long lddres;
+  float* dx; long long lddx;
+  void* dxb; int dxb_f32; long long lddxb;
+  float p_drop; unsigned long long seed; unsigned int site;
+  float* dgamma; float* dbeta;
+  int rows, d;
+};
+
+__global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
+  __shared__ float s_dg[MAXI * 128];
+  __shared__ float s_db[MAXI * 128];
+  const int d = a.d;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; }
+  __syncthreads();
+  float4 pg[MAXI], pb[MAXI];
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) { pg[i] = make_float4(0, 0, 0, 0); pb[i] = make_float4(0, 0, 0, 0); }
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+
+  for (long long r = (long long)blockIdx.x * wpb + wib; r < a.rows; r += (long long)gridDim.x * wpb) {
+    const long long irow = (r / a.group) * (long long)a.in_group_stride + a.in_offset + (r % a.group);
+    float4 xv[MAXI], gv[MAXI];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < d) {
+        xv[i] = ld4_any(a.x, r * a.ldx + c, a.x_f32);
+        gv[i] = ld4_any(a.dy, irow * a.lddy + c, a.dy_f32);
+        sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+      }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (a.gamma) {
+      mean = warp_sum(sum) / d;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < d) {
+          const float e0 = xv[i].x - mean, e1 = xv[i].y - mean, e2 = xv[i].z - mean, e3 = xv[i].w - mean;
+          sq += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+        }
+      }
+      rstd = rsqrtf(warp_sum(sq) / d + a.eps);
+    }
+    float sg = 0.f, sgx = 0.f;
+    if (a.gamma) {
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < d) {
+          const float4 gm = *reinterpret_cast<const float4*>(a.gamma + c);
+          float4 xh;
+          xh.x = (xv[i].x - mean) * rstd; xh.y = (xv[i].y - mean) * rstd;
+          xh.z = (xv[i].z - mean) * rstd; xh.w = (xv[i].w - mean) * rstd;
+          const float4 dy = gv[i];
+          pg[i].x += dy.x * xh.x; pg[i].y += dy.y * xh.y; pg[i].z += dy.z * xh.z; pg[i].w += dy.w * xh.w;
+          pb[i].x += dy.x; pb[i].y += dy.y; pb[i].z += dy.z; pb[i].w += dy.w;
+          float4 g;
+          g.x = dy.x * gm.x; g.y = dy.y * gm.y; g.z = dy.z * gm.z; g.w = dy.w * gm.w;
+          sg += g.x + g.y + g.z + g.w;
+          sgx += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+          gv[i] = g;
+          xv[i] = xh;
+        }
+      }
+      sg = warp_sum(sg) / d;
+      sgx = warp_sum(sgx) / d;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < d) {
+        float4 o = gv[i];
+        if (a.gamma) {
+          o.x = rstd * (gv[i].x - sg - xv[i].x * sgx);
+          o.y = rstd * (gv[i].y - sg - xv[i].y * sgx);
+          o.z = rstd * (gv[i].z - sg - xv[i].z * sgx);
+          o.w = rstd * (gv[i].w - sg - xv[i].w * sgx);
+        }
+        if (a.dres) {
+          const float4 q = *reinterpret_cast<const float4*>(a.dres + r * a.lddres + c);
+          o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+        }
+        if (a.dx) *reinterpret_cast<float4*>(a.dx + r * a.lddx + c) = o;
+        if (a.dxb) {
+          if (drop) {
+            const uint4 w = drop_words(a.seed, a.site, ((unsigned long long)r * d + c) >> 2);
+            o.x *= w.x >= thr ? inv_keep : 0.f;
+            o.y *= w.y >= thr ? inv_keep : 0.f;
+            o.z *= w.z >= thr ? inv_keep : 0.f;
+            o.w *= w.w >= thr ? inv_keep : 0.f;
+          }
+          st4_any(a.dxb, r * a.lddxb + c, a.dxb_f32, o);
+        }
+      }
+    }
+  }
+  if (a.gamma && a.dgamma) {
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < d) {
+        atomicAdd(&s_dg[c], pg[i].x); atomicAdd(&s_dg[c + 1], pg[i].y);
+        atomicAdd(&s_dg[c + 2], pg[i].z); atomicAdd(&s_dg[c + 3], pg[i].w);
+        atomicAdd(&s_db[c], pb[i].x); atomicAdd(&s_db[c + 1], pb[i].y);
+        atomicAdd(&s_db[c + 2], pb[i].z); atomicAdd(&s_db[c + 3], pb[i].w);
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      atomicAdd(a.dgamma + c, s_dg[c]);
+      atomicAdd(a.dbeta + c, s_db[c]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sums: out[c] += sum_r in[r, c]      (bias gradients; batch-sum of the learned pos-enc gradient)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, long long ld, float* __restrict__ out,
+                                                     int rows, int cols, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s = 0.f;
+  if (c < cols)
+    for (int r = r0 + ty; r < r1; r += 8) s += to_f(in[(long long)r * ld + c]);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) s += red[j][tx];
+    if (c < cols) atomicAdd(out + c, s);
+  }
+}
+
+// fp32 -> bf16 copy (weights, inputs)
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    Vec4<bf16>::st(out + i, *reinterpret_cast<const float4*>(in + i));
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace rowops
+
+using namespace rowops;
+
+extern "C" int mma_gather_rows(const long long* ids, const float* scale, const float* table, float* out, int rows,
+                               int d, cudaStream_t stream) {
+  if (rows <= 0) return MMA_OK;
+  gather_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, scale, table, out, rows, d);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_scatter_add_rows(const long long* ids, const float* scale, const float* g, float* dtable, int rows,
+                                    int d, long long pad_idx, cudaStream_t stream) {
+  if (rows <= 0) return MMA_OK;
+  scatter_add_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(ids, scale, g, dtable, rows, d, pad_idx);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_ln_fwd(const void* x, int x_f32, long long ldx, const float* gamma, const float* beta, float eps,
+                          void* y, int y_f32, long long ldy, void* y2, int y2_f32, long long ldy2, const float* add,
+                          long long ld_add, int rows, int d, int group, int out_group_stride, int out_offset,
+                          cudaStream_t stream) {
+  if (rows <= 0) return MMA_OK;
+  if (d > MAXI * 128 || (d & 3)) return MMA_ERR_UNSUPPORTED;
+  LnFwdArgs a{x, x_f32, ldx, gamma, beta, eps, y, y_f32, ldy, y2, y2_f32, ldy2, add, ld_add,
+              rows, d, group > 0 ? group : rows, out_group_stride, out_offset};
+  ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(a);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_ln_bwd(const void* dy, int dy_f32, long long lddy, int group, int in_group_stride, int in_offset,
+                          const void* x, int x_f32, long long ldx, const float* gamma, float eps, const float* dres,
+                          long long lddres, float* dx, long long lddx, void* dxb, int dxb_f32, long long lddxb,
+                          float p_drop, unsigned long long seed, unsigned int site, float* dgamma, float* dbeta,
+                          int rows, int d, cudaStream_t stream) {
+  if (rows <= 0) return MMA_OK;
+  if (d > MAXI * 128 || (d & 3)) return MMA_ERR_UNSUPPORTED;
+  LnBwdArgs a{dy, dy_f32, lddy, group > 0 ? group : rows, in_group_stride, in_offset, x, x_f32, ldx, gamma, eps,
+              dres, lddres, dx, lddx, dxb, dxb_f32, lddxb, p_drop, seed, site, dgamma, dbeta, rows, d};
+  int blocks = (rows + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  ln_bwd_kernel<<<blocks, 256, 0, stream>>>(a);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_colsum(const void* in, int in_f32, long long ld, float* out, int rows, int cols,
+                          cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return MMA_OK;
+  int by = (rows + 255) / 256;
+  if (by > 64) by = 64;
+  const int rpb = (rows + by - 1) / by;
+  dim3 grid((cols + 31) / 32, by);
+  if (in_f32) colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)in, ld, out, rows, cols, rpb);
+  else colsum_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)in, ld, out, rows, cols, rpb);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream) {
+  if (n <= 0) return MMA_OK;
+  const long long thr = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, stream>>>(in, (bf16*)out, n);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t stream) {
+  if (n <= 0) return MMA_OK;
+  cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)in, out, n);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}

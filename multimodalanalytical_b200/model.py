@@ -1,0 +1,479 @@
+"""Forward / backward of the multimodal encoder-decoder, written as an explicit schedule of kernel launches.
+
+Reference semantics (custom_modeling.py:108-199,220-243,271-320,420-508; modeling/utils.py:44-182,198-272):
+pre-LN encoder/decoder layers over packed-QKV attention, exact-erf GELU FFN (optionally GLU-gated), final
+LayerNorms, untied LM head, mean cross-entropy over non-pad targets.  There is no autograd graph: the
+backward pass is the hand-scheduled mirror of the forward pass, so every buffer, stream and gradient bucket
+is under our control (what a CUDA-graph capture and the overlapped gradient all-reduce need).
+
+Precision modes
+  "bf16": bf16 GEMM operands on tcgen05 (fp32 TMEM accumulate), fp32 residual stream / LN / softmax / loss,
+          fp32 master weights with a bf16 mirror.
+  "fp32": everything fp32 (SIMT GEMM) - the parity mode (logits/loss 1e-5, identical beam sequences).
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+
+from . import ops
+from ._lib import (EPI_ACCUM, EPI_DGELU, EPI_DGLU, EPI_DRELU, EPI_GELU, EPI_GLU_MUL, EPI_RELU, EPI_RESID, EPI_STORE)
+from .params import TOKEN_TYPES, ModelConfig, ParamStore
+
+NUM_SMS = 148
+
+
+class Engine:
+    def __init__(self, cfg: ModelConfig, params: ParamStore, precision: str = "bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(precision)
+        self.cfg, self.ps = cfg, params
+        self.precision = precision
+        self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.dev = params.device
+        self._bufs: Dict[Any, torch.Tensor] = {}
+        self.seed = 0x5EED0001
+        self.saved: Dict[str, Any] = {}
+        self.grad_ready_hook: Optional[Callable[[int], None]] = None  # called with the flat offset from which
+        #                                                               all gradients are final
+        self.ldv = (cfg.vocab_size + 7) // 8 * 8
+
+    # ------------------------------------------------------------------------------------- utils
+    def buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._bufs[key] = t
+        return t
+
+    def sync_weights(self):
+        """Refresh the bf16 mirror of the master weights (after load_state_dict / an external optimiser)."""
+        if self.precision == "bf16" and self.ps.bf16_dirty:
+            ops.cast_f32_bf16(self.ps.p, self.ps.pb)
+        self.ps.bf16_dirty = False
+
+    def W(self, name):
+        return self.ps.PB(name) if self.precision == "bf16" else self.ps.P(name)
+
+    def P(self, name):
+        return self.ps.P(name)
+
+    def G(self, name):
+        return self.ps.G(name)
+
+    @staticmethod
+    def _site(dec: bool, layer: int, k: int) -> int:
+        return (1024 if dec else 0) + 16 * layer + k
+
+    def _splits(self, n_out, k_in, rows):
+        tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+        kb = (rows + 63) // 64
+        s = max(1, NUM_SMS // tiles)
+        return max(1, min(s, kb // 2 if kb >= 2 else 1, 64))
+
+    # ----------------------------------------------------------------------------- linear helpers
+    def _lin_bwd(self, dy, x, wname, bname, rows, n_out, k_in, dx_epi=None, row_slice=None):
+        """dy: [rows, n_out]; x: [rows, k_in]; W: [n_out, k_in] (optionally a row slice of the named tensor)."""
+        Wt, Gw, Gb = self.W(wname), self.G(wname), self.G(bname)
+        if row_slice is not None:
+            Wt, Gw, Gb = Wt[row_slice], Gw[row_slice], Gb[row_slice]
+        if dx_epi is not None:
+            ops.gemm(dy, Wt, rows, k_in, n_out, dx_epi, b_mn=True)
+        ops.gemm(dy, x, n_out, k_in, rows, ops.make_epi(EPI_ACCUM, Gw, accumulate=2), a_mn=True, b_mn=True,
+                 splits=self._splits(n_out, k_in, rows))
+        ops.colsum(dy, Gb, rows=rows, cols=n_out)
+
+    # --------------------------------------------------------------------------------- embedding
+    def _pos_rows(self, L, tag):
+        ps, cfg = self.ps, self.cfg
+        e = ps.EMB + "positional_encodings."
+        if cfg.positional_encoding_type == "sin_cos":
+            return ps.buffers[e + "pos_enc"]
+        pl = self.buf(f"{tag}.posln", (L, cfg.d_model), torch.float32)
+        ops.ln_fwd(self.P(e + "pos_encodings.weight")[:L], self.P(e + "norm.weight"), self.P(e + "norm.bias"), pl)
+        return pl
+
+    def _embed(self, inputs: Dict[str, Any], L_total: int, tag: str, B: int):
+        cfg, d = self.cfg, self.cfg.d_model
+        x0 = self.buf(f"{tag}.x0", (B * L_total, d), torch.float32)
+        pos = self._pos_rows(L_total, tag)
+        recs: List[Dict[str, Any]] = []
+        off = 0
+        e = self.ps.EMB
+        for m, val in inputs.items():
+            mc = cfg.data_config[m]
+            base = f"{e}embedding_layer_dict.{m}."
+            if mc["type"] in TOKEN_TYPES:
+                ids = (val["tokenized_input"] if isinstance(val, dict) else val).contiguous()
+                scale = val["numerical_values"].contiguous().float() if isinstance(val, dict) else None
+                S_m = ids.shape[1]
+                pre = self.buf(f"{tag}.{m}.pre", (B * S_m, d), torch.float32)
+                ops.gather_rows(ids.view(-1), self.P(base + "weight"), pre, scale=None if scale is None else scale.view(-1))
+                rec = dict(kind="tok", ids=ids, scale=scale, pre=pre)
+            else:
+                xin = val.contiguous().float()
+                S_m = xin.shape[1]
+                h = xin.view(B * S_m, -1)
+                layers = cfg.embed_layers(m)
+                hs = [h]
+                for li, (o, i) in enumerate(layers):
+                    pre_n = base if len(layers) == 1 else f"{base}{2 * li}."
+                    out = self.buf(f"{tag}.{m}.h{li}", (B * S_m, o), torch.float32)
+                    kind = EPI_STORE if li == len(layers) - 1 else EPI_RELU
+                    ops.gemm(h, self.P(pre_n + "weight"), B * S_m, o, i,
+                             ops.make_epi(kind, out, bias=self.P(pre_n + "bias")), force_simt=True)
+                    h = out
+                    hs.append(out)
+                pre = h
+                rec = dict(kind="patch", hs=hs)
+            gam = bet = None
+            if cfg.multimodal_norm:
+                gam, bet = self.P(f"{e}embedding_norm_dict.{m}.weight"), self.P(f"{e}embedding_norm_dict.{m}.bias")
+            ops.ln_fwd(pre, gam, bet, x0, add=pos, group=S_m, out_group_stride=L_total, out_offset=off)
+            rec.update(m=m, off=off, S=S_m, pre=pre)
+            recs.append(rec)
+            off += S_m
+        if off != L_total:
+            raise ValueError(f"modalities cover {off} positions, mask has {L_total}")
+        return x0, recs
+
+    def _embed_bwd(self, dx0, recs, L_total: int, tag: str, B: int):
+        cfg, d = self.cfg, self.cfg.d_model
+        e = self.ps.EMB
+        for rec in recs:
+            m, off, S_m = rec["m"], rec["off"], rec["S"]
+            base = f"{e}embedding_layer_dict.{m}."
+            dpre = self.buf(f"{tag}.{m}.dpre", (B * S_m, d), torch.float32)
+            gam = dg = db = None
+            if cfg.multimodal_norm:
+                gam = self.P(f"{e}embedding_norm_dict.{m}.weight")
+                dg, db = self.G(f"{e}embedding_norm_dict.{m}.weight"), self.G(f"{e}embedding_norm_dict.{m}.bias")
+            ops.ln_bwd(dx0, rec["pre"], gam, dx=dpre, dgamma=dg, dbeta=db, group=S_m, in_group_stride=L_total,
+                       in_offset=off)
+            if rec["kind"] == "tok":
+                ops.scatter_add_rows(rec["ids"].view(-1), dpre, self.G(base + "weight"),
+                                     pad_idx=cfg.data_config[m]["pad_token_id"],
+                                     scale=None if rec["scale"] is None else rec["scale"].view(-1))
+            else:
+                layers = cfg.embed_layers(m)
+                hs = rec["hs"]
+                dy = dpre
+                for li in reversed(range(len(layers))):
+                    o, i = layers[li]
+                    pre_n = base if len(layers) == 1 else f"{base}{2 * li}."
+                    rows = B * S_m
+                    ops.gemm(dy, hs[li], o, i, rows, ops.make_epi(EPI_ACCUM, self.G(pre_n + "weight"), accumulate=1),
+                             a_mn=True, b_mn=True, force_simt=True)
+                    ops.colsum(dy, self.G(pre_n + "bias"), rows=rows, cols=o)
+                    if li > 0:
+                        dh = self.buf(f"{tag}.{m}.dh{li}", (rows, i), torch.float32)
+                        ops.gemm(dy, self.P(pre_n + "weight"), rows, i, o, ops.make_epi(EPI_DRELU, dh, aux=hs[li]),
+                                 b_mn=True, force_simt=True)
+                        dy = dh
+        if cfg.positional_encoding_type == "learned":
+            pe = e + "positional_encodings."
+            dpos = self.buf(f"{tag}.dposln", (L_total * d,), torch.float32)
+            dpos.zero_()
+            ops.colsum(dx0.view(B, L_total * d), dpos, rows=B, cols=L_total * d)
+            gtab = self.G(pe + "pos_encodings.weight")[:L_total]
+            ops.ln_bwd(dpos.view(L_total, d), self.P(pe + "pos_encodings.weight")[:L_total], self.P(pe + "norm.weight"),
+                       dx=gtab, dres=gtab, dgamma=self.G(pe + "norm.weight"), dbeta=self.G(pe + "norm.bias"))
+
+    # ----------------------------------------------------------------------------- layer forward
+    def _attn_block_fwd(self, tag, x, B, L, heads, wp, kmask, causal, p, site_a, site_r, train):
+        """x -> x + drop(out_proj(attn(LN(x))))  (self-attention).  Returns the new residual stream."""
+        d = self.cfg.d_model
+        M = B * L
+        dh = d // heads
+        T = self.adt
+        h = self.buf(tag + ".h", (M, d), T)
+        ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        qkv = self.buf(tag + ".qkv", (M, 3 * d), T)
+        ops.gemm(h, self.W(wp["in_w"]), M, 3 * d, d, ops.make_epi(EPI_STORE, qkv, bias=self.P(wp["in_b"])))
+        ctx = self.buf(tag + ".ctx", (M, d), T)
+        lse = self.buf(tag + ".lse", (B * heads * L,), torch.float32)
+        ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, lse, B, heads, L, L, dh, kmask=kmask,
+                     causal=causal, p_drop=p, seed=self.seed, site=site_a)
+        xo = self.buf(tag + ".xo", (M, d), torch.float32)
+        ops.gemm(ctx, self.W(wp["out_w"]), M, d, d,
+                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed, site=site_r))
+        if train:
+            self.saved[tag] = dict(x=x, h=h, qkv=qkv, ctx=ctx, lse=lse)
+        return xo
+
+    def _attn_block_bwd(self, tag, dx, dyb, B, L, heads, wp, kmask, causal, p, site_a, prev_site, first=False):
+        """dx: fp32 grad of the block output; dyb: low-precision (dropout-masked) copy.  Returns (dx_in, dyb_in)."""
+        d = self.cfg.d_model
+        M = B * L
+        dh = d // heads
+        T = self.adt
+        s = self.saved[tag]
+        dctx = self.buf("bw.dctx", (M, d), T)
+        self._lin_bwd(dyb, s["ctx"], wp["out_w"], wp["out_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dctx))
+        dqkv = self.buf("bw.dqkv", (M, 3 * d), T)
+        qkv = s["qkv"]
+        ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], s["ctx"], s["lse"], dctx, dqkv[:, :d],
+                     dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, heads, L, L, dh, kmask=kmask, causal=causal, p_drop=p,
+                     seed=self.seed, site=site_a)
+        dh_ = self.buf("bw.dh", (M, d), T)
+        self._lin_bwd(dqkv, s["h"], wp["in_w"], wp["in_b"], M, 3 * d, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
+        dx_in = self._other_dx(dx, M)
+        dyb_in = None if first else self.buf(f"bw.dyb.{M}", (M, d), T)
+        ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
+                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed, site=prev_site)
+        return dx_in, dyb_in
+
+    def _ffn_block_fwd(self, tag, x, M, f, wp, p, site_i, site_r, train):
+        d = self.cfg.d_model
+        T = self.adt
+        h = self.buf(tag + ".h", (M, d), T)
+        ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        a = self.buf(tag + ".a", (M, f), T)
+        z = self.buf(tag + ".z", (M, f), T)
+        z2 = None
+        if not self.cfg.gated_linear:
+            ops.gemm(h, self.W(wp["w1"]), M, f, d,
+                     ops.make_epi(EPI_GELU, a, out2=z if train else None, bias=self.P(wp["b1"]), p_drop=p,
+                                  seed=self.seed, site=site_i))
+        else:
+            z2 = self.buf(tag + ".z2", (M, f), T)
+            ops.gemm(h, self.W(wp["w1"]), M, f, d, ops.make_epi(EPI_STORE, z, bias=self.P(wp["b1"])))
+            ops.gemm(h, self.W(wp["wg"]), M, f, d,
+                     ops.make_epi(EPI_GLU_MUL, a, out2=z2, bias=self.P(wp["bg"]), aux=z, p_drop=p, seed=self.seed,
+                                  site=site_i))
+        xo = self.buf(tag + ".xo", (M, d), torch.float32)
+        ops.gemm(a, self.W(wp["w2"]), M, d, f,
+                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["b2"]), resid=x, p_drop=p, seed=self.seed, site=site_r))
+        if train:
+            self.saved[tag] = dict(x=x, h=h, a=a, z=z, z2=z2)
+        return xo
+
+    def _ffn_block_bwd(self, tag, dx, dyb, M, f, wp, p, site_i, prev_site):
+        d = self.cfg.d_model
+        T = self.adt
+        s = self.saved[tag]
+        dz = self.buf("bw.dz", (M, f), T)
+        dh_ = self.buf("bw.dh", (M, d), T)
+        if not self.cfg.gated_linear:
+            self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
+                          dx_epi=ops.make_epi(EPI_DGELU, dz, aux=s["z"], p_drop=p, seed=self.seed, site=site_i, drop_ld=f))
+            self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
+        else:
+            dz2 = self.buf("bw.dz2", (M, f), T)
+            self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
+                          dx_epi=ops.make_epi(EPI_DGLU, dz, out2=dz2, aux=s["z"], aux2=s["z2"], p_drop=p,
+                                              seed=self.seed, site=site_i, drop_ld=f))
+            # dh = dz W1 + dz2 Wg: the second product lands through the accumulate epilogue (fp32)
+            dh_ = self.buf("bw.dhs", (M, d), torch.float32)
+            self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=0))
+            self._lin_bwd(dz2, s["h"], wp["wg"], wp["bg"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=1))
+        dx_in = self._other_dx(dx, M)
+        dyb_in = self.buf(f"bw.dyb.{M}", (M, d), T)
+        ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
+                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed, site=prev_site)
+        return dx_in, dyb_in
+
+    def _other_dx(self, dx, M):
+        a = self.buf(f"bw.dx.{M}.0", (M, self.cfg.d_model), torch.float32)
+        if dx is None or dx.data_ptr() != a.data_ptr():
+            return a
+        return self.buf(f"bw.dx.{M}.1", (M, self.cfg.d_model), torch.float32)
+
+    @staticmethod
+    def _wp_attn(prefix, attn, norm):
+        return dict(in_w=f"{prefix}{attn}.in_proj_weight", in_b=f"{prefix}{attn}.in_proj_bias",
+                    out_w=f"{prefix}{attn}.out_proj.weight", out_b=f"{prefix}{attn}.out_proj.bias",
+                    n_w=f"{prefix}{norm}.weight", n_b=f"{prefix}{norm}.bias")
+
+    @staticmethod
+    def _wp_ffn(prefix, norm):
+        return dict(w1=prefix + "linear1.weight", b1=prefix + "linear1.bias", wg=prefix + "gate.weight",
+                    bg=prefix + "gate.bias", w2=prefix + "linear2.weight", b2=prefix + "linear2.bias",
+                    n_w=f"{prefix}{norm}.weight", n_b=f"{prefix}{norm}.bias")
+
+    # -------------------------------------------------------------------------------- cross-attn
+    def _cross_block_fwd(self, tag, x, mem, B, T_, S, heads, wp, kmask, p, site_a, site_r, train):
+        d = self.cfg.d_model
+        M, Me = B * T_, B * S
+        dh = d // heads
+        T = self.adt
+        h = self.buf(tag + ".h", (M, d), T)
+        ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        q = self.buf(tag + ".q", (M, d), T)
+        Win, bin_ = self.W(wp["in_w"]), self.P(wp["in_b"])
+        ops.gemm(h, Win[:d], M, d, d, ops.make_epi(EPI_STORE, q, bias=bin_[:d]))
+        kv = self.buf(tag + ".kv", (Me, 2 * d), T)
+        ops.gemm(mem, Win[d:], Me, 2 * d, d, ops.make_epi(EPI_STORE, kv, bias=bin_[d:]))
+        ctx = self.buf(tag + ".ctx", (M, d), T)
+        lse = self.buf(tag + ".lse", (B * heads * T_,), torch.float32)
+        ops.attn_fwd(q, kv[:, :d], kv[:, d:], ctx, lse, B, heads, T_, S, dh, kmask=kmask, causal=False, p_drop=p,
+                     seed=self.seed, site=site_a)
+        xo = self.buf(tag + ".xo", (M, d), torch.float32)
+        ops.gemm(ctx, self.W(wp["out_w"]), M, d, d,
+                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed, site=site_r))
+        if train:
+            self.saved[tag] = dict(x=x, h=h, q=q, kv=kv, ctx=ctx, lse=lse)
+        return xo
+
+    def _cross_block_bwd(self, tag, dx, dyb, mem, dmem, first_mem, B, T_, S, heads, wp, kmask, p, site_a, prev_site):
+        d = self.cfg.d_model
+        M, Me = B * T_, B * S
+        dh = d // heads
+        T = self.adt
+        s = self.saved[tag]
+        dctx = self.buf("bw.dctx", (M, d), T)
+        self._lin_bwd(dyb, s["ctx"], wp["out_w"], wp["out_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dctx))
+        dq = self.buf("bw.dq", (M, d), T)
+        dkv = self.buf("bw.dkv", (Me, 2 * d), T)
+        kv = s["kv"]
+        ops.attn_bwd(s["q"], kv[:, :d], kv[:, d:], s["ctx"], s["lse"], dctx, dq, dkv[:, :d], dkv[:, d:], B, heads, T_,
+                     S, dh, kmask=kmask, causal=False, p_drop=p, seed=self.seed, site=site_a)
+        dh_ = self.buf("bw.dh", (M, d), T)
+        self._lin_bwd(dq, s["h"], wp["in_w"], wp["in_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dh_),
+                      row_slice=slice(0, d))
+        self._lin_bwd(dkv, mem, wp["in_w"], wp["in_b"], Me, 2 * d, d,
+                      dx_epi=ops.make_epi(EPI_ACCUM, dmem, accumulate=0 if first_mem else 1),
+                      row_slice=slice(d, 3 * d))
+        dx_in = self._other_dx(dx, M)
+        dyb_in = self.buf(f"bw.dyb.{M}", (M, d), T)
+        ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
+                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed, site=prev_site)
+        return dx_in, dyb_in
+
+    # ------------------------------------------------------------------------------------ encoder
+    def encode(self, enc_inputs, enc_mask, train=False):
+        """-> memory [B*S, d] in the activation dtype (final encoder LayerNorm applied)."""
+        cfg = self.cfg
+        B, S = enc_mask.shape
+        p = cfg.dropout if train else 0.0
+        x, recs = self._embed(enc_inputs, S, "enc", B)
+        for i in range(cfg.encoder_layers):
+            pre = f"hf_model.encoder.layers.{i}."
+            tg = f"enc{i if train else ''}"
+            x = self._attn_block_fwd(tg + ".sa", x, B, S, cfg.encoder_attention_heads,
+                                     self._wp_attn(pre, "self_attn", "norm1"), enc_mask, False, p,
+                                     self._site(False, i, 0), self._site(False, i, 1), train)
+            x = self._ffn_block_fwd(tg + ".ff", x, B * S, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"), p,
+                                    self._site(False, i, 2), self._site(False, i, 3), train)
+        mem = self.buf("enc.mem", (B * S, cfg.d_model), self.adt)
+        ops.ln_fwd(x, self.P("hf_model.encoder.norm.weight"), self.P("hf_model.encoder.norm.bias"), mem)
+        if train:
+            self.saved["enc"] = dict(recs=recs, xL=x, mem=mem, B=B, S=S, mask=enc_mask)
+        return mem
+
+    def decode_teacher_forced(self, dec_ids, dec_mask, mem, enc_mask, train=False):
+        """-> final decoder hidden states [B*T, d] (activation dtype)."""
+        cfg = self.cfg
+        B, T_ = dec_ids.shape
+        S = enc_mask.shape[1]
+        p = cfg.dropout if train else 0.0
+        x, recs = self._embed({cfg.target_modality: dec_ids}, T_, "dec", B)
+        H = cfg.decoder_attention_heads
+        for i in range(cfg.decoder_layers):
+            pre = f"hf_model.decoder.layers.{i}."
+            tg = f"dec{i if train else ''}"
+            x = self._attn_block_fwd(tg + ".sa", x, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"), dec_mask, True,
+                                     p, self._site(True, i, 0), self._site(True, i, 1), train)
+            x = self._cross_block_fwd(tg + ".ca", x, mem, B, T_, S, H, self._wp_attn(pre, "multihead_attn", "norm2"),
+                                      enc_mask, p, self._site(True, i, 4), self._site(True, i, 5), train)
+            x = self._ffn_block_fwd(tg + ".ff", x, B * T_, cfg.decoder_ffn_dim, self._wp_ffn(pre, "norm3"), p,
+                                    self._site(True, i, 2), self._site(True, i, 3), train)
+        hT = self.buf("dec.hT", (B * T_, cfg.d_model), self.adt)
+        ops.ln_fwd(x, self.P("hf_model.decoder.norm.weight"), self.P("hf_model.decoder.norm.bias"), hT)
+        if train:
+            self.saved["dec"] = dict(recs=recs, xL=x, hT=hT, B=B, T=T_, mask=dec_mask)
+        return hT
+
+    # ------------------------------------------------------------------------------------ forward
+    def forward(self, enc_inputs, enc_mask, dec_ids, dec_mask, labels=None, train=False):
+        """enc_mask/dec_mask: uint8 [B, L], 1 = real token.  labels: int64 [B, T], -100 = ignore.
+        Returns dict(logits=[B, T, V] fp32 view, loss=device scalar or None)."""
+        cfg = self.cfg
+        self.sync_weights()
+        if train:
+            self.saved = {}
+        B, T_ = dec_ids.shape
+        mem = self.encode(enc_inputs, enc_mask, train)
+        hT = self.decode_teacher_forced(dec_ids, dec_mask, mem, enc_mask, train)
+        M = B * T_
+        V = cfg.vocab_size
+        logits = self.buf("logits", (M, self.ldv), torch.float32)
+        ops.gemm(hT, self.W("hf_model.token_ff.weight"), M, V, cfg.d_model,
+                 ops.make_epi(EPI_STORE, logits, bias=self.P("hf_model.token_ff.bias")))
+        out = {"logits": logits[:, :V].view(B, T_, V), "loss": None, "memory": mem}
+        if labels is not None:
+            labels = labels.contiguous().view(-1)
+            row_loss = self.buf("ce.row_loss", (M,), torch.float32)
+            row_lse = self.buf("ce.row_lse", (M,), torch.float32)
+            stats = self.buf("ce.stats", (2,), torch.float32)
+            ops.ce_fwd(logits, labels, V, row_loss, row_lse, stats, smoothing=cfg.label_smoothing)
+            out["loss"] = stats[0]
+            if train:
+                self.saved["ce"] = dict(logits=logits, labels=labels, row_lse=row_lse, stats=stats, M=M)
+        return out
+
+    # ----------------------------------------------------------------------------------- backward
+    def backward(self, gscale: float = 1.0):
+        """Accumulates d(loss * gscale)/d(param) into the flat gradient buffer (ParamStore.g)."""
+        cfg, ps = self.cfg, self.ps
+        d, V = cfg.d_model, cfg.vocab_size
+        T = self.adt
+        p = cfg.dropout
+        ce, dec, enc = self.saved["ce"], self.saved["dec"], self.saved["enc"]
+        B, T_, S = dec["B"], dec["T"], enc["S"]
+        M, Me = B * T_, B * S
+        H = cfg.decoder_attention_heads
+        notify = self.grad_ready_hook or (lambda off: None)
+
+        dlogits = self.buf("bw.dlogits", (M, self.ldv), T)
+        ops.ce_bwd(ce["logits"], ce["labels"], V, ce["row_lse"], ce["stats"], dlogits, gscale=gscale,
+                   smoothing=cfg.label_smoothing)
+        dl = dlogits[:, :V]
+        dhT = self.buf("bw.dh", (M, d), T)
+        self._lin_bwd(dl, dec["hT"], "hf_model.token_ff.weight", "hf_model.token_ff.bias", M, V, d,
+                      dx_epi=ops.make_epi(EPI_STORE, dhT))
+        last_site = self._site(True, cfg.decoder_layers - 1, 3)
+        dx = self._other_dx(None, M)
+        dyb = self.buf(f"bw.dyb.{M}", (M, d), T)
+        ops.ln_bwd(dhT, dec["xL"], self.P("hf_model.decoder.norm.weight"), dx=dx, dxb=dyb,
+                   dgamma=self.G("hf_model.decoder.norm.weight"), dbeta=self.G("hf_model.decoder.norm.bias"),
+                   p_drop=p, seed=self.seed, site=last_site)
+        notify(ps.offsets["hf_model.decoder.norm.weight"][0])
+
+        dmem = self.buf("bw.dmem", (Me, d), torch.float32)
+        for i in reversed(range(cfg.decoder_layers)):
+            pre = f"hf_model.decoder.layers.{i}."
+            tg = f"dec{i}"
+            dx, dyb = self._ffn_block_bwd(tg + ".ff", dx, dyb, M, cfg.decoder_ffn_dim, self._wp_ffn(pre, "norm3"), p,
+                                          self._site(True, i, 2), prev_site=self._site(True, i, 5))
+            dx, dyb = self._cross_block_bwd(tg + ".ca", dx, dyb, enc["mem"], dmem, i == cfg.decoder_layers - 1, B, T_,
+                                            S, H, self._wp_attn(pre, "multihead_attn", "norm2"), enc["mask"], p,
+                                            self._site(True, i, 4), prev_site=self._site(True, i, 1))
+            prev = self._site(True, i - 1, 3) if i > 0 else 0
+            dx, dyb = self._attn_block_bwd(tg + ".sa", dx, dyb, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"),
+                                           dec["mask"], True, p, self._site(True, i, 0), prev_site=prev, first=(i == 0))
+            notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
+        self._embed_bwd(dx, dec["recs"], T_, "dec", B)
+
+        # encoder: d(mem) arrives in fp32 from the cross-attention K/V projections
+        He = cfg.encoder_attention_heads
+        dxe = self._other_dx(None, Me)
+        dybe = self.buf(f"bw.dyb.{Me}", (Me, d), T)
+        ops.ln_bwd(dmem, enc["xL"], self.P("hf_model.encoder.norm.weight"), dx=dxe, dxb=dybe,
+                   dgamma=self.G("hf_model.encoder.norm.weight"), dbeta=self.G("hf_model.encoder.norm.bias"),
+                   p_drop=p, seed=self.seed, site=self._site(False, cfg.encoder_layers - 1, 3))
+        notify(ps.offsets["hf_model.encoder.norm.weight"][0])
+        for i in reversed(range(cfg.encoder_layers)):
+            pre = f"hf_model.encoder.layers.{i}."
+            tg = f"enc{i}"
+            dxe, dybe = self._ffn_block_bwd(tg + ".ff", dxe, dybe, Me, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"),
+                                            p, self._site(False, i, 2), prev_site=self._site(False, i, 1))
+            prev = self._site(False, i - 1, 3) if i > 0 else 0
+            dxe, dybe = self._attn_block_bwd(tg + ".sa", dxe, dybe, B, S, He, self._wp_attn(pre, "self_attn", "norm1"),
+                                             enc["mask"], False, p, self._site(False, i, 0), prev_site=prev,
+                                             first=(i == 0))
+            notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
+        self._embed_bwd(dxe, enc["recs"], S, "enc", B)
+        notify(0)

@@ -1,0 +1,258 @@
+"""Tensor-level wrappers over the C-ABI kernels.  torch is used for device memory and streams only:
+every function launches exactly the CUDA kernels of `lib/libmma_b200.so` on torch's current stream and
+raises if the library is unavailable.  No CPU or ATen fallback exists on purpose.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_ACCUM, EPI_DGELU, EPI_DGLU, EPI_DRELU, EPI_GELU, EPI_GLU_MUL, EPI_RELU, EPI_RESID, EPI_STORE,
+                   MMA_BF16, MMA_F32, Epi, check)
+
+LAUNCHES = 0  # number of kernel-launching C-ABI calls made (bench.py reports it as `gpu_launches`)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _ty(t):
+    if t.dtype == torch.float32:
+        return MMA_F32
+    if t.dtype == torch.bfloat16:
+        return MMA_BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("multimodalanalytical_b200 kernels need CUDA tensors (no CPU fallback)")
+
+
+def make_epi(kind, out, out2=None, bias=None, resid=None, aux=None, aux2=None, p_drop=0.0, seed=0, site=0,
+             alpha=1.0, accumulate=0, drop_ld=0):
+    e = Epi()
+    e.kind = kind
+    e.out_f32 = _ty(out)
+    e.out, e.ldo = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        assert out2.dtype == out.dtype
+        e.out2, e.ldo2 = out2.data_ptr(), out2.stride(0)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+        e.bias = bias.data_ptr()
+    if resid is not None:
+        e.resid, e.ldr, e.resid_f32 = resid.data_ptr(), resid.stride(0), _ty(resid)
+    if aux is not None:
+        e.aux, e.lda, e.aux_f32 = aux.data_ptr(), aux.stride(0), _ty(aux)
+    if aux2 is not None:
+        assert aux2.dtype == aux.dtype
+        e.aux2, e.lda2 = aux2.data_ptr(), aux2.stride(0)
+    e.p_drop, e.alpha, e.seed, e.site = float(p_drop), float(alpha), int(seed), int(site)
+    e.accumulate = int(accumulate)
+    e.drop_ld = int(drop_ld)
+    return e
+
+
+def _tc_ok(t, mn_major, rows, k):
+    """TMA needs a 16-byte aligned base and a 16-byte multiple row pitch."""
+    return t.dtype == torch.bfloat16 and t.data_ptr() % 16 == 0 and (t.stride(0) * 2) % 16 == 0 and t.stride(1) == 1
+
+
+def gemm(A, B, M, N, K, epi, a_mn=False, b_mn=False, splits=1, force_simt=False, max_ctas=0):
+    """C[M,N] = epi(A_op[M,K] @ B_op[N,K]^T).  `a_mn`/`b_mn`: operand memory is [K, rows] instead of
+    [rows, K].  bf16 operands run on the tcgen05 kernel, fp32 (or TMA-incompatible layouts) on the SIMT one."""
+    _need_cuda(A, B)
+    lib = _lib.load()
+    if epi.p_drop > 0 and epi.drop_ld == 0:
+        epi.drop_ld = N
+    if not force_simt and _tc_ok(A, a_mn, M, K) and _tc_ok(B, b_mn, N, K):
+        rc = lib.mma_gemm_bf16(A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn), M, N, K,
+                               C.byref(epi), splits, max_ctas, _stream())
+        check(rc, "mma_gemm_bf16")
+    else:
+        if epi.kind == EPI_ACCUM and epi.accumulate == 2:
+            epi.accumulate = 1  # the SIMT kernel never splits K: plain accumulate
+        sam, sak = (1, A.stride(0)) if a_mn else (A.stride(0), 1)
+        sbn, sbk = (1, B.stride(0)) if b_mn else (B.stride(0), 1)
+        rc = lib.mma_gemm_simt(A.data_ptr(), _ty(A), sam, sak, B.data_ptr(), _ty(B), sbn, sbk, M, N, K, C.byref(epi),
+                               _stream())
+        check(rc, "mma_gemm_simt")
+    _count()
+
+
+def gather_rows(ids, table, out, scale=None):
+    _need_cuda(ids, table, out)
+    assert ids.dtype == torch.int64 and ids.is_contiguous() and table.dtype == torch.float32 and out.dtype == torch.float32
+    check(_lib.load().mma_gather_rows(ids.data_ptr(), _p(scale), table.data_ptr(), out.data_ptr(), ids.numel(),
+                                      table.shape[1], _stream()), "mma_gather_rows")
+    _count()
+
+
+def scatter_add_rows(ids, g, dtable, pad_idx, scale=None):
+    _need_cuda(ids, g, dtable)
+    check(_lib.load().mma_scatter_add_rows(ids.data_ptr(), _p(scale), g.data_ptr(), dtable.data_ptr(), ids.numel(),
+                                           dtable.shape[1], int(pad_idx), _stream()), "mma_scatter_add_rows")
+    _count()
+
+
+def ln_fwd(x, gamma, beta, y, y2=None, add=None, group=0, out_group_stride=0, out_offset=0, eps=1e-5, rows=None,
+           d=None):
+    _need_cuda(x, y)
+    rows = x.shape[0] if rows is None else rows
+    d = x.shape[1] if d is None else d
+    check(_lib.load().mma_ln_fwd(
+        x.data_ptr(), _ty(x), x.stride(0), _p(gamma), _p(beta), eps, y.data_ptr(), _ty(y), y.stride(0),
+        _p(y2), _ty(y2) if y2 is not None else 0, y2.stride(0) if y2 is not None else 0,
+        _p(add), add.stride(0) if add is not None else 0, rows, d, group, out_group_stride, out_offset, _stream()),
+        "mma_ln_fwd")
+    _count()
+
+
+def ln_bwd(dy, x, gamma, dx=None, dres=None, dxb=None, dgamma=None, dbeta=None, p_drop=0.0, seed=0, site=0, group=0,
+           in_group_stride=0, in_offset=0, eps=1e-5, rows=None, d=None):
+    _need_cuda(dy, x)
+    rows = x.shape[0] if rows is None else rows
+    d = x.shape[1] if d is None else d
+    check(_lib.load().mma_ln_bwd(
+        dy.data_ptr(), _ty(dy), dy.stride(0), group, in_group_stride, in_offset, x.data_ptr(), _ty(x), x.stride(0),
+        _p(gamma), eps, _p(dres), dres.stride(0) if dres is not None else 0, _p(dx),
+        dx.stride(0) if dx is not None else 0, _p(dxb), _ty(dxb) if dxb is not None else 0,
+        dxb.stride(0) if dxb is not None else 0, float(p_drop), int(seed), int(site), _p(dgamma), _p(dbeta), rows, d,
+        _stream()), "mma_ln_bwd")
+    _count()
+
+
+def colsum(x, out, rows=None, cols=None):
+    _need_cuda(x, out)
+    rows = x.shape[0] if rows is None else rows
+    cols = x.shape[1] if cols is None else cols
+    check(_lib.load().mma_colsum(x.data_ptr(), _ty(x), x.stride(0), out.data_ptr(), rows, cols, _stream()),
+          "mma_colsum")
+    _count()
+
+
+def cast_f32_bf16(src, dst):
+    _need_cuda(src, dst)
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    check(_lib.load().mma_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "mma_cast_f32_bf16")
+    _count()
+
+
+def cast_bf16_f32(src, dst):
+    _need_cuda(src, dst)
+    check(_lib.load().mma_cast_bf16_f32(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "mma_cast_bf16_f32")
+    _count()
+
+
+def attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop=0.0, seed=0, site=0):
+    """q/k/v/o: 2-D views [B*L, ld] (row pitch = stride(0)); heads are column blocks of width dh."""
+    _need_cuda(q, k, v, o)
+    check(_lib.load().mma_attn_fwd(
+        q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+        o.stride(0), _p(lse), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, float(p_drop), int(seed), int(site), _ty(q),
+        _stream()), "mma_attn_fwd")
+    _count()
+
+
+def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop=0.0, seed=0,
+             site=0):
+    _need_cuda(q, k, v, o, dout, dq, dk, dv)
+    check(_lib.load().mma_attn_bwd(
+        q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+        o.stride(0), lse.data_ptr(), dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(),
+        dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, float(p_drop), int(seed),
+        int(site), _ty(q), _stream()), "mma_attn_bwd")
+    _count(2)
+
+
+def ce_fwd(logits, labels, V, row_loss, row_lse, stats, smoothing=0.0, ignore_index=-100):
+    _need_cuda(logits, labels)
+    assert logits.dtype == torch.float32 and labels.dtype == torch.int64
+    check(_lib.load().mma_ce_fwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), labels.numel(), V,
+                                 float(smoothing), ignore_index, row_loss.data_ptr(), row_lse.data_ptr(),
+                                 stats.data_ptr(), _stream()), "mma_ce_fwd")
+    _count(2)
+
+
+def ce_bwd(logits, labels, V, row_lse, stats, dlogits, gscale=1.0, smoothing=0.0, ignore_index=-100):
+    _need_cuda(logits, labels, dlogits)
+    check(_lib.load().mma_ce_bwd(logits.data_ptr(), logits.stride(0), labels.data_ptr(), row_lse.data_ptr(),
+                                 stats.data_ptr(), float(gscale), labels.numel(), V, float(smoothing), ignore_index,
+                                 dlogits.data_ptr(), _ty(dlogits), dlogits.stride(0), _stream()), "mma_ce_bwd")
+    _count()
+
+
+def grad_norm(g, workspace, norm):
+    _need_cuda(g, workspace, norm)
+    check(_lib.load().mma_grad_norm(g.data_ptr(), g.numel(), workspace.data_ptr(), norm.data_ptr(), _stream()),
+          "mma_grad_norm")
+    _count(2)
+
+
+def adam_step(p, g, m, v, p_bf16, hyper, norm=None, decoupled=True, zero_grad=True):
+    _need_cuda(p, g, m, v, hyper)
+    check(_lib.load().mma_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(p_bf16), p.numel(),
+                                    hyper.data_ptr(), _p(norm), int(decoupled), int(zero_grad), _stream()),
+          "mma_adam_step")
+    _count()
+
+
+def decode_embed(tok, table, gamma, beta, pos, cur_len, out, eps=1e-5):
+    _need_cuda(tok, table, out)
+    check(_lib.load().mma_decode_embed(tok.data_ptr(), table.data_ptr(), _p(gamma), _p(beta), eps, pos.data_ptr(),
+                                       cur_len.data_ptr(), out.data_ptr(), tok.numel(), table.shape[1], _stream()),
+          "mma_decode_embed")
+    _count()
+
+
+def decode_self_attn(q, knew, vnew, kcache, vcache, anc, cur_len, o, R, H, dh, Lmax):
+    _need_cuda(q, knew, vnew, kcache, vcache, o)
+    check(_lib.load().mma_decode_self_attn(
+        q.data_ptr(), q.stride(0), knew.data_ptr(), vnew.data_ptr(), knew.stride(0), kcache.data_ptr(),
+        vcache.data_ptr(), _p(anc), cur_len.data_ptr(), o.data_ptr(), o.stride(0), R, H, dh, Lmax, dh ** -0.5, _ty(q),
+        _stream()), "mma_decode_self_attn")
+    _count()
+
+
+def decode_cross_attn(q, kmem, vmem, kmask, cur_len, o, R, H, dh, S, beams):
+    _need_cuda(q, kmem, vmem, o)
+    check(_lib.load().mma_decode_cross_attn(
+        q.data_ptr(), q.stride(0), kmem.data_ptr(), vmem.data_ptr(), kmem.stride(0), _p(kmask), cur_len.data_ptr(),
+        o.data_ptr(), o.stride(0), R, H, dh, S, beams, dh ** -0.5, _ty(q), _stream()), "mma_decode_cross_attn")
+    _count()
+
+
+def beam_step(logits, V, st, extra_bias=None):
+    """st: decode.BeamState (device buffers)."""
+    check(_lib.load().mma_beam_step(
+        logits.data_ptr(), logits.stride(0), _p(extra_bias), st.B, st.K, V, st.L, st.pad_id, st.eos_id,
+        st.cur_len.data_ptr(), st.run_seq.data_ptr(), st.fin_seq.data_ptr(), st.run_score.data_ptr(),
+        st.fin_score.data_ptr(), st.fin_flag.data_ptr(), st.fin_len.data_ptr(), st.improvable.data_ptr(),
+        st.all_hit.data_ptr(), st.anc.data_ptr(), st.next_tok.data_ptr(), st.parent_row.data_ptr(), _stream()),
+        "mma_beam_step")
+    _count()
+
+
+def greedy_step(logits, V, st, extra_bias=None):
+    check(_lib.load().mma_greedy_step(
+        logits.data_ptr(), logits.stride(0), _p(extra_bias), st.B, V, st.L, st.pad_id, st.eos_id,
+        st.cur_len.data_ptr(), st.run_seq.data_ptr(), st.unfinished.data_ptr(), st.next_tok.data_ptr(), _stream()),
+        "mma_greedy_step")
+    _count()
+
+
+def advance(cur_len):
+    check(_lib.load().mma_advance(cur_len.data_ptr(), _stream()), "mma_advance")
+    _count()

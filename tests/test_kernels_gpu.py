@@ -1,0 +1,311 @@
+"""GPU unit tests of the individual CUDA kernels (called through the C ABI via ops.py) against plain
+PyTorch fp32 references of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from multimodalanalytical_b200 import ops
+    from multimodalanalytical_b200._lib import (EPI_ACCUM, EPI_DGELU, EPI_DGLU, EPI_GELU, EPI_GLU_MUL, EPI_RESID,
+                                                EPI_STORE)
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _rand(*shape, dtype=torch.float32, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------- GEMM
+GEMM_SHAPES = [(128, 128, 64), (256, 256, 512), (300, 200, 136), (1000, 512, 2048), (64, 48, 48), (130, 37, 48),
+               (4096, 1536, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_gemm_fwd_kmajor(M, N, K, dtype):
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    A, W = _rand(M, K, dtype=dt), _rand(N, K, dtype=dt, scale=K ** -0.5)
+    bias = _rand(N)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_STORE, out, bias=bias))
+    ref = A.float() @ W.float().T + bias
+    assert rel(out, ref) < (2e-5 if dtype == "f32" else 1e-5), "fp32-out"
+    out2 = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_STORE, out2, bias=bias))
+    assert rel(out2.float(), ref) < (2e-5 if dtype == "f32" else 1e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 200), (1000, 48, 37 + 3), (512, 512, 2048), (130, 48, 40)])
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_gemm_dgrad_b_mnmajor(M, N, K, dtype):
+    """dx[M,N] = dy[M,K] @ W[K,N]  (W stored [K(out of fwd), N(in of fwd)] row-major = MN-major B)."""
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    dy, W = _rand(M, K, dtype=dt), _rand(K, N, dtype=dt, scale=K ** -0.5)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(dy, W, M, N, K, ops.make_epi(EPI_STORE, out), b_mn=True)
+    assert rel(out, dy.float() @ W.float()) < 2e-5
+
+
+@pytest.mark.parametrize("R,N,K", [(512, 128, 64), (1000, 200, 48), (4096, 512, 512), (777, 37, 48), (9216, 2048, 512)])
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("splits", [1, 5])
+def test_gemm_wgrad_mnmajor_splitk(R, N, K, dtype, splits):
+    """dW[N,K] = dy[R,N]^T @ x[R,K]; both operands MN-major, reduction over rows, optional split-K."""
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    dy, x = _rand(R, N, dtype=dt, scale=R ** -0.5), _rand(R, K, dtype=dt)
+    out = torch.zeros(N, K, device=DEV, dtype=torch.float32)
+    ops.gemm(dy, x, N, K, R, ops.make_epi(EPI_ACCUM, out, accumulate=2 if splits > 1 else 0), a_mn=True, b_mn=True,
+             splits=splits)
+    assert rel(out, dy.float().T @ x.float()) < 3e-5
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_gemm_epilogues(dtype):
+    dt = torch.bfloat16 if dtype == "bf16" else torch.float32
+    tol = 1e-2 if dtype == "bf16" else 2e-5
+    M, N, K = 300, 256, 128
+    A, W, bias = _rand(M, K, dtype=dt), _rand(N, K, dtype=dt, scale=K ** -0.5), _rand(N)
+    acc = A.float() @ W.float().T
+    # GELU (+ pre-activation copy)
+    z, a = torch.empty(M, N, device=DEV, dtype=dt), torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_GELU, a, out2=z, bias=bias))
+    assert rel(z.float(), acc + bias) < tol
+    assert rel(a.float(), torch.nn.functional.gelu(acc + bias)) < tol
+    # residual
+    resid = _rand(M, N)
+    o = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_RESID, o, bias=bias, resid=resid))
+    assert rel(o, resid + acc + bias) < 2e-5
+    # dGELU
+    zz = _rand(M, N, dtype=dt)
+    o2 = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_DGELU, o2, aux=zz))
+    zf = zz.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).backward(acc)
+    assert rel(o2.float(), zf.grad) < tol
+    # GLU forward: out = gelu(z1) * (acc + bias), out2 = acc + bias
+    o3, z2 = torch.empty(M, N, device=DEV, dtype=dt), torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_GLU_MUL, o3, out2=z2, bias=bias, aux=zz))
+    assert rel(o3.float(), torch.nn.functional.gelu(zz.float()) * (acc + bias)) < tol
+    # GLU backward
+    z1, z2b = _rand(M, N, dtype=dt, seed=3), _rand(M, N, dtype=dt, seed=4)
+    d1, d2 = torch.empty(M, N, device=DEV, dtype=dt), torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_DGLU, d1, out2=d2, aux=z1, aux2=z2b))
+    z1f, z2f = z1.float().requires_grad_(True), z2b.float().requires_grad_(True)
+    (torch.nn.functional.gelu(z1f) * z2f).backward(acc)
+    assert rel(d1.float(), z1f.grad) < tol and rel(d2.float(), z2f.grad) < tol
+    # accumulate (beta = 1)
+    base = _rand(M, N)
+    o4 = base.clone()
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_ACCUM, o4, accumulate=1))
+    assert rel(o4, base + acc) < 2e-5
+
+
+def test_gemm_dropout_mask_consistency():
+    """RESID-epilogue dropout (forward) and ln_bwd's masked copy (backward) must use the same mask."""
+    M, N, K, p = 256, 128, 64, 0.25
+    A, W = _rand(M, K, dtype=torch.bfloat16), _rand(N, K, dtype=torch.bfloat16)
+    resid = torch.zeros(M, N, device=DEV)
+    o = torch.empty(M, N, device=DEV)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_RESID, o, resid=resid, p_drop=p, seed=77, site=5))
+    acc = A.float() @ W.float().T
+    keep = (o != 0)
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.02
+    assert rel(o[keep], (acc / (1 - p))[keep]) < 1e-5
+    x = _rand(M, N)
+    dy = torch.ones(M, N, device=DEV)
+    dxb = torch.empty(M, N, device=DEV)
+    ops.ln_bwd(dy, x, None, dxb=dxb, p_drop=p, seed=77, site=5)
+    assert torch.equal(dxb != 0, keep)
+
+
+# ------------------------------------------------------------------------------------------- row ops
+@pytest.mark.parametrize("d", [512, 48, 1024])
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+def test_layernorm_fwd_bwd(d, xdt):
+    rows = 777
+    x = _rand(rows, d, dtype=xdt) * 2 + 0.5
+    gamma, beta = _rand(d) + 1.0, _rand(d)
+    y = torch.empty(rows, d, device=DEV)
+    yb = torch.empty(rows, d, device=DEV, dtype=torch.bfloat16)
+    ops.ln_fwd(x, gamma, beta, y, y2=yb)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (d,), gr, br)
+    assert rel(y, ref) < 1e-5
+    assert rel(yb.float(), ref) < 1e-2
+    dy = _rand(rows, d, seed=9)
+    dres = _rand(rows, d, seed=10)
+    ref.backward(dy)
+    dx = torch.empty(rows, d, device=DEV)
+    dg, db = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    ops.ln_bwd(dy, x, gamma, dx=dx, dres=dres, dgamma=dg, dbeta=db)
+    assert rel(dx, xr.grad + dres) < 2e-5
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+
+
+def test_embed_gather_ln_pos_concat_and_scatter():
+    B, S1, S2, d, vocab = 5, 7, 4, 64, 30
+    ids = torch.randint(0, vocab, (B, S1), device=DEV)
+    table = _rand(vocab, d)
+    scale = _rand(B, S1).abs() + 0.5
+    pre2 = _rand(B * S2, d)
+    g1, b1, g2, b2 = _rand(d) + 1, _rand(d), _rand(d, seed=2) + 1, _rand(d, seed=3)
+    pos = _rand(64, d)
+    out = torch.zeros(B * (S1 + S2), d, device=DEV)
+    pre1 = torch.empty(B * S1, d, device=DEV)
+    ops.gather_rows(ids.reshape(-1), table, pre1, scale=scale.reshape(-1))
+    ops.ln_fwd(pre1, g1, b1, out, add=pos, group=S1, out_group_stride=S1 + S2, out_offset=0)
+    ops.ln_fwd(pre2, g2, b2, out, add=pos, group=S2, out_group_stride=S1 + S2, out_offset=S1)
+    e1 = torch.nn.functional.layer_norm(table[ids] * scale[..., None], (d,), g1, b1)
+    e2 = torch.nn.functional.layer_norm(pre2.view(B, S2, d), (d,), g2, b2)
+    ref = torch.cat([e1, e2], dim=1) + pos[: S1 + S2]
+    assert rel(out.view(B, S1 + S2, d), ref) < 1e-5
+    # scatter-add with padding row skipped
+    g = _rand(B * S1, d, seed=5)
+    dt = torch.zeros(vocab, d, device=DEV)
+    ops.scatter_add_rows(ids.reshape(-1), g, dt, pad_idx=0, scale=scale.reshape(-1))
+    ref_dt = torch.zeros(vocab, d, device=DEV).index_add_(0, ids.reshape(-1), g * scale.reshape(-1, 1))
+    ref_dt[0] = 0
+    assert rel(dt, ref_dt) < 1e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_colsum(dt):
+    x = _rand(3001, 300, dtype=dt)
+    out = torch.zeros(300, device=DEV)
+    ops.colsum(x, out)
+    assert rel(out, x.float().sum(0)) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, kmask, causal, H):
+    B, Lq, d = q.shape
+    Lk = k.shape[1]
+    dh = d // H
+    qh = q.view(B, Lq, H, dh).transpose(1, 2)
+    kh = k.view(B, Lk, H, dh).transpose(1, 2)
+    vh = v.view(B, Lk, H, dh).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
+    if kmask is not None:
+        s = s.masked_fill(~kmask.bool()[:, None, None, :], float("-inf"))
+    if causal:
+        s = s + torch.triu(torch.full((Lq, Lk), float("-inf"), device=q.device), diagonal=1)
+    return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Lq, d)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,causal,masked", [
+    (3, 4, 57, 57, 16, True, True), (2, 8, 36, 36, 64, False, True), (2, 8, 64, 36, 64, False, True),
+    (2, 2, 130, 199, 32, False, False), (1, 8, 128, 128, 64, True, False)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_attention_fwd_bwd(B, H, Lq, Lk, dh, causal, masked, dt):
+    d = H * dh
+    tol = 2e-5 if dt == torch.float32 else 2e-2
+    q, k, v = _rand(B, Lq, d, dtype=dt, seed=1), _rand(B, Lk, d, dtype=dt, seed=2), _rand(B, Lk, d, dtype=dt, seed=3)
+    kmask = None
+    if masked:
+        kmask = torch.ones(B, Lk, dtype=torch.uint8, device=DEV)
+        for b in range(B):
+            kmask[b, Lk - 1 - 3 * b - (b % 2) * 2: Lk - (b % 2) * 2] = 0
+        kmask[:, 0] = 1
+    o = torch.empty(B * Lq, d, device=DEV, dtype=dt)
+    lse = torch.empty(B * H * Lq, device=DEV)
+    ops.attn_fwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), o, lse, B, H, Lq, Lk, dh, kmask=kmask, causal=causal)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qr, kr, vr, kmask, causal, H)
+    assert rel(o.view(B, Lq, d).float(), ref) < tol
+    do = _rand(B, Lq, d, dtype=dt, seed=4)
+    ref.backward(do.float())
+    dq, dk, dv = (torch.empty_like(t).view(-1, d) for t in (q, k, v))
+    ops.attn_bwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), o, lse, do.view(-1, d), dq, dk, dv, B, H, Lq, Lk, dh,
+                 kmask=kmask, causal=causal)
+    assert rel(dq.view_as(q).float(), qr.grad) < tol
+    assert rel(dk.view_as(k).float(), kr.grad) < tol
+    assert rel(dv.view_as(v).float(), vr.grad) < tol
+
+
+def test_attention_packed_qkv_views():
+    """q/k/v as column slices of one packed [M, 3d] buffer (how the model calls it)."""
+    B, H, L, dh = 2, 4, 33, 16
+    d = H * dh
+    qkv = _rand(B * L, 3 * d)
+    o = torch.empty(B * L, d, device=DEV)
+    lse = torch.empty(B * H * L, device=DEV)
+    ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], o, lse, B, H, L, L, dh, causal=True)
+    ref = _attn_ref(qkv[:, :d].reshape(B, L, d), qkv[:, d:2 * d].reshape(B, L, d), qkv[:, 2 * d:].reshape(B, L, d),
+                    None, True, H)
+    assert rel(o.view(B, L, d), ref) < 2e-5
+
+
+def test_attention_dropout_statistics_and_grad_consistency():
+    B, H, L, dh, p = 2, 2, 64, 16, 0.3
+    d = H * dh
+    q, k = _rand(B * L, d, seed=1), _rand(B * L, d, seed=2)
+    v = torch.ones(B * L, d, device=DEV)
+    o = torch.empty(B * L, d, device=DEV)
+    lse = torch.empty(B * H * L, device=DEV)
+    ops.attn_fwd(q, k, v, o, lse, B, H, L, L, dh, p_drop=p, seed=5, site=3)
+    # with V == 1 the output is sum_j keep_ij p_ij / (1-p): mean 1
+    assert abs(o.mean().item() - 1.0) < 0.02 and o.std().item() > 0.01
+    o2 = torch.empty_like(o)
+    ops.attn_fwd(q, k, v, o2, lse, B, H, L, L, dh, p_drop=p, seed=5, site=3)
+    assert torch.equal(o, o2)
+
+
+# ------------------------------------------------------------------------------------------- loss / optimiser
+@pytest.mark.parametrize("V,smooth", [(200, 0.0), (37, 0.0), (26, 0.1)])
+def test_cross_entropy(V, smooth):
+    rows = 501
+    ld = (V + 7) // 8 * 8
+    logits = torch.zeros(rows, ld, device=DEV)
+    logits[:, :V] = _rand(rows, V) * 3
+    labels = torch.randint(0, V, (rows,), device=DEV)
+    labels[::7] = -100
+    rl, rlse, stats = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV), torch.empty(2, device=DEV)
+    ops.ce_fwd(logits, labels, V, rl, rlse, stats, smoothing=smooth)
+    xr = logits[:, :V].clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(xr, labels, ignore_index=-100, label_smoothing=smooth)
+    assert abs(stats[0].item() - ref.item()) < 1e-5 * abs(ref.item())
+    assert stats[1].item() == (labels != -100).sum().item()
+    ref.backward()
+    for dt in (torch.float32, torch.bfloat16):
+        dl = torch.full((rows, ld), 7.0, device=DEV, dtype=dt)
+        ops.ce_bwd(logits, labels, V, rlse, stats, dl, smoothing=smooth)
+        assert rel(dl[:, :V].float(), xr.grad) < (1e-5 if dt == torch.float32 else 1e-2)
+        assert (dl[:, V:] == 0).all()
+
+
+@pytest.mark.parametrize("decoupled", [True, False])
+def test_adam_step_matches_torch(decoupled):
+    n = 100_003
+    p0, g0 = _rand(n), _rand(n, seed=1) * 3
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref_p], lr=1e-2, betas=(0.9, 0.999), eps=1e-8,
+                                                                weight_decay=0.01)
+    p, g = p0.clone(), g0.clone()
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    pb = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    ws, norm = torch.empty(1024, device=DEV), torch.empty(1, device=DEV)
+    for t in range(1, 4):
+        ref_p.grad = g0.clone()
+        total = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        g.copy_(g0)
+        ops.grad_norm(g, ws, norm)
+        assert abs(norm.item() - total.item()) < 1e-4 * total.item()
+        hyper = torch.tensor([1e-2, 0.9, 0.999, 1e-8, 0.01, 1 - 0.9 ** t, 1 - 0.999 ** t, 1.0, 1.0], device=DEV)
+        ops.adam_step(p, g, m, v, pb, hyper, norm=norm, decoupled=decoupled)
+        assert rel(p, ref_p.data) < 1e-5
+        assert (g == 0).all()
+    assert rel(pb.float(), p) < 1e-2
