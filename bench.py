@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the spectra -> SMILES hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+Headline metric (BASELINE.json, configs[1] = "C2"): training spectra/s of the IR-only structure-elucidation
+model (custom_model.yaml: d=512, 6+6 layers, 8 heads, ffn 2048; Formula[B,15] + IR patches [B,21,75] -> S=36;
+T=64 target tokens, V=200; bf16; per-GPU batch 256; AdamW + OneCycle + clip 1.0; dropout 0.1), one step =
+forward + backward + optimiser on one synthetic batch.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 3247
+C2 = dict(B=256, S_formula=15, P=21, ps=75, T=64, V=200, d=512, layers=6, heads=8, ffn=2048)
+
+
+def flops_per_sample_train(c, gated=False):
+    """algorithmic forward MACs x 2 x 3 (fwd + bwd)."""
+    d, f, S, T, V = c["d"], c["ffn"], c["S_formula"] + c["P"], c["T"], c["V"]
+    g = 1 if gated else 0
+    enc = c["layers"] * (S * (4 * d * d + (2 + g) * d * f) + 2 * S * S * d)
+    dec = c["layers"] * (T * (6 * d * d + (2 + g) * d * f) + 2 * S * d * d + T * (T + 1) * d + 2 * T * S * d)
+    emb = c["P"] * c["ps"] * d
+    head = T * d * V
+    return 2.0 * 3.0 * (enc + dec + emb + head)
+
+
+def data_config(c):
+    return {
+        "Formula": {"type": "text", "target": False, "vocab_size": 64, "pad_token_id": 0, "preprocessor_arguments": {}},
+        "IR": {"type": "1D_patches", "target": False, "preprocessor_arguments": {"patch_size": c["ps"]}},
+        "Smiles": {"type": "text", "target": True, "vocab_size": c["V"], "pad_token_id": 0, "preprocessor_arguments": {}},
+    }
+
+
+def model_kwargs(c, dropout=0.1):
+    return dict(model_type="CustomModel", model_name="facebook/bart-base", d_model=c["d"], num_heads=c["heads"],
+                encoder_attention_heads=c["heads"], decoder_attention_heads=c["heads"], encoder_layers=c["layers"],
+                decoder_layers=c["layers"], encoder_ffn_dim=c["ffn"], decoder_ffn_dim=c["ffn"], multimodal_norm=True,
+                positional_encoding_type="sin_cos", gated_linear=False, max_position_embeddings=1024,
+                optimiser="adamw", lr=1e-3, weight_decay=0.0, adam_beta1=0.9, adam_beta2=0.999, dropout=dropout,
+                n_beams=10)
+
+
+class Tok:
+    def __init__(self, v):
+        self.vocab_size, self.pad_token_id, self.bos_token_id, self.eos_token_id = v, 0, 2, 3
+
+    def batch_decode(self, seqs, skip_special_tokens=True):
+        return [" ".join(str(t) for t in s if t > 3) for s in seqs.tolist()]
+
+
+def synth_batch(c, B, seed, pin=False):
+    """Collator wire format (seq-first, True = pad; data/datamodules.py:201-218), no padding, on the host."""
+    g = torch.Generator().manual_seed(seed)
+    f = torch.randint(4, 64, (c["S_formula"], B), generator=g)
+    ir = torch.randn(c["P"], B, c["ps"], generator=g)
+    t = torch.randint(4, c["V"], (c["T"] + 1, B), generator=g)
+    t[0] = 2
+    batch = {
+        "encoder_input": {"Formula": f, "IR": ir},
+        "encoder_pad_mask": torch.zeros(c["S_formula"] + c["P"], B, dtype=torch.bool),
+        "decoder_input": {"Smiles": t[:-1].contiguous()},
+        "decoder_pad_mask": torch.zeros(c["T"], B, dtype=torch.bool),
+        "target": t[1:].contiguous(),
+    }
+    if pin:
+        batch = map_batch(batch, lambda x: x.pin_memory())
+    return batch
+
+
+def map_batch(b, fn):
+    if isinstance(b, dict):
+        return {k: map_batch(v, fn) for k, v in b.items()}
+    return fn(b) if isinstance(b, torch.Tensor) else b
+
+
+def batch_bytes(b):
+    if isinstance(b, dict):
+        return sum(batch_bytes(v) for v in b.values())
+    return b.numel() * b.element_size() if isinstance(b, torch.Tensor) else 0
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]
+            out = {"sm_mhz": sorted(busy)[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# --------------------------------------------------------------------------------------------- CPU (oracle)
+def cpu_train_baseline(c, B, steps, warmup):
+    """The reference algorithm (oracle port, torch-CPU fp32, dropout 0.1, AdamW + OneCycleLR + clip 1.0) on all host
+    cores: spectra/s over `steps` timed steps of batch B."""
+    from oracle import spectra_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = orc.OracleConfig(d_model=c["d"], encoder_layers=c["layers"], decoder_layers=c["layers"],
+                           encoder_attention_heads=c["heads"], decoder_attention_heads=c["heads"],
+                           data_config=data_config(c), dropout=0.1, training=True)
+    sd = orc.init_state_dict(cfg, vocab=c["V"], enc_ffn=c["ffn"], dec_ffn=c["ffn"], seed=SEED)
+    leaves = []
+    for k, v in sd.items():
+        if v.is_floating_point() and not k.endswith("pos_enc") and ".decoder.embedding." not in k:
+            v.requires_grad_(True)
+            leaves.append(v)
+    opt = torch.optim.AdamW(leaves, lr=1e-3, weight_decay=0.0)
+    sch = torch.optim.lr_scheduler.OneCycleLR(opt, 1e-3, total_steps=max(steps + warmup, 10))
+    times = []
+    for i in range(warmup + steps):
+        batch = synth_batch(c, B, SEED + i)
+        t0 = time.perf_counter()
+        out = orc.wrapper_forward(sd, cfg, batch)
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(leaves, 1.0)
+        opt.step()
+        sch.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return B * len(times) / total, total / len(times)
+
+
+def cpu_decode_baseline(c, B, K):
+    from oracle import spectra_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = orc.OracleConfig(d_model=c["d"], encoder_layers=c["layers"], decoder_layers=c["layers"],
+                           encoder_attention_heads=c["heads"], decoder_attention_heads=c["heads"],
+                           data_config=data_config(c))
+    sd = orc.init_state_dict(cfg, vocab=c["V"], enc_ffn=c["ffn"], dec_ffn=c["ffn"], seed=SEED)
+    batch = synth_batch(c, B, SEED)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        orc.generate(sd, cfg, batch, n_beams=K)
+    dt = time.perf_counter() - t0
+    return B / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = dict(C2)
+    B = 64
+    val, s_per_step = cpu_train_baseline(c, B, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": "train spectra/s", "value": val, "unit": "spectra/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(c, B),
+        "cpu_baseline": {"value": val, "unit": "spectra/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} timed train steps (fwd+bwd+clip+AdamW) of batch {B}, C2 shapes, fp32"},
+        "e2e": {"value": val, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(c, B):
+    return {"workload": "C2 IR->SMILES training step (custom_model.yaml d512/6+6/8h/ffn2048, S=15+21 patches of 75, "
+                        "T=64, V=200, AdamW+OneCycle+clip1.0, dropout 0.1)",
+            "per_gpu_batch": B, "seq_len_enc": c["S_formula"] + c["P"], "seq_len_dec": c["T"],
+            "l2": "per-step activations+grads (>1 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# --------------------------------------------------------------------------------------------- GPU
+def time_dominant_gemm(eng, c, B):
+    """The dominant kernel is the tcgen05 GEMM; time its largest instance (decoder FFN-1, M=B*T, N=ffn, K=d)
+    alone with CUDA events on the launching stream."""
+    from multimodalanalytical_b200 import ops
+    from multimodalanalytical_b200._lib import EPI_GELU
+    M, N, K = B * c["T"], c["ffn"], c["d"]
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = eng.W("hf_model.decoder.layers.0.linear1.weight")
+    bias = eng.P("hf_model.decoder.layers.0.linear1.bias")
+    o1 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    epi = ops.make_epi(EPI_GELU, o1, out2=o2, bias=bias)
+    for _ in range(3):
+        ops.gemm(a, w, M, N, K, epi)
+    ts = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gemm(a, w, M, N, K, epi)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    t = sorted(ts)[len(ts) // 2]
+    return 2.0 * M * N * K / t / 1e12, t, (M, N, K)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from multimodalanalytical_b200 import ops
+    from multimodalanalytical_b200.trainer import FusedTrainer
+    from multimodalanalytical_b200.wrapper import HFWrapper
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the accelerated path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c = dict(C2)
+    B = args.batch or c["B"]
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_src = "measured"
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    else:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+        peak_src = "fallback"
+
+    mk = model_kwargs(c)
+    total_steps = args.steps + args.warmup + 8
+    model = HFWrapper(data_config=data_config(c), target_tokenizer=Tok(c["V"]), num_steps=2 * total_steps + 16,
+                      precision="bf16", seed=SEED, **mk)
+    trainer = FusedTrainer(model, clip_grad=1.0, acc_batches=1)
+    nb = 4
+    host_batches = [synth_batch(c, B, SEED + 1000 * rank + i, pin=True) for i in range(nb)]
+    dev_batches = [map_batch(b, lambda x: x.cuda()) for b in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, warmup, e2e):
+        for i in range(warmup):
+            loss = trainer.train_step(batches[i % nb], i)
+            if e2e:
+                float(loss)
+        barrier()
+        l0 = ops.LAUNCHES
+        sampler = ClockSampler(local) if (rank == 0 and not e2e) else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            loss = trainer.train_step(batches[i % nb], i)
+            if e2e:
+                float(loss)  # device -> host read of the step's result
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) * 1e-3, ops.LAUNCHES - l0, clocks, float(loss)
+
+    t_dev, launches, clocks, last_loss = timed(dev_batches, args.steps, args.warmup, e2e=False)
+    t_e2e, _, _, _ = timed(host_batches, args.steps, max(3, args.warmup // 2), e2e=True)
+    value = world * B * args.steps / t_dev
+    e2e_value = world * B * args.steps / t_e2e
+    fl = flops_per_sample_train(c)
+    step_tflops = value / world * fl / 1e12
+
+    line = {
+        "metric": "train spectra/s", "value": value, "unit": "spectra/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(c, B),
+        "e2e": {"value": e2e_value, "unit": "spectra/s", "h2d_bytes_per_step": batch_bytes(host_batches[0]),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "last_loss": last_loss,
+    }
+    if rank == 0:
+        line["clocks"] = clocks
+        tf, t_k, shape = time_dominant_gemm(model.engine, c, B)
+        line["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                            "frac": tf / peaks["bf16_tflops"], "traffic": None, "kernel": "gemm_tc_kernel<128,K,K>",
+                            "shape_MNK": shape, "us_per_launch": t_k * 1e6, "peak_source": f"{peak_src} burst"}
+        line["step_roofline"] = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16_tflops_sustained"],
+                                 "unit": "TFLOP/s", "frac": step_tflops / peaks["bf16_tflops_sustained"],
+                                 "flops_per_sample": fl, "peak_source": f"{peak_src} sustained"}
+        if not args.no_decode:
+            line["decode"] = bench_decode(model, c, args)
+        if world == 1 and not args.no_cpu:
+            cb = 64
+            cv, cs = cpu_train_baseline(c, cb, steps=3, warmup=1)
+            line["cpu_baseline"] = {"value": cv, "unit": "spectra/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"3 timed train steps of batch {cb} (C2 shapes, fp32, oracle port)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_decode(model, c, args):
+    """Secondary metric: beam-10 molecules/s (KV-cached, CUDA-graph replayed step), random-init weights never emit
+    EOS early so every hypothesis runs the full 127 steps."""
+    B, K = args.decode_batch, 10
+    batch = map_batch(synth_batch(c, B, SEED + 7), lambda x: x.cuda())
+    model.eval()
+    model.generate(batch, n_beams=K)  # warm-up + graph capture
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    e0.record()
+    for _ in range(reps):
+        out = model.generate(batch, n_beams=K)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / reps
+    return {"metric": "beam-10 decode molecules/s", "value": B / t, "unit": "molecules/s", "batch": B, "beams": K,
+            "steps": int(out.shape[1]) - 1, "ms_per_batch": t * 1e3, "dtype": "bf16"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--decode-batch", type=int, default=64)
+    ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

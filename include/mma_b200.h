@@ -1,0 +1,141 @@
+/* C ABI of libmma_b200.so - the sm_100a kernels behind the spectra -> SMILES hot path.
+ *
+ * Conventions ("C-ABI op layer"):
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller (PyTorch's caching
+ *     allocator in this repo); kernels never allocate or free; outputs are pre-allocated;
+ *   - every function launches on the cudaStream_t passed last and returns immediately with an int status:
+ *     0 ok, -1 bad argument, -2 launch failure, -3 unsupported shape/type, -4 driver / tensor-map failure;
+ *   - no exceptions cross the boundary, no global mutable state apart from a mutex-guarded TMA-descriptor cache;
+ *   - element-type tags: MMA_BF16 = 0, MMA_F32 = 1;  `ld*` arguments are row pitches in ELEMENTS.
+ *
+ * The reference has no native layer: each entry point replaces the ATen / cuBLAS /
+ * transformers call the reference makes implicitly at the cited line of /root/reference/src/analytical_fm.
+ */
+#ifndef MMA_B200_H
+#define MMA_B200_H
+
+#include <cuda_runtime_api.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMA_BF16 0
+#define MMA_F32 1
+
+/* GEMM epilogues, shared by the tcgen05 and the SIMT kernel */
+enum {
+  EPI_STORE = 0,   /* out = acc*alpha + bias                                   (nn.Linear)                    */
+  EPI_GELU = 1,    /* z = acc+bias; out2 = z; out = drop(gelu(z))              (linear1 + exact-erf GELU)     */
+  EPI_RESID = 2,   /* out = resid + drop(acc + bias)                           (out_proj / linear2 + residual)*/
+  EPI_DGELU = 3,   /* out = acc * dropmask * gelu'(aux)                        (backward of EPI_GELU)         */
+  EPI_GLU_MUL = 4, /* z2 = acc+bias; out2 = z2; out = drop(gelu(aux) * z2)     (GLU gate, custom_modeling.py:137-152) */
+  EPI_DGLU = 5,    /* backward of EPI_GLU_MUL: out = d z1, out2 = d z2                                          */
+  EPI_ACCUM = 6,   /* out(f32) (+)= acc*alpha; accumulate 0 overwrite / 1 add / 2 atomic add (split-K wgrad)   */
+  EPI_RELU = 7,    /* out = relu(acc + bias)                                   (patch-embedding MLPs, utils.py:121-134) */
+  EPI_DRELU = 8    /* out = acc * [aux > 0]                                                                   */
+};
+
+typedef struct Epi {
+  int kind;
+  int out_f32, aux_f32, resid_f32; /* element types of out/out2, aux/aux2, resid */
+  void* out;
+  void* out2;
+  const float* bias;
+  const void* resid;
+  const void* aux;
+  const void* aux2;
+  long long ldo, ldo2, ldr, lda, lda2;
+  float p_drop; /* dropout probability of this site (0 = off); mask = Philox4x32-10(seed, site, element) */
+  float alpha;
+  unsigned long long seed;
+  unsigned int site;
+  int accumulate;
+  long long drop_ld; /* logical row width indexing the dropout stream */
+} Epi;
+
+/* ---- dense contractions ------------------------------------------------------------------------------------
+ * C[M,N] = epi(A_op[M,K] * B_op[N,K]^T).  a_mn / b_mn = 0: operand memory is [rows, K] row-major (K-major);
+ * = 1: memory is [K, rows] row-major (MN-major), which yields dgrad (dy * W) and wgrad (dy^T * x) without
+ * transposed copies.  bf16 operands, fp32 accumulation in TMEM (tcgen05.mma, TMA-fed, persistent CTAs).
+ * Replaces: nn.Linear / F.linear inside nn.MultiheadAttention, linear1/linear2/gate, token_ff
+ * (custom_modeling.py:108-199, 418, 486) and their autograd backward.                                          */
+int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N,
+                  int K, const Epi* ep, int splits, int max_ctas, cudaStream_t stream);
+/* fp32 SIMT GEMM with arbitrary element strides (fp32 parity mode; patch embeddings with K = 75/125/1/2,
+ * modeling/utils.py:119-134).  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk].                          */
+int mma_gemm_simt(const void* A, int a_type, long long sam, long long sak, const void* B, int b_type,
+                  long long sbn, long long sbk, int M, int N, int K, const Epi* ep, cudaStream_t stream);
+
+/* ---- embedding / LayerNorm / reductions (HBM-bound) ----------------------------------------------------------
+ * nn.Embedding gather (+ XVal scale), modeling/utils.py:102-106,154-160 */
+int mma_gather_rows(const long long* ids, const float* scale, const float* table, float* out, int rows, int d,
+                    cudaStream_t stream);
+/* embedding backward: dtable[ids[r]] += g[r]*scale[r], padding row skipped (padding_idx) */
+int mma_scatter_add_rows(const long long* ids, const float* scale, const float* g, float* dtable, int rows, int d,
+                         long long pad_idx, cudaStream_t stream);
+/* LayerNorm forward fused with the positional-encoding add and the multimodal concat-by-offset write
+ * (modeling/utils.py:165-180; pre-LN norms custom_modeling.py:129,176,350,399).  Output row of input row r is
+ * (r / group) * out_group_stride + out_offset + r % group; gamma == NULL skips the norm.                        */
+int mma_ln_fwd(const void* x, int x_f32, long long ldx, const float* gamma, const float* beta, float eps, void* y,
+               int y_f32, long long ldy, void* y2, int y2_f32, long long ldy2, const float* add, long long ld_add,
+               int rows, int d, int group, int out_group_stride, int out_offset, cudaStream_t stream);
+/* LayerNorm backward (+ residual-gradient add, + dropout-masked low-precision copy for the previous branch) */
+int mma_ln_bwd(const void* dy, int dy_f32, long long lddy, int group, int in_group_stride, int in_offset,
+               const void* x, int x_f32, long long ldx, const float* gamma, float eps, const float* dres,
+               long long lddres, float* dx, long long lddx, void* dxb, int dxb_f32, long long lddxb, float p_drop,
+               unsigned long long seed, unsigned int site, float* dgamma, float* dbeta, int rows, int d,
+               cudaStream_t stream);
+/* out[c] += sum_r in[r,c]  (bias gradients) */
+int mma_colsum(const void* in, int in_f32, long long ld, float* out, int rows, int cols, cudaStream_t stream);
+int mma_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
+int mma_cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t stream);
+
+/* ---- attention (F.scaled_dot_product_attention inside nn.MultiheadAttention; masks custom_modeling.py:233-234,
+ * 299-318).  q/k/v/o are [B*L, ld] with head h at columns [h*dh, (h+1)*dh); kmask[B,Lk] 1 = real token.         */
+int mma_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                 const unsigned char* kmask, void* o, long long ldo, float* lse, int B, int H, int Lq, int Lk, int dh,
+                 int causal, float scale, float p_drop, unsigned long long seed, unsigned int site, int type,
+                 cudaStream_t stream);
+int mma_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                 const unsigned char* kmask, const void* o, long long ldo, const float* lse, const void* dout,
+                 long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv, int B,
+                 int H, int Lq, int Lk, int dh, int causal, float scale, float p_drop, unsigned long long seed,
+                 unsigned int site, int type, cudaStream_t stream);
+
+/* ---- loss (nn.CrossEntropyLoss, custom_modeling.py:490-491; ignore_index -100 set at wrapper.py:389) --------- */
+int mma_ce_fwd(const float* logits, long long ld, const long long* labels, int rows, int V, float smoothing,
+               long long ignore_index, float* row_loss, float* row_lse, float* stats, cudaStream_t stream);
+int mma_ce_bwd(const float* logits, long long ld, const long long* labels, const float* row_lse, const float* stats,
+               float gscale, int rows, int V, float smoothing, long long ignore_index, void* dlogits, int d_f32,
+               long long ldd, cudaStream_t stream);
+
+/* ---- optimiser (torch.optim.Adam/AdamW + clip_grad_norm_, wrapper.py:329-344, trainer/trainer.py:65) --------- */
+int mma_grad_norm(const float* g, long long n, float* workspace, float* norm, cudaStream_t stream);
+int mma_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, const float* hyper,
+                  const float* norm, int decoupled, int zero_grad, cudaStream_t stream);
+
+/* ---- KV-cached decoding (replaces transformers generate(use_cache=False), wrapper.py:443-451) ---------------- */
+int mma_decode_embed(const int* tok, const float* table, const float* gamma, const float* beta, float eps,
+                     const float* pos, const int* cur_len, float* out, int rows, int d, cudaStream_t stream);
+int mma_decode_self_attn(const void* q, long long ldq, const void* knew, const void* vnew, long long ldkv,
+                         void* kcache, void* vcache, const int* anc, const int* cur_len, void* o, long long ldo, int R,
+                         int H, int dh, int Lmax, float scale, int type, cudaStream_t stream);
+int mma_decode_cross_attn(const void* q, long long ldq, const void* kmem, const void* vmem, long long ldm,
+                          const unsigned char* kmask, const int* cur_len, void* o, long long ldo, int R, int H, int dh,
+                          int S, int beams, float scale, int type, cudaStream_t stream);
+/* one beam-search step for B spectra x K beams (transformers GenerationMixin._beam_search semantics) */
+int mma_beam_step(const float* logits, long long ldl, const float* extra_bias, int B, int K, int V, int L, int pad_id,
+                  int eos_id, const int* cur_len, int* run_seq, int* fin_seq, float* run_score, float* fin_score,
+                  unsigned char* fin_flag, int* fin_len, unsigned char* improvable, unsigned char* all_hit, int* anc,
+                  int* next_tok, int* parent_row, cudaStream_t stream);
+/* greedy step (GenerationMixin._sample with do_sample=False) */
+int mma_greedy_step(const float* logits, long long ldl, const float* extra_bias, int R, int V, int L, int pad_id,
+                    int eos_id, const int* cur_len, int* seq, unsigned char* unfinished, int* next_tok,
+                    cudaStream_t stream);
+int mma_advance(int* cur_len, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMA_B200_H */

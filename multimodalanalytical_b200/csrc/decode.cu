@@ -53,7 +53,7 @@ struct AttnArgs {
   const void* knew; const void* vnew; long long ldkv;   // self: this step's K/V rows [R, ldkv]
   void* kc; void* vc;                // self: cache [Lmax][R][d];  cross: memory K / V [B][S][ldm] (head offset applied)
   long long ldm;                     // cross: row pitch of memory K/V
-  const int* anc;                    // self: [R][Lmax] ancestor rows (nullptr: identity)
+  const int* anc;                    // self: [2][R][Lmax] ancestor rows, buffer cur_len&1 is live (nullptr: identity)
   const unsigned char* kmask;        // cross: [B][S]
   const int* cur_len;
   void* o; long long ldo;
@@ -92,7 +92,8 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
     Kb = reinterpret_cast<const T*>(a.kc) + h * DH;
     Vb = reinterpret_cast<const T*>(a.vc) + h * DH;
     pitch = (long long)a.R * a.d;  // per position
-    anc = a.anc ? a.anc + (long long)r * a.Lmax : nullptr;
+    // the beam step ping-pongs the ancestor table on cur_len parity: [2][R][Lmax]
+    anc = a.anc ? a.anc + ((long long)((t + 1) & 1) * a.R + r) * a.Lmax : nullptr;
   } else {
     const int b = r / a.beams;
     nkeys = a.S;

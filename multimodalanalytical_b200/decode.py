@@ -1,0 +1,225 @@
+"""KV-cached greedy / beam-search generation.
+
+Reference path: `HFWrapper.generate` (wrapper.py:409-453) -> transformers `generate(num_beams=K,
+num_return_sequences=K, use_cache=False)`; the semantics of `_sample` / `_beam_search` (length penalty 1.0,
+early_stopping False, ForcedEOS at max_length 128, `pad_token_id or eos_token_id` fill) are restated in
+`oracle/spectra_oracle.py` and implemented on the device in csrc/decode.cu.
+
+Differences in HOW (not WHAT): the encoder runs once per spectrum; cross-attention K/V are projected once per
+spectrum and shared by its K beams; self-attention K/V are cached and beams are re-ordered through an
+ancestor table instead of copying the cache; the per-step schedule reads `cur_len` from device memory so it
+is captured once in a CUDA graph and replayed for all 127 steps.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import ops
+from ._lib import EPI_GELU, EPI_GLU_MUL, EPI_RESID, EPI_STORE
+from .model import Engine
+
+
+class BeamState:
+    """Device-resident search state for B spectra x K beams (K == 1: greedy)."""
+
+    def __init__(self, B, K, L, pad_id, bos_id, eos_id, device):
+        self.B, self.K, self.L = B, K, L
+        self.pad_id, self.bos_id, self.eos_id = pad_id, bos_id, eos_id
+        dev = device
+        R = B * K
+        i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+        self.cur_len = torch.empty(1, dtype=i32, device=dev)
+        self.next_tok = torch.empty(R, dtype=i32, device=dev)
+        self.parent_row = torch.empty(R, dtype=i32, device=dev)
+        if K == 1:
+            self.run_seq = torch.empty(B, L, dtype=i32, device=dev)
+            self.unfinished = torch.empty(B, dtype=u8, device=dev)
+            self.anc = None
+        else:
+            self.run_seq = torch.empty(2, B, K, L, dtype=i32, device=dev)
+            self.fin_seq = torch.empty(2, B, K, L, dtype=i32, device=dev)
+            self.run_score = torch.empty(B, K, dtype=f32, device=dev)
+            self.fin_score = torch.empty(B, K, dtype=f32, device=dev)
+            self.fin_flag = torch.empty(B, K, dtype=u8, device=dev)
+            self.fin_len = torch.empty(B, K, dtype=i32, device=dev)
+            self.improvable = torch.empty(B, dtype=u8, device=dev)
+            self.all_hit = torch.empty(B, dtype=u8, device=dev)
+            self.anc = torch.empty(2, R, L, dtype=i32, device=dev)
+        self.reset()
+
+    def reset(self):
+        """(Re)initialise in place, so a captured CUDA graph over these buffers stays valid."""
+        self.cur_len.fill_(1)
+        self.next_tok.fill_(self.bos_id)
+        self.parent_row.copy_(torch.arange(self.B * self.K, dtype=torch.int32, device=self.cur_len.device))
+        if self.K == 1:
+            self.run_seq.fill_(self.pad_id)
+            self.run_seq[:, 0] = self.bos_id
+            self.unfinished.fill_(1)
+            return
+        fill = self.pad_id if self.pad_id else self.eos_id  # transformers: `pad_token_id or eos_token_id`
+        self.run_seq.fill_(fill)
+        self.run_seq[:, :, :, 0] = self.bos_id
+        self.fin_seq.copy_(self.run_seq)
+        self.run_score.zero_()
+        self.run_score[:, 1:] = -1.0e9
+        self.fin_score.fill_(-1.0e9)
+        self.fin_flag.zero_()
+        self.fin_len.zero_()
+        self.improvable.fill_(1)
+        self.all_hit.zero_()
+        self.anc.zero_()
+
+
+class Generator:
+    def __init__(self, engine: Engine):
+        self.eng = engine
+        self._graphs: Dict[Any, Any] = {}
+        self._states: Dict[Any, BeamState] = {}
+
+    # one decoder step for R rows; every shape is static and cur_len lives on the device
+    def _step(self, st: BeamState, ctx: Dict[str, Any], extra_bias=None):
+        eng, cfg = self.eng, self.eng.cfg
+        d, H = cfg.d_model, cfg.decoder_attention_heads
+        dh = d // H
+        R, K, L = st.B * st.K, st.K, st.L
+        T = eng.adt
+        f = cfg.decoder_ffn_dim
+        e = eng.ps.EMB
+        tm = cfg.target_modality
+        gam = bet = None
+        if cfg.multimodal_norm:
+            gam, bet = eng.P(f"{e}embedding_norm_dict.{tm}.weight"), eng.P(f"{e}embedding_norm_dict.{tm}.bias")
+        x = eng.buf("g.x", (R, d), torch.float32)
+        ops.decode_embed(st.next_tok, eng.P(f"{e}embedding_layer_dict.{tm}.weight"), gam, bet, ctx["pos"], st.cur_len, x)
+        h = eng.buf("g.h", (R, d), T)
+        qkv = eng.buf("g.qkv", (R, 3 * d), T)
+        att = eng.buf("g.att", (R, d), T)
+        q = eng.buf("g.q", (R, d), T)
+        a = eng.buf("g.a", (R, f), T)
+        z = eng.buf("g.z", (R, f), T)
+        xa = eng.buf("g.xa", (R, d), torch.float32)
+        xb = eng.buf("g.xb", (R, d), torch.float32)
+        for i in range(cfg.decoder_layers):
+            p = f"hf_model.decoder.layers.{i}."
+            ops.ln_fwd(x, eng.P(p + "norm1.weight"), eng.P(p + "norm1.bias"), h)
+            ops.gemm(h, eng.W(p + "self_attn.in_proj_weight"), R, 3 * d, d,
+                     ops.make_epi(EPI_STORE, qkv, bias=eng.P(p + "self_attn.in_proj_bias")))
+            ops.decode_self_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx["kc"][i], ctx["vc"][i], st.anc,
+                                 st.cur_len, att, R, H, dh, L)
+            ops.gemm(att, eng.W(p + "self_attn.out_proj.weight"), R, d, d,
+                     ops.make_epi(EPI_RESID, xa, bias=eng.P(p + "self_attn.out_proj.bias"), resid=x))
+            ops.ln_fwd(xa, eng.P(p + "norm2.weight"), eng.P(p + "norm2.bias"), h)
+            ops.gemm(h, eng.W(p + "multihead_attn.in_proj_weight")[:d], R, d, d,
+                     ops.make_epi(EPI_STORE, q, bias=eng.P(p + "multihead_attn.in_proj_bias")[:d]))
+            kv = ctx["kvmem"][i]
+            ops.decode_cross_attn(q, kv[:, :d], kv[:, d:], ctx["enc_mask"], st.cur_len, att, R, H, dh, ctx["S"], K)
+            ops.gemm(att, eng.W(p + "multihead_attn.out_proj.weight"), R, d, d,
+                     ops.make_epi(EPI_RESID, xb, bias=eng.P(p + "multihead_attn.out_proj.bias"), resid=xa))
+            ops.ln_fwd(xb, eng.P(p + "norm3.weight"), eng.P(p + "norm3.bias"), h)
+            if not cfg.gated_linear:
+                ops.gemm(h, eng.W(p + "linear1.weight"), R, f, d, ops.make_epi(EPI_GELU, a, bias=eng.P(p + "linear1.bias")))
+            else:
+                ops.gemm(h, eng.W(p + "linear1.weight"), R, f, d, ops.make_epi(EPI_STORE, z, bias=eng.P(p + "linear1.bias")))
+                ops.gemm(h, eng.W(p + "gate.weight"), R, f, d,
+                         ops.make_epi(EPI_GLU_MUL, a, bias=eng.P(p + "gate.bias"), aux=z))
+            ops.gemm(a, eng.W(p + "linear2.weight"), R, d, f,
+                     ops.make_epi(EPI_RESID, x, bias=eng.P(p + "linear2.bias"), resid=xb))
+        ops.ln_fwd(x, eng.P("hf_model.decoder.norm.weight"), eng.P("hf_model.decoder.norm.bias"), h)
+        V = cfg.vocab_size
+        logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
+        ops.gemm(h, eng.W("hf_model.token_ff.weight"), R, V, d,
+                 ops.make_epi(EPI_STORE, logits, bias=eng.P("hf_model.token_ff.bias")))
+        if K == 1:
+            ops.greedy_step(logits, V, st, extra_bias)
+        else:
+            ops.beam_step(logits, V, st, extra_bias)
+        ops.advance(st.cur_len)
+
+    @torch.no_grad()
+    def generate(self, enc_inputs, enc_mask, n_beams: int = 1, max_length: Optional[int] = None, extra_bias=None,
+                 use_graph: bool = True, check_every: int = 8, return_scores: bool = False):
+        """enc_inputs: {modality: batch-first tensor}; enc_mask: uint8 [B, S] (1 = real token).
+        Returns int64 [B * n_beams, L <= max_length]; row b*K + r is the r-th best hypothesis of spectrum b."""
+        eng, cfg = self.eng, self.eng.cfg
+        eng.sync_weights()
+        B, S = enc_mask.shape
+        K = int(n_beams)
+        L = int(max_length or cfg.max_length)
+        d = cfg.d_model
+        R = B * K
+        T = eng.adt
+        mask_buf = eng.buf("g.enc_mask", (B, S), torch.uint8)
+        mask_buf.copy_(enc_mask)
+        mem = eng.encode(enc_inputs, mask_buf, train=False)
+        skey = (B, K, L)
+        st = self._states.get(skey)
+        if st is None:
+            st = self._states[skey] = BeamState(B, K, L, cfg.pad_token_id, cfg.bos_token_id, cfg.eos_token_id, eng.dev)
+        else:
+            st.reset()
+        # cross-attention K/V once per spectrum and layer
+        kvmem = eng.buf("g.kvmem", (cfg.decoder_layers, B * S, 2 * d), T)
+        for i in range(cfg.decoder_layers):
+            p = f"hf_model.decoder.layers.{i}.multihead_attn."
+            ops.gemm(mem, eng.W(p + "in_proj_weight")[d:], B * S, 2 * d, d,
+                     ops.make_epi(EPI_STORE, kvmem[i], bias=eng.P(p + "in_proj_bias")[d:]))
+        kc = eng.buf("g.kc", (cfg.decoder_layers, L, R, d), T)
+        vc = eng.buf("g.vc", (cfg.decoder_layers, L, R, d), T)
+        pos = eng._pos_rows(L, "g")
+        ctx = dict(kvmem=kvmem, kc=kc, vc=vc, pos=pos, enc_mask=mask_buf, S=S)
+
+        graph = None
+        if use_graph:
+            # every buffer touched by a step (workspace, caches, search state) is cached by shape, so the captured
+            # step is reusable across calls of the same (B, K, L, S)
+            gkey = (B, K, L, S, 0 if extra_bias is None else extra_bias.data_ptr())
+            graph = self._graphs.get(gkey)
+            if graph is None:
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._step(st, ctx, extra_bias)  # warm-up: builds tensor maps, sets kernel attributes
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                st.reset()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    self._step(st, ctx, extra_bias)
+                st.reset()
+                self._graphs[gkey] = graph
+
+        steps = 0
+        max_steps = L - 1
+        while steps < max_steps:
+            n = min(check_every, max_steps - steps)
+            for _ in range(n):
+                if graph is not None:
+                    graph.replay()
+                else:
+                    self._step(st, ctx, extra_bias)
+            steps += n
+            if K == 1:
+                if not bool(st.unfinished.any().item()):
+                    break
+            else:
+                if not (bool(st.improvable.any().item()) and not bool(st.all_hit.all().item())):
+                    break
+        cur = int(st.cur_len.item())
+        if K == 1:
+            seq = st.run_seq.to(torch.int64)
+            is_eos = seq == cfg.eos_token_id
+            has = is_eos.any(dim=1)
+            first = torch.where(has, is_eos.float().argmax(dim=1), torch.full_like(has, cur - 1, dtype=torch.int64))
+            out_len = min(cur, int(first.max().item()) + 1)
+            return seq[:, :out_len].contiguous()
+        fin = st.fin_seq[cur & 1].reshape(R, L).to(torch.int64)
+        out_len = 1 + int(st.fin_len.max().item())
+        out = fin[:, :out_len].contiguous()
+        if return_scores:
+            return out, st.fin_score.reshape(R).clone()
+        return out
+

@@ -1,0 +1,152 @@
+"""Built-in training / prediction loop for the accelerated path.
+
+Replaces what Lightning does around `HFWrapper` in the reference (trainer/trainer.py:9-73: DDP, gradient
+accumulation, clip 1.0, optimiser + OneCycleLR stepping) with a fused schedule:
+  forward -> backward (gradient buckets all-reduced over NCCL on a side stream as they complete, back to
+  front) -> global-norm clip + Adam/AdamW + bf16-mirror refresh + grad zeroing in one kernel pass.
+Lightning itself still works with the module (wrapper.py); this loop is what bench.py measures.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict, Optional
+
+import torch
+
+from . import ops
+from .wrapper import HFWrapper
+
+
+def one_cycle(step: int, total_steps: int, max_lr: float, pct_start: float = 0.3, div_factor: float = 25.0,
+              final_div_factor: float = 1e4, base_momentum: float = 0.85, max_momentum: float = 0.95):
+    """(lr, beta1) of torch.optim.lr_scheduler.OneCycleLR (defaults, cos annealing, cycle_momentum=True) after
+    `step` scheduler steps - what the reference gets from OneCycleLR(optim, lr, total_steps) (wrapper.py:341)."""
+    initial_lr = max_lr / div_factor
+    min_lr = initial_lr / final_div_factor
+    p1_end = float(pct_start * total_steps) - 1
+    p2_end = total_steps - 1
+
+    def cos(start, end, pct):
+        return end + (start - end) / 2.0 * (math.cos(math.pi * pct) + 1)
+
+    if step <= p1_end:
+        pct = step / p1_end if p1_end > 0 else 1.0
+        return cos(initial_lr, max_lr, pct), cos(max_momentum, base_momentum, pct)
+    pct = (step - p1_end) / (p2_end - p1_end) if p2_end > p1_end else 1.0
+    pct = min(pct, 1.0)
+    return cos(max_lr, min_lr, pct), cos(base_momentum, max_momentum, pct)
+
+
+class FusedTrainer:
+    BUCKET_ELEMS = 8 * 1024 * 1024  # 32 MB of fp32 gradients per all-reduce
+
+    def __init__(self, module: HFWrapper, clip_grad: float = 1.0, acc_batches: int = 1, process_group=None,
+                 eps: float = 1e-8):
+        self.m = module
+        self.eng, self.ps = module.engine, module.store
+        self.clip_grad, self.acc, self.eps = clip_grad, max(1, acc_batches), eps
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if self._dist() else 1
+        self.opt_step = 0
+        self.micro = 0
+        dev = self.ps.device
+        self.ps.ensure_optimizer_state()
+        # ring of pinned staging rows: the async H2D of step i must not be overwritten by step i+1's host writes
+        self.hyper_ring = torch.zeros(64, 9, dtype=torch.float32)
+        if dev.type == "cuda":
+            self.hyper_ring = self.hyper_ring.pin_memory()
+        self.hyper = torch.zeros(9, dtype=torch.float32, device=dev)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.norm_ws = torch.zeros(1024, dtype=torch.float32, device=dev)
+        self.comm_stream = torch.cuda.Stream() if (self._dist() and dev.type == "cuda") else None
+        self._ready_hi = self.ps.numel
+        self._sync_now = False
+        self.eng.grad_ready_hook = self._on_grads_ready
+
+    def _dist(self):
+        return torch.distributed.is_available() and torch.distributed.is_initialized() and \
+            torch.distributed.get_world_size(self.pg) > 1
+
+    # gradient buckets complete back to front; reduce each as soon as it is final
+    def _on_grads_ready(self, off: int):
+        if not self._sync_now or self.world == 1:
+            return
+        while self._ready_hi - off >= self.BUCKET_ELEMS or (off == 0 and self._ready_hi > 0):
+            lo = max(off, self._ready_hi - self.BUCKET_ELEMS)
+            self._allreduce(lo, self._ready_hi)
+            self._ready_hi = lo
+
+    def _allreduce(self, lo, hi):
+        g = self.ps.g[lo:hi]
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                torch.distributed.all_reduce(g, group=self.pg)
+        else:
+            torch.distributed.all_reduce(g, group=self.pg)
+
+    def train_step(self, batch: Dict[str, Any], batch_idx: int = 0):
+        """One micro-batch: forward + backward (+ optimiser step every `acc_batches`).  Returns the loss scalar
+        (device tensor; no host sync)."""
+        m, eng = self.m, self.eng
+        m.train()
+        eng.seed += 1
+        self.micro += 1
+        self._sync_now = (self.micro % self.acc) == 0
+        self._ready_hi = self.ps.numel
+        input_ids, attention_mask = m._relayout(batch, training=True)
+        dec_in = m._to_dev(batch["decoder_input"][m.target_modality]).transpose(1, 0).contiguous()
+        dec_mask = (~m._to_dev(batch["decoder_pad_mask"])).T.to(torch.uint8).contiguous()
+        labels = m._to_dev(batch["target"]).T.contiguous().clone()
+        labels[labels == m.target_tokenizer.pad_token_id] = -100
+        out = eng.forward(input_ids, attention_mask, dec_in, dec_mask, labels=labels, train=True)
+        eng.backward(gscale=1.0)
+        if self._sync_now:
+            self.optimizer_step()
+        return out["loss"]
+
+    def optimizer_step(self):
+        m, ps = self.m, self.ps
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        lr, beta1 = one_cycle(self.opt_step, m.num_steps, m.lr)
+        if m.num_steps <= 0:
+            lr, beta1 = m.lr, m.adam_beta1
+        t = self.opt_step + 1
+        h = self.hyper_ring[self.opt_step % 64]
+        h[0], h[1], h[2], h[3], h[4] = lr, beta1, m.adam_beta2, self.eps, m.weight_decay
+        h[5], h[6] = 1.0 - beta1 ** t, 1.0 - m.adam_beta2 ** t
+        h[7] = self.clip_grad if self.clip_grad else 0.0
+        h[8] = 1.0 / (self.world * self.acc)
+        self.hyper.copy_(h, non_blocking=True)
+        norm = None
+        if self.clip_grad:
+            ops.grad_norm(ps.g, self.norm_ws, self.norm)
+            norm = self.norm
+        ops.adam_step(ps.p, ps.g, ps.m, ps.v, ps.pb if self.eng.precision == "bf16" else None, self.hyper, norm=norm,
+                      decoupled=(m.optimiser == "adamw"), zero_grad=True)
+        ps.bf16_dirty = False
+        self.opt_step += 1
+
+    def fit(self, batches, epochs: int = 1, log_every: int = 10, log=print):
+        step = 0
+        for ep in range(epochs):
+            for i, batch in enumerate(batches):
+                loss = self.train_step(batch, i)
+                if log and step % log_every == 0:
+                    log(f"epoch {ep} step {step} train_loss {float(loss):.4f}")
+                step += 1
+        return step
+
+
+@torch.no_grad()
+def predict(module: HFWrapper, batches, n_beams: Optional[int] = None):
+    """trainer.predict(model, datamodule) of the reference CLI (cli/training.py:190-206), minus Lightning."""
+    outs = []
+    if n_beams is not None:
+        module.n_beams = n_beams
+    for i, batch in enumerate(batches):
+        outs.append(module.predict_step(batch, i))
+    return outs

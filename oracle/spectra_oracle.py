@@ -63,6 +63,8 @@ class OracleConfig:
     align_config: Optional[Dict[str, Any]] = None
     target_modality: str = "Smiles"
     data_config: Dict[str, Any] = field(default_factory=dict)
+    dropout: float = 0.0       # reference default 0.1 (bart-base config); only applied when `training`
+    training: bool = False
 
 
 # --------------------------------------------------------------------------------------------
@@ -127,7 +129,13 @@ def embed_modalities(sd, cfg: OracleConfig, inputs: Dict[str, Any], emb_prefix="
 # --------------------------------------------------------------------------------------------
 # transformer blocks (custom_modeling.py:108-199 over torch's norm_first layer equations)
 # --------------------------------------------------------------------------------------------
-def _mha(xq, xkv, sd, p, n_heads, add_mask):
+def _drop(x, cfg):
+    if cfg is not None and cfg.training and cfg.dropout > 0:
+        return F.dropout(x, cfg.dropout, True)
+    return x
+
+
+def _mha(xq, xkv, sd, p, n_heads, add_mask, cfg=None):
     """Packed-QKV multi-head attention; `add_mask` is an additive float mask broadcastable to
     [B, H, Lq, Lk] (0 / -inf), as torch's F.multi_head_attention_forward builds it."""
     B, Lq, d = xq.shape
@@ -143,17 +151,17 @@ def _mha(xq, xkv, sd, p, n_heads, add_mask):
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(dh)
     if add_mask is not None:
         s = s + add_mask
-    a = torch.softmax(s, dim=-1)
+    a = _drop(torch.softmax(s, dim=-1), cfg)
     o = torch.matmul(a, v).transpose(1, 2).reshape(B, Lq, d)
     return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
 
 
-def _ffn(h, sd, p, gated):
+def _ffn(h, sd, p, gated, cfg=None):
     """W2 * (gelu(W1 h) [ * (Wg h) ])  (custom_modeling.py:137-152,184-199); exact erf GELU."""
     u = F.gelu(F.linear(h, sd[p + "linear1.weight"], sd[p + "linear1.bias"]))
     if gated:
         u = u * F.linear(h, sd[p + "gate.weight"], sd[p + "gate.bias"])
-    return F.linear(u, sd[p + "linear2.weight"], sd[p + "linear2.bias"])
+    return F.linear(_drop(u, cfg), sd[p + "linear2.weight"], sd[p + "linear2.bias"])
 
 
 def _key_pad_mask(valid):  # valid: [B, L] (1 = real token) -> additive [B,1,1,L]
@@ -168,9 +176,9 @@ def encoder_stack(sd, cfg: OracleConfig, x, attention_mask, prefix="hf_model.enc
     for i in range(cfg.encoder_layers):
         p = f"{prefix}layers.{i}."
         h = _ln(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
-        x = x + _mha(h, h, sd, p + "self_attn.", cfg.encoder_attention_heads, km)
+        x = x + _drop(_mha(h, h, sd, p + "self_attn.", cfg.encoder_attention_heads, km, cfg), cfg)
         h = _ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-        x = x + _ffn(h, sd, p, cfg.gated_linear)
+        x = x + _drop(_ffn(h, sd, p, cfg.gated_linear, cfg), cfg)
     return _ln(x, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"])
 
 
@@ -185,11 +193,11 @@ def decoder_stack(sd, cfg: OracleConfig, ids, memory, memory_mask, dec_mask=None
     for i in range(cfg.decoder_layers):
         p = f"{prefix}layers.{i}."
         h = _ln(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
-        x = x + _mha(h, h, sd, p + "self_attn.", cfg.decoder_attention_heads, self_mask)
+        x = x + _drop(_mha(h, h, sd, p + "self_attn.", cfg.decoder_attention_heads, self_mask, cfg), cfg)
         h = _ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
-        x = x + _mha(h, memory, sd, p + "multihead_attn.", cfg.decoder_attention_heads, mem_mask)
+        x = x + _drop(_mha(h, memory, sd, p + "multihead_attn.", cfg.decoder_attention_heads, mem_mask, cfg), cfg)
         h = _ln(x, sd[p + "norm3.weight"], sd[p + "norm3.bias"])
-        x = x + _ffn(h, sd, p, cfg.gated_linear)
+        x = x + _drop(_ffn(h, sd, p, cfg.gated_linear, cfg), cfg)
     return _ln(x, sd[prefix + "norm.weight"], sd[prefix + "norm.bias"])
 
 
