@@ -37,6 +37,48 @@ def one_cycle(step: int, total_steps: int, max_lr: float, pct_start: float = 0.3
     return cos(max_lr, min_lr, pct), cos(base_momentum, max_momentum, pct)
 
 
+class GradBucketer:
+    """Back-to-front bucketed all-reduce of a flat gradient buffer.
+
+    The engine's backward reports `on_ready(off)`: every gradient at flat offset >= off is final.  Full buckets are
+    all-reduced (SUM) right away on a side stream (NCCL) so the transfer overlaps the rest of backward; `finish()`
+    joins the side stream.  On CPU tensors (gloo; used by the tests) the reduction is synchronous."""
+
+    def __init__(self, flat_grad: torch.Tensor, bucket_elems: int, process_group=None):
+        self.g, self.bucket, self.pg = flat_grad, int(bucket_elems), process_group
+        self.comm_stream = torch.cuda.Stream() if flat_grad.is_cuda else None
+        self.hi = flat_grad.numel()
+        self.launched = []
+
+    def reset(self):
+        self.hi = self.g.numel()
+        self.launched = []
+
+    def on_ready(self, off: int):
+        while self.hi - off >= self.bucket or (off == 0 and self.hi > 0):
+            lo = max(off, self.hi - self.bucket)
+            self._allreduce(lo, self.hi)
+            self.hi = lo
+
+    def _allreduce(self, lo, hi):
+        g = self.g[lo:hi]
+        self.launched.append((lo, hi))
+        if self.comm_stream is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                torch.distributed.all_reduce(g, group=self.pg)
+        else:
+            torch.distributed.all_reduce(g, group=self.pg)
+
+    def finish(self):
+        if self.hi > 0:
+            self.on_ready(0)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+
 class FusedTrainer:
     BUCKET_ELEMS = 8 * 1024 * 1024  # 32 MB of fp32 gradients per all-reduce
 
@@ -58,8 +100,7 @@ class FusedTrainer:
         self.hyper = torch.zeros(9, dtype=torch.float32, device=dev)
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.norm_ws = torch.zeros(1024, dtype=torch.float32, device=dev)
-        self.comm_stream = torch.cuda.Stream() if (self._dist() and dev.type == "cuda") else None
-        self._ready_hi = self.ps.numel
+        self.bucketer = GradBucketer(self.ps.g, self.BUCKET_ELEMS, process_group) if self.world > 1 else None
         self._sync_now = False
         self.eng.grad_ready_hook = self._on_grads_ready
 
@@ -69,23 +110,8 @@ class FusedTrainer:
 
     # gradient buckets complete back to front; reduce each as soon as it is final
     def _on_grads_ready(self, off: int):
-        if not self._sync_now or self.world == 1:
-            return
-        while self._ready_hi - off >= self.BUCKET_ELEMS or (off == 0 and self._ready_hi > 0):
-            lo = max(off, self._ready_hi - self.BUCKET_ELEMS)
-            self._allreduce(lo, self._ready_hi)
-            self._ready_hi = lo
-
-    def _allreduce(self, lo, hi):
-        g = self.ps.g[lo:hi]
-        if self.comm_stream is not None:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            self.comm_stream.wait_event(ev)
-            with torch.cuda.stream(self.comm_stream):
-                torch.distributed.all_reduce(g, group=self.pg)
-        else:
-            torch.distributed.all_reduce(g, group=self.pg)
+        if self._sync_now and self.bucketer is not None:
+            self.bucketer.on_ready(off)
 
     def train_step(self, batch: Dict[str, Any], batch_idx: int = 0):
         """One micro-batch: forward + backward (+ optimiser step every `acc_batches`).  Returns the loss scalar
@@ -95,7 +121,8 @@ class FusedTrainer:
         eng.seed += 1
         self.micro += 1
         self._sync_now = (self.micro % self.acc) == 0
-        self._ready_hi = self.ps.numel
+        if self.bucketer is not None:
+            self.bucketer.reset()
         input_ids, attention_mask = m._relayout(batch, training=True)
         dec_in = m._to_dev(batch["decoder_input"][m.target_modality]).transpose(1, 0).contiguous()
         dec_mask = (~m._to_dev(batch["decoder_pad_mask"])).T.to(torch.uint8).contiguous()
@@ -109,8 +136,8 @@ class FusedTrainer:
 
     def optimizer_step(self):
         m, ps = self.m, self.ps
-        if self.comm_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if self.bucketer is not None:
+            self.bucketer.finish()
         lr, beta1 = one_cycle(self.opt_step, m.num_steps, m.lr)
         if m.num_steps <= 0:
             lr, beta1 = m.lr, m.adam_beta1
