@@ -46,7 +46,7 @@ typedef struct Epi {
   const void* aux;
   const void* aux2;
   long long ldo, ldo2, ldr, lda, lda2;
-  float p_drop; /* dropout probability of this site (0 = off); mask = Philox4x32-10(seed, site, element) */
+  float p_drop; /* dropout probability of this site (0 = off); mask = counter hash of (seed, site, element index) */
   float alpha;
   unsigned long long seed;
   unsigned int site;
@@ -65,7 +65,7 @@ int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
 /* fp32 SIMT GEMM with arbitrary element strides (fp32 parity mode; patch embeddings with K = 75/125/1/2,
  * modeling/utils.py:119-134).  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk].                          */
 int mma_gemm_simt(const void* A, int a_type, long long sam, long long sak, const void* B, int b_type,
-                  long long sbn, long long sbk, int M, int N, int K, const Epi* ep, cudaStream_t stream);
+                  long long sbn, long long sbk, int M, int N, int K, const Epi* ep, int splits, cudaStream_t stream);
 
 /* ---- embedding / LayerNorm / reductions (HBM-bound) ----------------------------------------------------------
  * nn.Embedding gather (+ XVal scale), modeling/utils.py:102-106,154-160 */
@@ -102,6 +102,17 @@ int mma_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
                  long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv, int B,
                  int H, int Lq, int Lk, int dh, int causal, float scale, float p_drop, unsigned long long seed,
                  unsigned int site, int type, cudaStream_t stream);
+
+/* tensor-core variants (mma.sync m16n8k16, bf16, head dim 64); dsum = fp32 workspace [B*H*Lq] */
+int mma_attn_fwd_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                    const unsigned char* kmask, void* o, long long ldo, float* lse, int B, int H, int Lq, int Lk,
+                    int causal, float scale, float p_drop, unsigned long long seed, unsigned int site,
+                    cudaStream_t stream);
+int mma_attn_bwd_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                    const unsigned char* kmask, const void* o, long long ldo, const float* lse, float* dsum,
+                    const void* dout, long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv,
+                    long long lddv, int B, int H, int Lq, int Lk, int causal, float scale, float p_drop,
+                    unsigned long long seed, unsigned int site, cudaStream_t stream);
 
 /* ---- loss (nn.CrossEntropyLoss, custom_modeling.py:490-491; ignore_index -100 set at wrapper.py:389) --------- */
 int mma_ce_fwd(const float* logits, long long ld, const long long* labels, int rows, int V, float smoothing,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "trainops.cu", "decode.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "trainops.cu", "decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -86,7 +86,7 @@ _lib = None
 _vp, _i, _ll, _f, _ull, _u = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_uint
 _SIGS = {
     "mma_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, C.POINTER(Epi), _i, _i, _vp],
-    "mma_gemm_simt": [_vp, _i, _ll, _ll, _vp, _i, _ll, _ll, _i, _i, _i, C.POINTER(Epi), _vp],
+    "mma_gemm_simt": [_vp, _i, _ll, _ll, _vp, _i, _ll, _ll, _i, _i, _i, C.POINTER(Epi), _i, _vp],
     "mma_gather_rows": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "mma_scatter_add_rows": [_vp, _vp, _vp, _vp, _i, _i, _ll, _vp],
     "mma_ln_fwd": [_vp, _i, _ll, _vp, _vp, _f, _vp, _i, _ll, _vp, _i, _ll, _vp, _ll, _i, _i, _i, _i, _i, _vp],
@@ -97,6 +97,9 @@ _SIGS = {
     "mma_cast_bf16_f32": [_vp, _vp, _ll, _vp],
     "mma_attn_fwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _ull, _u, _i,
                      _vp],
+    "mma_attn_fwd_tc": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
+    "mma_attn_bwd_tc": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll,
+                        _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
     "mma_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i,
                      _i, _i, _i, _i, _f, _f, _ull, _u, _i, _vp],
     "mma_ce_fwd": [_vp, _ll, _vp, _i, _i, _f, _ll, _vp, _vp, _vp, _vp],

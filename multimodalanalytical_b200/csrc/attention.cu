@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(Args a) {
   const bool drop = a.p_drop > 0.f;
   const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
   // causal: keys beyond the last query of this CTA are never needed
   const int k_end = a.causal ? min(a.Lk, q0 + QT) : a.Lk;
 
@@ -105,8 +106,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(Args a) {
       m[qi] = mn;
       if (drop) {
         const unsigned long long e = (((unsigned long long)b * a.H + h) * a.Lq + i) * (unsigned long long)a.Lk;
-        p0 *= drop_scale1(a.seed, a.site, e + ja, thr, inv_keep);
-        p1 *= drop_scale1(a.seed, a.site, e + jb, thr, inv_keep);
+        p0 *= drop_scale1(dkey, e + ja, thr, inv_keep);
+        p1 *= drop_scale1(dkey, e + jb, thr, inv_keep);
       }
       float* pw = ps + warp * KT;
       __syncwarp();
@@ -182,6 +183,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(Args a) {
   const bool drop = a.p_drop > 0.f;
   const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
   const int k_end = a.causal ? min(a.Lk, q0 + QT) : a.Lk;
 
   for (int j0 = 0; j0 < k_end; j0 += KT) {
@@ -215,8 +217,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(Args a) {
       float p1 = vb ? __expf(s1 - lse[qi]) : 0.f;
       if (drop) {
         const unsigned long long e = (((unsigned long long)b * a.H + h) * a.Lq + i) * (unsigned long long)a.Lk;
-        d0 *= drop_scale1(a.seed, a.site, e + ja, thr, inv_keep);
-        d1 *= drop_scale1(a.seed, a.site, e + jb, thr, inv_keep);
+        d0 *= drop_scale1(dkey, e + ja, thr, inv_keep);
+        d1 *= drop_scale1(dkey, e + jb, thr, inv_keep);
       }
       float* pw = ps + warp * KT;
       __syncwarp();
@@ -284,6 +286,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(Args a) {
   const bool drop = a.p_drop > 0.f;
   const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
   // causal: queries before this CTA's first key never see it
   const int i_begin = a.causal ? (k0 / KT) * KT : 0;
 
@@ -333,8 +336,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(Args a) {
       float k0s = 1.f, k1s = 1.f;
       if (drop) {
         const unsigned long long eb = ((unsigned long long)b * a.H + h) * a.Lq;
-        k0s = drop_scale1(a.seed, a.site, (eb + ia) * (unsigned long long)a.Lk + j, thr, inv_keep);
-        k1s = drop_scale1(a.seed, a.site, (eb + ib) * (unsigned long long)a.Lk + j, thr, inv_keep);
+        k0s = drop_scale1(dkey, (eb + ia) * (unsigned long long)a.Lk + j, thr, inv_keep);
+        k1s = drop_scale1(dkey, (eb + ib) * (unsigned long long)a.Lk + j, thr, inv_keep);
       }
       float* pw = ps + warp * 2 * KT;
       __syncwarp();

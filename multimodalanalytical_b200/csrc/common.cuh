@@ -89,194 +89,265 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- Philox4x32-10 counter RNG: dropout masks are a pure function of (seed, site, element) so the
-// backward pass regenerates them instead of storing them -------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-    const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += W0;
-    k.y += W1;
-  }
-  return c;
+// ---- dropout masks are a pure function of (seed, site, element index): backward regenerates them instead of
+// storing them.  Counter-based 32-bit mixer (lowbias32 finaliser), ~10 integer ops per element - cheap enough
+// to live inside GEMM epilogues and attention inner loops. -------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x7FEB352Du;
+  h ^= h >> 15;
+  h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
 }
-// random words for elements 4*g .. 4*g+3 of dropout site `site`
-__device__ __forceinline__ uint4 drop_words(unsigned long long seed, unsigned int site, unsigned long long g) {
-  return philox4x32_10(make_uint4((uint32_t)g, (uint32_t)(g >> 32), site, 0x5eedu),
-                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+__device__ __forceinline__ uint32_t drop_key(unsigned long long seed, unsigned int site) {
+  return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9E3779B9u) ^ (site * 0x85EBCA77u + 0x165667B1u));
+}
+__device__ __forceinline__ uint32_t drop_rand(uint32_t key, unsigned long long e) {
+  return mix32(((uint32_t)e * 0x9E3779B1u) ^ key ^ ((uint32_t)(e >> 32) * 0xC2B2AE3Du));
 }
 __device__ __forceinline__ uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;
   return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
 }
-// keep-scale (0 or 1/(1-p)) of a single element e
-__device__ __forceinline__ float drop_scale1(unsigned long long seed, unsigned int site, unsigned long long e,
-                                             uint32_t thr, float inv_keep) {
-  const uint4 w = drop_words(seed, site, e >> 2);
-  const uint32_t r = (e & 3) == 0 ? w.x : (e & 3) == 1 ? w.y : (e & 3) == 2 ? w.z : w.w;
-  return r >= thr ? inv_keep : 0.0f;
+// keep-scale (0 or 1/(1-p)) of element e
+__device__ __forceinline__ float drop_scale1(uint32_t key, unsigned long long e, uint32_t thr, float inv_keep) {
+  return drop_rand(key, e) >= thr ? inv_keep : 0.0f;
 }
 
-// ---- the GEMM epilogue: `n` consecutive columns of one output row --------------------------------
-// v[] holds the fp32 accumulators for columns col .. col+n-1 of row `row`; ncols is the logical N.
+// erf with |error| < 1.5e-7 (Abramowitz-Stegun 7.1.26): 1 rcp + 1 ex2 + 6 fma; used when the result is rounded to
+// bf16 anyway.  The fp32 parity path keeps erff().
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float r = 1.0f - p * exp2f(-1.4426950408889634f * ax * ax);
+  return copysignf(r, x);
+}
+template <bool FAST> __device__ __forceinline__ float gelu_t(float x) {
+  const float e = FAST ? erf_fast(x * 0.70710678118654752440f) : erff(x * 0.70710678118654752440f);
+  return 0.5f * x * (1.0f + e);
+}
+template <bool FAST> __device__ __forceinline__ float dgelu_t(float x) {
+  const float e = FAST ? erf_fast(x * 0.70710678118654752440f) : erff(x * 0.70710678118654752440f);
+  const float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
+  return 0.5f * (1.0f + e) + x * pdf;
+}
+
+// ---- vector row-segment loads / stores used by the epilogue ------------------------------------------
 template <int NV>
-__device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int col, int ncols, float (&v)[NV]) {
-  const int nvalid = min(NV, ncols - col);
-  if (nvalid <= 0) return;
-  const bool drop = ep.p_drop > 0.0f;
-  const uint32_t thr = drop ? drop_threshold(ep.p_drop) : 0u;
-  const float inv_keep = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
-  float ds[NV];
-  if (drop) {
-    const unsigned long long e0 = (unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)col;
-    if ((e0 & 3) == 0 && (NV % 4) == 0) {
+__device__ __forceinline__ void ld_row_f32(float (&x)[NV], const float* p, int nvalid) {
+  if (nvalid == NV && (NV % 4) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < NV; j += 4) {
-        const uint4 w = drop_words(ep.seed, ep.site, (e0 + j) >> 2);
-        ds[j] = w.x >= thr ? inv_keep : 0.f;
-        ds[j + 1] = w.y >= thr ? inv_keep : 0.f;
-        ds[j + 2] = w.z >= thr ? inv_keep : 0.f;
-        ds[j + 3] = w.w >= thr ? inv_keep : 0.f;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) ds[j] = drop_scale1(ep.seed, ep.site, e0 + j, thr, inv_keep);
+    for (int j = 0; j < NV; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p + j);
+      x[j] = v.x; x[j + 1] = v.y; x[j + 2] = v.z; x[j + 3] = v.w;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < NV; ++j) ds[j] = 1.0f;
+    for (int j = 0; j < NV; ++j) x[j] = j < nvalid ? p[j] : 0.f;
   }
-  float o1[NV], o2[NV];
-  bool has2 = false;
-  switch (ep.kind) {
-    case EPI_STORE: {
+}
+template <int NV>
+__device__ __forceinline__ void ld_row_bf16(float (&x)[NV], const bf16* p, int nvalid) {
+  if (nvalid == NV && (NV % 8) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j) o1[j] = v[j] * ep.alpha + ((ep.bias && j < nvalid) ? ep.bias[col + j] : 0.f);
-    } break;
-    case EPI_GELU: {
-      has2 = ep.out2 != nullptr;
+    for (int j = 0; j < NV; j += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p + j);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float z = v[j] + ((ep.bias && j < nvalid) ? ep.bias[col + j] : 0.f);
-        o2[j] = z;
-        o1[j] = gelu_f(z) * ds[j];
+      for (int w = 0; w < 4; ++w) {
+        const float2 f = __bfloat1622float2(h[w]);
+        x[j + 2 * w] = f.x;
+        x[j + 2 * w + 1] = f.y;
       }
-    } break;
-    case EPI_RESID: {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float y = v[j] + ((ep.bias && j < nvalid) ? ep.bias[col + j] : 0.f);
-        const float r = j < nvalid ? ld_any(ep.resid, row * ep.ldr + col + j, ep.resid_f32) : 0.f;
-        o1[j] = r + y * ds[j];
-      }
-    } break;
-    case EPI_DGELU: {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float z = j < nvalid ? ld_any(ep.aux, row * ep.lda + col + j, ep.aux_f32) : 0.f;
-        o1[j] = v[j] * ds[j] * dgelu_f(z);
-      }
-    } break;
-    case EPI_GLU_MUL: {
-      has2 = ep.out2 != nullptr;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float z2 = v[j] + ((ep.bias && j < nvalid) ? ep.bias[col + j] : 0.f);
-        const float z1 = j < nvalid ? ld_any(ep.aux, row * ep.lda + col + j, ep.aux_f32) : 0.f;
-        o2[j] = z2;
-        o1[j] = gelu_f(z1) * z2 * ds[j];
-      }
-    } break;
-    case EPI_DGLU: {
-      has2 = true;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float z1 = j < nvalid ? ld_any(ep.aux, row * ep.lda + col + j, ep.aux_f32) : 0.f;
-        const float z2 = j < nvalid ? ld_any(ep.aux2, row * ep.lda2 + col + j, ep.aux_f32) : 0.f;
-        const float da = v[j] * ds[j];
-        o1[j] = da * z2 * dgelu_f(z1);
-        o2[j] = da * gelu_f(z1);
-      }
-    } break;
-    case EPI_RELU: {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) o1[j] = fmaxf(v[j] + ((ep.bias && j < nvalid) ? ep.bias[col + j] : 0.f), 0.f);
-    } break;
-    case EPI_DRELU: {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float h = j < nvalid ? ld_any(ep.aux, row * ep.lda + col + j, ep.aux_f32) : 0.f;
-        o1[j] = h > 0.f ? v[j] : 0.f;
-      }
-    } break;
-    case EPI_ACCUM: {
-      float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col;
-      if (ep.accumulate == 2) {
-#pragma unroll
-        for (int j = 0; j < NV; ++j)
-          if (j < nvalid) atomicAdd(o + j, v[j] * ep.alpha);
-      } else if (ep.accumulate == 1) {
-#pragma unroll
-        for (int j = 0; j < NV; ++j)
-          if (j < nvalid) o[j] += v[j] * ep.alpha;
-      } else {
-#pragma unroll
-        for (int j = 0; j < NV; ++j)
-          if (j < nvalid) o[j] = v[j] * ep.alpha;
-      }
-      return;
     }
-    default:
-      return;
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) x[j] = j < nvalid ? __bfloat162float(p[j]) : 0.f;
   }
-  // ---- stores (vectorised when the row segment is 16-byte aligned and full) ----
-  auto store_vec = [&](void* base, long long ld, float (&x)[NV]) {
-    if (ep.out_f32) {
-      float* o = reinterpret_cast<float*>(base) + row * ld + col;
-      if (nvalid == NV && (NV % 4) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+}
+template <int NV>
+__device__ __forceinline__ void ld_row_any(float (&x)[NV], const void* base, long long idx, int is_f32, int nvalid) {
+  if (is_f32) ld_row_f32<NV>(x, reinterpret_cast<const float*>(base) + idx, nvalid);
+  else ld_row_bf16<NV>(x, reinterpret_cast<const bf16*>(base) + idx, nvalid);
+}
+template <int NV>
+__device__ __forceinline__ void st_row_any(void* base, long long idx, int is_f32, const float (&x)[NV], int nvalid) {
+  if (is_f32) {
+    float* o = reinterpret_cast<float*>(base) + idx;
+    if (nvalid == NV && (NV % 4) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
-      } else {
+      for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+    } else {
 #pragma unroll
-        for (int j = 0; j < NV; ++j)
-          if (j < nvalid) o[j] = x[j];
+      for (int j = 0; j < NV; ++j)
+        if (j < nvalid) o[j] = x[j];
+    }
+  } else {
+    bf16* o = reinterpret_cast<bf16*>(base) + idx;
+    if (nvalid == NV && (NV % 8) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(x[j], x[j + 1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(x[j + 2], x[j + 3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(x[j + 4], x[j + 5]);
+        __nv_bfloat162 d = __floats2bfloat162_rn(x[j + 6], x[j + 7]);
+        uint4 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&b);
+        u.z = *reinterpret_cast<uint32_t*>(&c);
+        u.w = *reinterpret_cast<uint32_t*>(&d);
+        *reinterpret_cast<uint4*>(o + j) = u;
+      }
+    } else if (nvalid == NV && (NV % 4) == 0 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(x[j], x[j + 1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(x[j + 2], x[j + 3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(o + j) = u;
       }
     } else {
-      bf16* o = reinterpret_cast<bf16*>(base) + row * ld + col;
-      if (nvalid == NV && (NV % 8) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-        for (int j = 0; j < NV; j += 8) {
-          __nv_bfloat162 a = __floats2bfloat162_rn(x[j], x[j + 1]);
-          __nv_bfloat162 b = __floats2bfloat162_rn(x[j + 2], x[j + 3]);
-          __nv_bfloat162 c = __floats2bfloat162_rn(x[j + 4], x[j + 5]);
-          __nv_bfloat162 d = __floats2bfloat162_rn(x[j + 6], x[j + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&a);
-          u.y = *reinterpret_cast<uint32_t*>(&b);
-          u.z = *reinterpret_cast<uint32_t*>(&c);
-          u.w = *reinterpret_cast<uint32_t*>(&d);
-          *reinterpret_cast<uint4*>(o + j) = u;
-        }
-      } else if (nvalid == NV && (NV % 4) == 0 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
-#pragma unroll
-        for (int j = 0; j < NV; j += 4) {
-          __nv_bfloat162 a = __floats2bfloat162_rn(x[j], x[j + 1]);
-          __nv_bfloat162 b = __floats2bfloat162_rn(x[j + 2], x[j + 3]);
-          uint2 u;
-          u.x = *reinterpret_cast<uint32_t*>(&a);
-          u.y = *reinterpret_cast<uint32_t*>(&b);
-          *reinterpret_cast<uint2*>(o + j) = u;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NV; ++j)
-          if (j < nvalid) o[j] = __float2bfloat16_rn(x[j]);
-      }
+      for (int j = 0; j < NV; ++j)
+        if (j < nvalid) o[j] = __float2bfloat16_rn(x[j]);
     }
-  };
-  store_vec(ep.out, ep.ldo, o1);
-  if (has2) store_vec(ep.out2, ep.ldo2, o2);
+  }
+}
+
+// ---- the GEMM epilogue: NV consecutive columns of one output row -------------------------------------
+// v[] holds the fp32 accumulators for columns col .. col+NV-1 of row `row`; ncols is the logical N.
+// KIND >= 0 fixes the epilogue at compile time (tcgen05 kernels); KIND < 0 dispatches on ep.kind.
+// FAST selects the bf16-grade erf.
+template <int NV, int KIND, bool FAST>
+__device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int col, int ncols, float (&v)[NV]) {
+  const int nvalid = min(NV, ncols - col);
+  if (nvalid <= 0) return;
+  const int kind = KIND >= 0 ? KIND : ep.kind;
+  if (kind == EPI_ACCUM) {
+    float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col;
+    if (ep.accumulate == 2) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (j < nvalid) atomicAdd(o + j, v[j] * ep.alpha);
+    } else if (ep.accumulate == 1) {
+      float cur[NV];
+      ld_row_f32<NV>(cur, o, nvalid);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) cur[j] += v[j] * ep.alpha;
+      st_row_any<NV>(ep.out, row * ep.ldo + col, 1, cur, nvalid);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] *= ep.alpha;
+      st_row_any<NV>(ep.out, row * ep.ldo + col, 1, v, nvalid);
+    }
+    return;
+  }
+  // bias
+  if (ep.bias && (kind == EPI_STORE || kind == EPI_GELU || kind == EPI_RESID || kind == EPI_GLU_MUL || kind == EPI_RELU)) {
+    float bv[NV];
+    ld_row_f32<NV>(bv, ep.bias + col, nvalid);
+    if (kind == EPI_STORE) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = fmaf(v[j], ep.alpha, bv[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] += bv[j];
+    }
+  } else if (kind == EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] *= ep.alpha;
+  }
+  // dropout keep-scales, applied in place where the kind says so
+  const bool drop = ep.p_drop > 0.0f &&
+                    (kind == EPI_GELU || kind == EPI_RESID || kind == EPI_DGELU || kind == EPI_GLU_MUL || kind == EPI_DGLU);
+  const uint32_t thr = drop ? drop_threshold(ep.p_drop) : 0u;
+  const float inv_keep = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
+  const uint32_t dkey = drop ? drop_key(ep.seed, ep.site) : 0u;
+  const unsigned long long e0 = (unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)col;
+
+  switch (kind) {
+    case EPI_STORE:
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+      break;
+    case EPI_RELU: {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+    } break;
+    case EPI_GELU: {
+      if (ep.out2) st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, v, nvalid);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float y = gelu_t<FAST>(v[j]);
+        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        v[j] = y;
+      }
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+    } break;
+    case EPI_RESID: {
+      float r[NV];
+      ld_row_any<NV>(r, ep.resid, row * ep.ldr + col, ep.resid_f32, nvalid);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float y = v[j];
+        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        v[j] = r[j] + y;
+      }
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+    } break;
+    case EPI_DGELU: {
+      float z[NV];
+      ld_row_any<NV>(z, ep.aux, row * ep.lda + col, ep.aux_f32, nvalid);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float y = v[j] * dgelu_t<FAST>(z[j]);
+        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        v[j] = y;
+      }
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+    } break;
+    case EPI_DRELU: {
+      float z[NV];
+      ld_row_any<NV>(z, ep.aux, row * ep.lda + col, ep.aux_f32, nvalid);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = z[j] > 0.f ? v[j] : 0.f;
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+    } break;
+    case EPI_GLU_MUL: {
+      float z1[NV];
+      ld_row_any<NV>(z1, ep.aux, row * ep.lda + col, ep.aux_f32, nvalid);
+      if (ep.out2) st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, v, nvalid);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float y = gelu_t<FAST>(z1[j]) * v[j];
+        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        v[j] = y;
+      }
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+    } break;
+    case EPI_DGLU: {
+      float z1[NV], z2[NV];
+      ld_row_any<NV>(z1, ep.aux, row * ep.lda + col, ep.aux_f32, nvalid);
+      ld_row_any<NV>(z2, ep.aux2, row * ep.lda2 + col, ep.aux_f32, nvalid);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float da = v[j];
+        if (drop) da *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        v[j] = da * z2[j] * dgelu_t<FAST>(z1[j]);   // d z1
+        z2[j] = da * gelu_t<FAST>(z1[j]);           // d z2
+      }
+      st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+      st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, z2, nvalid);
+    } break;
+    default:
+      break;
+  }
 }

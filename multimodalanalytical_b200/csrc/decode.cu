@@ -61,18 +61,49 @@ struct AttnArgs {
   float scale;
 };
 
+__device__ __forceinline__ void ld8(const float* p, float (&x)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&x)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float2 f = __bfloat1622float2(h[w]);
+    x[2 * w] = f.x;
+    x[2 * w + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&x)[8]) {
+  uint4 u;
+  __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(x[4], x[5]), d = __floats2bfloat162_rn(x[6], x[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// One warp per (row, head).  G = DH/8 lanes share a key (each owns one 8-element chunk -> 16-byte loads, a key row
+// is one coalesced 128-byte line for DH = 64); KPP = 32/G keys are scored per pass; online softmax across passes.
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
-  constexpr int CPL = (DH + 31) / 32;
-  __shared__ float qsh[4][DH];
-  __shared__ float psh[4][32];
+  constexpr int G = DH / 8;
+  constexpr int KPP = 32 / G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 4 + warp;
   if (gw >= a.R * a.H) return;
   const int r = gw / a.H, h = gw % a.H;
   const int t = *a.cur_len - 1;
-  const T* q = reinterpret_cast<const T*>(a.q) + (long long)r * a.ldq + h * DH;
-  for (int c = lane; c < DH; c += 32) qsh[warp][c] = to_f(q[c]) * a.scale;
+  const int sub = lane % G, kslot = lane / G;
+  float qreg[8];
+  ld8(reinterpret_cast<const T*>(a.q) + (long long)r * a.ldq + h * DH + sub * 8, qreg);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) qreg[c] *= a.scale;
   int nkeys;
   const T *Kb, *Vb;
   long long pitch;
@@ -80,35 +111,35 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
   const unsigned char* km = nullptr;
   if (!a.cross) {
     // append this step's K/V for (r, h) at position t, then attend over t+1 positions
-    T* kc = reinterpret_cast<T*>(a.kc) + ((long long)t * a.R + r) * a.d + h * DH;
-    T* vc = reinterpret_cast<T*>(a.vc) + ((long long)t * a.R + r) * a.d + h * DH;
-    const T* kn = reinterpret_cast<const T*>(a.knew) + (long long)r * a.ldkv + h * DH;
-    const T* vn = reinterpret_cast<const T*>(a.vnew) + (long long)r * a.ldkv + h * DH;
-    for (int c = lane; c < DH; c += 32) {
-      kc[c] = kn[c];
-      vc[c] = vn[c];
+    if (lane < G) {
+      float tmp[8];
+      const long long dst = ((long long)t * a.R + r) * a.d + h * DH + lane * 8;
+      ld8(reinterpret_cast<const T*>(a.knew) + (long long)r * a.ldkv + h * DH + lane * 8, tmp);
+      st8(reinterpret_cast<T*>(a.kc) + dst, tmp);
+      ld8(reinterpret_cast<const T*>(a.vnew) + (long long)r * a.ldkv + h * DH + lane * 8, tmp);
+      st8(reinterpret_cast<T*>(a.vc) + dst, tmp);
     }
     nkeys = t + 1;
-    Kb = reinterpret_cast<const T*>(a.kc) + h * DH;
-    Vb = reinterpret_cast<const T*>(a.vc) + h * DH;
+    Kb = reinterpret_cast<const T*>(a.kc) + h * DH + sub * 8;
+    Vb = reinterpret_cast<const T*>(a.vc) + h * DH + sub * 8;
     pitch = (long long)a.R * a.d;  // per position
     // the beam step ping-pongs the ancestor table on cur_len parity: [2][R][Lmax]
     anc = a.anc ? a.anc + ((long long)((t + 1) & 1) * a.R + r) * a.Lmax : nullptr;
   } else {
     const int b = r / a.beams;
     nkeys = a.S;
-    Kb = reinterpret_cast<const T*>(a.kc) + (long long)b * a.S * a.ldm + h * DH;
-    Vb = reinterpret_cast<const T*>(a.vc) + (long long)b * a.S * a.ldm + h * DH;
+    Kb = reinterpret_cast<const T*>(a.kc) + (long long)b * a.S * a.ldm + h * DH + sub * 8;
+    Vb = reinterpret_cast<const T*>(a.vc) + (long long)b * a.S * a.ldm + h * DH + sub * 8;
     pitch = a.ldm;
     km = a.kmask ? a.kmask + (long long)b * a.S : nullptr;
   }
   __syncwarp();
-  float m = -INFINITY, l = 0.f, o[CPL];
+  float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
-  for (int cc = 0; cc < CPL; ++cc) o[cc] = 0.f;
-  for (int j0 = 0; j0 < nkeys; j0 += 32) {
-    const int j = j0 + lane;
-    bool valid = j < nkeys && (!km || km[j]);
+  for (int c = 0; c < 8; ++c) o[c] = 0.f;
+  for (int j0 = 0; j0 < nkeys; j0 += KPP) {
+    const int j = j0 + kslot;
+    const bool valid = j < nkeys && (!km || km[j]);
     long long off = 0;
     if (j < nkeys) {
       if (!a.cross) {
@@ -118,14 +149,16 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
         off = (long long)j * pitch;
       }
     }
-    float s = -INFINITY;
+    float s = 0.f;
     if (valid) {
-      const T* kr = Kb + off;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int c = 0; c < DH; ++c) acc = fmaf(qsh[warp][c], to_f(kr[c]), acc);
-      s = acc;
+      float kx[8];
+      ld8(Kb + off, kx);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) s = fmaf(qreg[c], kx[c], s);
     }
+#pragma unroll
+    for (int w = 1; w < G; w <<= 1) s += __shfl_xor_sync(0xffffffffu, s, w);
+    if (!valid) s = -INFINITY;
     const float mt = warp_max(s);
     const float mn = fmaxf(m, mt);
     float p = 0.f, corr = 1.f;
@@ -133,32 +166,26 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
       p = valid ? __expf(s - mn) : 0.f;
       corr = m == -INFINITY ? 0.f : __expf(m - mn);
     }
-    l = l * corr + warp_sum(p);
+    l = l * corr + warp_sum(p) * (1.0f / G);
     m = mn;
-    __syncwarp();
-    psh[warp][lane] = p;
-    __syncwarp();
+    float vx[8];
 #pragma unroll
-    for (int cc = 0; cc < CPL; ++cc) o[cc] *= corr;
-    const int cnt = min(32, nkeys - j0);
-    for (int jj = 0; jj < cnt; ++jj) {
-      const float pj = psh[warp][jj];
-      const long long offj = __shfl_sync(0xffffffffu, off, jj);
-      if (pj != 0.f) {
+    for (int c = 0; c < 8; ++c) vx[c] = 0.f;
+    if (p != 0.f) ld8(Vb + off, vx);
 #pragma unroll
-        for (int cc = 0; cc < CPL; ++cc) {
-          const int c = lane + cc * 32;
-          if (c < DH) o[cc] = fmaf(pj, to_f(Vb[offj + c]), o[cc]);
-        }
-      }
-    }
+    for (int c = 0; c < 8; ++c) o[c] = fmaf(p, vx[c], o[c] * corr);
   }
-  T* out = reinterpret_cast<T*>(a.o) + (long long)r * a.ldo + h * DH;
-  const float inv = l > 0.f ? 1.f / l : 0.f;
+  // combine the KPP key slots (lanes with equal `sub`)
 #pragma unroll
-  for (int cc = 0; cc < CPL; ++cc) {
-    const int c = lane + cc * 32;
-    if (c < DH) out[c] = from_f<T>(o[cc] * inv);
+  for (int w = G; w < 32; w <<= 1) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] += __shfl_xor_sync(0xffffffffu, o[c], w);
+  }
+  if (kslot == 0) {
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] *= inv;
+    st8(reinterpret_cast<T*>(a.o) + (long long)r * a.ldo + h * DH + sub * 8, o);
   }
 }
 

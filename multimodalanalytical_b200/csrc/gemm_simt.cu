@@ -11,7 +11,7 @@ constexpr int TM = 64, TN = 64, TK = 16;
 template <typename TA, typename TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(const TA* __restrict__ A, long long sam, long long sak,
                                                     const TB* __restrict__ B, long long sbn, long long sbk, int M,
-                                                    int N, int K, Epi ep) {
+                                                    int N, int K, int k_per_split, Epi ep) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int t = threadIdx.x;
@@ -24,14 +24,17 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const TA* __restrict__ A, lo
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  // split-K over grid.z (host guarantees an atomic EPI_ACCUM epilogue when gridDim.z > 1)
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
 #pragma unroll
     for (int e = t; e < TM * TK; e += 256) {
       int m, k;
       if (sak == 1) { k = e % TK; m = e / TK; } else { m = e % TM; k = e / TM; }
       const long long gm = m0 + m;
       const int gk = k0 + k;
-      As[k][m] = (gm < M && gk < K) ? to_f(A[gm * sam + gk * sak]) : 0.f;
+      As[k][m] = (gm < M && gk < k_end) ? to_f(A[gm * sam + gk * sak]) : 0.f;
     }
 #pragma unroll
     for (int e = t; e < TN * TK; e += 256) {
@@ -39,7 +42,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const TA* __restrict__ A, lo
       if (sbk == 1) { k = e % TK; n = e / TK; } else { n = e % TN; k = e / TN; }
       const long long gn = n0 + n;
       const int gk = k0 + k;
-      Bs[k][n] = (gn < N && gk < K) ? to_f(B[gn * sbn + gk * sbk]) : 0.f;
+      Bs[k][n] = (gn < N && gk < k_end) ? to_f(B[gn * sbn + gk * sbk]) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -58,24 +61,29 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const TA* __restrict__ A, lo
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const long long row = m0 + ty * 4 + i;
-    if (row < M) epilogue_store<4>(ep, row, (int)(n0 + tx * 4), N, acc[i]);
+    if (row < M) epilogue_store<4, -1, false>(ep, row, (int)(n0 + tx * 4), N, acc[i]);
   }
 }
 }  // namespace simt
 
 extern "C" int mma_gemm_simt(const void* A, int a_type, long long sam, long long sak, const void* B, int b_type,
-                             long long sbn, long long sbk, int M, int N, int K, const Epi* ep, cudaStream_t stream) {
+                             long long sbn, long long sbk, int M, int N, int K, const Epi* ep, int splits,
+                             cudaStream_t stream) {
   using namespace simt;
   if (M <= 0 || N <= 0 || K <= 0 || !ep) return MMA_ERR_ARG;
-  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM);
+  if (splits < 1) splits = 1;
+  if (splits > 1 && !(ep->kind == EPI_ACCUM && ep->accumulate == 2)) return MMA_ERR_ARG;
+  int kps = ((K + splits - 1) / splits + TK - 1) / TK * TK;
+  splits = (K + kps - 1) / kps;
+  dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, splits);
   if (a_type == MMA_F32 && b_type == MMA_F32)
-    sgemm_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)A, sam, sak, (const float*)B, sbn, sbk, M, N, K, *ep);
+    sgemm_kernel<float, float><<<grid, 256, 0, stream>>>((const float*)A, sam, sak, (const float*)B, sbn, sbk, M, N, K, kps, *ep);
   else if (a_type == MMA_BF16 && b_type == MMA_BF16)
-    sgemm_kernel<bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)A, sam, sak, (const bf16*)B, sbn, sbk, M, N, K, *ep);
+    sgemm_kernel<bf16, bf16><<<grid, 256, 0, stream>>>((const bf16*)A, sam, sak, (const bf16*)B, sbn, sbk, M, N, K, kps, *ep);
   else if (a_type == MMA_F32 && b_type == MMA_BF16)
-    sgemm_kernel<float, bf16><<<grid, 256, 0, stream>>>((const float*)A, sam, sak, (const bf16*)B, sbn, sbk, M, N, K, *ep);
+    sgemm_kernel<float, bf16><<<grid, 256, 0, stream>>>((const float*)A, sam, sak, (const bf16*)B, sbn, sbk, M, N, K, kps, *ep);
   else
-    sgemm_kernel<bf16, float><<<grid, 256, 0, stream>>>((const bf16*)A, sam, sak, (const float*)B, sbn, sbk, M, N, K, *ep);
+    sgemm_kernel<bf16, float><<<grid, 256, 0, stream>>>((const bf16*)A, sam, sak, (const float*)B, sbn, sbk, M, N, K, kps, *ep);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

@@ -24,7 +24,8 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -118,13 +119,14 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t tile_addr, int k16) 
 template <int BN>
 struct Cfg {
   static constexpr int STAGES = BN <= 128 ? 6 : 4;
+  static_assert(BN == 128 || BN == 256, "tile N must be 128 or 256");
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                int splits, Epi ep) {
@@ -153,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tfull[i]), 1);
-      mbar_init(smem_u32(&tempty[i]), 4);
+      mbar_init(smem_u32(&tempty[i]), NUM_EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -253,7 +255,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================= epilogue warps (TMEM -> registers -> global) =================
-    const int q = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int q = warp & 3;           // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    constexpr int COLS = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -263,12 +267,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(smem_u32(&tfull[acc]), acc_phase);
       tc_fence_after();
       const long long row = (long long)m0 + q * 32 + lane;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < COLS; c0 += 32) {
         float v[32];
         tmem_ld32(t_row + (uint32_t)c0, v);
-        if (row < M && n0 + c0 < N) epilogue_store<32>(ep, row, n0 + c0, N, v);
+        const int col = n0 + half * COLS + c0;
+        if (row < M && col < N) epilogue_store<32, KIND, true>(ep, row, col, N, v);
       }
       tc_fence_before();
       __syncwarp();
@@ -368,11 +373,11 @@ static int num_sms() {
   return n;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int KIND>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int K, int splits, const Epi& ep,
                   int max_ctas, cudaStream_t stream) {
   using C = Cfg<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, KIND>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess)
@@ -385,6 +390,44 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, 
   kern<<<grid, NUM_THREADS, C::SMEM, stream>>>(tmA, tmB, M, N, K, splits, ep);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
+}
+
+template <int BN>
+static int dispatch(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N, int K,
+                    const Epi& ep, int splits, int max_ctas, cudaStream_t stream) {
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!a_mn) rc = make_map(&tmA, A, (unsigned long long)K, (unsigned long long)M, lda, BK, BM);
+  else rc = make_map(&tmA, A, (unsigned long long)M, (unsigned long long)K, lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tmB, B, (unsigned long long)K, (unsigned long long)N, ldb, BK, BN);
+  else rc = make_map(&tmB, B, (unsigned long long)N, (unsigned long long)K, ldb, 64, BK);
+  if (rc) return rc;
+#define MMA_LAUNCH(AM, BM_, KD) return launch<BN, AM, BM_, KD>(tmA, tmB, M, N, K, splits, ep, max_ctas, stream)
+  if (!a_mn && !b_mn) {  // forward products
+    switch (ep.kind) {
+      case EPI_STORE: MMA_LAUNCH(false, false, EPI_STORE);
+      case EPI_GELU: MMA_LAUNCH(false, false, EPI_GELU);
+      case EPI_RESID: MMA_LAUNCH(false, false, EPI_RESID);
+      case EPI_GLU_MUL: MMA_LAUNCH(false, false, EPI_GLU_MUL);
+      default: MMA_LAUNCH(false, false, -1);
+    }
+  }
+  if (!a_mn && b_mn) {  // dgrad
+    switch (ep.kind) {
+      case EPI_STORE: MMA_LAUNCH(false, true, EPI_STORE);
+      case EPI_DGELU: MMA_LAUNCH(false, true, EPI_DGELU);
+      case EPI_DGLU: MMA_LAUNCH(false, true, EPI_DGLU);
+      case EPI_ACCUM: MMA_LAUNCH(false, true, EPI_ACCUM);
+      default: MMA_LAUNCH(false, true, -1);
+    }
+  }
+  if (a_mn && b_mn) {  // wgrad
+    if (ep.kind == EPI_ACCUM) MMA_LAUNCH(true, true, EPI_ACCUM);
+    MMA_LAUNCH(true, true, -1);
+  }
+  MMA_LAUNCH(true, false, -1);
+#undef MMA_LAUNCH
 }
 
 }  // namespace tc
@@ -400,17 +443,8 @@ extern "C" int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   if (splits < 1) splits = 1;
   if (splits > num_kb) splits = num_kb;
   if (splits > 1 && !(ep->kind == EPI_ACCUM && ep->accumulate == 2)) return MMA_ERR_ARG;
-  const int BN = 128;
-  CUtensorMap tmA, tmB;
-  int rc;
-  if (!a_mn) rc = make_map(&tmA, A, (unsigned long long)K, (unsigned long long)M, lda, BK, BM);
-  else rc = make_map(&tmA, A, (unsigned long long)M, (unsigned long long)K, lda, 64, BK);
-  if (rc) return rc;
-  if (!b_mn) rc = make_map(&tmB, B, (unsigned long long)K, (unsigned long long)N, ldb, BK, BN);
-  else rc = make_map(&tmB, B, (unsigned long long)N, (unsigned long long)K, ldb, 64, BK);
-  if (rc) return rc;
-  if (!a_mn && !b_mn) return launch<128, false, false>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
-  if (!a_mn && b_mn) return launch<128, false, true>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
-  if (a_mn && b_mn) return launch<128, true, true>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
-  return launch<128, true, false>(tmA, tmB, M, N, K, splits, *ep, max_ctas, stream);
+  // 128x256 tiles halve the A re-reads from L2; use them when the 256-wide tiling still fills the machine
+  const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256) * splits;
+  if (N >= 256 && tiles256 >= 120) return dispatch<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, *ep, splits, max_ctas, stream);
+  return dispatch<128>(A, lda, a_mn, B, ldb, b_mn, M, N, K, *ep, splits, max_ctas, stream);
 }

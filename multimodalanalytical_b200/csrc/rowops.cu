@@ -6,7 +6,7 @@
 
 namespace rowops {
 
-constexpr int MAXI = 8;  // a lane owns float4 columns lane*4 + 128*i, i < MAXI  ->  d <= 1024
+constexpr int MAXI = 8;  // a lane owns float4 columns lane*4 + 128*i, i < NI <= MAXI  ->  d <= 1024
 
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
@@ -86,16 +86,17 @@ struct LnFwdArgs {
   int rows, d, group, out_group_stride, out_offset;
 };
 
+template <int NI>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs a) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.rows) return;
   const long long r = warp;
   const long long orow = (r / a.group) * (long long)a.out_group_stride + a.out_offset + (r % a.group);
   const int d = a.d;
-  float4 xv[MAXI];
+  float4 xv[NI];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXI; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < d) {
       xv[i] = ld4_any(a.x, r * a.ldx + c, a.x_f32);
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs a) {
     mean = warp_sum(sum) / d;
     float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < d) {
         const float dx = xv[i].x - mean, dy = xv[i].y - mean, dz = xv[i].z - mean, dw = xv[i].w - mean;
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs a) {
     rstd = rsqrtf(warp_sum(sq) / d + a.eps);
   }
 #pragma unroll
-  for (int i = 0; i < MAXI; ++i) {
+  for (int i = 0; i < NI; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < d) {
       float4 o = xv[i];
@@ -161,26 +162,28 @@ struct LnBwdArgs {
   int rows, d;
 };
 
+template <int NI>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
-  __shared__ float s_dg[MAXI * 128];
-  __shared__ float s_db[MAXI * 128];
+  __shared__ float s_dg[NI * 128];
+  __shared__ float s_db[NI * 128];
   const int d = a.d;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   for (int c = threadIdx.x; c < d; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; }
   __syncthreads();
-  float4 pg[MAXI], pb[MAXI];
+  float4 pg[NI], pb[NI];
 #pragma unroll
-  for (int i = 0; i < MAXI; ++i) { pg[i] = make_float4(0, 0, 0, 0); pb[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NI; ++i) { pg[i] = make_float4(0, 0, 0, 0); pb[i] = make_float4(0, 0, 0, 0); }
   const bool drop = a.p_drop > 0.f;
   const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
 
   for (long long r = (long long)blockIdx.x * wpb + wib; r < a.rows; r += (long long)gridDim.x * wpb) {
     const long long irow = (r / a.group) * (long long)a.in_group_stride + a.in_offset + (r % a.group);
-    float4 xv[MAXI], gv[MAXI];
+    float4 xv[NI], gv[NI];
     float sum = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < d) {
         xv[i] = ld4_any(a.x, r * a.ldx + c, a.x_f32);
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
       mean = warp_sum(sum) / d;
       float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < MAXI; ++i) {
+      for (int i = 0; i < NI; ++i) {
         const int c = lane * 4 + i * 128;
         if (c < d) {
           const float e0 = xv[i].x - mean, e1 = xv[i].y - mean, e2 = xv[i].z - mean, e3 = xv[i].w - mean;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
     float sg = 0.f, sgx = 0.f;
     if (a.gamma) {
 #pragma unroll
-      for (int i = 0; i < MAXI; ++i) {
+      for (int i = 0; i < NI; ++i) {
         const int c = lane * 4 + i * 128;
         if (c < d) {
           const float4 gm = *reinterpret_cast<const float4*>(a.gamma + c);
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
       sgx = warp_sum(sgx) / d;
     }
 #pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < d) {
         float4 o = gv[i];
@@ -244,11 +247,11 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
         if (a.dx) *reinterpret_cast<float4*>(a.dx + r * a.lddx + c) = o;
         if (a.dxb) {
           if (drop) {
-            const uint4 w = drop_words(a.seed, a.site, ((unsigned long long)r * d + c) >> 2);
-            o.x *= w.x >= thr ? inv_keep : 0.f;
-            o.y *= w.y >= thr ? inv_keep : 0.f;
-            o.z *= w.z >= thr ? inv_keep : 0.f;
-            o.w *= w.w >= thr ? inv_keep : 0.f;
+            const unsigned long long e = (unsigned long long)r * d + c;
+            o.x *= drop_scale1(dkey, e, thr, inv_keep);
+            o.y *= drop_scale1(dkey, e + 1, thr, inv_keep);
+            o.z *= drop_scale1(dkey, e + 2, thr, inv_keep);
+            o.w *= drop_scale1(dkey, e + 3, thr, inv_keep);
           }
           st4_any(a.dxb, r * a.lddxb + c, a.dxb_f32, o);
         }
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
   }
   if (a.gamma && a.dgamma) {
 #pragma unroll
-    for (int i = 0; i < MAXI; ++i) {
+    for (int i = 0; i < NI; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < d) {
         atomicAdd(&s_dg[c], pg[i].x); atomicAdd(&s_dg[c + 1], pg[i].y);
@@ -339,7 +342,13 @@ extern "C" int mma_ln_fwd(const void* x, int x_f32, long long ldx, const float* 
   if (d > MAXI * 128 || (d & 3)) return MMA_ERR_UNSUPPORTED;
   LnFwdArgs a{x, x_f32, ldx, gamma, beta, eps, y, y_f32, ldy, y2, y2_f32, ldy2, add, ld_add,
               rows, d, group > 0 ? group : rows, out_group_stride, out_offset};
-  ln_fwd_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(a);
+  const int ni = (d + 127) / 128;
+  const int blocks = (rows + 7) / 8;
+  if (ni <= 1) ln_fwd_kernel<1><<<blocks, 256, 0, stream>>>(a);
+  else if (ni <= 2) ln_fwd_kernel<2><<<blocks, 256, 0, stream>>>(a);
+  else if (ni <= 4) ln_fwd_kernel<4><<<blocks, 256, 0, stream>>>(a);
+  else if (ni <= 6) ln_fwd_kernel<6><<<blocks, 256, 0, stream>>>(a);
+  else ln_fwd_kernel<8><<<blocks, 256, 0, stream>>>(a);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }
@@ -353,9 +362,15 @@ extern "C" int mma_ln_bwd(const void* dy, int dy_f32, long long lddy, int group,
   if (d > MAXI * 128 || (d & 3)) return MMA_ERR_UNSUPPORTED;
   LnBwdArgs a{dy, dy_f32, lddy, group > 0 ? group : rows, in_group_stride, in_offset, x, x_f32, ldx, gamma, eps,
               dres, lddres, dx, lddx, dxb, dxb_f32, lddxb, p_drop, seed, site, dgamma, dbeta, rows, d};
-  int blocks = (rows + 7) / 8;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  ln_bwd_kernel<<<blocks, 256, 0, stream>>>(a);
+  const int ni = (d + 127) / 128;
+  int blocks = (rows + 15) / 16;  // >= 2 rows per warp so the dgamma/dbeta partials amortise their flush
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  if (ni <= 1) ln_bwd_kernel<1><<<blocks, 256, 0, stream>>>(a);
+  else if (ni <= 2) ln_bwd_kernel<2><<<blocks, 256, 0, stream>>>(a);
+  else if (ni <= 4) ln_bwd_kernel<4><<<blocks, 256, 0, stream>>>(a);
+  else if (ni <= 6) ln_bwd_kernel<6><<<blocks, 256, 0, stream>>>(a);
+  else ln_bwd_kernel<8><<<blocks, 256, 0, stream>>>(a);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

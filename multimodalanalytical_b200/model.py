@@ -216,7 +216,7 @@ class Engine:
         qkv = s["qkv"]
         ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], s["ctx"], s["lse"], dctx, dqkv[:, :d],
                      dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, heads, L, L, dh, kmask=kmask, causal=causal, p_drop=p,
-                     seed=self.seed, site=site_a)
+                     seed=self.seed, site=site_a, dsum=self.buf("bw.dsum", (B * heads * L,), torch.float32))
         dh_ = self.buf("bw.dh", (M, d), T)
         self._lin_bwd(dqkv, s["h"], wp["in_w"], wp["in_b"], M, 3 * d, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
         dx_in = self._other_dx(dx, M)
@@ -329,7 +329,8 @@ class Engine:
         dkv = self.buf("bw.dkv", (Me, 2 * d), T)
         kv = s["kv"]
         ops.attn_bwd(s["q"], kv[:, :d], kv[:, d:], s["ctx"], s["lse"], dctx, dq, dkv[:, :d], dkv[:, d:], B, heads, T_,
-                     S, dh, kmask=kmask, causal=False, p_drop=p, seed=self.seed, site=site_a)
+                     S, dh, kmask=kmask, causal=False, p_drop=p, seed=self.seed, site=site_a,
+                     dsum=self.buf("bw.dsum", (B * heads * T_,), torch.float32))
         dh_ = self.buf("bw.dh", (M, d), T)
         self._lin_bwd(dq, s["h"], wp["in_w"], wp["in_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dh_),
                       row_slice=slice(0, d))

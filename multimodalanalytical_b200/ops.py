@@ -82,12 +82,17 @@ def gemm(A, B, M, N, K, epi, a_mn=False, b_mn=False, splits=1, force_simt=False,
                                C.byref(epi), splits, max_ctas, _stream())
         check(rc, "mma_gemm_bf16")
     else:
-        if epi.kind == EPI_ACCUM and epi.accumulate == 2:
-            epi.accumulate = 1  # the SIMT kernel never splits K: plain accumulate
+        ssplit = 1
+        if epi.kind == EPI_ACCUM and epi.accumulate in (1, 2):
+            # few output tiles + long reduction (weight gradients): split K over CTAs with atomic accumulation
+            tiles = ((M + 63) // 64) * ((N + 63) // 64)
+            if tiles < 148 and K >= 1024:
+                ssplit = max(1, min(64, K // 256, 296 // tiles))
+            epi.accumulate = 2 if ssplit > 1 else 1
         sam, sak = (1, A.stride(0)) if a_mn else (A.stride(0), 1)
         sbn, sbk = (1, B.stride(0)) if b_mn else (B.stride(0), 1)
         rc = lib.mma_gemm_simt(A.data_ptr(), _ty(A), sam, sak, B.data_ptr(), _ty(B), sbn, sbk, M, N, K, C.byref(epi),
-                               _stream())
+                               ssplit, _stream())
         check(rc, "mma_gemm_simt")
     _count()
 
@@ -156,9 +161,21 @@ def cast_bf16_f32(src, dst):
     _count()
 
 
+def _attn_tc_ok(dh, *ts):
+    return dh == 64 and all(t.dtype == torch.bfloat16 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in ts)
+
+
 def attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop=0.0, seed=0, site=0):
-    """q/k/v/o: 2-D views [B*L, ld] (row pitch = stride(0)); heads are column blocks of width dh."""
+    """q/k/v/o: 2-D views [B*L, ld] (row pitch = stride(0)); heads are column blocks of width dh.
+    bf16 with head dim 64 runs on the tensor-core kernels, everything else on the SIMT fp32-arithmetic ones."""
     _need_cuda(q, k, v, o)
+    if _attn_tc_ok(dh, q, k, v, o):
+        check(_lib.load().mma_attn_fwd_tc(
+            q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+            o.stride(0), _p(lse), B, H, Lq, Lk, int(causal), dh ** -0.5, float(p_drop), int(seed), int(site),
+            _stream()), "mma_attn_fwd_tc")
+        _count()
+        return
     check(_lib.load().mma_attn_fwd(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
         o.stride(0), _p(lse), B, H, Lq, Lk, dh, int(causal), dh ** -0.5, float(p_drop), int(seed), int(site), _ty(q),
@@ -167,8 +184,18 @@ def attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop
 
 
 def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop=0.0, seed=0,
-             site=0):
+             site=0, dsum=None):
     _need_cuda(q, k, v, o, dout, dq, dk, dv)
+    if _attn_tc_ok(dh, q, k, v, o, dout, dq, dk, dv):
+        if dsum is None:
+            dsum = torch.empty(B * H * Lq, dtype=torch.float32, device=q.device)
+        check(_lib.load().mma_attn_bwd_tc(
+            q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+            o.stride(0), lse.data_ptr(), dsum.data_ptr(), dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0),
+            dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Lq, Lk, int(causal), dh ** -0.5,
+            float(p_drop), int(seed), int(site), _stream()), "mma_attn_bwd_tc")
+        _count(2)
+        return
     check(_lib.load().mma_attn_bwd(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
         o.stride(0), lse.data_ptr(), dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(),

@@ -309,3 +309,65 @@ def test_adam_step_matches_torch(decoupled):
         assert rel(p, ref_p.data) < 1e-5
         assert (g == 0).all()
     assert rel(pb.float(), p) < 1e-2
+
+
+def test_tc_attention_dropout_forward_backward_use_one_mask():
+    """bf16 / head-dim-64 tensor-core path: recover the dropout mask from a forward with V = I, then check the
+    forward output and all three gradients against autograd with that mask."""
+    B, H, L, dh, p = 2, 2, 64, 64, 0.2
+    d = H * dh
+    dt = torch.bfloat16
+    q, k = _rand(B * L, d, dtype=dt, seed=1), _rand(B * L, d, dtype=dt, seed=2)
+    eye = torch.eye(L, dh, device=DEV).repeat(B, H).to(dt)  # V[b, j, h*dh + c] = [j == c]
+    o = torch.empty(B * L, d, device=DEV, dtype=dt)
+    lse = torch.empty(B * H * L, device=DEV)
+    ops.attn_fwd(q, k, eye, o, lse, B, H, L, L, dh, causal=True, p_drop=p, seed=11, site=7)
+    pd = o.view(B, L, H, dh).permute(0, 2, 1, 3).float()  # P_drop [B,H,Lq,Lk]
+    qh = q.view(B, L, H, dh).permute(0, 2, 1, 3).float()
+    kh = k.view(B, L, H, dh).permute(0, 2, 1, 3).float()
+    s = qh @ kh.transpose(-1, -2) / math.sqrt(dh) + torch.triu(torch.full((L, L), float("-inf"), device=DEV), 1)
+    pr = torch.softmax(s, -1)
+    causal = torch.tril(torch.ones(L, L, device=DEV, dtype=torch.bool))
+    keep = (pd != 0)
+    frac = keep[..., causal].float().mean().item()
+    assert abs(frac - (1 - p)) < 0.03, frac
+    assert rel(pd[keep], (pr / (1 - p))[keep]) < 2e-2
+    # gradients with the recovered mask
+    v = _rand(B * L, d, dtype=dt, seed=3)
+    do = _rand(B * L, d, dtype=dt, seed=4)
+    o2 = torch.empty_like(o)
+    ops.attn_fwd(q, k, v, o2, lse, B, H, L, L, dh, causal=True, p_drop=p, seed=11, site=7)
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ops.attn_bwd(q, k, v, o2, lse, do, dq, dk, dv, B, H, L, L, dh, causal=True, p_drop=p, seed=11, site=7)
+    qr, kr, vr = (t.float().view(B, L, H, dh).permute(0, 2, 1, 3).detach().requires_grad_(True) for t in (q, k, v))
+    sr = qr @ kr.transpose(-1, -2) / math.sqrt(dh) + torch.triu(torch.full((L, L), float("-inf"), device=DEV), 1)
+    ref = (torch.softmax(sr, -1) * keep / (1 - p)) @ vr
+    assert rel(o2.view(B, L, H, dh).permute(0, 2, 1, 3).float(), ref) < 2e-2
+    ref.backward(do.view(B, L, H, dh).permute(0, 2, 1, 3).float())
+    for got, want in ((dq, qr.grad), (dk, kr.grad), (dv, vr.grad)):
+        assert rel(got.view(B, L, H, dh).permute(0, 2, 1, 3).float(), want) < 3e-2
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,causal", [(2, 8, 199, 199, False), (2, 8, 96, 199, False), (3, 8, 100, 100, True)])
+def test_tc_attention_multi_tile(B, H, Lq, Lk, causal):
+    """sequences longer than one 64-row tile (C4 multimodal shapes) on the tensor-core path."""
+    dh, dt = 64, torch.bfloat16
+    d = H * dh
+    q, k, v = _rand(B, Lq, d, dtype=dt, seed=1), _rand(B, Lk, d, dtype=dt, seed=2), _rand(B, Lk, d, dtype=dt, seed=3)
+    kmask = torch.ones(B, Lk, dtype=torch.uint8, device=DEV)
+    kmask[0, 70:90] = 0
+    kmask[1, Lk - 5:] = 0
+    o = torch.empty(B * Lq, d, device=DEV, dtype=dt)
+    lse = torch.empty(B * H * Lq, device=DEV)
+    ops.attn_fwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), o, lse, B, H, Lq, Lk, dh, kmask=kmask, causal=causal)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qr, kr, vr, kmask, causal, H)
+    assert rel(o.view(B, Lq, d).float(), ref) < 2e-2
+    do = _rand(B, Lq, d, dtype=dt, seed=4)
+    ref.backward(do.float())
+    dq, dk, dv = (torch.empty_like(t).view(-1, d) for t in (q, k, v))
+    ops.attn_bwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), o, lse, do.view(-1, d), dq, dk, dv, B, H, Lq, Lk, dh,
+                 kmask=kmask, causal=causal)
+    assert rel(dq.view_as(q).float(), qr.grad) < 3e-2
+    assert rel(dk.view_as(k).float(), kr.grad) < 3e-2
+    assert rel(dv.view_as(v).float(), vr.grad) < 3e-2
