@@ -22,6 +22,7 @@ extern "C" {
 
 #define MMA_BF16 0
 #define MMA_F32 1
+#define MMA_SITE_SEED_INDIRECT 0x80000000u /* in any `site` argument: `seed` holds a device pointer to the seed */
 
 /* GEMM epilogues, shared by the tcgen05 and the SIMT kernel */
 enum {
@@ -49,7 +50,7 @@ typedef struct Epi {
   float p_drop; /* dropout probability of this site (0 = off); mask = counter hash of (seed, site, element index) */
   float alpha;
   unsigned long long seed;
-  unsigned int site;
+  unsigned int site; /* bit 31 (MMA_SITE_SEED_INDIRECT): `seed` is the device address of the 64-bit seed */
   int accumulate;
   long long drop_ld; /* logical row width indexing the dropout stream */
 } Epi;
@@ -114,6 +115,18 @@ int mma_attn_bwd_tc(const void* q, long long ldq, const void* k, long long ldk, 
                     long long lddv, int B, int H, int Lq, int Lk, int causal, float scale, float p_drop,
                     unsigned long long seed, unsigned int site, cudaStream_t stream);
 
+/* tcgen05 / TMEM single-tile variants (bf16, head dim 64, Lq <= 128 and Lk <= 128; two (batch, head) problems are
+ * packed per 128x128 tile when both lengths are <= 64) */
+int mma_attn_fwd_t5(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                    const unsigned char* kmask, void* o, long long ldo, float* lse, int B, int H, int Lq, int Lk,
+                    int causal, float scale, float p_drop, unsigned long long seed, unsigned int site,
+                    cudaStream_t stream);
+int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                    const unsigned char* kmask, const void* o, long long ldo, const float* lse, const void* dout,
+                    long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
+                    int B, int H, int Lq, int Lk, int causal, float scale, float p_drop, unsigned long long seed,
+                    unsigned int site, cudaStream_t stream);
+
 /* ---- loss (nn.CrossEntropyLoss, custom_modeling.py:490-491; ignore_index -100 set at wrapper.py:389) --------- */
 int mma_ce_fwd(const float* logits, long long ld, const long long* labels, int rows, int V, float smoothing,
                long long ignore_index, float* row_loss, float* row_lse, float* stats, cudaStream_t stream);
@@ -125,6 +138,8 @@ int mma_ce_bwd(const float* logits, long long ld, const long long* labels, const
 int mma_grad_norm(const float* g, long long n, float* workspace, float* norm, cudaStream_t stream);
 int mma_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, long long n, const float* hyper,
                   const float* norm, int decoupled, int zero_grad, cudaStream_t stream);
+
+int mma_add_u64(unsigned long long* p, unsigned long long inc, cudaStream_t stream);
 
 /* ---- KV-cached decoding (replaces transformers generate(use_cache=False), wrapper.py:443-451) ---------------- */
 int mma_decode_embed(const int* tok, const float* table, const float* gamma, const float* beta, float eps,

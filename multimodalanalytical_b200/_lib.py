@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "trainops.cu", "decode.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -100,12 +100,16 @@ _SIGS = {
     "mma_attn_fwd_tc": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
     "mma_attn_bwd_tc": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll,
                         _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
+    "mma_attn_fwd_t5": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
+    "mma_attn_bwd_t5": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll,
+                        _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
     "mma_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i,
                      _i, _i, _i, _i, _f, _f, _ull, _u, _i, _vp],
     "mma_ce_fwd": [_vp, _ll, _vp, _i, _i, _f, _ll, _vp, _vp, _vp, _vp],
     "mma_ce_bwd": [_vp, _ll, _vp, _vp, _vp, _f, _i, _i, _f, _ll, _vp, _i, _ll, _vp],
     "mma_grad_norm": [_vp, _ll, _vp, _vp, _vp],
     "mma_adam_step": [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _vp],
+    "mma_add_u64": [_vp, _ull, _vp],
     "mma_decode_embed": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp],
     "mma_decode_self_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
     "mma_decode_cross_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp],

@@ -1,0 +1,488 @@
+// tcgen05 / TMEM attention for short sequences (bf16, head dim 64): the shapes of this path (S ~ 27-128 encoder
+// positions, T <= 128 target positions) fit ONE 128-row score tile, so forward and backward are single-shot
+// kernels with every matrix product on the 5th-generation tensor cores:
+//
+//   forward   S = Q K^T -> row softmax in registers (one thread per row) -> P (bf16, smem) -> O = P V
+//   backward  S = Q K^T, dP = dO V^T -> P, dS (bf16, smem) -> dV = P^T dO, dK = dS^T Q, dQ = dS K
+//
+// Operands are TMA-loaded 128B-swizzled tiles used directly as K-major or MN-major UMMA operands (the P / dS
+// tiles serve as K-major A for "x K / x V" and as MN-major A for the transposed products - no transposes).
+// PACK = 2 packs two (batch, head) problems of <= 64 queries and <= 64 keys into one 128x128 tile (rows 0-63 /
+// keys 0-63 = problem A, rows 64-127 / keys 64-127 = problem B; the off-diagonal blocks of P / dS are written as
+// zeros so the packed products stay block-diagonal).  PACK = 1 is one problem with <= 128 queries and keys.
+// Longer sequences use the streaming mma.sync kernels (attention_mma.cu).  Masks / dropout stream: as everywhere.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace at5 {
+using namespace tma;
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint32_t TILE = 128 * 128;  // bytes of a [128 rows x 64 bf16] tile
+
+struct Args {
+  int B, H, Lq, Lk, causal, nprob;
+  float scale, p_drop;
+  unsigned long long seed;
+  unsigned int site;
+  const unsigned char* kmask;
+  bf16* o; long long ldo;
+  float* lse;
+  // backward
+  const bf16* o_in; const bf16* dout; long long lddo;
+  bf16* dq; bf16* dk; bf16* dv;
+  long long lddq, lddk, lddv;
+};
+
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptors (128B swizzle), see gemm_tc.cu
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) {  // rows of 128 B, 8-row groups 1024 B apart
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr, uint32_t atom_stride) {  // k rows of 128 B
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((atom_stride >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ constexpr uint32_t idesc(int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// write 8 bf16 (one 16-byte chunk) of row r, logical column c (multiple of 8) of a [128 x 64] swizzled tile
+__device__ __forceinline__ void st_chunk(uint8_t* tile, int r, int c, uint4 v) {
+  *reinterpret_cast<uint4*>(tile + r * 128 + ((((c >> 3) ^ (r & 7))) << 4)) = v;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// which (batch, head, local row) a tile row belongs to
+template <int PACK>
+struct RowMap {
+  int prob, b, h, i;   // problem index, batch, head, local row index
+  bool exists;
+  int key_col0;        // first score column of this row's problem
+  __device__ RowMap(const Args& a, int row) {
+    const int sub = PACK == 2 ? (row >> 6) : 0;
+    prob = blockIdx.x * PACK + sub;
+    exists = prob < a.nprob;
+    const int pp = exists ? prob : 0;
+    b = pp / a.H;
+    h = pp % a.H;
+    i = PACK == 2 ? (row & 63) : row;
+    key_col0 = sub * 64;
+  }
+};
+
+template <int PACK>
+__device__ __forceinline__ void issue_tile_loads(const Args& a, const CUtensorMap* tm, uint32_t dst, uint32_t bar, int L) {
+  // two 64-row boxes: rows [0,64) and [64,128) of the tile
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int prob = PACK == 2 ? blockIdx.x * 2 + s : blockIdx.x;
+    if (prob >= a.nprob) prob = a.nprob - 1;  // dummy (masked) when the pair is incomplete
+    const int b = prob / a.H, h = prob % a.H;
+    const int row0 = b * L + (PACK == 2 ? 0 : s * 64);
+    tma_load_2d(dst + s * 8192, tm, bar, h * 64, row0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int PACK>
+__global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                                                  const __grid_constant__ CUtensorMap tv, Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // no static smem in this kernel: the window starts 1024-aligned
+  uint8_t* sQ = smem;               // after S is formed, sQ|sK (32 KB) is reused for P (two 64-key atoms)
+  uint8_t* sK = smem + TILE;
+  uint8_t* sV = smem + 2 * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t bar = smem_u32(&bars[0]);
+    mbar_expect_tx(bar, 3 * TILE);
+    issue_tile_loads<PACK>(a, &tq, smem_u32(sQ), bar, a.Lq);
+    issue_tile_loads<PACK>(a, &tk, smem_u32(sK), bar, a.Lk);
+    issue_tile_loads<PACK>(a, &tv, smem_u32(sV), bar, a.Lk);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // S[128 x 128] = Q K^T
+      tc_mma_bf16(tm, desc_kmajor(smem_u32(sQ) + k * 32), desc_kmajor(smem_u32(sK) + k * 32), idesc(128, false, false), k > 0);
+    tc_commit(smem_u32(&bars[1]));
+  }
+  const int row = warp * 32 + lane;
+  const RowMap<PACK> rm(a, row);
+  const unsigned char* km = a.kmask ? a.kmask + (long long)rm.b * a.Lk : nullptr;
+  const float sl2 = a.scale * LOG2E;
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
+  const unsigned long long ebase = (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)a.Lk;
+  constexpr int NCH = PACK == 2 ? 2 : 4;  // 32-column chunks of this row's problem
+  const uint32_t t_row = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)rm.key_col0;
+
+  mbar_wait(smem_u32(&bars[1]), 0);
+  tc_fence_after();
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    float s[32];
+    tmem_ld32f(t_row + ch * 32, s);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int j = ch * 32 + c;
+      const bool ok = j < a.Lk && (!km || km[j]) && (!a.causal || j <= rm.i);
+      if (ok) mx = fmaxf(mx, s[c] * sl2);
+    }
+  }
+  // every thread has read what it needs for the max; P overwrites sQ|sK only after the S product has retired (bars[1])
+  float l = 0.f;
+  uint8_t* sP = sQ;
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    float s[32];
+    tmem_ld32f(t_row + ch * 32, s);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int j = ch * 32 + c;
+      const bool ok = j < a.Lk && (!km || km[j]) && (!a.causal || j <= rm.i);
+      float p = ok ? ex2_approx(s[c] * sl2 - mx) : 0.f;
+      l += p;
+      if (drop) p *= drop_scale1(dkey, ebase + j, thr, inv_keep);
+      s[c] = p;
+    }
+    const int kcol = rm.key_col0 + ch * 32;  // column in the packed 128-wide K dimension
+    uint8_t* atom = sP + (kcol >> 6) * TILE;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      uint4 u;
+      u.x = pack2(s[c], s[c + 1]); u.y = pack2(s[c + 2], s[c + 3]);
+      u.z = pack2(s[c + 4], s[c + 5]); u.w = pack2(s[c + 6], s[c + 7]);
+      st_chunk(atom, row, (kcol & 63) + c, u);
+    }
+  }
+  if (PACK == 2) {  // zero the other problem's key block of this row
+    uint8_t* atom = sP + ((rm.key_col0 >> 6) ^ 1) * TILE;
+#pragma unroll
+    for (int c = 0; c < 64; c += 8) st_chunk(atom, row, c, make_uint4(0, 0, 0, 0));
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // O[128 x 64] = P[128 x 128] V[128 x 64]
+      tc_mma_bf16(tm, desc_kmajor(smem_u32(sP) + (k >> 2) * TILE + (k & 3) * 32),
+                  desc_mnmajor(smem_u32(sV) + k * 2048, TILE), idesc(64, false, true), k > 0);
+    tc_commit(smem_u32(&bars[2]));
+  }
+  mbar_wait(smem_u32(&bars[2]), 0);
+  tc_fence_after();
+  {
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const bool wr = rm.exists && rm.i < a.Lq;
+    bf16* orow = a.o + ((long long)rm.b * a.Lq + rm.i) * a.ldo + rm.h * 64;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      float v[32];
+      tmem_ld32f(tm + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
+      if (wr) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 u;
+          u.x = pack2(v[c] * inv, v[c + 1] * inv); u.y = pack2(v[c + 2] * inv, v[c + 3] * inv);
+          u.z = pack2(v[c + 4] * inv, v[c + 5] * inv); u.w = pack2(v[c + 6] * inv, v[c + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + ch * 32 + c) = u;
+        }
+      }
+    }
+    if (wr && a.lse) a.lse[((long long)rm.b * a.H + rm.h) * a.Lq + rm.i] = l > 0.f ? mx / LOG2E + logf(l) : -INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(128) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+template <int PACK>
+__global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                                                  const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                                                  Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // no static smem in this kernel: the window starts 1024-aligned
+  // layout (ascending): Pd atom 0 | dS atom 0 | dS atom 1 | Q | K | dO | V (= Pd atom 1 once dP has retired)
+  uint8_t* sPd0 = smem;
+  uint8_t* sdS = smem + TILE;
+  uint8_t* sQ = smem + 3 * TILE;
+  uint8_t* sK = smem + 4 * TILE;
+  uint8_t* sDO = smem + 5 * TILE;
+  uint8_t* sV = smem + 6 * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  if (threadIdx.x == 0) {
+    const uint32_t bar = smem_u32(&bars[0]);
+    mbar_expect_tx(bar, 4 * TILE);
+    issue_tile_loads<PACK>(a, &tq, smem_u32(sQ), bar, a.Lq);
+    issue_tile_loads<PACK>(a, &tk, smem_u32(sK), bar, a.Lk);
+    issue_tile_loads<PACK>(a, &tv, smem_u32(sV), bar, a.Lk);
+    issue_tile_loads<PACK>(a, &tdo, smem_u32(sDO), bar, a.Lq);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // S = Q K^T -> cols [0,128)
+      tc_mma_bf16(tm, desc_kmajor(smem_u32(sQ) + k * 32), desc_kmajor(smem_u32(sK) + k * 32), idesc(128, false, false), k > 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // dP = dO V^T -> cols [128,256)
+      tc_mma_bf16(tm + 128, desc_kmajor(smem_u32(sDO) + k * 32), desc_kmajor(smem_u32(sV) + k * 32), idesc(128, false, false), k > 0);
+    tc_commit(smem_u32(&bars[1]));
+  }
+  const int row = warp * 32 + lane;
+  const RowMap<PACK> rm(a, row);
+  const bool qvalid = rm.exists && rm.i < a.Lq;
+  const unsigned char* km = a.kmask ? a.kmask + (long long)rm.b * a.Lk : nullptr;
+  // D_i = sum_c dO[i,c] O[i,c] and lse_i while the tensor core works
+  float Di = 0.f, lse2 = 0.f;
+  if (qvalid) {
+    const uint4* po = reinterpret_cast<const uint4*>(a.o_in + ((long long)rm.b * a.Lq + rm.i) * a.ldo + rm.h * 64);
+    const uint4* pd = reinterpret_cast<const uint4*>(a.dout + ((long long)rm.b * a.Lq + rm.i) * a.lddo + rm.h * 64);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const uint4 x = po[u], y = pd[u];
+      const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&x);
+      const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float2 xf = __bfloat1622float2(xb[w]), yf = __bfloat1622float2(yb[w]);
+        Di += xf.x * yf.x + xf.y * yf.y;
+      }
+    }
+    lse2 = a.lse[((long long)rm.b * a.H + rm.h) * a.Lq + rm.i] * LOG2E;
+  }
+  const float sl2 = a.scale * LOG2E;
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
+  const unsigned long long ebase = (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)a.Lk;
+  constexpr int NCH = PACK == 2 ? 2 : 4;
+  const uint32_t t_row = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)rm.key_col0;
+
+  mbar_wait(smem_u32(&bars[1]), 0);  // S and dP are in TMEM; V's smem is free (becomes Pd atom 1)
+  tc_fence_after();
+#pragma unroll 1
+  for (int ch = 0; ch < NCH; ++ch) {
+    float s[32], dp[32];
+    tmem_ld32f(t_row + ch * 32, s);
+    tmem_ld32f(t_row + 128 + ch * 32, dp);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const int j = ch * 32 + c;
+      const bool ok = qvalid && j < a.Lk && (!km || km[j]) && (!a.causal || j <= rm.i);
+      const float p = ok ? ex2_approx(s[c] * sl2 - lse2) : 0.f;
+      const float keep = drop ? drop_scale1(dkey, ebase + j, thr, inv_keep) : 1.f;
+      s[c] = p * keep;                      // P_drop
+      dp[c] = p * (dp[c] * keep - Di);      // dS
+    }
+    const int kcol = rm.key_col0 + ch * 32;
+    uint8_t* pa = (kcol >> 6) ? sV : sPd0;
+    uint8_t* da = sdS + (kcol >> 6) * TILE;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      uint4 u, w;
+      u.x = pack2(s[c], s[c + 1]); u.y = pack2(s[c + 2], s[c + 3]);
+      u.z = pack2(s[c + 4], s[c + 5]); u.w = pack2(s[c + 6], s[c + 7]);
+      w.x = pack2(dp[c], dp[c + 1]); w.y = pack2(dp[c + 2], dp[c + 3]);
+      w.z = pack2(dp[c + 4], dp[c + 5]); w.w = pack2(dp[c + 6], dp[c + 7]);
+      st_chunk(pa, row, (kcol & 63) + c, u);
+      st_chunk(da, row, (kcol & 63) + c, w);
+    }
+  }
+  if (PACK == 2) {
+    const int other = (rm.key_col0 >> 6) ^ 1;
+    uint8_t* pa = other ? sV : sPd0;
+    uint8_t* da = sdS + other * TILE;
+#pragma unroll
+    for (int c = 0; c < 64; c += 8) {
+      st_chunk(pa, row, c, make_uint4(0, 0, 0, 0));
+      st_chunk(da, row, c, make_uint4(0, 0, 0, 0));
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    const uint32_t pd_stride = smem_u32(sV) - smem_u32(sPd0);  // distance between the two key atoms of Pd
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // dV[keys x 64] = Pd^T dO     -> cols [0,64)
+      tc_mma_bf16(tm, desc_mnmajor(smem_u32(sPd0) + k * 2048, pd_stride), desc_mnmajor(smem_u32(sDO) + k * 2048, TILE),
+                  idesc(64, true, true), k > 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // dK[keys x 64] = dS^T Q      -> cols [64,128)
+      tc_mma_bf16(tm + 64, desc_mnmajor(smem_u32(sdS) + k * 2048, TILE), desc_mnmajor(smem_u32(sQ) + k * 2048, TILE),
+                  idesc(64, true, true), k > 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // dQ[q x 64] = dS K           -> cols [128,192)
+      tc_mma_bf16(tm + 128, desc_kmajor(smem_u32(sdS) + (k >> 2) * TILE + (k & 3) * 32),
+                  desc_mnmajor(smem_u32(sK) + k * 2048, TILE), idesc(64, false, true), k > 0);
+    tc_commit(smem_u32(&bars[2]));
+  }
+  mbar_wait(smem_u32(&bars[2]), 0);
+  tc_fence_after();
+  {
+    // row r is query r of its problem for dQ and key r of its problem for dK / dV
+    const bool kvalid = rm.exists && rm.i < a.Lk;
+    bf16* dqrow = a.dq + ((long long)rm.b * a.Lq + rm.i) * a.lddq + rm.h * 64;
+    bf16* dkrow = a.dk + ((long long)rm.b * a.Lk + rm.i) * a.lddk + rm.h * 64;
+    bf16* dvrow = a.dv + ((long long)rm.b * a.Lk + rm.i) * a.lddv + rm.h * 64;
+    const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int part = 0; part < 6; ++part) {  // dV lo/hi, dK lo/hi, dQ lo/hi
+      float v[32];
+      tmem_ld32f(tl + part * 32, v);
+      const int which = part >> 1, half = part & 1;
+      const bool wr = which == 2 ? qvalid : kvalid;
+      const float sc = which == 0 ? 1.f : a.scale;
+      bf16* dst = (which == 0 ? dvrow : which == 1 ? dkrow : dqrow) + half * 32;
+      if (wr) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 u;
+          u.x = pack2(v[c] * sc, v[c + 1] * sc); u.y = pack2(v[c + 2] * sc, v[c + 3] * sc);
+          u.z = pack2(v[c + 4] * sc, v[c + 5] * sc); u.w = pack2(v[c + 6] * sc, v[c + 7] * sc);
+          *reinterpret_cast<uint4*>(dst + c) = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256) : "memory");
+  }
+}
+
+static int map64(CUtensorMap* m, const void* p, int H, long long rows, long long ld) {
+  return make_map(m, p, (unsigned long long)H * 64, (unsigned long long)rows, (unsigned long long)ld, 64, 64);
+}
+
+}  // namespace at5
+
+// Single-tile tcgen05 attention.  Requirements (checked): bf16, head dim 64, Lk <= 128, Lq <= 128, 16-byte aligned
+// views with pitches that are multiples of 8 elements.  q/k/v/o/dout are [B*L, ld] views with head h at columns
+// [64h, 64h+64).
+extern "C" int mma_attn_fwd_t5(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                               long long ldv, const unsigned char* kmask, void* o, long long ldo, float* lse, int B,
+                               int H, int Lq, int Lk, int causal, float scale, float p_drop, unsigned long long seed,
+                               unsigned int site, cudaStream_t stream) {
+  using namespace at5;
+  if (B <= 0 || Lq <= 0 || Lk <= 0) return MMA_OK;
+  if (Lq > 128 || Lk > 128 || ((ldq | ldk | ldv | ldo) & 7)) return MMA_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = map64(&tq, q, H, (long long)B * Lq, ldq))) return rc;
+  if ((rc = map64(&tk, k, H, (long long)B * Lk, ldk))) return rc;
+  if ((rc = map64(&tv, v, H, (long long)B * Lk, ldv))) return rc;
+  Args a{};
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nprob = B * H; a.scale = scale; a.p_drop = p_drop;
+  a.seed = seed; a.site = site; a.kmask = kmask; a.o = (bf16*)o; a.ldo = ldo; a.lse = lse;
+  const int smem = 3 * TILE + 64;
+  if (Lq <= 64 && Lk <= 64) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+    fwd_kernel<2><<<(a.nprob + 1) / 2, 128, smem, stream>>>(tq, tk, tv, a);
+  } else {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+    fwd_kernel<1><<<a.nprob, 128, smem, stream>>>(tq, tk, tv, a);
+  }
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                               long long ldv, const unsigned char* kmask, const void* o, long long ldo,
+                               const float* lse, const void* dout, long long lddo, void* dq, long long lddq, void* dk,
+                               long long lddk, void* dv, long long lddv, int B, int H, int Lq, int Lk, int causal,
+                               float scale, float p_drop, unsigned long long seed, unsigned int site,
+                               cudaStream_t stream) {
+  using namespace at5;
+  if (B <= 0 || Lq <= 0 || Lk <= 0) return MMA_OK;
+  if (Lq > 128 || Lk > 128 || ((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 7)) return MMA_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = map64(&tq, q, H, (long long)B * Lq, ldq))) return rc;
+  if ((rc = map64(&tk, k, H, (long long)B * Lk, ldk))) return rc;
+  if ((rc = map64(&tv, v, H, (long long)B * Lk, ldv))) return rc;
+  if ((rc = map64(&tdo, dout, H, (long long)B * Lq, lddo))) return rc;
+  Args a{};
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nprob = B * H; a.scale = scale; a.p_drop = p_drop;
+  a.seed = seed; a.site = site; a.kmask = kmask; a.lse = const_cast<float*>(lse);
+  a.o_in = (const bf16*)o; a.ldo = ldo; a.dout = (const bf16*)dout; a.lddo = lddo;
+  a.dq = (bf16*)dq; a.dk = (bf16*)dk; a.dv = (bf16*)dv; a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
+  const int smem = 7 * TILE + 64;  // 2 CTAs per SM
+  if (Lq <= 64 && Lk <= 64) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+    bwd_kernel<2><<<(a.nprob + 1) / 2, 128, smem, stream>>>(tq, tk, tv, tdo, a);
+  } else {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+    bwd_kernel<1><<<a.nprob, 128, smem, stream>>>(tq, tk, tv, tdo, a);
+  }
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}

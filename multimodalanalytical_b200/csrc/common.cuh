@@ -71,13 +71,6 @@ __device__ __forceinline__ void st_any(void* p, long long i, int is_f32, float v
   else reinterpret_cast<bf16*>(p)[i] = __float2bfloat16_rn(v);
 }
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float dgelu_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -100,42 +93,72 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16;
   return h;
 }
+// site bit 31 set: `seed` is the DEVICE ADDRESS of the 64-bit seed (a captured CUDA graph advances the seed on the
+// device between replays; the launch parameters stay constant).
+#define MMA_SITE_SEED_INDIRECT 0x80000000u
 __device__ __forceinline__ uint32_t drop_key(unsigned long long seed, unsigned int site) {
+  if (site & MMA_SITE_SEED_INDIRECT) {
+    seed = *reinterpret_cast<const unsigned long long*>(seed);
+    site &= ~MMA_SITE_SEED_INDIRECT;
+  }
   return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9E3779B9u) ^ (site * 0x85EBCA77u + 0x165667B1u));
 }
-__device__ __forceinline__ uint32_t drop_rand(uint32_t key, unsigned long long e) {
-  return mix32(((uint32_t)e * 0x9E3779B1u) ^ key ^ ((uint32_t)(e >> 32) * 0xC2B2AE3Du));
-}
+// one 32-bit hash serves two neighbouring elements (16 random bits each; p is quantised to 1/65536)
+__device__ __forceinline__ uint32_t drop_pair(uint32_t key, uint32_t pair_idx) { return mix32((pair_idx * 0x9E3779B1u) ^ key); }
 __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  return t >= 4294967295.0 ? 0xffffffffu : (uint32_t)t;
+  const float t = p * 65536.0f + 0.5f;
+  return t >= 65535.0f ? 65535u : (uint32_t)t;
 }
-// keep-scale (0 or 1/(1-p)) of element e
+// keep-scale (0 or 1/(1-p)) of element e (the element index is taken modulo 2^32)
 __device__ __forceinline__ float drop_scale1(uint32_t key, unsigned long long e, uint32_t thr, float inv_keep) {
-  return drop_rand(key, e) >= thr ? inv_keep : 0.0f;
+  const uint32_t e32 = (uint32_t)e;
+  const uint32_t r = drop_pair(key, e32 >> 1);
+  return ((r >> ((e32 & 1u) << 4)) & 0xFFFFu) >= thr ? inv_keep : 0.0f;
 }
 
-// erf with |error| < 1.5e-7 (Abramowitz-Stegun 7.1.26): 1 rcp + 1 ex2 + 6 fma; used when the result is rounded to
-// bf16 anyway.  The fp32 parity path keeps erff().
-__device__ __forceinline__ float erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float r = 1.0f - p * exp2f(-1.4426950408889634f * ax * ax);
-  return copysignf(r, x);
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// Phi(x) = 0.5 (1 + erf(x / sqrt 2)) and e = exp(-x^2 / 2).  FAST: Abramowitz-Stegun 7.1.26 (|erf error| < 1.5e-7) on
+// rcp.approx / ex2.approx - used when the result is rounded to bf16 anyway; the fp32 parity path keeps erff().
+template <bool FAST> __device__ __forceinline__ void normal_cdf_exp(float x, float& cdf, float& e) {
+  if (FAST) {
+    const float u = fabsf(x) * 0.70710678118654752440f;
+    const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    e = ex2_approx(-0.72134752044448170368f * x * x);
+    const float half_erfc = 0.5f * p * t * e;
+    cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  } else {
+    cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    e = expf(-0.5f * x * x);
+  }
 }
 template <bool FAST> __device__ __forceinline__ float gelu_t(float x) {
-  const float e = FAST ? erf_fast(x * 0.70710678118654752440f) : erff(x * 0.70710678118654752440f);
-  return 0.5f * x * (1.0f + e);
+  float cdf, e;
+  normal_cdf_exp<FAST>(x, cdf, e);
+  return x * cdf;
 }
 template <bool FAST> __device__ __forceinline__ float dgelu_t(float x) {
-  const float e = FAST ? erf_fast(x * 0.70710678118654752440f) : erff(x * 0.70710678118654752440f);
-  const float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
-  return 0.5f * (1.0f + e) + x * pdf;
+  float cdf, e;
+  normal_cdf_exp<FAST>(x, cdf, e);
+  return fmaf(x * 0.39894228040143267794f, e, cdf);
+}
+template <bool FAST> __device__ __forceinline__ void gelu_both(float x, float& g, float& dg) {
+  float cdf, e;
+  normal_cdf_exp<FAST>(x, cdf, e);
+  g = x * cdf;
+  dg = fmaf(x * 0.39894228040143267794f, e, cdf);
 }
 
 // ---- vector row-segment loads / stores used by the epilogue ------------------------------------------
@@ -271,7 +294,21 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
   const uint32_t thr = drop ? drop_threshold(ep.p_drop) : 0u;
   const float inv_keep = drop ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
   const uint32_t dkey = drop ? drop_key(ep.seed, ep.site) : 0u;
-  const unsigned long long e0 = (unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)col;
+  const uint32_t e0 = (uint32_t)((unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)col);
+  float ds[NV];
+  if (drop) {
+    if ((e0 & 1u) == 0 && (NV % 2) == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 2) {
+        const uint32_t r = drop_pair(dkey, (e0 + j) >> 1);
+        ds[j] = (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+        ds[j + 1] = (r >> 16) >= thr ? inv_keep : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) ds[j] = drop_scale1(dkey, e0 + j, thr, inv_keep);
+    }
+  }
 
   switch (kind) {
     case EPI_STORE:
@@ -287,7 +324,7 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         float y = gelu_t<FAST>(v[j]);
-        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        if (drop) y *= ds[j];
         v[j] = y;
       }
       st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
@@ -298,7 +335,7 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         float y = v[j];
-        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        if (drop) y *= ds[j];
         v[j] = r[j] + y;
       }
       st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
@@ -309,7 +346,7 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         float y = v[j] * dgelu_t<FAST>(z[j]);
-        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        if (drop) y *= ds[j];
         v[j] = y;
       }
       st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
@@ -328,7 +365,7 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         float y = gelu_t<FAST>(z1[j]) * v[j];
-        if (drop) y *= drop_scale1(dkey, e0 + j, thr, inv_keep);
+        if (drop) y *= ds[j];
         v[j] = y;
       }
       st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
@@ -340,9 +377,11 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         float da = v[j];
-        if (drop) da *= drop_scale1(dkey, e0 + j, thr, inv_keep);
-        v[j] = da * z2[j] * dgelu_t<FAST>(z1[j]);   // d z1
-        z2[j] = da * gelu_t<FAST>(z1[j]);           // d z2
+        if (drop) da *= ds[j];
+        float g, dg;
+        gelu_both<FAST>(z1[j], g, dg);
+        v[j] = da * z2[j] * dg;  // d z1
+        z2[j] = da * g;          // d z2
       }
       st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
       st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, z2, nvalid);

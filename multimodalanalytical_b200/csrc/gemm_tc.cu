@@ -13,66 +13,29 @@
 // (128B swizzle), two TMEM accumulator stages so the epilogue of tile i overlaps the mainloop of
 // tile i+1.  The epilogue (bias / GELU / GLU / residual / dropout / split-K accumulate) is shared
 // with the SIMT fp32 GEMM (common.cuh).
-#include <cuda.h>
-
-#include <mutex>
-#include <unordered_map>
-
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace tc {
+using namespace tma;
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int NUM_EPI_WARPS = 8;  // two warps per TMEM lane quarter, each takes half of the tile's columns
+constexpr int NUM_EPI_WARPS = 16;  // four warps per TMEM lane quarter, each drains a quarter of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must trap (error returned to the host), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
       : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -256,8 +219,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ================= epilogue warps (TMEM -> registers -> global) =================
     const int q = warp & 3;           // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
-    constexpr int COLS = BN / 2;
+    const int half = (warp - 2) >> 2;  // which slice of the tile's columns this warp drains
+    constexpr int COLS = BN / (NUM_EPI_WARPS / 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -269,11 +232,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long row = (long long)m0 + q * 32 + lane;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS);
 #pragma unroll 1
-      for (int c0 = 0; c0 < COLS; c0 += 32) {
-        float v[32];
-        tmem_ld32(t_row + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < COLS; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
         const int col = n0 + half * COLS + c0;
-        if (row < M && col < N) epilogue_store<32, KIND, true>(ep, row, col, N, v);
+        if (row < M && col < N) epilogue_store<16, KIND, true>(ep, row, col, N, v);
       }
       tc_fence_before();
       __syncwarp();
@@ -294,75 +257,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
-// host side: tensor maps (cached) + launch
+// host side: launch (tensor maps: tma.cuh)
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-struct MapKey {
-  const void* ptr;
-  unsigned long long d0, d1, ld;
-  unsigned int b0, b1;
-  bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
-  }
-};
-struct MapKeyHash {
-  size_t operator()(const MapKey& k) const {
-    size_t h = reinterpret_cast<size_t>(k.ptr);
-    h = h * 1000003u ^ k.d0;
-    h = h * 1000003u ^ k.d1;
-    h = h * 1000003u ^ k.ld;
-    h = h * 1000003u ^ ((size_t)k.b0 << 16 | k.b1);
-    return h;
-  }
-};
-
-// 2-D bf16 tensor map: inner extent d0 (contiguous), outer extent d1, row pitch ld elements.
-static int make_map(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1,
-                    unsigned long long ld, unsigned int b0, unsigned int b1) {
-  static std::mutex mu;
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, d0, d1, ld, b0, b1};
-  {
-    std::lock_guard<std::mutex> g(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) {
-      *out = it->second;
-      return MMA_OK;
-    }
-  }
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) return MMA_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return MMA_ERR_ARG;
-  cuuint64_t dims[2] = {d0, d1};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {b0, b1};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return MMA_ERR_DRIVER;
-  std::lock_guard<std::mutex> g(mu);
-  if (cache.size() > 65536) cache.clear();
-  cache.emplace(key, *out);
-  return MMA_OK;
-}
-
 static int num_sms() {
   static int n = 0;
   if (!n) {

@@ -163,24 +163,25 @@ struct LnBwdArgs {
 };
 
 template <int NI>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
-  __shared__ float s_dg[NI * 128];
-  __shared__ float s_db[NI * 128];
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdArgs a) {
+  // warp-private dgamma / dbeta accumulators (plain read-modify-write, no atomics): [warp][2][NI*128]
+  extern __shared__ float s_acc[];
   const int d = a.d;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) { s_dg[c] = 0.f; s_db[c] = 0.f; }
+  float* my_dg = s_acc + (size_t)wib * 2 * NI * 128;
+  float* my_db = my_dg + NI * 128;
+  for (int c = threadIdx.x; c < wpb * 2 * NI * 128; c += blockDim.x) s_acc[c] = 0.f;
   __syncthreads();
-  float4 pg[NI], pb[NI];
-#pragma unroll
-  for (int i = 0; i < NI; ++i) { pg[i] = make_float4(0, 0, 0, 0); pb[i] = make_float4(0, 0, 0, 0); }
   const bool drop = a.p_drop > 0.f;
   const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
   const uint32_t dkey = drop_key(a.seed, a.site);
+  const bool acc_params = a.gamma && a.dgamma;
 
   for (long long r = (long long)blockIdx.x * wpb + wib; r < a.rows; r += (long long)gridDim.x * wpb) {
     const long long irow = (r / a.group) * (long long)a.in_group_stride + a.in_offset + (r % a.group);
-    float4 xv[NI], gv[NI];
+    // every global load of the row is issued up front (dres may alias dx, so the compiler cannot hoist it itself)
+    float4 xv[NI], gv[NI], rv[NI];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
@@ -188,8 +189,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
       if (c < d) {
         xv[i] = ld4_any(a.x, r * a.ldx + c, a.x_f32);
         gv[i] = ld4_any(a.dy, irow * a.lddy + c, a.dy_f32);
-        sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+        rv[i] = a.dres ? *reinterpret_cast<const float4*>(a.dres + r * a.lddres + c) : make_float4(0, 0, 0, 0);
       }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < d) sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
     }
     float mean = 0.f, rstd = 1.f;
     if (a.gamma) {
@@ -216,8 +222,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
           xh.x = (xv[i].x - mean) * rstd; xh.y = (xv[i].y - mean) * rstd;
           xh.z = (xv[i].z - mean) * rstd; xh.w = (xv[i].w - mean) * rstd;
           const float4 dy = gv[i];
-          pg[i].x += dy.x * xh.x; pg[i].y += dy.y * xh.y; pg[i].z += dy.z * xh.z; pg[i].w += dy.w * xh.w;
-          pb[i].x += dy.x; pb[i].y += dy.y; pb[i].z += dy.z; pb[i].w += dy.w;
+          if (acc_params) {
+            float4 pg = *reinterpret_cast<float4*>(my_dg + c), pb = *reinterpret_cast<float4*>(my_db + c);
+            pg.x += dy.x * xh.x; pg.y += dy.y * xh.y; pg.z += dy.z * xh.z; pg.w += dy.w * xh.w;
+            pb.x += dy.x; pb.y += dy.y; pb.z += dy.z; pb.w += dy.w;
+            *reinterpret_cast<float4*>(my_dg + c) = pg;
+            *reinterpret_cast<float4*>(my_db + c) = pb;
+          }
           float4 g;
           g.x = dy.x * gm.x; g.y = dy.y * gm.y; g.z = dy.z * gm.z; g.w = dy.w * gm.w;
           sg += g.x + g.y + g.z + g.w;
@@ -240,10 +251,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
           o.z = rstd * (gv[i].z - sg - xv[i].z * sgx);
           o.w = rstd * (gv[i].w - sg - xv[i].w * sgx);
         }
-        if (a.dres) {
-          const float4 q = *reinterpret_cast<const float4*>(a.dres + r * a.lddres + c);
-          o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
-        }
+        o.x += rv[i].x; o.y += rv[i].y; o.z += rv[i].z; o.w += rv[i].w;
         if (a.dx) *reinterpret_cast<float4*>(a.dx + r * a.lddx + c) = o;
         if (a.dxb) {
           if (drop) {
@@ -258,21 +266,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
       }
     }
   }
-  if (a.gamma && a.dgamma) {
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int c = lane * 4 + i * 128;
-      if (c < d) {
-        atomicAdd(&s_dg[c], pg[i].x); atomicAdd(&s_dg[c + 1], pg[i].y);
-        atomicAdd(&s_dg[c + 2], pg[i].z); atomicAdd(&s_dg[c + 3], pg[i].w);
-        atomicAdd(&s_db[c], pb[i].x); atomicAdd(&s_db[c + 1], pb[i].y);
-        atomicAdd(&s_db[c + 2], pb[i].z); atomicAdd(&s_db[c + 3], pb[i].w);
-      }
-    }
+  if (acc_params) {
     __syncthreads();
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
-      atomicAdd(a.dgamma + c, s_dg[c]);
-      atomicAdd(a.dbeta + c, s_db[c]);
+      float sg = 0.f, sb = 0.f;
+      for (int w = 0; w < wpb; ++w) {
+        sg += s_acc[(size_t)w * 2 * NI * 128 + c];
+        sb += s_acc[(size_t)w * 2 * NI * 128 + NI * 128 + c];
+      }
+      atomicAdd(a.dgamma + c, sg);
+      atomicAdd(a.dbeta + c, sb);
     }
   }
 }
@@ -363,14 +366,25 @@ extern "C" int mma_ln_bwd(const void* dy, int dy_f32, long long lddy, int group,
   LnBwdArgs a{dy, dy_f32, lddy, group > 0 ? group : rows, in_group_stride, in_offset, x, x_f32, ldx, gamma, eps,
               dres, lddres, dx, lddx, dxb, dxb_f32, lddxb, p_drop, seed, site, dgamma, dbeta, rows, d};
   const int ni = (d + 127) / 128;
-  int blocks = (rows + 15) / 16;  // >= 2 rows per warp so the dgamma/dbeta partials amortise their flush
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  int blocks = (rows + 31) / 32;  // >= 4 rows per warp: the dgamma/dbeta flush is amortised
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
-  if (ni <= 1) ln_bwd_kernel<1><<<blocks, 256, 0, stream>>>(a);
-  else if (ni <= 2) ln_bwd_kernel<2><<<blocks, 256, 0, stream>>>(a);
-  else if (ni <= 4) ln_bwd_kernel<4><<<blocks, 256, 0, stream>>>(a);
-  else if (ni <= 6) ln_bwd_kernel<6><<<blocks, 256, 0, stream>>>(a);
-  else ln_bwd_kernel<8><<<blocks, 256, 0, stream>>>(a);
+#define LN_BWD_LAUNCH(NI_)                                                                                   \
+  do {                                                                                                       \
+    const size_t smem = sizeof(float) * 8 * 2 * (NI_) * 128;                                                 \
+    static bool attr = false;                                                                                \
+    if (!attr && smem > 48 * 1024) {                                                                         \
+      cudaFuncSetAttribute(ln_bwd_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    ln_bwd_kernel<NI_><<<blocks, 256, smem, stream>>>(a);                                                    \
+  } while (0)
+  if (ni <= 1) LN_BWD_LAUNCH(1);
+  else if (ni <= 2) LN_BWD_LAUNCH(2);
+  else if (ni <= 4) LN_BWD_LAUNCH(4);
+  else if (ni <= 6) LN_BWD_LAUNCH(6);
+  else LN_BWD_LAUNCH(8);
+#undef LN_BWD_LAUNCH
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

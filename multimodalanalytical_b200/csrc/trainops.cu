@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   }
 }
 
+__global__ void add_u64_kernel(unsigned long long* p, unsigned long long inc) { *p += inc; }
+
 }  // namespace trainops
 
 using namespace trainops;
@@ -218,6 +220,13 @@ extern "C" int mma_adam_step(float* p, float* g, float* m, float* v, void* p_bf1
   long long want = (n + 255) / 256;
   int blocks = (int)(want > 148 * 16 ? 148 * 16 : want);
   adam_kernel<<<blocks, 256, 0, stream>>>(p, g, m, v, (bf16*)p_bf16, n, hyper, norm, decoupled, zero_grad);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+// *p += inc on the device (dropout seed of a replayed CUDA graph)
+extern "C" int mma_add_u64(unsigned long long* p, unsigned long long inc, cudaStream_t stream) {
+  add_u64_kernel<<<1, 1, 0, stream>>>(p, inc);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

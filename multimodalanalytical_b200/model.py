@@ -34,6 +34,9 @@ class Engine:
         self.dev = params.device
         self._bufs: Dict[Any, torch.Tensor] = {}
         self.seed = 0x5EED0001
+        # dropout seed lives on the device: a captured CUDA graph advances it between replays (ops.add_u64) while its
+        # launch parameters stay constant (kernels dereference it: MMA_SITE_SEED_INDIRECT)
+        self.seed_dev = torch.full((1,), self.seed, dtype=torch.int64, device=self.dev) if self.dev.type == "cuda" else None
         self.saved: Dict[str, Any] = {}
         self.grad_ready_hook: Optional[Callable[[int], None]] = None  # called with the flat offset from which
         #                                                               all gradients are final
@@ -63,9 +66,16 @@ class Engine:
     def G(self, name):
         return self.ps.G(name)
 
-    @staticmethod
-    def _site(dec: bool, layer: int, k: int) -> int:
-        return (1024 if dec else 0) + 16 * layer + k
+    def _site(self, dec: bool, layer: int, k: int) -> int:
+        return ((1024 if dec else 0) + 16 * layer + k) | 0x80000000
+
+    @property
+    def seed_arg(self) -> int:
+        return self.seed_dev.data_ptr()
+
+    def next_seed(self):
+        """Fresh dropout masks for the next training step (stream-ordered, graph-capturable)."""
+        ops.add_u64(self.seed_dev, 1)
 
     def _splits(self, n_out, k_in, rows):
         tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
@@ -195,10 +205,10 @@ class Engine:
         ctx = self.buf(tag + ".ctx", (M, d), T)
         lse = self.buf(tag + ".lse", (B * heads * L,), torch.float32)
         ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, lse, B, heads, L, L, dh, kmask=kmask,
-                     causal=causal, p_drop=p, seed=self.seed, site=site_a)
+                     causal=causal, p_drop=p, seed=self.seed_arg, site=site_a)
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
         ops.gemm(ctx, self.W(wp["out_w"]), M, d, d,
-                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed, site=site_r))
+                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed_arg, site=site_r))
         if train:
             self.saved[tag] = dict(x=x, h=h, qkv=qkv, ctx=ctx, lse=lse)
         return xo
@@ -216,13 +226,13 @@ class Engine:
         qkv = s["qkv"]
         ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], s["ctx"], s["lse"], dctx, dqkv[:, :d],
                      dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, heads, L, L, dh, kmask=kmask, causal=causal, p_drop=p,
-                     seed=self.seed, site=site_a, dsum=self.buf("bw.dsum", (B * heads * L,), torch.float32))
+                     seed=self.seed_arg, site=site_a, dsum=self.buf("bw.dsum", (B * heads * L,), torch.float32))
         dh_ = self.buf("bw.dh", (M, d), T)
         self._lin_bwd(dqkv, s["h"], wp["in_w"], wp["in_b"], M, 3 * d, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
         dx_in = self._other_dx(dx, M)
         dyb_in = None if first else self.buf(f"bw.dyb.{M}", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
-                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed, site=prev_site)
+                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
 
     def _ffn_block_fwd(self, tag, x, M, f, wp, p, site_i, site_r, train):
@@ -236,16 +246,16 @@ class Engine:
         if not self.cfg.gated_linear:
             ops.gemm(h, self.W(wp["w1"]), M, f, d,
                      ops.make_epi(EPI_GELU, a, out2=z if train else None, bias=self.P(wp["b1"]), p_drop=p,
-                                  seed=self.seed, site=site_i))
+                                  seed=self.seed_arg, site=site_i))
         else:
             z2 = self.buf(tag + ".z2", (M, f), T)
             ops.gemm(h, self.W(wp["w1"]), M, f, d, ops.make_epi(EPI_STORE, z, bias=self.P(wp["b1"])))
             ops.gemm(h, self.W(wp["wg"]), M, f, d,
-                     ops.make_epi(EPI_GLU_MUL, a, out2=z2, bias=self.P(wp["bg"]), aux=z, p_drop=p, seed=self.seed,
+                     ops.make_epi(EPI_GLU_MUL, a, out2=z2, bias=self.P(wp["bg"]), aux=z, p_drop=p, seed=self.seed_arg,
                                   site=site_i))
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
         ops.gemm(a, self.W(wp["w2"]), M, d, f,
-                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["b2"]), resid=x, p_drop=p, seed=self.seed, site=site_r))
+                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["b2"]), resid=x, p_drop=p, seed=self.seed_arg, site=site_r))
         if train:
             self.saved[tag] = dict(x=x, h=h, a=a, z=z, z2=z2)
         return xo
@@ -258,13 +268,13 @@ class Engine:
         dh_ = self.buf("bw.dh", (M, d), T)
         if not self.cfg.gated_linear:
             self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
-                          dx_epi=ops.make_epi(EPI_DGELU, dz, aux=s["z"], p_drop=p, seed=self.seed, site=site_i, drop_ld=f))
+                          dx_epi=ops.make_epi(EPI_DGELU, dz, aux=s["z"], p_drop=p, seed=self.seed_arg, site=site_i, drop_ld=f))
             self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
         else:
             dz2 = self.buf("bw.dz2", (M, f), T)
             self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
                           dx_epi=ops.make_epi(EPI_DGLU, dz, out2=dz2, aux=s["z"], aux2=s["z2"], p_drop=p,
-                                              seed=self.seed, site=site_i, drop_ld=f))
+                                              seed=self.seed_arg, site=site_i, drop_ld=f))
             # dh = dz W1 + dz2 Wg: the second product lands through the accumulate epilogue (fp32)
             dh_ = self.buf("bw.dhs", (M, d), torch.float32)
             self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=0))
@@ -272,7 +282,7 @@ class Engine:
         dx_in = self._other_dx(dx, M)
         dyb_in = self.buf(f"bw.dyb.{M}", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
-                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed, site=prev_site)
+                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
 
     def _other_dx(self, dx, M):
@@ -309,10 +319,10 @@ class Engine:
         ctx = self.buf(tag + ".ctx", (M, d), T)
         lse = self.buf(tag + ".lse", (B * heads * T_,), torch.float32)
         ops.attn_fwd(q, kv[:, :d], kv[:, d:], ctx, lse, B, heads, T_, S, dh, kmask=kmask, causal=False, p_drop=p,
-                     seed=self.seed, site=site_a)
+                     seed=self.seed_arg, site=site_a)
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
         ops.gemm(ctx, self.W(wp["out_w"]), M, d, d,
-                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed, site=site_r))
+                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed_arg, site=site_r))
         if train:
             self.saved[tag] = dict(x=x, h=h, q=q, kv=kv, ctx=ctx, lse=lse)
         return xo
@@ -329,7 +339,7 @@ class Engine:
         dkv = self.buf("bw.dkv", (Me, 2 * d), T)
         kv = s["kv"]
         ops.attn_bwd(s["q"], kv[:, :d], kv[:, d:], s["ctx"], s["lse"], dctx, dq, dkv[:, :d], dkv[:, d:], B, heads, T_,
-                     S, dh, kmask=kmask, causal=False, p_drop=p, seed=self.seed, site=site_a,
+                     S, dh, kmask=kmask, causal=False, p_drop=p, seed=self.seed_arg, site=site_a,
                      dsum=self.buf("bw.dsum", (B * heads * T_,), torch.float32))
         dh_ = self.buf("bw.dh", (M, d), T)
         self._lin_bwd(dq, s["h"], wp["in_w"], wp["in_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dh_),
@@ -340,7 +350,7 @@ class Engine:
         dx_in = self._other_dx(dx, M)
         dyb_in = self.buf(f"bw.dyb.{M}", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
-                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed, site=prev_site)
+                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
 
     # ------------------------------------------------------------------------------------ encoder
@@ -440,7 +450,7 @@ class Engine:
         dyb = self.buf(f"bw.dyb.{M}", (M, d), T)
         ops.ln_bwd(dhT, dec["xL"], self.P("hf_model.decoder.norm.weight"), dx=dx, dxb=dyb,
                    dgamma=self.G("hf_model.decoder.norm.weight"), dbeta=self.G("hf_model.decoder.norm.bias"),
-                   p_drop=p, seed=self.seed, site=last_site)
+                   p_drop=p, seed=self.seed_arg, site=last_site)
         notify(ps.offsets["hf_model.decoder.norm.weight"][0])
 
         dmem = self.buf("bw.dmem", (Me, d), torch.float32)
@@ -452,7 +462,7 @@ class Engine:
             dx, dyb = self._cross_block_bwd(tg + ".ca", dx, dyb, enc["mem"], dmem, i == cfg.decoder_layers - 1, B, T_,
                                             S, H, self._wp_attn(pre, "multihead_attn", "norm2"), enc["mask"], p,
                                             self._site(True, i, 4), prev_site=self._site(True, i, 1))
-            prev = self._site(True, i - 1, 3) if i > 0 else 0
+            prev = self._site(True, i - 1, 3) if i > 0 else self._site(True, 0, 15)
             dx, dyb = self._attn_block_bwd(tg + ".sa", dx, dyb, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"),
                                            dec["mask"], True, p, self._site(True, i, 0), prev_site=prev, first=(i == 0))
             notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
@@ -464,14 +474,14 @@ class Engine:
         dybe = self.buf(f"bw.dyb.{Me}", (Me, d), T)
         ops.ln_bwd(dmem, enc["xL"], self.P("hf_model.encoder.norm.weight"), dx=dxe, dxb=dybe,
                    dgamma=self.G("hf_model.encoder.norm.weight"), dbeta=self.G("hf_model.encoder.norm.bias"),
-                   p_drop=p, seed=self.seed, site=self._site(False, cfg.encoder_layers - 1, 3))
+                   p_drop=p, seed=self.seed_arg, site=self._site(False, cfg.encoder_layers - 1, 3))
         notify(ps.offsets["hf_model.encoder.norm.weight"][0])
         for i in reversed(range(cfg.encoder_layers)):
             pre = f"hf_model.encoder.layers.{i}."
             tg = f"enc{i}"
             dxe, dybe = self._ffn_block_bwd(tg + ".ff", dxe, dybe, Me, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"),
                                             p, self._site(False, i, 2), prev_site=self._site(False, i, 1))
-            prev = self._site(False, i - 1, 3) if i > 0 else 0
+            prev = self._site(False, i - 1, 3) if i > 0 else self._site(False, 0, 15)
             dxe, dybe = self._attn_block_bwd(tg + ".sa", dxe, dybe, B, S, He, self._wp_attn(pre, "self_attn", "norm1"),
                                              enc["mask"], False, p, self._site(False, i, 0), prev_site=prev,
                                              first=(i == 0))

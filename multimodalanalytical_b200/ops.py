@@ -3,6 +3,7 @@ every function launches exactly the CUDA kernels of `lib/libmma_b200.so` on torc
 raises if the library is unavailable.  No CPU or ATen fallback exists on purpose.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -11,6 +12,9 @@ from ._lib import (EPI_ACCUM, EPI_DGELU, EPI_DGLU, EPI_DRELU, EPI_GELU, EPI_GLU_
                    MMA_BF16, MMA_F32, Epi, check)
 
 LAUNCHES = 0  # number of kernel-launching C-ABI calls made (bench.py reports it as `gpu_launches`)
+# bf16 / head-dim-64 attention: "tcgen05" = single-tile TMEM kernels when Lq, Lk <= 128 (else the streaming mma.sync
+# kernels); "mma" = always the mma.sync kernels (kept selectable for A/B measurements and tests)
+ATTN_IMPL = os.environ.get("MMA_ATTN_IMPL", "tcgen05")
 
 
 def _count(n=1):
@@ -169,6 +173,13 @@ def attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop
     """q/k/v/o: 2-D views [B*L, ld] (row pitch = stride(0)); heads are column blocks of width dh.
     bf16 with head dim 64 runs on the tensor-core kernels, everything else on the SIMT fp32-arithmetic ones."""
     _need_cuda(q, k, v, o)
+    if _attn_tc_ok(dh, q, k, v, o) and Lq <= 128 and Lk <= 128 and ATTN_IMPL == "tcgen05":
+        check(_lib.load().mma_attn_fwd_t5(
+            q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+            o.stride(0), _p(lse), B, H, Lq, Lk, int(causal), dh ** -0.5, float(p_drop), int(seed), int(site),
+            _stream()), "mma_attn_fwd_t5")
+        _count()
+        return
     if _attn_tc_ok(dh, q, k, v, o):
         check(_lib.load().mma_attn_fwd_tc(
             q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
@@ -186,6 +197,14 @@ def attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop
 def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop=0.0, seed=0,
              site=0, dsum=None):
     _need_cuda(q, k, v, o, dout, dq, dk, dv)
+    if _attn_tc_ok(dh, q, k, v, o, dout, dq, dk, dv) and Lq <= 128 and Lk <= 128 and ATTN_IMPL == "tcgen05":
+        check(_lib.load().mma_attn_bwd_t5(
+            q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+            o.stride(0), lse.data_ptr(), dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(),
+            dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Lq, Lk, int(causal), dh ** -0.5, float(p_drop), int(seed),
+            int(site), _stream()), "mma_attn_bwd_t5")
+        _count()
+        return
     if _attn_tc_ok(dh, q, k, v, o, dout, dq, dk, dv):
         if dsum is None:
             dsum = torch.empty(B * H * Lq, dtype=torch.float32, device=q.device)
@@ -233,6 +252,12 @@ def adam_step(p, g, m, v, p_bf16, hyper, norm=None, decoupled=True, zero_grad=Tr
     check(_lib.load().mma_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(p_bf16), p.numel(),
                                     hyper.data_ptr(), _p(norm), int(decoupled), int(zero_grad), _stream()),
           "mma_adam_step")
+    _count()
+
+
+def add_u64(t, inc=1):
+    """t: int64 device scalar holding the dropout seed; advanced on the stream (graph-capturable)."""
+    check(_lib.load().mma_add_u64(t.data_ptr(), int(inc), _stream()), "mma_add_u64")
     _count()
 
 

@@ -83,8 +83,10 @@ class FusedTrainer:
     BUCKET_ELEMS = 8 * 1024 * 1024  # 32 MB of fp32 gradients per all-reduce
 
     def __init__(self, module: HFWrapper, clip_grad: float = 1.0, acc_batches: int = 1, process_group=None,
-                 eps: float = 1e-8):
+                 eps: float = 1e-8, use_graph: bool = True):
         self.m = module
+        self.use_graph = use_graph
+        self._graphs: Dict[Any, Any] = {}
         self.eng, self.ps = module.engine, module.store
         self.clip_grad, self.acc, self.eps = clip_grad, max(1, acc_batches), eps
         self.pg = process_group
@@ -113,31 +115,88 @@ class FusedTrainer:
         if self._sync_now and self.bucketer is not None:
             self.bucketer.on_ready(off)
 
-    def train_step(self, batch: Dict[str, Any], batch_idx: int = 0):
-        """One micro-batch: forward + backward (+ optimiser step every `acc_batches`).  Returns the loss scalar
-        (device tensor; no host sync)."""
-        m, eng = self.m, self.eng
-        m.train()
-        eng.seed += 1
-        self.micro += 1
-        self._sync_now = (self.micro % self.acc) == 0
-        if self.bucketer is not None:
-            self.bucketer.reset()
+    def _prepare(self, batch):
+        """Collator dict -> device tensors in the engine's layout (what HFWrapper.forward does, wrapper.py:356-389)."""
+        m = self.m
         input_ids, attention_mask = m._relayout(batch, training=True)
         dec_in = m._to_dev(batch["decoder_input"][m.target_modality]).transpose(1, 0).contiguous()
         dec_mask = (~m._to_dev(batch["decoder_pad_mask"])).T.to(torch.uint8).contiguous()
         labels = m._to_dev(batch["target"]).T.contiguous().clone()
         labels[labels == m.target_tokenizer.pad_token_id] = -100
-        out = eng.forward(input_ids, attention_mask, dec_in, dec_mask, labels=labels, train=True)
-        eng.backward(gscale=1.0)
-        if self._sync_now:
-            self.optimizer_step()
+        return input_ids, attention_mask, dec_in, dec_mask, labels
+
+    @staticmethod
+    def _flat(inputs):
+        ids, am, di, dm, lb = inputs
+        out = []
+        for k, v in ids.items():
+            if isinstance(v, dict):
+                out += [(f"{k}.{kk}", t) for kk, t in v.items()]
+            else:
+                out.append((k, v))
+        return out + [("enc_mask", am), ("dec_in", di), ("dec_mask", dm), ("labels", lb)]
+
+    def _step_body(self, inputs):
+        ids, am, di, dm, lb = inputs
+        self.eng.next_seed()
+        out = self.eng.forward(ids, am, di, dm, labels=lb, train=True)
+        self.eng.backward(gscale=1.0)
         return out["loss"]
 
-    def optimizer_step(self):
-        m, ps = self.m, self.ps
+    def train_step(self, batch: Dict[str, Any], batch_idx: int = 0):
+        """One micro-batch: forward + backward (+ optimiser step every `acc_batches`).  Returns the loss scalar
+        (device tensor; no host sync).  With `use_graph` the whole step (seed advance, forward, backward, clip,
+        Adam) is captured once per input-shape signature and replayed."""
+        m = self.m
+        m.train()
+        self.micro += 1
+        self._sync_now = (self.micro % self.acc) == 0
         if self.bucketer is not None:
-            self.bucketer.finish()
+            self.bucketer.reset()
+        inputs = self._prepare(batch)
+        if self.use_graph and self.acc == 1 and self.bucketer is None:
+            return self._graphed_step(inputs)
+        loss = self._step_body(inputs)
+        if self._sync_now:
+            self._write_hyper()
+            self._optimizer_kernels()
+            self.opt_step += 1
+        return loss
+
+    def _graphed_step(self, inputs):
+        flat = self._flat(inputs)
+        key = tuple((n, tuple(t.shape), t.dtype) for n, t in flat)
+        ent = self._graphs.get(key)
+        if ent is None:
+            # first sight of this shape: run it eagerly (allocates workspaces, builds tensor maps), keep the inputs as
+            # the static buffers of the graph captured on the next step of this shape
+            loss = self._step_body(inputs)
+            self._write_hyper()
+            self._optimizer_kernels()
+            self.opt_step += 1
+            self._graphs[key] = {"static": inputs, "graph": None, "loss": None}
+            return loss
+        for (_, dst), (_, src) in zip(self._flat(ent["static"]), flat):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._write_hyper()
+        if ent["graph"] is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.LAUNCHES
+            with torch.cuda.graph(g):
+                ent["loss"] = self._step_body(ent["static"])
+                self._optimizer_kernels()
+            ent["graph"], ent["launches"] = g, ops.LAUNCHES - n0
+            ops.LAUNCHES = n0
+        ent["graph"].replay()
+        ops.LAUNCHES += ent["launches"]  # kernels executed by the replay
+        self.opt_step += 1
+        return ent["loss"]
+
+    def _write_hyper(self):
+        """Stage this optimiser step's scalars (OneCycle lr / beta1, bias corrections, clip, grad scale) on the device."""
+        m = self.m
         lr, beta1 = one_cycle(self.opt_step, m.num_steps, m.lr)
         if m.num_steps <= 0:
             lr, beta1 = m.lr, m.adam_beta1
@@ -148,13 +207,22 @@ class FusedTrainer:
         h[7] = self.clip_grad if self.clip_grad else 0.0
         h[8] = 1.0 / (self.world * self.acc)
         self.hyper.copy_(h, non_blocking=True)
+
+    def _optimizer_kernels(self):
+        ps = self.ps
+        if self.bucketer is not None:
+            self.bucketer.finish()
         norm = None
         if self.clip_grad:
             ops.grad_norm(ps.g, self.norm_ws, self.norm)
             norm = self.norm
         ops.adam_step(ps.p, ps.g, ps.m, ps.v, ps.pb if self.eng.precision == "bf16" else None, self.hyper, norm=norm,
-                      decoupled=(m.optimiser == "adamw"), zero_grad=True)
+                      decoupled=(self.m.optimiser == "adamw"), zero_grad=True)
         ps.bf16_dirty = False
+
+    def optimizer_step(self):
+        self._write_hyper()
+        self._optimizer_kernels()
         self.opt_step += 1
 
     def fit(self, batches, epochs: int = 1, log_every: int = 10, log=print):

@@ -264,7 +264,7 @@ class HFWrapper(_Base):
     # ---------------------------------------------------------------------------------------- hooks
     def training_step(self, batch: Dict[str, Any], batch_idx: int) -> torch.Tensor:
         self.train()
-        self.engine.seed += 1  # fresh dropout masks every step
+        self.engine.next_seed()  # fresh dropout masks every step
         model_output = self.forward(batch)
         loss = model_output.loss
         if (batch_idx % 10) == 0:

@@ -371,3 +371,35 @@ def test_tc_attention_multi_tile(B, H, Lq, Lk, causal):
     assert rel(dq.view_as(q).float(), qr.grad) < 3e-2
     assert rel(dk.view_as(k).float(), kr.grad) < 3e-2
     assert rel(dv.view_as(v).float(), vr.grad) < 3e-2
+
+
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+@pytest.mark.parametrize("B,H,Lq,Lk,causal", [(5, 8, 36, 36, False), (3, 8, 64, 64, True), (3, 8, 64, 36, False),
+                                              (2, 8, 57, 27, False), (2, 8, 100, 128, False), (3, 4, 128, 128, True),
+                                              (1, 1, 20, 20, True)])
+def test_bf16_dh64_attention_both_tensor_core_paths(impl, B, H, Lq, Lk, causal, monkeypatch):
+    """tcgen05 single-tile kernels (packed pairs when L <= 64, incl. an odd number of problems) and the streaming
+    mma.sync kernels on the shapes of this path."""
+    monkeypatch.setattr(ops, "ATTN_IMPL", impl)
+    dh, dt = 64, torch.bfloat16
+    d = H * dh
+    if causal and Lq != Lk:
+        pytest.skip("causal is self-attention only")
+    q, k, v = _rand(B, Lq, d, dtype=dt, seed=1), _rand(B, Lk, d, dtype=dt, seed=2), _rand(B, Lk, d, dtype=dt, seed=3)
+    kmask = torch.ones(B, Lk, dtype=torch.uint8, device=DEV)
+    kmask[0, 5:9] = 0
+    kmask[B - 1, Lk - 3:] = 0
+    o = torch.empty(B * Lq, d, device=DEV, dtype=dt)
+    lse = torch.empty(B * H * Lq, device=DEV)
+    ops.attn_fwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), o, lse, B, H, Lq, Lk, dh, kmask=kmask, causal=causal)
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = _attn_ref(qr, kr, vr, kmask, causal, H)
+    assert rel(o.view(B, Lq, d).float(), ref) < 2e-2
+    do = _rand(B, Lq, d, dtype=dt, seed=4)
+    ref.backward(do.float())
+    dq, dk, dv = (torch.empty_like(t).view(-1, d) for t in (q, k, v))
+    ops.attn_bwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), o, lse, do.view(-1, d), dq, dk, dv, B, H, Lq, Lk, dh,
+                 kmask=kmask, causal=causal)
+    assert rel(dq.view_as(q).float(), qr.grad) < 3e-2
+    assert rel(dk.view_as(k).float(), kr.grad) < 3e-2
+    assert rel(dv.view_as(v).float(), vr.grad) < 3e-2
