@@ -63,6 +63,12 @@ typedef struct Epi {
  * (custom_modeling.py:108-199, 418, 486) and their autograd backward.                                          */
 int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, int M, int N,
                   int K, const Epi* ep, int splits, int max_ctas, cudaStream_t stream);
+/* Grouped weight gradients of one layer in one persistent launch (count <= 8): out[g][Nout,Kin] += dy[g]^T x[g] and
+ * dbias[g][Nout] += colsum(dy[g]) (bias gradient fused as an all-ones MMA column).  dy[g]: bf16 [R, Nout] pitch
+ * lddy[g]; x[g]: bf16 [R, Kin] pitch ldx[g]; the arrays are HOST arrays of device pointers / sizes.               */
+int mma_wgrad_group(int count, const void* const* dy, const long long* lddy, const void* const* x,
+                    const long long* ldx, float* const* out, const long long* ldo, float* const* dbias,
+                    const int* Nout, const int* Kin, const int* R, cudaStream_t stream);
 /* fp32 SIMT GEMM with arbitrary element strides (fp32 parity mode; patch embeddings with K = 75/125/1/2,
  * modeling/utils.py:119-134).  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk].                          */
 int mma_gemm_simt(const void* A, int a_type, long long sam, long long sak, const void* B, int b_type,

@@ -326,7 +326,225 @@ static int dispatch(const void* A, long long lda, int a_mn, const void* B, long 
 #undef MMA_LAUNCH
 }
 
+// ------------------------------------------------------------------------------------------------
+// Grouped weight-gradient kernel: up to 8 independent  dW_g[Nout_g, Kin_g] += dy_g^T x_g  products (one backward
+// layer's worth) in ONE persistent launch, so that the ~100-130 output tiles of a layer fill the machine without
+// split-K / atomics.  Tiles are 128 x 256, both operands MN-major (rows of dy / x are the reduction dimension).
+// The bias gradient db_g[n] = sum_r dy_g[r, n] rides along for free on the first tile column of every tile row: one
+// extra N=16 MMA per k-step multiplies the same dy tile with a constant all-ones B tile into 32 spare TMEM columns.
+// ------------------------------------------------------------------------------------------------
+struct alignas(64) WgProblem {
+  CUtensorMap tmA;  // dy [R, Nout]: dims {Nout, R}, box {64, 64}
+  CUtensorMap tmB;  // x  [R, Kin] : dims {Kin, R},  box {64, 64}
+  float* out;       // [Nout, Kin] fp32, accumulated (+=)
+  float* dbias;     // [Nout] fp32, accumulated (+=), may be null
+  long long ldo;
+  int M, N, R;      // Nout, Kin, rows
+  int tiles_n, tile_begin;
+};
+struct WgGroup {
+  WgProblem p[8];
+  int count, total_tiles;
+};
+
+constexpr int WG_BN = 256;
+constexpr int WG_STAGES = 4;
+constexpr uint32_t WG_A_BYTES = BM * BK * 2, WG_B_BYTES = WG_BN * BK * 2;
+constexpr uint32_t WG_ONES_BYTES = 16 * 128;
+constexpr uint32_t WG_SMEM = WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + WG_ONES_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_group_kernel(const __grid_constant__ WgGroup grp) {
+  constexpr int STAGES = WG_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * WG_A_BYTES;
+  uint8_t* sOnes = sB + STAGES * WG_B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + WG_ONES_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < (int)(WG_ONES_BYTES / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs (swizzle-invariant: every element equal)
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&full[i]), 1);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    mbar_init(smem_u32(tfull), 1);
+    mbar_init(smem_u32(tempty), NUM_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the ones tile is read by the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto locate = [&](int tile, int& g, int& m0, int& n0) {
+    g = 0;
+#pragma unroll 1
+    for (int i = 1; i < grp.count; ++i)
+      if (tile >= grp.p[i].tile_begin) g = i;
+    const int t = tile - grp.p[g].tile_begin;
+    n0 = (t % grp.p[g].tiles_n) * WG_BN;
+    m0 = (t / grp.p[g].tiles_n) * BM;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < grp.total_tiles; tile += gridDim.x) {
+        int g, m0, n0;
+        locate(tile, g, m0, n0);
+        const WgProblem& P = grp.p[g];
+        const int num_kb = (P.R + BK - 1) / BK;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full[stage]);
+          mbar_expect_tx(fb, WG_A_BYTES + WG_B_BYTES);
+          const uint32_t a_dst = smem_u32(sA + stage * WG_A_BYTES);
+          const uint32_t b_dst = smem_u32(sB + stage * WG_B_BYTES);
+#pragma unroll
+          for (int a = 0; a < BM / 64; ++a) tma_load_2d(a_dst + a * (BK * 128), &P.tmA, fb, m0 + a * 64, kb * BK);
+#pragma unroll
+          for (int a = 0; a < WG_BN / 64; ++a) tma_load_2d(b_dst + a * (BK * 128), &P.tmB, fb, n0 + a * 64, kb * BK);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_main = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                      ((uint32_t)(WG_BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      constexpr uint32_t idesc_bias = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) |
+                                      ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int tile = blockIdx.x; tile < grp.total_tiles; tile += gridDim.x) {
+        int g, m0, n0;
+        locate(tile, g, m0, n0);
+        const WgProblem& P = grp.p[g];
+        const int num_kb = (P.R + BK - 1) / BK;
+        const bool with_bias = n0 == 0 && P.dbias != nullptr;
+        mbar_wait(smem_u32(tempty), tphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * WG_A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * WG_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc<true>(a_addr, k);
+            tc_mma_bf16(tmem_base, ad, make_smem_desc<true>(b_addr, k), idesc_main, (kb > 0 || k > 0) ? 1u : 0u);
+            if (with_bias)
+              tc_mma_bf16(tmem_base + WG_BN, ad, make_smem_desc<false>(smem_u32(sOnes), k), idesc_bias,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(smem_u32(&empty[stage]));
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(smem_u32(tfull));
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int slice = (warp - 2) >> 2;
+    constexpr int COLS = WG_BN / (NUM_EPI_WARPS / 4);
+    uint32_t tphase = 0;
+    for (int tile = blockIdx.x; tile < grp.total_tiles; tile += gridDim.x) {
+      int g, m0, n0;
+      locate(tile, g, m0, n0);
+      const WgProblem& P = grp.p[g];
+      Epi ep{};
+      ep.kind = EPI_ACCUM;
+      ep.out_f32 = 1;
+      ep.out = P.out;
+      ep.ldo = P.ldo;
+      ep.alpha = 1.0f;
+      ep.accumulate = 1;
+      mbar_wait(smem_u32(tfull), tphase);
+      tc_fence_after();
+      const long long row = (long long)m0 + q * 32 + lane;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < COLS; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_row + (uint32_t)(slice * COLS + c0), v);
+        const int col = n0 + slice * COLS + c0;
+        if (row < P.M && col < P.N) epilogue_store<16, EPI_ACCUM, true>(ep, row, col, P.N, v);
+      }
+      if (slice == 0 && n0 == 0 && P.dbias != nullptr) {
+        float v[16];
+        tmem_ld16(t_row + (uint32_t)WG_BN, v);
+        if (row < P.M) P.dbias[row] += v[0];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(tempty));
+      tphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace tc
+
+// Grouped wgrad (+ bias grad): for g < count:  out[g][Nout, Kin] += dy[g]^T x[g];  dbias[g][Nout] += colsum(dy[g]).
+// dy[g]: bf16 [R, Nout] pitch lddy;  x[g]: bf16 [R, Kin] pitch ldx.  Every output tile has one writer: no atomics.
+extern "C" int mma_wgrad_group(int count, const void* const* dy, const long long* lddy, const void* const* x,
+                               const long long* ldx, float* const* out, const long long* ldo, float* const* dbias,
+                               const int* Nout, const int* Kin, const int* R, cudaStream_t stream) {
+  using namespace tc;
+  if (count < 1 || count > 8) return MMA_ERR_ARG;
+  WgGroup grp{};
+  int tiles = 0;
+  for (int g = 0; g < count; ++g) {
+    WgProblem& P = grp.p[g];
+    if (Nout[g] <= 0 || Kin[g] <= 0 || R[g] <= 0) return MMA_ERR_ARG;
+    int rc = make_map(&P.tmA, dy[g], (unsigned long long)Nout[g], (unsigned long long)R[g], lddy[g], 64, BK);
+    if (rc) return rc;
+    rc = make_map(&P.tmB, x[g], (unsigned long long)Kin[g], (unsigned long long)R[g], ldx[g], 64, BK);
+    if (rc) return rc;
+    P.out = out[g];
+    P.dbias = dbias ? dbias[g] : nullptr;
+    P.ldo = ldo[g];
+    P.M = Nout[g];
+    P.N = Kin[g];
+    P.R = R[g];
+    P.tiles_n = (Kin[g] + WG_BN - 1) / WG_BN;
+    P.tile_begin = tiles;
+    tiles += ((Nout[g] + BM - 1) / BM) * P.tiles_n;
+  }
+  grp.count = count;
+  grp.total_tiles = tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM) != cudaSuccess)
+      return MMA_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  wgrad_group_kernel<<<grid, NUM_THREADS, WG_SMEM, stream>>>(grp);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
 
 // C[M,N] = epi(A_op * B_op^T).  a_mn / b_mn: 0 = operand memory is [rows, K] (K-major), 1 = [K, rows].
 // lda / ldb: row pitch of the operand's memory in elements.  splits > 1 splits the K loop across CTAs

@@ -41,6 +41,8 @@ class Engine:
         self.grad_ready_hook: Optional[Callable[[int], None]] = None  # called with the flat offset from which
         #                                                               all gradients are final
         self.ldv = (cfg.vocab_size + 7) // 8 * 8
+        self._wq: List[Any] = []  # weight / bias gradient products deferred to one grouped launch per layer
+        self.group_wgrad = True
 
     # ------------------------------------------------------------------------------------- utils
     def buf(self, name, shape, dtype):
@@ -85,15 +87,24 @@ class Engine:
 
     # ----------------------------------------------------------------------------- linear helpers
     def _lin_bwd(self, dy, x, wname, bname, rows, n_out, k_in, dx_epi=None, row_slice=None):
-        """dy: [rows, n_out]; x: [rows, k_in]; W: [n_out, k_in] (optionally a row slice of the named tensor)."""
+        """dy: [rows, n_out]; x: [rows, k_in]; W: [n_out, k_in] (optionally a row slice of the named tensor).
+        dgrad is launched now; wgrad + bias grad are queued for the layer's grouped launch (`_flush_wgrads`)."""
         Wt, Gw, Gb = self.W(wname), self.G(wname), self.G(bname)
         if row_slice is not None:
             Wt, Gw, Gb = Wt[row_slice], Gw[row_slice], Gb[row_slice]
         if dx_epi is not None:
             ops.gemm(dy, Wt, rows, k_in, n_out, dx_epi, b_mn=True)
+        if self.group_wgrad and self.precision == "bf16" and ops.wgrad_group_ok(dy, x, n_out, k_in):
+            self._wq.append((dy, x, Gw, Gb, n_out, k_in, rows))
+            return
         ops.gemm(dy, x, n_out, k_in, rows, ops.make_epi(EPI_ACCUM, Gw, accumulate=2), a_mn=True, b_mn=True,
                  splits=self._splits(n_out, k_in, rows))
         ops.colsum(dy, Gb, rows=rows, cols=n_out)
+
+    def _flush_wgrads(self):
+        if self._wq:
+            ops.wgrad_group(self._wq)
+            self._wq = []
 
     # --------------------------------------------------------------------------------- embedding
     def _pos_rows(self, L, tag):
@@ -213,7 +224,8 @@ class Engine:
             self.saved[tag] = dict(x=x, h=h, qkv=qkv, ctx=ctx, lse=lse)
         return xo
 
-    def _attn_block_bwd(self, tag, dx, dyb, B, L, heads, wp, kmask, causal, p, site_a, prev_site, first=False):
+    def _attn_block_bwd(self, tag, dx, dyb, B, L, heads, wp, kmask, causal, p, site_a, prev_site, first=False,
+                        out_tag="x"):
         """dx: fp32 grad of the block output; dyb: low-precision (dropout-masked) copy.  Returns (dx_in, dyb_in)."""
         d = self.cfg.d_model
         M = B * L
@@ -230,7 +242,7 @@ class Engine:
         dh_ = self.buf("bw.dh", (M, d), T)
         self._lin_bwd(dqkv, s["h"], wp["in_w"], wp["in_b"], M, 3 * d, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
         dx_in = self._other_dx(dx, M)
-        dyb_in = None if first else self.buf(f"bw.dyb.{M}", (M, d), T)
+        dyb_in = None if first else self.buf(f"bw.dyb.{out_tag}", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
@@ -280,7 +292,7 @@ class Engine:
             self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=0))
             self._lin_bwd(dz2, s["h"], wp["wg"], wp["bg"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=1))
         dx_in = self._other_dx(dx, M)
-        dyb_in = self.buf(f"bw.dyb.{M}", (M, d), T)
+        dyb_in = self.buf("bw.dyb.ffn_in", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
@@ -348,7 +360,7 @@ class Engine:
                       dx_epi=ops.make_epi(EPI_ACCUM, dmem, accumulate=0 if first_mem else 1),
                       row_slice=slice(d, 3 * d))
         dx_in = self._other_dx(dx, M)
-        dyb_in = self.buf(f"bw.dyb.{M}", (M, d), T)
+        dyb_in = self.buf("bw.dyb.ca_in", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
@@ -405,6 +417,7 @@ class Engine:
         self.sync_weights()
         if train:
             self.saved = {}
+            self._wq = []
         B, T_ = dec_ids.shape
         mem = self.encode(enc_inputs, enc_mask, train)
         hT = self.decode_teacher_forced(dec_ids, dec_mask, mem, enc_mask, train)
@@ -445,9 +458,12 @@ class Engine:
         dhT = self.buf("bw.dh", (M, d), T)
         self._lin_bwd(dl, dec["hT"], "hf_model.token_ff.weight", "hf_model.token_ff.bias", M, V, d,
                       dx_epi=ops.make_epi(EPI_STORE, dhT))
+        self._flush_wgrads()
         last_site = self._site(True, cfg.decoder_layers - 1, 3)
         dx = self._other_dx(None, M)
-        dyb = self.buf(f"bw.dyb.{M}", (M, d), T)
+        # the masked low-precision gradient handed to the layer below alternates between two buffers: it must stay
+        # alive until that layer's grouped weight-gradient launch
+        dyb = self.buf(f"bw.dyb.x{cfg.decoder_layers % 2}", (M, d), T)
         ops.ln_bwd(dhT, dec["xL"], self.P("hf_model.decoder.norm.weight"), dx=dx, dxb=dyb,
                    dgamma=self.G("hf_model.decoder.norm.weight"), dbeta=self.G("hf_model.decoder.norm.bias"),
                    p_drop=p, seed=self.seed_arg, site=last_site)
@@ -464,14 +480,16 @@ class Engine:
                                             self._site(True, i, 4), prev_site=self._site(True, i, 1))
             prev = self._site(True, i - 1, 3) if i > 0 else self._site(True, 0, 15)
             dx, dyb = self._attn_block_bwd(tg + ".sa", dx, dyb, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"),
-                                           dec["mask"], True, p, self._site(True, i, 0), prev_site=prev, first=(i == 0))
+                                           dec["mask"], True, p, self._site(True, i, 0), prev_site=prev, first=(i == 0),
+                                           out_tag=f"x{i % 2}")
+            self._flush_wgrads()
             notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
         self._embed_bwd(dx, dec["recs"], T_, "dec", B)
 
         # encoder: d(mem) arrives in fp32 from the cross-attention K/V projections
         He = cfg.encoder_attention_heads
         dxe = self._other_dx(None, Me)
-        dybe = self.buf(f"bw.dyb.{Me}", (Me, d), T)
+        dybe = self.buf(f"bw.dyb.x{cfg.encoder_layers % 2}", (Me, d), T)
         ops.ln_bwd(dmem, enc["xL"], self.P("hf_model.encoder.norm.weight"), dx=dxe, dxb=dybe,
                    dgamma=self.G("hf_model.encoder.norm.weight"), dbeta=self.G("hf_model.encoder.norm.bias"),
                    p_drop=p, seed=self.seed_arg, site=self._site(False, cfg.encoder_layers - 1, 3))
@@ -484,7 +502,8 @@ class Engine:
             prev = self._site(False, i - 1, 3) if i > 0 else self._site(False, 0, 15)
             dxe, dybe = self._attn_block_bwd(tg + ".sa", dxe, dybe, B, S, He, self._wp_attn(pre, "self_attn", "norm1"),
                                              enc["mask"], False, p, self._site(False, i, 0), prev_site=prev,
-                                             first=(i == 0))
+                                             first=(i == 0), out_tag=f"x{i % 2}")
+            self._flush_wgrads()
             notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
         self._embed_bwd(dxe, enc["recs"], S, "enc", B)
         notify(0)

@@ -101,6 +101,32 @@ def gemm(A, B, M, N, K, epi, a_mn=False, b_mn=False, splits=1, force_simt=False,
     _count()
 
 
+def wgrad_group_ok(dy, x, n_out, k_in):
+    return (_tc_ok(dy, True, 0, 0) and _tc_ok(x, True, 0, 0) and n_out % 8 == 0 and k_in % 8 == 0)
+
+
+def wgrad_group(items):
+    """items: list of (dy [R, Nout] bf16, x [R, Kin] bf16, dW [Nout, Kin] fp32, db [Nout] fp32 | None, Nout, Kin, R).
+    One persistent tcgen05 launch per <= 8 items: dW += dy^T x, db += colsum(dy)."""
+    lib = _lib.load()
+    for i0 in range(0, len(items), 8):
+        chunk = items[i0:i0 + 8]
+        n = len(chunk)
+        VP, LL, IN = C.c_void_p * n, C.c_longlong * n, C.c_int * n
+        dy = VP(*[it[0].data_ptr() for it in chunk])
+        lddy = LL(*[it[0].stride(0) for it in chunk])
+        x = VP(*[it[1].data_ptr() for it in chunk])
+        ldx = LL(*[it[1].stride(0) for it in chunk])
+        out = VP(*[it[2].data_ptr() for it in chunk])
+        ldo = LL(*[it[2].stride(0) for it in chunk])
+        db = VP(*[(it[3].data_ptr() if it[3] is not None else 0) for it in chunk])
+        nout = IN(*[it[4] for it in chunk])
+        kin = IN(*[it[5] for it in chunk])
+        rr = IN(*[it[6] for it in chunk])
+        check(lib.mma_wgrad_group(n, dy, lddy, x, ldx, out, ldo, db, nout, kin, rr, _stream()), "mma_wgrad_group")
+        _count()
+
+
 def gather_rows(ids, table, out, scale=None):
     _need_cuda(ids, table, out)
     assert ids.dtype == torch.int64 and ids.is_contiguous() and table.dtype == torch.float32 and out.dtype == torch.float32

@@ -2,7 +2,7 @@
 # kernel tests + model tests + bench (+ optional ncu) in one GPU call
 mkdir -p gpurun_out
 rm -f gpurun_out/round_summary.txt
-for grp in "test_gemm" "test_layernorm or test_embed or test_colsum" "test_attention or test_tc_attention or test_bf16_dh64" "test_cross_entropy or test_adam"; do
+for grp in "test_gemm or test_grouped" "test_layernorm or test_embed or test_colsum" "test_attention or test_tc_attention or test_bf16_dh64" "test_cross_entropy or test_adam"; do
   name=$(echo "$grp" | tr ' ' '_')
   timeout 900 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "$grp" --timeout 300 --no-header -p no:cacheprovider > "gpurun_out/k_${name}.log" 2>&1
   echo "kernels[$grp] -> exit $?" | tee -a gpurun_out/round_summary.txt

@@ -403,3 +403,24 @@ def test_bf16_dh64_attention_both_tensor_core_paths(impl, B, H, Lq, Lk, causal, 
     assert rel(dq.view_as(q).float(), qr.grad) < 3e-2
     assert rel(dk.view_as(k).float(), kr.grad) < 3e-2
     assert rel(dv.view_as(v).float(), vr.grad) < 3e-2
+
+
+def test_grouped_wgrad_with_fused_bias_grad():
+    """One persistent launch for several dW += dy^T x products (+ db += colsum(dy)), incl. ragged sizes, pitched
+    operand views and pre-existing gradient content (accumulation)."""
+    dt = torch.bfloat16
+    specs = [(4096, 1536, 512), (4096, 512, 512), (2304, 1024, 512), (4096, 2048, 512), (4096, 512, 2048),
+             (1000, 200, 48), (777, 144, 48)]
+    items, refs = [], []
+    for i, (R, n_out, k_in) in enumerate(specs):
+        wide = _rand(R, n_out + 64, dtype=dt, scale=R ** -0.5, seed=i)
+        dy = wide[:, 32:32 + n_out] if n_out % 64 == 0 else wide[:, :n_out]  # a pitched view
+        x = _rand(R, k_in, dtype=dt, seed=100 + i)
+        dw0, db0 = _rand(n_out, k_in, seed=200 + i), _rand(n_out, seed=300 + i)
+        dw, db = dw0.clone(), db0.clone()
+        items.append((dy, x, dw, db, n_out, k_in, R))
+        refs.append((dw0 + dy.float().T @ x.float(), db0 + dy.float().sum(0)))
+    ops.wgrad_group(items)
+    for it, (rw, rb) in zip(items, refs):
+        assert rel(it[2], rw) < 3e-5, it[4:]
+        assert rel(it[3], rb) < 3e-5, it[4:]
