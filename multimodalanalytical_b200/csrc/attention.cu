@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(Args a) {
       l[qi] = l[qi] * corr + warp_sum(p0 + p1);
       m[qi] = mn;
       if (drop) {
-        const unsigned long long e = (((unsigned long long)b * a.H + h) * a.Lq + i) * (unsigned long long)a.Lk;
+        const unsigned long long e = (((unsigned long long)b * a.H + h) * a.Lq + i) * (unsigned long long)((a.Lk + 1) & ~1);
         p0 *= drop_scale1(dkey, e + ja, thr, inv_keep);
         p1 *= drop_scale1(dkey, e + jb, thr, inv_keep);
       }
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(Args a) {
       float p0 = va ? __expf(s0 - lse[qi]) : 0.f;
       float p1 = vb ? __expf(s1 - lse[qi]) : 0.f;
       if (drop) {
-        const unsigned long long e = (((unsigned long long)b * a.H + h) * a.Lq + i) * (unsigned long long)a.Lk;
+        const unsigned long long e = (((unsigned long long)b * a.H + h) * a.Lq + i) * (unsigned long long)((a.Lk + 1) & ~1);
         d0 *= drop_scale1(dkey, e + ja, thr, inv_keep);
         d1 *= drop_scale1(dkey, e + jb, thr, inv_keep);
       }
@@ -336,8 +336,8 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(Args a) {
       float k0s = 1.f, k1s = 1.f;
       if (drop) {
         const unsigned long long eb = ((unsigned long long)b * a.H + h) * a.Lq;
-        k0s = drop_scale1(dkey, (eb + ia) * (unsigned long long)a.Lk + j, thr, inv_keep);
-        k1s = drop_scale1(dkey, (eb + ib) * (unsigned long long)a.Lk + j, thr, inv_keep);
+        k0s = drop_scale1(dkey, (eb + ia) * (unsigned long long)((a.Lk + 1) & ~1) + j, thr, inv_keep);
+        k1s = drop_scale1(dkey, (eb + ib) * (unsigned long long)((a.Lk + 1) & ~1) + j, thr, inv_keep);
       }
       float* pw = ps + warp * 2 * KT;
       __syncwarp();

@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args a) {
           const int col = j0 + n * 8 + 2 * t + (e & 1);
           const int row = row0 + r * 8;
           const unsigned long long ei =
-              (((unsigned long long)b * a.H + h) * a.Lq + row) * (unsigned long long)a.Lk + col;
+              (((unsigned long long)b * a.H + h) * a.Lq + row) * (unsigned long long)((a.Lk + 1) & ~1) + col;
           pd *= drop_scale1(dkey, ei, thr, inv_keep);
         }
         s[n][e] = pd;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(Args a) {
         float dpe = dp[n][e];
         if (drop) {
           const unsigned long long ei =
-              (((unsigned long long)b * a.H + h) * a.Lq + row) * (unsigned long long)a.Lk + col;
+              (((unsigned long long)b * a.H + h) * a.Lq + row) * (unsigned long long)((a.Lk + 1) & ~1) + col;
           dpe *= drop_scale1(dkey, ei, thr, inv_keep);
         }
         s[n][e] = p * (dpe - Di[r]);
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(NT) bwd_dkv_kernel(Args a) {
         float keep = 1.f;
         if (drop) {
           const unsigned long long ei =
-              (((unsigned long long)b * a.H + h) * a.Lq + qi) * (unsigned long long)a.Lk + kr;
+              (((unsigned long long)b * a.H + h) * a.Lq + qi) * (unsigned long long)((a.Lk + 1) & ~1) + kr;
           keep = drop_scale1(dkey, ei, thr, inv_keep);
         }
         st[n][e] = p * keep;                              // P_drop^T

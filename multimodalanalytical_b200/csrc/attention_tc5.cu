@@ -105,6 +105,25 @@ __device__ __forceinline__ void issue_tile_loads(const Args& a, const CUtensorMa
   }
 }
 
+
+// Validity bits of the keys [ch*32, ch*32+32) of this row's problem: key < Lk, key-padding mask (warp ballot: all rows
+// of a warp belong to the same problem), causal j <= i.
+template <int NCH>
+__device__ __forceinline__ void key_valid_bits(uint32_t (&bits)[NCH], const unsigned char* km, int Lk, int causal, int i,
+                                               int lane) {
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    const int j = ch * 32 + lane;
+    const bool ok = j < Lk && (!km || km[j] != 0);
+    uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (causal) {
+      const int hi = i - ch * 32;  // keys 0..hi of this chunk are visible
+      m &= hi >= 31 ? 0xffffffffu : hi < 0 ? 0u : ((2u << hi) - 1u);
+    }
+    bits[ch] = m;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int PACK>
 __global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
@@ -151,23 +170,25 @@ __global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtens
   const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
   const uint32_t dkey = drop_key(a.seed, a.site);
-  const unsigned long long ebase = (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)a.Lk;
+  const unsigned long long ebase = (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)((a.Lk + 1) & ~1);
   constexpr int NCH = PACK == 2 ? 2 : 4;  // 32-column chunks of this row's problem
   const uint32_t t_row = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)rm.key_col0;
 
-  mbar_wait(smem_u32(&bars[1]), 0);
+  uint32_t vbits[NCH];
+  key_valid_bits<NCH>(vbits, km, a.Lk, a.causal, rm.i, lane);
+  const uint32_t ebase32 = (uint32_t)ebase;  // even: the dropout row pitch is padded to a multiple of 2
+
+  if (lane == 0) mbar_wait(smem_u32(&bars[1]), 0);  // one poller per warp
+  __syncwarp();
   tc_fence_after();
   float mx = -INFINITY;
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     float s[32];
     tmem_ld32f(t_row + ch * 32, s);
+    const uint32_t vb = vbits[ch];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int j = ch * 32 + c;
-      const bool ok = j < a.Lk && (!km || km[j]) && (!a.causal || j <= rm.i);
-      if (ok) mx = fmaxf(mx, s[c] * sl2);
-    }
+    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (vb >> c) & 1u ? s[c] * sl2 : -INFINITY);
   }
   // every thread has read what it needs for the max; P overwrites sQ|sK only after the S product has retired (bars[1])
   float l = 0.f;
@@ -176,14 +197,19 @@ __global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtens
   for (int ch = 0; ch < NCH; ++ch) {
     float s[32];
     tmem_ld32f(t_row + ch * 32, s);
+    const uint32_t vb = vbits[ch];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int j = ch * 32 + c;
-      const bool ok = j < a.Lk && (!km || km[j]) && (!a.causal || j <= rm.i);
-      float p = ok ? ex2_approx(s[c] * sl2 - mx) : 0.f;
-      l += p;
-      if (drop) p *= drop_scale1(dkey, ebase + j, thr, inv_keep);
-      s[c] = p;
+    for (int c = 0; c < 32; c += 2) {
+      float p0 = (vb >> c) & 1u ? ex2_approx(s[c] * sl2 - mx) : 0.f;
+      float p1 = (vb >> (c + 1)) & 1u ? ex2_approx(s[c + 1] * sl2 - mx) : 0.f;
+      l += p0 + p1;
+      if (drop) {
+        const uint32_t r = drop_pair(dkey, (ebase32 + (uint32_t)(ch * 32 + c)) >> 1);
+        p0 *= (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+        p1 *= (r >> 16) >= thr ? inv_keep : 0.f;
+      }
+      s[c] = p0;
+      s[c + 1] = p1;
     }
     const int kcol = rm.key_col0 + ch * 32;  // column in the packed 128-wide K dimension
     uint8_t* atom = sP + (kcol >> 6) * TILE;
@@ -211,7 +237,8 @@ __global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtens
                   desc_mnmajor(smem_u32(sV) + k * 2048, TILE), idesc(64, false, true), k > 0);
     tc_commit(smem_u32(&bars[2]));
   }
-  mbar_wait(smem_u32(&bars[2]), 0);
+  if (lane == 0) mbar_wait(smem_u32(&bars[2]), 0);  // one poller per warp
+  __syncwarp();
   tc_fence_after();
   {
     const float inv = l > 0.f ? 1.f / l : 0.f;
@@ -315,25 +342,37 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
   const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
   const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
   const uint32_t dkey = drop_key(a.seed, a.site);
-  const unsigned long long ebase = (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)a.Lk;
+  const unsigned long long ebase = (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)((a.Lk + 1) & ~1);
   constexpr int NCH = PACK == 2 ? 2 : 4;
   const uint32_t t_row = tm + ((uint32_t)(warp * 32) << 16) + (uint32_t)rm.key_col0;
 
-  mbar_wait(smem_u32(&bars[1]), 0);  // S and dP are in TMEM; V's smem is free (becomes Pd atom 1)
+  uint32_t vbits[NCH];
+  key_valid_bits<NCH>(vbits, km, a.Lk, a.causal, rm.i, lane);
+  const uint32_t ebase32 = (uint32_t)ebase;
+
+  if (lane == 0) mbar_wait(smem_u32(&bars[1]), 0);  // one poller per warp
+  __syncwarp();
   tc_fence_after();
 #pragma unroll 1
   for (int ch = 0; ch < NCH; ++ch) {
     float s[32], dp[32];
     tmem_ld32f(t_row + ch * 32, s);
     tmem_ld32f(t_row + 128 + ch * 32, dp);
+    const uint32_t vb = qvalid ? vbits[ch] : 0u;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const int j = ch * 32 + c;
-      const bool ok = qvalid && j < a.Lk && (!km || km[j]) && (!a.causal || j <= rm.i);
-      const float p = ok ? ex2_approx(s[c] * sl2 - lse2) : 0.f;
-      const float keep = drop ? drop_scale1(dkey, ebase + j, thr, inv_keep) : 1.f;
-      s[c] = p * keep;                      // P_drop
-      dp[c] = p * (dp[c] * keep - Di);      // dS
+    for (int c = 0; c < 32; c += 2) {
+      const float p0 = (vb >> c) & 1u ? ex2_approx(s[c] * sl2 - lse2) : 0.f;
+      const float p1 = (vb >> (c + 1)) & 1u ? ex2_approx(s[c + 1] * sl2 - lse2) : 0.f;
+      float k0 = 1.f, k1 = 1.f;
+      if (drop) {
+        const uint32_t r = drop_pair(dkey, (ebase32 + (uint32_t)(ch * 32 + c)) >> 1);
+        k0 = (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+        k1 = (r >> 16) >= thr ? inv_keep : 0.f;
+      }
+      s[c] = p0 * k0;                        // P_drop
+      s[c + 1] = p1 * k1;
+      dp[c] = p0 * (dp[c] * k0 - Di);        // dS
+      dp[c + 1] = p1 * (dp[c + 1] * k1 - Di);
     }
     const int kcol = rm.key_col0 + ch * 32;
     uint8_t* pa = (kcol >> 6) ? sV : sPd0;
@@ -379,7 +418,8 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
                   desc_mnmajor(smem_u32(sK) + k * 2048, TILE), idesc(64, false, true), k > 0);
     tc_commit(smem_u32(&bars[2]));
   }
-  mbar_wait(smem_u32(&bars[2]), 0);
+  if (lane == 0) mbar_wait(smem_u32(&bars[2]), 0);  // one poller per warp
+  __syncwarp();
   tc_fence_after();
   {
     // row r is query r of its problem for dQ and key r of its problem for dK / dV

@@ -390,3 +390,120 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
       break;
   }
 }
+
+// ---- split epilogue for the software-pipelined tcgen05 kernels ---------------------------------------------
+// epi_prefetch issues the global loads an epilogue needs besides the accumulator (residual / saved activations /
+// the running gradient) so they overlap the TMEM read of the same chunk; epi_finish consumes them.  The bias comes
+// from shared memory (staged once per tile).  Semantics are identical to epilogue_store<NV, KIND, FAST>.
+template <int NV>
+struct EpiIn {
+  float a[NV];
+  float b[NV];
+};
+
+template <int NV, int KIND>
+__device__ __forceinline__ void epi_prefetch(const Epi& ep, long long row, int col, int ncols, bool row_ok, EpiIn<NV>& in) {
+  const int nvalid = row_ok ? min(NV, ncols - col) : 0;
+  if (nvalid <= 0) return;
+  if (KIND == EPI_RESID) ld_row_any<NV>(in.a, ep.resid, row * ep.ldr + col, ep.resid_f32, nvalid);
+  if (KIND == EPI_DGELU || KIND == EPI_GLU_MUL || KIND == EPI_DGLU || KIND == EPI_DRELU)
+    ld_row_any<NV>(in.a, ep.aux, row * ep.lda + col, ep.aux_f32, nvalid);
+  if (KIND == EPI_DGLU) ld_row_any<NV>(in.b, ep.aux2, row * ep.lda2 + col, ep.aux_f32, nvalid);
+  if (KIND == EPI_ACCUM) {
+    if (ep.accumulate == 1) ld_row_f32<NV>(in.a, reinterpret_cast<const float*>(ep.out) + row * ep.ldo + col, nvalid);
+  }
+}
+
+template <int NV, int KIND, bool FAST>
+__device__ __forceinline__ void epi_finish(const Epi& ep, long long row, int col, int ncols, bool row_ok, float (&v)[NV],
+                                           EpiIn<NV>& in, const float* bias_s) {
+  const int nvalid = row_ok ? min(NV, ncols - col) : 0;
+  if (nvalid <= 0) return;
+  if (KIND == EPI_ACCUM) {
+    float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col;
+    if (ep.accumulate == 2) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (j < nvalid) atomicAdd(o + j, v[j] * ep.alpha);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) v[j] = ep.accumulate == 1 ? fmaf(v[j], ep.alpha, in.a[j]) : v[j] * ep.alpha;
+      st_row_any<NV>(ep.out, row * ep.ldo + col, 1, v, nvalid);
+    }
+    return;
+  }
+  if (KIND == EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = bias_s ? fmaf(v[j], ep.alpha, bias_s[j]) : v[j] * ep.alpha;
+    st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+    return;
+  }
+  if (bias_s && (KIND == EPI_GELU || KIND == EPI_RESID || KIND == EPI_GLU_MUL || KIND == EPI_RELU)) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] += bias_s[j];
+  }
+  const bool drop = ep.p_drop > 0.0f &&
+                    (KIND == EPI_GELU || KIND == EPI_RESID || KIND == EPI_DGELU || KIND == EPI_GLU_MUL || KIND == EPI_DGLU);
+  float ds[NV];
+  if (drop) {
+    const uint32_t thr = drop_threshold(ep.p_drop);
+    const float inv_keep = 1.0f / (1.0f - ep.p_drop);
+    const uint32_t dkey = drop_key(ep.seed, ep.site);
+    const uint32_t e0 = (uint32_t)((unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)col);
+    if ((e0 & 1u) == 0 && (NV % 2) == 0) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 2) {
+        const uint32_t r = drop_pair(dkey, (e0 + j) >> 1);
+        ds[j] = (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+        ds[j + 1] = (r >> 16) >= thr ? inv_keep : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) ds[j] = drop_scale1(dkey, e0 + j, thr, inv_keep);
+    }
+  }
+  if (KIND == EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (KIND == EPI_GELU) {
+    if (ep.out2) st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, v, nvalid);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float y = gelu_t<FAST>(v[j]);
+      if (drop) y *= ds[j];
+      v[j] = y;
+    }
+  } else if (KIND == EPI_RESID) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = in.a[j] + (drop ? v[j] * ds[j] : v[j]);
+  } else if (KIND == EPI_DGELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float y = v[j] * dgelu_t<FAST>(in.a[j]);
+      if (drop) y *= ds[j];
+      v[j] = y;
+    }
+  } else if (KIND == EPI_DRELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = in.a[j] > 0.f ? v[j] : 0.f;
+  } else if (KIND == EPI_GLU_MUL) {
+    if (ep.out2) st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, v, nvalid);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float y = gelu_t<FAST>(in.a[j]) * v[j];
+      if (drop) y *= ds[j];
+      v[j] = y;
+    }
+  } else if (KIND == EPI_DGLU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float da = drop ? v[j] * ds[j] : v[j];
+      float g, dg;
+      gelu_both<FAST>(in.a[j], g, dg);
+      v[j] = da * in.b[j] * dg;
+      in.b[j] = da * g;
+    }
+    st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, in.b, nvalid);
+  }
+  st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+}

@@ -224,7 +224,10 @@ constexpr int MAXK = 64;  // beams (2K candidates <= 128)
 __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
   extern __shared__ uint32_t cand[];  // [K*V] ordered keys of accumulated log-probs
   __shared__ float s_lse[MAXK];
-  __shared__ unsigned long long s_red[8];
+  __shared__ unsigned long long s_wkeys[8 * 2 * MAXK];  // per-warp top-2K keys
+  __shared__ float s_live[2 * MAXK];
+  __shared__ float s_ms[3 * MAXK];
+  __shared__ unsigned char s_hit[2 * MAXK];
   __shared__ float c_score[2 * MAXK];
   __shared__ int c_idx[2 * MAXK];
   __shared__ int n_run_src[MAXK];     // candidate slot feeding running beam k
@@ -263,93 +266,122 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
     cand[i] = f2ord(lp + a.run_score[b * K + k]);
   }
   __syncthreads();
-  // 3. top-2K, descending, ties -> lowest flat index
+  // 3. top-2K, descending, ties -> lowest flat index.  Two levels without block-wide syncs per pick: every warp
+  //    extracts the top-2K of its own slice of the K*V candidates (shuffle arg-max, owner warp marks "taken"), then
+  //    warp 0 extracts the top-2K of the nwarp*2K survivors.
   const int keep = 2 * K;
-  for (int sel = 0; sel < keep; ++sel) {
-    unsigned long long best = 0ull;
-    for (int i = threadIdx.x; i < K * V; i += blockDim.x) {
-      const uint32_t o = cand[i];
-      if (o) {
-        const unsigned long long key = ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
-        best = key > best ? key : best;
+  const int KV = K * V;
+  {
+    const int per_warp = (KV + nwarp - 1) / nwarp;
+    const int lo = warp * per_warp, hi = min(KV, lo + per_warp);
+    for (int sel = 0; sel < keep; ++sel) {
+      unsigned long long best = 0ull;
+      for (int i = lo + lane; i < hi; i += 32) {
+        const uint32_t o = cand[i];
+        if (o) {
+          const unsigned long long key = ((unsigned long long)o << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+          best = key > best ? key : best;
+        }
       }
-    }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
-      best = other > best ? other : best;
-    }
-    if (lane == 0) s_red[warp] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long bb = 0ull;
-      for (int w = 0; w < nwarp; ++w) bb = s_red[w] > bb ? s_red[w] : bb;
-      if (bb) {
-        const int idx = (int)(0xffffffffu - (uint32_t)(bb & 0xffffffffull));
-        c_idx[sel] = idx;
-        c_score[sel] = ord2f((uint32_t)(bb >> 32));
-        cand[idx] = 0u;  // taken
-      } else {  // fewer than 2K candidates (K*V < 2K): pad with -inf on slot 0
-        c_idx[sel] = 0;
-        c_score[sel] = -INFINITY;
+      for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
+        best = other > best ? other : best;
       }
+      if (lane == 0) {
+        s_wkeys[warp * 2 * MAXK + sel] = best;
+        if (best) cand[(int)(0xffffffffu - (uint32_t)(best & 0xffffffffull))] = 0u;
+      }
+      __syncwarp();
     }
-    __syncthreads();
   }
-  // 4. serial bookkeeping (tiny): live beams, finished pool, early-stop heuristic
-  if (threadIdx.x == 0) {
-    const bool improvable = a.improvable[b] != 0;
-    bool hits[2 * MAXK];
-    bool used[3 * MAXK];
-    float live[2 * MAXK];
-    bool allh = true;
-    for (int c = 0; c < keep; ++c) {
-      const int tok = c_idx[c] % V;
-      hits[c] = (tok == a.eos_id) || (cur + 1 >= L);
-      allh = allh && hits[c];
-      live[c] = c_score[c] + (hits[c] ? 1.0f : 0.0f) * NEG;
-      used[c] = false;
-    }
-    for (int k = 0; k < K; ++k) {  // top-K of live, ties -> lowest slot
-      int bi = -1;
-      for (int c = 0; c < keep; ++c)
-        if (!used[c] && (bi < 0 || live[c] > live[bi])) bi = c;
-      used[bi] = true;
-      n_run_src[k] = bi;
-      n_run_score[k] = live[bi];
-    }
-    // finished pool: old K slots followed by the 2K candidates
-    float ms[3 * MAXK];
-    const float glen = (float)(cur + 1 - 1);  // generated length incl. this token (prompt length 1)
-    for (int k = 0; k < K; ++k) ms[k] = a.fin_score[b * K + k];
-    for (int c = 0; c < keep; ++c) {
-      const bool just = hits[c] && c < K;
-      float fs = c_score[c] / glen;
-      fs = fs + (improvable ? 0.0f : 1.0f) * NEG;
-      fs = fs + (just ? 0.0f : 1.0f) * NEG;
-      ms[K + c] = fs;
-    }
-    for (int i = 0; i < K + keep; ++i) used[i] = false;
-    bool any_unfinished = false;
-    float worst = INFINITY;
-    for (int k = 0; k < K; ++k) {
-      int bi = -1;
-      for (int i = 0; i < K + keep; ++i)
-        if (!used[i] && (bi < 0 || ms[i] > ms[bi])) bi = i;
-      used[bi] = true;
-      n_fin_src[k] = bi;
-      n_fin_score[k] = ms[bi];
-      if (bi < K) {
-        n_fin_flag[k] = a.fin_flag[b * K + bi];
-        n_fin_len[k] = a.fin_len[b * K + bi];
-      } else {
-        const int c = bi - K;
-        n_fin_flag[k] = (hits[c] && c < K) ? 1 : 0;
-        n_fin_len[k] = cur + 1 - 1;
+  __syncthreads();
+  if (warp == 0) {
+    const int n = nwarp * keep;
+    for (int sel = 0; sel < keep; ++sel) {
+      unsigned long long best = 0ull;
+      int where = -1;
+      for (int i = lane; i < n; i += 32) {
+        const unsigned long long key = s_wkeys[(i / keep) * 2 * MAXK + (i % keep)];
+        if (key > best) { best = key; where = i; }
       }
-      if (!n_fin_flag[k]) any_unfinished = true;
-      worst = fminf(worst, ms[bi]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
+        const int ow = __shfl_xor_sync(0xffffffffu, where, off);
+        if (other > best) { best = other; where = ow; }
+      }
+      if (lane == 0) {
+        if (best) {
+          c_idx[sel] = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
+          c_score[sel] = ord2f((uint32_t)(best >> 32));
+          s_wkeys[(where / keep) * 2 * MAXK + (where % keep)] = 0ull;
+        } else {  // fewer than 2K candidates (K*V < 2K): pad with -inf on slot 0
+          c_idx[sel] = 0;
+          c_score[sel] = -INFINITY;
+        }
+      }
+      __syncwarp();
     }
+  }
+  __syncthreads();
+  // 4. live beams / finished pool by parallel ranking (rank = number of strictly better entries, ties -> lower slot)
+  const bool improvable = a.improvable[b] != 0;
+  const float glen = (float)(cur + 1 - 1);  // generated length incl. this token (prompt length 1)
+  if (threadIdx.x < keep) {
+    const int c = threadIdx.x;
+    const int tok = c_idx[c] % V;
+    const bool hit = (tok == a.eos_id) || (cur + 1 >= L);
+    s_hit[c] = hit ? 1 : 0;
+    s_live[c] = c_score[c] + (hit ? 1.0f : 0.0f) * NEG;
+    const bool just = hit && c < K;
+    float fs = c_score[c] / glen;
+    fs = fs + (improvable ? 0.0f : 1.0f) * NEG;
+    fs = fs + (just ? 0.0f : 1.0f) * NEG;
+    s_ms[K + c] = fs;
+  }
+  if (threadIdx.x < K) s_ms[threadIdx.x] = a.fin_score[b * K + threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x < keep) {
+    const int c = threadIdx.x;
+    const float mine = s_live[c];
+    int rank = 0;
+    for (int u = 0; u < keep; ++u) {
+      const float o = s_live[u];
+      rank += (o > mine || (o == mine && u < c)) ? 1 : 0;
+    }
+    if (rank < K) {
+      n_run_src[rank] = c;
+      n_run_score[rank] = mine;
+    }
+  }
+  if (threadIdx.x < K + keep) {
+    const int t = threadIdx.x;
+    const float mine = s_ms[t];
+    int rank = 0;
+    for (int u = 0; u < K + keep; ++u) {
+      const float o = s_ms[u];
+      rank += (o > mine || (o == mine && u < t)) ? 1 : 0;
+    }
+    if (rank < K) {
+      n_fin_src[rank] = t;
+      n_fin_score[rank] = mine;
+      if (t < K) {
+        n_fin_flag[rank] = a.fin_flag[b * K + t];
+        n_fin_len[rank] = a.fin_len[b * K + t];
+      } else {
+        const int c = t - K;
+        n_fin_flag[rank] = (s_hit[c] && c < K) ? 1 : 0;
+        n_fin_len[rank] = cur + 1 - 1;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    bool allh = true;
+    for (int c = 0; c < keep; ++c) allh = allh && s_hit[c];
+    float worst = INFINITY;
+    for (int k = 0; k < K; ++k) worst = fminf(worst, n_fin_score[k]);
     // early-stop heuristic with cur_len already advanced: best live sum / (cur_len+1 - prompt)
     const float best_possible = n_run_score[0] / (float)(cur + 1 - 1);
     bool can = false;
@@ -357,7 +389,6 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
       const float w = n_fin_flag[k] ? worst : NEG;
       can = can || (best_possible > w);
     }
-    (void)any_unfinished;
     a.improvable[b] = (improvable && can) ? 1 : 0;
     a.all_hit[b] = allh ? 1 : 0;
   }

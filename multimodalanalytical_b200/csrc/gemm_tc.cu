@@ -13,6 +13,8 @@
 // (128B swizzle), two TMEM accumulator stages so the epilogue of tile i overlaps the mainloop of
 // tile i+1.  The epilogue (bias / GELU / GLU / residual / dropout / split-K accumulate) is shared
 // with the SIMT fp32 GEMM (common.cuh).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -24,6 +26,17 @@ constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int NUM_EPI_WARPS = 16;  // four warps per TMEM lane quarter, each drains a quarter of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -85,7 +98,7 @@ struct Cfg {
   static_assert(BN == 128 || BN == 256, "tile N must be 128 or 256");
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
-  static constexpr uint32_t SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN /*bias*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
 };
 
@@ -105,6 +118,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* sBias = reinterpret_cast<float*>(bars) + 64;  // [BN], 256 bytes past the barrier block start
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -227,16 +241,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int t2 = tile / splits;
       const int n0 = (t2 % tiles_n) * BN;
       const int m0 = (t2 / tiles_n) * BM;
-      mbar_wait(smem_u32(&tfull[acc]), acc_phase);
-      tc_fence_after();
       const long long row = (long long)m0 + q * 32 + lane;
+      const bool row_ok = row < M;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS);
+      const int col0 = n0 + half * COLS;
+      if (KIND >= 0) {
+        // software-pipelined epilogue: bias staged in smem and the first chunk's side inputs fetched while the MMAs
+        // of this tile are still running; chunk c+1's TMEM read and global loads overlap chunk c's math and stores
+        constexpr int NCH = COLS / 16;
+        const bool use_bias = ep.bias != nullptr && KIND != EPI_ACCUM && KIND != EPI_DGELU && KIND != EPI_DGLU && KIND != EPI_DRELU;
+        epi_bar_sync();  // every epilogue warp is done with the previous tile's bias
+        const int et = threadIdx.x - 64;
+        if (use_bias && et < BN) sBias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
+        EpiIn<16> in[2];
+        epi_prefetch<16, KIND>(ep, row, col0, N, row_ok, in[0]);
+        epi_bar_sync();
+        if (lane == 0) mbar_wait(smem_u32(&tfull[acc]), acc_phase);  // one poller per warp
+        __syncwarp();
+        tc_fence_after();
+        uint32_t raw[2][16];
+        if (KIND == EPI_STORE && ep.accumulate == 101) {  // experiment: no TMEM reads, no stores (handshake only)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        tmem_ld16_nowait(t_row, raw[0]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          tmem_wait_ld();
+          if (c + 1 < NCH) {
+            tmem_ld16_nowait(t_row + (uint32_t)((c + 1) * 16), raw[(c + 1) & 1]);
+            epi_prefetch<16, KIND>(ep, row, col0 + (c + 1) * 16, N, row_ok, in[(c + 1) & 1]);
+          }
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
+          if (KIND == EPI_STORE && ep.accumulate == 100) {  // experiment: epilogue without global stores
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sacc += v[j];
+            if (sacc == 123.456f) reinterpret_cast<float*>(ep.out)[0] = sacc;
+            continue;
+          }
+          epi_finish<16, KIND, true>(ep, row, col0 + c * 16, N, row_ok, v, in[c & 1],
+                                     use_bias ? sBias + half * COLS + c * 16 : nullptr);
+        }
+      } else {
+        if (lane == 0) mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+        __syncwarp();
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < COLS; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_row + (uint32_t)c0, v);
-        const int col = n0 + half * COLS + c0;
-        if (row < M && col < N) epilogue_store<16, KIND, true>(ep, row, col, N, v);
+        for (int c0 = 0; c0 < COLS; c0 += 16) {
+          float v[16];
+          tmem_ld16(t_row + (uint32_t)c0, v);
+          const int col = col0 + c0;
+          if (row_ok && col < N) epilogue_store<16, KIND, true>(ep, row, col, N, v);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -557,6 +619,14 @@ extern "C" int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   if (splits < 1) splits = 1;
   if (splits > num_kb) splits = num_kb;
   if (splits > 1 && !(ep->kind == EPI_ACCUM && ep->accumulate == 2)) return MMA_ERR_ARG;
+  // MMA_GEMM_BN=128|256 forces the tile width (experiments)
+  static int forced_bn = -1;
+  if (forced_bn < 0) {
+    const char* e = getenv("MMA_GEMM_BN");
+    forced_bn = e ? atoi(e) : 0;
+  }
+  if (forced_bn == 128) return dispatch<128>(A, lda, a_mn, B, ldb, b_mn, M, N, K, *ep, splits, max_ctas, stream);
+  if (forced_bn == 256 && N >= 256) return dispatch<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, *ep, splits, max_ctas, stream);
   // 128x256 tiles halve the A re-reads from L2; use them when the 256-wide tiling still fills the machine
   const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256) * splits;
   if (N >= 256 && tiles256 >= 120) return dispatch<256>(A, lda, a_mn, B, ldb, b_mn, M, N, K, *ep, splits, max_ctas, stream);
