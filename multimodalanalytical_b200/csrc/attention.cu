@@ -35,6 +35,7 @@ struct Args {
 
 template <typename T, int DH>
 __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(Args a) {
+  pdl_trigger();
   extern __shared__ float sm[];
   float* Ks = sm;                          // [KT][DH+1]
   float* Vs = Ks + KT * (DH + 1);          // [KT][DH+1]
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_fwd_kernel(Args a) {
 //   p_ij = exp(s_ij - lse_i);  dp_ij = dO_i . V_j;  ds_ij = p_ij * (dp_ij * keep_ij - D_i);  dQ_i = scale * sum_j ds_ij K_j
 template <typename T, int DH>
 __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(Args a) {
+  pdl_trigger();
   extern __shared__ float sm[];
   float* Ks = sm;
   float* Vs = Ks + KT * (DH + 1);
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dq_kernel(Args a) {
 //   dV_j = sum_i (p_ij * keep_ij) dO_i;   dK_j = scale * sum_i ds_ij Q_i
 template <typename T, int DH>
 __global__ void __launch_bounds__(NWARP * 32) attn_bwd_dkv_kernel(Args a) {
+  pdl_trigger();
   extern __shared__ float sm[];
   float* Qs = sm;                            // [KT][DH+1]   query tile (pre-scaled)
   float* DOs = Qs + KT * (DH + 1);           // [KT][DH+1]

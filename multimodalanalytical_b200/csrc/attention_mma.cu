@@ -121,6 +121,7 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 // ------------------------------------------------------------------------------------------------ forward
 __global__ void __launch_bounds__(NT) fwd_kernel(Args a) {
+  pdl_trigger();
   __shared__ __align__(128) uint8_t sQ[64 * 128];
   __shared__ __align__(128) uint8_t sK[64 * 128];
   __shared__ __align__(128) uint8_t sV[64 * 128];
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args a) {
 
 // ------------------------------------------------------------------------------------------------ backward: dQ
 __global__ void __launch_bounds__(NT) bwd_dq_kernel(Args a) {
+  pdl_trigger();
   __shared__ __align__(128) uint8_t sQ[64 * 128];
   __shared__ __align__(128) uint8_t sDO[64 * 128];
   __shared__ __align__(128) uint8_t sK[64 * 128];
@@ -329,6 +331,7 @@ __global__ void __launch_bounds__(NT) bwd_dq_kernel(Args a) {
 
 // ------------------------------------------------------------------------------------------------ backward: dK, dV
 __global__ void __launch_bounds__(NT) bwd_dkv_kernel(Args a) {
+  pdl_trigger();
   __shared__ __align__(128) uint8_t sK[64 * 128];
   __shared__ __align__(128) uint8_t sV[64 * 128];
   __shared__ __align__(128) uint8_t sQ[64 * 128];

@@ -128,6 +128,7 @@ __device__ __forceinline__ void key_valid_bits(uint32_t (&bits)[NCH], const unsi
 template <int PACK>
 __global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                                                   const __grid_constant__ CUtensorMap tv, Args a) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];  // no static smem in this kernel: the window starts 1024-aligned
   uint8_t* sQ = smem;               // after S is formed, sQ|sK (32 KB) is reused for P (two 64-key atoms)
   uint8_t* sK = smem + TILE;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtens
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
+  pdl_wait();
   if (threadIdx.x == 0) {
     const uint32_t bar = smem_u32(&bars[0]);
     mbar_expect_tx(bar, 3 * TILE);
@@ -273,6 +275,7 @@ template <int PACK>
 __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                                                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                                                   Args a) {
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];  // no static smem in this kernel: the window starts 1024-aligned
   // layout (ascending): Pd atom 0 | dS atom 0 | dS atom 1 | Q | K | dO | V (= Pd atom 1 once dP has retired)
   uint8_t* sPd0 = smem;
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
   __syncthreads();
   tc_fence_after();
   const uint32_t tm = *tmem_slot;
+  pdl_wait();
   if (threadIdx.x == 0) {
     const uint32_t bar = smem_u32(&bars[0]);
     mbar_expect_tx(bar, 4 * TILE);
@@ -483,11 +487,11 @@ extern "C" int mma_attn_fwd_t5(const void* q, long long ldq, const void* k, long
   if (Lq <= 64 && Lk <= 64) {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    fwd_kernel<2><<<(a.nprob + 1) / 2, 128, smem, stream>>>(tq, tk, tv, a);
+    if (launch_pdl(fwd_kernel<2>, dim3((a.nprob + 1) / 2), dim3(128), smem, stream, tq, tk, tv, a) != cudaSuccess) return MMA_ERR_LAUNCH;
   } else {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    fwd_kernel<1><<<a.nprob, 128, smem, stream>>>(tq, tk, tv, a);
+    if (launch_pdl(fwd_kernel<1>, dim3(a.nprob), dim3(128), smem, stream, tq, tk, tv, a) != cudaSuccess) return MMA_ERR_LAUNCH;
   }
   MMA_CHECK_LAUNCH();
   return MMA_OK;
@@ -517,11 +521,11 @@ extern "C" int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long
   if (Lq <= 64 && Lk <= 64) {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    bwd_kernel<2><<<(a.nprob + 1) / 2, 128, smem, stream>>>(tq, tk, tv, tdo, a);
+    if (launch_pdl(bwd_kernel<2>, dim3((a.nprob + 1) / 2), dim3(128), smem, stream, tq, tk, tv, tdo, a) != cudaSuccess) return MMA_ERR_LAUNCH;
   } else {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    bwd_kernel<1><<<a.nprob, 128, smem, stream>>>(tq, tk, tv, tdo, a);
+    if (launch_pdl(bwd_kernel<1>, dim3(a.nprob), dim3(128), smem, stream, tq, tk, tv, tdo, a) != cudaSuccess) return MMA_ERR_LAUNCH;
   }
   MMA_CHECK_LAUNCH();
   return MMA_OK;

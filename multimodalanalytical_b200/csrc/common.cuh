@@ -56,6 +56,31 @@ struct Epi {
   long long drop_ld;  // logical row width used to index the dropout stream (== N of the fwd GEMM)
 };
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every kernel of the library calls pdl_trigger() first thing: the next kernel in the stream, if it was launched
+// with the programmatic-stream-serialization attribute (the tcgen05 kernels are), may then start its prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) while this one is still running.  Such a kernel calls
+// pdl_wait() before it touches global memory: it returns once all prerequisite grids have completed and flushed.
+// Both are no-ops for plainly launched kernels.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- small numeric helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(bf16 x) { return __bfloat162float(x); }
@@ -393,50 +418,42 @@ __device__ __forceinline__ void epilogue_store(const Epi& ep, long long row, int
 
 // ---- split epilogue for the software-pipelined tcgen05 kernels ---------------------------------------------
 // epi_prefetch issues the global loads an epilogue needs besides the accumulator (residual / saved activations /
-// the running gradient) so they overlap the TMEM read of the same chunk; epi_finish consumes them.  The bias comes
-// from shared memory (staged once per tile).  Semantics are identical to epilogue_store<NV, KIND, FAST>.
-template <int NV>
+// the running gradient) so they overlap the TMEM read of the same chunk; epi_math consumes them and leaves the
+// primary output in v[] and the secondary one (pre-activation copy, GLU gate, d z2) in o2[].  Storing is the
+// caller's business (shared-memory staged, coalesced).  Semantics identical to epilogue_store<NV, KIND, FAST>.
+template <int NV, int KIND>
 struct EpiIn {
   float a[NV];
-  float b[NV];
+  float b[KIND == EPI_DGLU ? NV : 1];
 };
 
 template <int NV, int KIND>
-__device__ __forceinline__ void epi_prefetch(const Epi& ep, long long row, int col, int ncols, bool row_ok, EpiIn<NV>& in) {
+__device__ __forceinline__ void epi_prefetch(const Epi& ep, long long row, int col, int ncols, bool row_ok,
+                                             EpiIn<NV, KIND>& in) {
   const int nvalid = row_ok ? min(NV, ncols - col) : 0;
   if (nvalid <= 0) return;
   if (KIND == EPI_RESID) ld_row_any<NV>(in.a, ep.resid, row * ep.ldr + col, ep.resid_f32, nvalid);
   if (KIND == EPI_DGELU || KIND == EPI_GLU_MUL || KIND == EPI_DGLU || KIND == EPI_DRELU)
     ld_row_any<NV>(in.a, ep.aux, row * ep.lda + col, ep.aux_f32, nvalid);
-  if (KIND == EPI_DGLU) ld_row_any<NV>(in.b, ep.aux2, row * ep.lda2 + col, ep.aux_f32, nvalid);
+  if constexpr (KIND == EPI_DGLU) ld_row_any<NV>(in.b, ep.aux2, row * ep.lda2 + col, ep.aux_f32, nvalid);
   if (KIND == EPI_ACCUM) {
     if (ep.accumulate == 1) ld_row_f32<NV>(in.a, reinterpret_cast<const float*>(ep.out) + row * ep.ldo + col, nvalid);
   }
 }
 
+// returns true when o2[] holds a second output
 template <int NV, int KIND, bool FAST>
-__device__ __forceinline__ void epi_finish(const Epi& ep, long long row, int col, int ncols, bool row_ok, float (&v)[NV],
-                                           EpiIn<NV>& in, const float* bias_s) {
-  const int nvalid = row_ok ? min(NV, ncols - col) : 0;
-  if (nvalid <= 0) return;
+__device__ __forceinline__ bool epi_math(const Epi& ep, long long row, int col, float (&v)[NV], float (&o2)[NV],
+                                         EpiIn<NV, KIND>& in, const float* bias_s) {
   if (KIND == EPI_ACCUM) {
-    float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col;
-    if (ep.accumulate == 2) {
 #pragma unroll
-      for (int j = 0; j < NV; ++j)
-        if (j < nvalid) atomicAdd(o + j, v[j] * ep.alpha);
-    } else {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) v[j] = ep.accumulate == 1 ? fmaf(v[j], ep.alpha, in.a[j]) : v[j] * ep.alpha;
-      st_row_any<NV>(ep.out, row * ep.ldo + col, 1, v, nvalid);
-    }
-    return;
+    for (int j = 0; j < NV; ++j) v[j] = ep.accumulate == 1 ? fmaf(v[j], ep.alpha, in.a[j]) : v[j] * ep.alpha;
+    return false;
   }
   if (KIND == EPI_STORE) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = bias_s ? fmaf(v[j], ep.alpha, bias_s[j]) : v[j] * ep.alpha;
-    st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
-    return;
+    return false;
   }
   if (bias_s && (KIND == EPI_GELU || KIND == EPI_RESID || KIND == EPI_GLU_MUL || KIND == EPI_RELU)) {
 #pragma unroll
@@ -462,13 +479,15 @@ __device__ __forceinline__ void epi_finish(const Epi& ep, long long row, int col
       for (int j = 0; j < NV; ++j) ds[j] = drop_scale1(dkey, e0 + j, thr, inv_keep);
     }
   }
+  bool has2 = false;
   if (KIND == EPI_RELU) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
   } else if (KIND == EPI_GELU) {
-    if (ep.out2) st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, v, nvalid);
+    has2 = ep.out2 != nullptr;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
+      o2[j] = v[j];
       float y = gelu_t<FAST>(v[j]);
       if (drop) y *= ds[j];
       v[j] = y;
@@ -487,23 +506,42 @@ __device__ __forceinline__ void epi_finish(const Epi& ep, long long row, int col
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = in.a[j] > 0.f ? v[j] : 0.f;
   } else if (KIND == EPI_GLU_MUL) {
-    if (ep.out2) st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, v, nvalid);
+    has2 = ep.out2 != nullptr;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
+      o2[j] = v[j];
       float y = gelu_t<FAST>(in.a[j]) * v[j];
       if (drop) y *= ds[j];
       v[j] = y;
     }
-  } else if (KIND == EPI_DGLU) {
+  } else if constexpr (KIND == EPI_DGLU) {
+    has2 = true;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const float da = drop ? v[j] * ds[j] : v[j];
       float g, dg;
       gelu_both<FAST>(in.a[j], g, dg);
       v[j] = da * in.b[j] * dg;
-      in.b[j] = da * g;
+      o2[j] = da * g;
     }
-    st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, in.b, nvalid);
   }
-  st_row_any<NV>(ep.out, row * ep.ldo + col, ep.out_f32, v, nvalid);
+  return has2;
+}
+
+template <int NV, int KIND, bool FAST>
+__device__ __forceinline__ void epi_finish(const Epi& ep, long long row, int col, int ncols, bool row_ok, float (&v)[NV],
+                                           EpiIn<NV, KIND>& in, const float* bias_s) {
+  const int nvalid = row_ok ? min(NV, ncols - col) : 0;
+  if (nvalid <= 0) return;
+  if (KIND == EPI_ACCUM && ep.accumulate == 2) {
+    float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (j < nvalid) atomicAdd(o + j, v[j] * ep.alpha);
+    return;
+  }
+  float o2[NV];
+  const bool has2 = epi_math<NV, KIND, FAST>(ep, row, col, v, o2, in, bias_s);
+  if (has2) st_row_any<NV>(ep.out2, row * ep.ldo2 + col, ep.out_f32, o2, nvalid);
+  st_row_any<NV>(ep.out, row * ep.ldo + col, KIND == EPI_ACCUM ? 1 : ep.out_f32, v, nvalid);
 }

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict
                                                            const float* __restrict__ beta, float eps,
                                                            const float* __restrict__ pos, const int* __restrict__ cur_len,
                                                            float* __restrict__ out, int rows, int d) {
+  pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const int t = *cur_len - 1;
@@ -92,6 +93,7 @@ __device__ __forceinline__ void st8(bf16* p, const float (&x)[8]) {
 // is one coalesced 128-byte line for DH = 64); KPP = 32/G keys are scored per pass; online softmax across passes.
 template <typename T, int DH>
 __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
+  pdl_trigger();
   constexpr int G = DH / 8;
   constexpr int KPP = 32 / G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -222,6 +224,7 @@ struct BeamArgs {
 constexpr int MAXK = 64;  // beams (2K candidates <= 128)
 
 __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
+  pdl_trigger();
   extern __shared__ uint32_t cand[];  // [K*V] ordered keys of accumulated log-probs
   __shared__ float s_lse[MAXK];
   __shared__ unsigned long long s_wkeys[8 * 2 * MAXK];  // per-warp top-2K keys
@@ -440,6 +443,7 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
                                                           int pad_id, int eos_id, const int* __restrict__ cur_len,
                                                           int* __restrict__ seq, unsigned char* __restrict__ unfinished,
                                                           int* __restrict__ next_tok) {
+  pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= R) return;
   const int cur = *cur_len;
@@ -467,7 +471,8 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
   }
 }
 
-__global__ void advance_kernel(int* cur_len) { *cur_len += 1; }
+__global__ void advance_kernel(int* cur_len) {
+  pdl_trigger(); *cur_len += 1; }
 
 template <typename T>
 static int launch_attn(const AttnArgs& a, int dh, cudaStream_t s) {

@@ -12,6 +12,7 @@ template <typename TA, typename TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(const TA* __restrict__ A, long long sam, long long sak,
                                                     const TB* __restrict__ B, long long sbn, long long sbk, int M,
                                                     int N, int K, int k_per_split, Epi ep) {
+  pdl_trigger();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int t = threadIdx.x;

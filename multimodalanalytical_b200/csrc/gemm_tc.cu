@@ -92,13 +92,95 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t tile_addr, int k16) 
   return d;
 }
 
+
+// ---- coalesced epilogue stores -------------------------------------------------------------------------------
+// tcgen05.ld hands every thread one ROW of the accumulator; storing that directly makes each warp-wide store touch
+// 32 different 128-byte lines with 16 bytes each.  Instead each epilogue warp parks its rows in a private,
+// XOR-swizzled [32 rows][128 B] shared-memory tile and writes it out with 8 lanes per row: full, contiguous lines.
+//   mode 0: one bf16 output, 64 columns per staged row     mode 1: one fp32 output, 32 columns per staged row
+//   mode 2: two bf16 outputs, 32 + 32 columns per staged row
+__device__ __forceinline__ uint4 pack8_bf16(const float* x) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+  __nv_bfloat162 c = __floats2bfloat162_rn(x[4], x[5]), d = __floats2bfloat162_rn(x[6], x[7]);
+  uint4 u;
+  u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+  u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+  return u;
+}
+__device__ __forceinline__ void stage_put(uint8_t* st, int lane, int chunk, uint4 v) {
+  *reinterpret_cast<uint4*>(st + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
+}
+__device__ __forceinline__ void stage_chunk(uint8_t* st, int lane, int mode, int cs, const float (&o1)[16],
+                                            const float (&o2)[16]) {
+  if (mode == 0) {
+    stage_put(st, lane, cs * 2, pack8_bf16(o1));
+    stage_put(st, lane, cs * 2 + 1, pack8_bf16(o1 + 8));
+  } else if (mode == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      stage_put(st, lane, cs * 4 + i, make_uint4(__float_as_uint(o1[4 * i]), __float_as_uint(o1[4 * i + 1]),
+                                                 __float_as_uint(o1[4 * i + 2]), __float_as_uint(o1[4 * i + 3])));
+  } else {
+    stage_put(st, lane, cs * 2, pack8_bf16(o1));
+    stage_put(st, lane, cs * 2 + 1, pack8_bf16(o1 + 8));
+    stage_put(st, lane, 4 + cs * 2, pack8_bf16(o2));
+    stage_put(st, lane, 4 + cs * 2 + 1, pack8_bf16(o2 + 8));
+  }
+}
+// write the staged rows out: row0 = first tile row of this warp, colbase = first staged column, ncols = columns staged
+__device__ __forceinline__ void stage_flush(const uint8_t* st, int lane, int mode, const Epi& ep, long long row0,
+                                            int colbase, int ncols, int M, int N) {
+#pragma unroll
+  for (int p = 0; p < 8; ++p) {
+    const int r = p * 4 + (lane >> 3), ch = lane & 7;
+    const long long row = row0 + r;
+    const uint4 val = *reinterpret_cast<const uint4*>(st + r * 128 + ((ch ^ (r & 7)) << 4));
+    if (row >= M) continue;
+    if (mode == 1) {
+      const int c = ch * 4;
+      if (c >= ncols) continue;
+      const int col = colbase + c;
+      float* dst = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col;
+      if (col + 4 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        *reinterpret_cast<uint4*>(dst) = val;
+      } else {
+        const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (col + j < N) dst[j] = __uint_as_float(w[j]);
+      }
+    } else {
+      const int which = mode == 2 ? (ch >> 2) : 0;
+      const int c = (mode == 2 ? (ch & 3) : ch) * 8;
+      if (c >= ncols) continue;
+      const int col = colbase + c;
+      bf16* dst = reinterpret_cast<bf16*>(which ? ep.out2 : ep.out) + row * (which ? ep.ldo2 : ep.ldo) + col;
+      if (col + 8 <= N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        *reinterpret_cast<uint4*>(dst) = val;
+      } else {
+        const bf16* e = reinterpret_cast<const bf16*>(&val);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col + j < N) dst[j] = e[j];
+      }
+    }
+  }
+}
+
+// Staged (coalesced) epilogue stores cost one pipeline stage of shared memory.  Measured on B200 (scripts/gemm_bench.py):
+// they help the plain-store K=512 products (58 -> 49 us) but lose on the arithmetic-heavy epilogues and on every
+// large-K product (one stage less), and the C2 training step as a whole got slower - so they are off.
+constexpr bool kStagedStores = false;
+
 template <int BN>
 struct Cfg {
-  static constexpr int STAGES = BN <= 128 ? 6 : 4;
+  static constexpr int STAGES = kStagedStores ? (BN <= 128 ? 4 : 3) : (BN <= 128 ? 6 : 4);
   static_assert(BN == 128 || BN == 256, "tile N must be 128 or 256");
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
-  static constexpr uint32_t SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * BN /*bias*/;
+  static constexpr uint32_t STAGE_BYTES = 32 * 128;  // per epilogue warp: [32 rows][128 B]
+  static constexpr uint32_t SMEM = STAGES * (A_BYTES + B_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/ +
+                                   4 * BN /*bias*/ + (kStagedStores ? NUM_EPI_WARPS * STAGE_BYTES : 0);
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
 };
 
@@ -106,6 +188,7 @@ template <int BN, bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
                int splits, Epi ep) {
+  pdl_trigger();
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -119,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* sBias = reinterpret_cast<float*>(bars) + 64;  // [BN], 256 bytes past the barrier block start
+  uint8_t* sStage = reinterpret_cast<uint8_t*>(sBias + BN);  // [NUM_EPI_WARPS][32 rows][128 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -146,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   const int tiles_m = (M + BM - 1) / BM;
   const int tiles_n = (N + BN - 1) / BN;
@@ -253,20 +338,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epi_bar_sync();  // every epilogue warp is done with the previous tile's bias
         const int et = threadIdx.x - 64;
         if (use_bias && et < BN) sBias[et] = (n0 + et < N) ? ep.bias[n0 + et] : 0.f;
-        EpiIn<16> in[2];
+        EpiIn<16, KIND> in[2];
         epi_prefetch<16, KIND>(ep, row, col0, N, row_ok, in[0]);
         epi_bar_sync();
         if (lane == 0) mbar_wait(smem_u32(&tfull[acc]), acc_phase);  // one poller per warp
         __syncwarp();
         tc_fence_after();
+        // store mode: 0 one bf16 output, 1 one fp32 output, 2 two bf16 outputs, 3 direct (atomics / fp32 pairs)
+        const bool dual = (KIND == EPI_DGLU) || ((KIND == EPI_GELU || KIND == EPI_GLU_MUL) && ep.out2 != nullptr);
+        const bool f32out = KIND == EPI_ACCUM ? true : ep.out_f32 != 0;
+        const int mode = (!kStagedStores || (KIND == EPI_ACCUM && ep.accumulate == 2)) ? 3
+                         : dual ? (f32out ? 3 : 2) : (f32out ? 1 : 0);
+        const int group = mode == 0 ? (COLS / 16 < 4 ? COLS / 16 : 4) : 2;  // chunks per staged row
+        uint8_t* st = sStage + (warp - 2) * C::STAGE_BYTES;
+        const long long row0 = (long long)m0 + q * 32;
         uint32_t raw[2][16];
-        if (KIND == EPI_STORE && ep.accumulate == 101) {  // experiment: no TMEM reads, no stores (handshake only)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          continue;
-        }
         tmem_ld16_nowait(t_row, raw[0]);
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
@@ -278,15 +364,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
-          if (KIND == EPI_STORE && ep.accumulate == 100) {  // experiment: epilogue without global stores
-            float sacc = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sacc += v[j];
-            if (sacc == 123.456f) reinterpret_cast<float*>(ep.out)[0] = sacc;
-            continue;
+          const float* bs = use_bias ? sBias + half * COLS + c * 16 : nullptr;
+          if (mode == 3) {
+            epi_finish<16, KIND, true>(ep, row, col0 + c * 16, N, row_ok, v, in[c & 1], bs);
+          } else {
+            float o2[16];
+            epi_math<16, KIND, true>(ep, row, col0 + c * 16, v, o2, in[c & 1], bs);
+            const int cs = c % group;
+            stage_chunk(st, lane, mode, cs, v, o2);
+            if (cs == group - 1) {
+              __syncwarp();
+              stage_flush(st, lane, mode, ep, row0, col0 + (c - cs) * 16, group * 16, M, N);
+              __syncwarp();
+            }
           }
-          epi_finish<16, KIND, true>(ep, row, col0 + c * 16, N, row_ok, v, in[c & 1],
-                                     use_bias ? sBias + half * COLS + c * 16 : nullptr);
         }
       } else {
         if (lane == 0) mbar_wait(smem_u32(&tfull[acc]), acc_phase);
@@ -345,8 +436,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, 
   const int total = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   int grid = total < num_sms() ? total : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, NUM_THREADS, C::SMEM, stream>>>(tmA, tmB, M, N, K, splits, ep);
-  MMA_CHECK_LAUNCH();
+  if (launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, tmA, tmB, M, N, K, splits, ep) != cudaSuccess)
+    return MMA_ERR_LAUNCH;
   return MMA_OK;
 }
 
@@ -416,6 +507,7 @@ constexpr uint32_t WG_ONES_BYTES = 16 * 128;
 constexpr uint32_t WG_SMEM = WG_STAGES * (WG_A_BYTES + WG_B_BYTES) + WG_ONES_BYTES + 1024 + 256;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_group_kernel(const __grid_constant__ WgGroup grp) {
+  pdl_trigger();
   constexpr int STAGES = WG_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -450,6 +542,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_group_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   auto locate = [&](int tile, int& g, int& m0, int& n0) {
     g = 0;
@@ -603,8 +696,8 @@ extern "C" int mma_wgrad_group(int count, const void* const* dy, const long long
     attr_set = true;
   }
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  wgrad_group_kernel<<<grid, NUM_THREADS, WG_SMEM, stream>>>(grp);
-  MMA_CHECK_LAUNCH();
+  if (launch_pdl(wgrad_group_kernel, dim3(grid), dim3(NUM_THREADS), WG_SMEM, stream, grp) != cudaSuccess)
+    return MMA_ERR_LAUNCH;
   return MMA_OK;
 }
 

@@ -42,6 +42,7 @@ __device__ __forceinline__ void st4_any(void* p, long long i, int f32, float4 v)
 // ---------------------------------------------------------------------------------------------
 __global__ void gather_rows_kernel(const long long* __restrict__ ids, const float* __restrict__ scale,
                                    const float* __restrict__ table, float* __restrict__ out, int rows, int d) {
+  pdl_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* src = table + ids[warp] * (long long)d;
@@ -62,6 +63,7 @@ __global__ void gather_rows_kernel(const long long* __restrict__ ids, const floa
 __global__ void scatter_add_rows_kernel(const long long* __restrict__ ids, const float* __restrict__ scale,
                                         const float* __restrict__ g, float* __restrict__ dtable, int rows, int d,
                                         long long pad_idx) {
+  pdl_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const long long id = ids[warp];
@@ -88,6 +90,7 @@ struct LnFwdArgs {
 
 template <int NI>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs a) {
+  pdl_trigger();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.rows) return;
   const long long r = warp;
@@ -164,6 +167,7 @@ struct LnBwdArgs {
 
 template <int NI>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdArgs a) {
+  pdl_trigger();
   // warp-private dgamma / dbeta accumulators (plain read-modify-write, no atomics): [warp][2][NI*128]
   extern __shared__ float s_acc[];
   const int d = a.d;
@@ -286,6 +290,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, long long ld, float* __restrict__ out,
                                                      int rows, int cols, int rows_per_block) {
+  pdl_trigger();
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -305,6 +310,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, l
 
 // fp32 -> bf16 copy (weights, inputs)
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  pdl_trigger();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     Vec4<bf16>::st(out + i, *reinterpret_cast<const float4*>(in + i));
@@ -313,6 +319,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
   }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __bfloat162float(in[i]);
 }

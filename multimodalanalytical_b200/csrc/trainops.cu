@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
                                                       const long long* __restrict__ labels, int rows, int V,
                                                       float smoothing, long long ignore_index,
                                                       float* __restrict__ row_loss, float* __restrict__ row_lse) {
+  pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float* x = logits + (long long)r * ld;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_loss,
                                                          const long long* __restrict__ labels, int rows,
                                                          long long ignore_index, float* __restrict__ out) {
+  pdl_trigger();
   __shared__ float ssum[1024];
   __shared__ float scnt[1024];
   float s = 0.f, n = 0.f;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
                                                      const float* __restrict__ stats, float gscale, int rows, int V,
                                                      float smoothing, long long ignore_index, T* __restrict__ dlogits,
                                                      long long ldd) {
+  pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const long long y = labels[r];
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const float* __restrict__ l
 // stage 1: per-block partial sums of squares;  stage 2: one block finishes -> norm[0] = ||g||_2
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n,
                                                             float* __restrict__ partial) {
+  pdl_trigger();
   __shared__ float red[8];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -126,6 +130,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 }
 __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partial, int nblocks,
                                                           float* __restrict__ norm) {
+  pdl_trigger();
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < nblocks; i += 256) s += partial[i];
@@ -144,6 +149,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
                                                    float* __restrict__ v, bf16* __restrict__ pb, long long n,
                                                    const float* __restrict__ hyper, const float* __restrict__ norm,
                                                    int decoupled, int zero_grad) {
+  pdl_trigger();
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
   const float bc1 = hyper[5], bc2 = hyper[6], max_norm = hyper[7], gs = hyper[8];
   float clip = gs;
@@ -170,7 +176,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
   }
 }
 
-__global__ void add_u64_kernel(unsigned long long* p, unsigned long long inc) { *p += inc; }
+__global__ void add_u64_kernel(unsigned long long* p, unsigned long long inc) {
+  pdl_trigger(); *p += inc; }
 
 }  // namespace trainops
 
