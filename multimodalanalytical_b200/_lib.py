@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 

@@ -187,8 +187,12 @@ struct Cfg {
 template <int BN, bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               int splits, Epi ep) {
+               int splits_dbg, Epi ep) {
   pdl_trigger();
+  // diagnostics (MMA_GEMM_DBG, scripts/gemm_bench.py): bit0 epilogue skips its global loads / stores, bit1 no TMA
+  // loads and no MMAs (epilogue alone), bit2 TMA loads but no MMAs.  Zero in production.
+  const int splits = splits_dbg & 0xFFFF;
+  const int dbg = splits_dbg >> 16;
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -242,7 +246,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ================= TMA producer =================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total && !(dbg & 2); tile += gridDim.x) {
         const int split = tile % splits;
         const int t2 = tile / splits;
         const int n0 = (t2 % tiles_n) * BN;
@@ -292,14 +296,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1 && !(dbg & 2); ++kb) {
           mbar_wait(smem_u32(&full[stage]), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * C::A_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * C::B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            tc_mma_bf16(d_tmem, make_smem_desc<A_MN>(a_addr, k), make_smem_desc<B_MN>(b_addr, k), idesc,
+            if (!(dbg & 4)) tc_mma_bf16(d_tmem, make_smem_desc<A_MN>(a_addr, k), make_smem_desc<B_MN>(b_addr, k), idesc,
                         (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(smem_u32(&empty[stage]));  // smem slot is free once these MMAs retire
@@ -327,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = (t2 % tiles_n) * BN;
       const int m0 = (t2 / tiles_n) * BM;
       const long long row = (long long)m0 + q * 32 + lane;
-      const bool row_ok = row < M;
+      const bool row_ok = row < M && !(dbg & 1);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS);
       const int col0 = n0 + half * COLS;
       if (KIND >= 0) {
@@ -436,7 +440,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, 
   const int total = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * splits;
   int grid = total < num_sms() ? total : num_sms();
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  if (launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, tmA, tmB, M, N, K, splits, ep) != cudaSuccess)
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("MMA_GEMM_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  if (launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, tmA, tmB, M, N, K, splits | (dbg << 16), ep) != cudaSuccess)
     return MMA_ERR_LAUNCH;
   return MMA_OK;
 }
@@ -701,6 +710,10 @@ extern "C" int mma_wgrad_group(int count, const void* const* dy, const long long
   return MMA_OK;
 }
 
+extern "C" int mma_gemm2_eligible(int a_mn, int b_mn, int M, int N, int K, const Epi* ep, int splits);
+extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long long ldb, int b_mn, int M, int N, int K,
+                              const Epi* ep, cudaStream_t stream);
+
 // C[M,N] = epi(A_op * B_op^T).  a_mn / b_mn: 0 = operand memory is [rows, K] (K-major), 1 = [K, rows].
 // lda / ldb: row pitch of the operand's memory in elements.  splits > 1 splits the K loop across CTAs
 // (requires ep->kind == EPI_ACCUM with accumulate == 2).  max_ctas <= 0: one CTA per SM.
@@ -712,6 +725,9 @@ extern "C" int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void*
   if (splits < 1) splits = 1;
   if (splits > num_kb) splits = num_kb;
   if (splits > 1 && !(ep->kind == EPI_ACCUM && ep->accumulate == 2)) return MMA_ERR_ARG;
+  // large products: CTA-pair kernel (256 x 256 tiles, TMA epilogue), gemm_tc2.cu
+  if (max_ctas <= 0 && mma_gemm2_eligible(a_mn, b_mn, M, N, K, ep, splits))
+    return mma_gemm2_bf16(A, lda, B, ldb, b_mn, M, N, K, ep, stream);
   // MMA_GEMM_BN=128|256 forces the tile width (experiments)
   static int forced_bn = -1;
   if (forced_bn < 0) {

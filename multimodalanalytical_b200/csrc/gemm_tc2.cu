@@ -1,0 +1,627 @@
+// 2-CTA (cta_group::2) tcgen05 GEMM for the large products of the training step.
+//
+//   C[M,N] = epilogue( A[M,K] * B_op[N,K]^T )      bf16 operands, fp32 accumulate in TMEM
+//
+// A CTA pair (a 2x1 cluster on one TPC) owns a 256 x 256 output tile: each CTA stages its own 128 rows of A and HALF
+// of the B tile (128 of the 256 columns) per k-step, the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which
+// reads both halves, and every CTA drains its own 128 x 256 accumulator.  Against the single-CTA 128 x 256 kernel
+// (gemm_tc.cu) this cuts the L2 -> shared-memory operand traffic by a third (32 KB instead of 48 KB per CTA and
+// k-step) - the K = 512 products of the d = 512 model are bound by exactly that traffic - and frees ~96 KB of shared
+// memory for the epilogue.
+//
+// Epilogue: no per-thread global loads / stores.  tcgen05.ld hands each thread one accumulator ROW, so direct global
+// accesses touch 32 different lines per warp instruction (measured: the epilogue, not the MMA, bounded every K = 512
+// product).  Here each epilogue warp owns three private 2 KB shared-memory boxes ([32 rows][64 bytes], 64-byte
+// swizzle): side inputs (residual / saved pre-activation / running gradient) arrive by TMA loads prefetched one box
+// ahead, results leave by TMA stores (cp.async.bulk.tensor ... bulk_group).  The 16 epilogue warps never synchronise
+// with each other.
+//
+// Roles per CTA (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only; both CTAs allocate
+// TMEM), warps 2..17 = epilogue.  Two TMEM accumulator stages (2 x 256 columns) overlap epilogue and mainloop.
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace tc2 {
+using namespace tma;
+
+constexpr int BM = 128;      // rows per CTA; the pair tile is 2 * BM x BN
+constexpr int BN = 256;      // pair-tile columns (each CTA loads BN / 2 rows of B)
+constexpr int BK = 64;       // 64 bf16 = one 128-byte swizzle row
+constexpr int STAGES = 4;
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr uint32_t A_BYTES = BM * BK * 2;
+constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+constexpr uint32_t BOX_BYTES = 32 * 64;                 // one epilogue box: 32 rows x 64 bytes
+constexpr uint32_t EPI_WARP_BYTES = 3 * BOX_BYTES;
+constexpr uint32_t BAR_BYTES = 512;
+constexpr uint32_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + NUM_EPI_WARPS * EPI_WARP_BYTES + BAR_BYTES;
+static_assert(SMEM <= 232448, "shared memory budget");
+
+// ---- PTX wrappers that only this kernel needs -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of one CTA of a pair: data lands in this CTA's shared memory, the bytes are counted on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of the pair arrives on the mbarrier at this shared-memory offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, 128B swizzle (same layouts as gemm_tc.cu)
+template <bool MN_MAJOR>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t tile_addr, int k16) {
+  uint32_t addr, lbo, sbo;
+  if (!MN_MAJOR) {
+    addr = tile_addr + (uint32_t)k16 * 32u;
+    lbo = 16;
+    sbo = 1024;
+  } else {
+    addr = tile_addr + (uint32_t)k16 * 2048u;
+    lbo = BK * 128;
+    sbo = 1024;
+  }
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- epilogue math on one 16-column chunk of one row ------------------------------------------------------------
+// Semantics identical to epilogue_store<16, KIND, true> (common.cuh); the dropout key / threshold are hoisted.
+struct DropCtx {
+  bool on;
+  uint32_t thr, key;
+  float inv_keep;
+};
+template <int KIND>
+__device__ __forceinline__ void chunk_math(const Epi& ep, const DropCtx& dc, long long row, int col, float (&v)[16],
+                                           float (&o2)[16], const float (&in)[16], const float (&bv)[16], bool has_bias) {
+  if (KIND == EPI_ACCUM) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = ep.accumulate == 1 ? fmaf(v[j], ep.alpha, in[j]) : v[j] * ep.alpha;
+    return;
+  }
+  if (KIND == EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = has_bias ? fmaf(v[j], ep.alpha, bv[j]) : v[j] * ep.alpha;
+    return;
+  }
+  if (has_bias && (KIND == EPI_GELU || KIND == EPI_RESID)) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] += bv[j];
+  }
+  float ds[16];
+  if (dc.on) {
+    const uint32_t e0 = (uint32_t)((unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)col);
+    if ((e0 & 1u) == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const uint32_t r = drop_pair(dc.key, (e0 + j) >> 1);
+        ds[j] = (r & 0xFFFFu) >= dc.thr ? dc.inv_keep : 0.f;
+        ds[j + 1] = (r >> 16) >= dc.thr ? dc.inv_keep : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ds[j] = drop_scale1(dc.key, e0 + j, dc.thr, dc.inv_keep);
+    }
+  }
+  if (KIND == EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      o2[j] = v[j];
+      float y = gelu_t<true>(v[j]);
+      if (dc.on) y *= ds[j];
+      v[j] = y;
+    }
+  } else if (KIND == EPI_RESID) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = in[j] + (dc.on ? v[j] * ds[j] : v[j]);
+  } else if (KIND == EPI_DGELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float y = v[j] * dgelu_t<true>(in[j]);
+      if (dc.on) y *= ds[j];
+      v[j] = y;
+    }
+  }
+}
+
+// 16-byte piece `k` (0..3) of row `lane` inside a [32][64 B] box; swz = 1: CU_TENSOR_MAP_SWIZZLE_64B
+__device__ __forceinline__ uint32_t box_off(int lane, int k, int swz) {
+  return (uint32_t)(lane * 64 + ((k ^ (swz ? ((lane >> 1) & 3) : 0)) << 4));
+}
+
+// IO32: side input and outputs are fp32 (16 columns per box); otherwise bf16 (32 columns per box)
+template <bool B_MN, int KIND, bool IO32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+             const __grid_constant__ CUtensorMap tmIn, int M, int N, int K, int flags, Epi ep) {
+  pdl_trigger();
+  // flags: bit0 epilogue boxes use the 64-byte swizzle; diagnostics (MMA_GEMM_DBG): bit8 epilogue skips TMA loads /
+  // stores, bit9 no operand loads and no MMAs, bit10 operand loads but no MMAs
+  const int swz = flags & 1;
+  const int dbg = flags >> 8;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint8_t* sEpi = sB + STAGES * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + NUM_EPI_WARPS * EPI_WARP_BYTES);
+  uint64_t* full = bars;                       // [STAGES]  (only the leader's are used)
+  uint64_t* empty = bars + STAGES;             // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;         // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;    // [2]       (only the leader's are used)
+  uint64_t* inbar = bars + 2 * STAGES + 4;     // [NUM_EPI_WARPS][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 2 * NUM_EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmOut)) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&full[i]), 1);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull[i]), 1);
+      mbar_init(smem_u32(&tempty[i]), 2 * NUM_EPI_WARPS);  // the epilogue warps of BOTH CTAs
+    }
+    for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) mbar_init(smem_u32(&inbar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated, before any cross-CTA arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
+
+  const int tiles_n = (N + BN - 1) / BN;
+  const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
+  const int total = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0 && !(dbg & 2)) {
+      // ================= TMA producer (both CTAs) =================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total; tile += npairs) {
+        const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
+        const int nb0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full[stage]);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + B_BYTES));  // both CTAs' bytes land on this barrier
+          const uint32_t fb = mapa(fb_local, 0);
+          const uint32_t a_dst = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_dst = smem_u32(sB + stage * B_BYTES);
+          tma_load_2d_2sm(a_dst, &tmA, fb, kb * BK, m0);
+          if (!B_MN) {
+            tma_load_2d_2sm(b_dst, &tmB, fb, kb * BK, nb0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < (BN / 2) / 64; ++a) tma_load_2d_2sm(b_dst + a * (BK * 128), &tmB, fb, nb0 + a * 64, kb * BK);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ================= MMA issuer (one thread of the leader CTA) =================
+      // instruction descriptor: c=f32 [4,6), a=bf16 [7,10), b=bf16 [10,13), b_major bit16, N>>3 [17,23), M>>4 [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total; tile += npairs) {
+        mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb && !(dbg & 2); ++kb) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            if (!(dbg & 4))
+              tc_mma2_bf16(d_tmem, make_smem_desc<false>(a_addr, k), make_smem_desc<B_MN>(b_addr, k), idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit2_mc(smem_u32(&empty[stage]));  // frees the slot in both CTAs once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit2_mc(smem_u32(&tfull[acc]));  // accumulator complete -> epilogue warps of both CTAs
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (TMEM -> registers -> shared boxes -> TMA store) =================
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quarter this warp may read: rows [32 q, 32 q + 32) of the CTA tile
+    const int s = ew >> 2;    // 64-column slice of the tile
+    constexpr int CPB = IO32 ? 1 : 2;        // 16-column chunks per box
+    constexpr int NBOX = 4 / CPB;            // boxes per tile and warp
+    constexpr int BOXCOLS = 16 * CPB;
+    constexpr bool IN_KIND = KIND == EPI_RESID || KIND == EPI_DGELU || KIND == EPI_ACCUM;
+    const bool has_in = IN_KIND && (KIND != EPI_ACCUM || ep.accumulate == 1) && !(dbg & 1);
+    const bool has_out2 = KIND == EPI_GELU && ep.out2 != nullptr;
+    const bool has_bias = ep.bias != nullptr && (KIND == EPI_STORE || KIND == EPI_GELU || KIND == EPI_RESID);
+    uint8_t* myb = sEpi + ew * EPI_WARP_BYTES;
+    // box roles: kinds with a side input: [0], [1] = input ring, [2] = output; otherwise [0] = output, [1] = output 2
+    const uint32_t b_in0 = smem_u32(myb), b_out = smem_u32(myb + (IN_KIND ? 2 : 0) * BOX_BYTES);
+    const uint32_t b_out2 = smem_u32(myb + BOX_BYTES);
+    const uint32_t ibar0 = smem_u32(&inbar[2 * ew]);
+    const uint32_t tempty_leader0 = mapa(smem_u32(&tempty[0]), 0);
+
+    DropCtx dc;
+    dc.on = ep.p_drop > 0.0f && (KIND == EPI_GELU || KIND == EPI_RESID || KIND == EPI_DGELU);
+    dc.thr = dc.on ? drop_threshold(ep.p_drop) : 0u;
+    dc.inv_keep = dc.on ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
+    dc.key = dc.on ? drop_key(ep.seed, ep.site) : 0u;
+
+    // coordinates of this warp's rows / columns in tile `tile`
+    auto rows_of = [&](int tile) { return (tile / tiles_n) * (2 * BM) + (int)rank * BM + q * 32; };
+    auto cols_of = [&](int tile) { return (tile % tiles_n) * BN + s * 64; };
+    // side-input boxes: load number n goes to ring slot n & 1 and completes phase (n >> 1) & 1 of that slot's
+    // barrier.  Boxes entirely outside the output (tail rows / columns) are neither loaded nor waited for, so only
+    // live boxes are counted; every lane keeps the same counters.
+    uint32_t issued = 0, consumed = 0;
+    auto issue_in = [&](int tile, int box) {
+      const int r0 = rows_of(tile), c = cols_of(tile) + box * BOXCOLS;
+      if (r0 >= M || c >= N) return;
+      if (lane == 0) {
+        const uint32_t bar = ibar0 + (issued & 1u) * 8u;
+        mbar_expect_tx(bar, BOX_BYTES);
+        tma_load_2d(b_in0 + (issued & 1u) * BOX_BYTES, &tmIn, bar, c, r0);
+      }
+      ++issued;
+    };
+    if (has_in && pair < total) issue_in(pair, 0);
+
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total; tile += npairs) {
+      const int r0 = rows_of(tile);
+      const int c0 = cols_of(tile);
+      const long long row = (long long)r0 + lane;
+      // this warp's 64 bias values, two per lane (read back with shuffles)
+      float b_lo = 0.f, b_hi = 0.f;
+      if (has_bias) {
+        if (c0 + lane < N) b_lo = ep.bias[c0 + lane];
+        if (c0 + 32 + lane < N) b_hi = ep.bias[c0 + 32 + lane];
+      }
+      mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + s * 64);
+      uint32_t raw[2][16];
+      tmem_ld16_nowait(t_row, raw[0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int box = c / CPB;
+        const bool first = (c % CPB) == 0, last = (c % CPB) == CPB - 1;
+        const int bcol = c0 + box * BOXCOLS;            // first column of this box
+        const bool live = r0 < M && bcol < N && !(dbg & 1);  // warp-uniform: the box touches the output at all
+        if (first && has_in) {
+          __syncwarp();  // every lane is done reading the ring slot the next load overwrites
+          if (box + 1 < NBOX) issue_in(tile, box + 1);
+          else if (tile + npairs < total) issue_in(tile + npairs, 0);
+          if (live) mbar_wait(ibar0 + (consumed & 1u) * 8u, (consumed >> 1) & 1u);
+        }
+        tmem_wait_ld();
+        if (c + 1 < 4) {
+          tmem_ld16_nowait(t_row + (uint32_t)((c + 1) * 16), raw[(c + 1) & 1]);
+        } else {
+          // the accumulator stage is drained: hand it back to the MMA issuer (leader CTA)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader0 + (uint32_t)acc * 8u);
+        }
+        float v[16], o2[16], in[16], bv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
+        if (has_in && live) {
+          const uint8_t* ib = myb + (consumed & 1u) * BOX_BYTES;
+          if (IO32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float4 f = *reinterpret_cast<const float4*>(ib + box_off(lane, k, swz));
+              in[4 * k] = f.x; in[4 * k + 1] = f.y; in[4 * k + 2] = f.z; in[4 * k + 3] = f.w;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint4 u = *reinterpret_cast<const uint4*>(ib + box_off(lane, 2 * (c % CPB) + k, swz));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                const float2 f = __bfloat1622float2(h[w]);
+                in[8 * k + 2 * w] = f.x;
+                in[8 * k + 2 * w + 1] = f.y;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) in[j] = 0.f;
+        }
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bv[j] = __shfl_sync(0xffffffffu, c < 2 ? b_lo : b_hi, (16 * (c & 1) + j) & 31);
+        }
+        chunk_math<KIND>(ep, dc, row, c0 + c * 16, v, o2, in, bv, has_bias);
+        if (first) {
+          // the TMA store that last read the output box(es) must have finished reading shared memory
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
+        if (IO32) {
+          uint8_t* ob = myb + (IN_KIND ? 2 : 0) * BOX_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<float4*>(ob + box_off(lane, k, swz)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        } else {
+          uint8_t* ob = myb + (IN_KIND ? 2 : 0) * BOX_BYTES;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            *reinterpret_cast<uint4*>(ob + box_off(lane, 2 * (c % CPB) + k, swz)) =
+                make_uint4(pack2_bf16(v[8 * k], v[8 * k + 1]), pack2_bf16(v[8 * k + 2], v[8 * k + 3]),
+                           pack2_bf16(v[8 * k + 4], v[8 * k + 5]), pack2_bf16(v[8 * k + 6], v[8 * k + 7]));
+          if (has_out2) {
+            uint8_t* ob2 = myb + BOX_BYTES;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              *reinterpret_cast<uint4*>(ob2 + box_off(lane, 2 * (c % CPB) + k, swz)) =
+                  make_uint4(pack2_bf16(o2[8 * k], o2[8 * k + 1]), pack2_bf16(o2[8 * k + 2], o2[8 * k + 3]),
+                             pack2_bf16(o2[8 * k + 4], o2[8 * k + 5]), pack2_bf16(o2[8 * k + 6], o2[8 * k + 7]));
+          }
+        }
+        if (last) {
+          fence_async_smem();  // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0 && live) {
+            tma_store_2d(&tmOut, b_out, bcol, r0);
+            if (has_out2) tma_store_2d(&tmOut2, b_out2, bcol, r0);
+            bulk_commit();
+          }
+          if (has_in && live) ++consumed;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits while its peer may still signal its barriers or read its operand tiles
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <bool B_MN, int KIND, bool IO32>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
+                  const CUtensorMap& tmIn, int M, int N, int K, int flags, const Epi& ep, cudaStream_t stream) {
+  auto kern = gemm2_kernel<B_MN, KIND, IO32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return MMA_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int total = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  // persistent grid = the CTA pairs that can be co-resident (a GPC with an odd SM count strands one SM)
+  static int max_pairs = 0;
+  if (!max_pairs) {
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(2 * (num_sms() / 2));
+    q.blockDim = dim3(NUM_THREADS);
+    q.dynamicSmemBytes = SMEM;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) n = num_sms() / 2;
+    max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+    if (getenv("MMA_GEMM2_VERBOSE")) fprintf(stderr, "[gemm2] co-resident CTA pairs: %d\n", n);
+  }
+  int pairs = max_pairs;
+  if (total < pairs) pairs = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;  // the cluster shape is a compile-time attribute of the kernel (__cluster_dims__)
+  if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmOut2, tmIn, M, N, K, flags, ep) != cudaSuccess) return MMA_ERR_LAUNCH;
+  return MMA_OK;
+}
+
+}  // namespace tc2
+
+// Which products go to the pair kernel: A K-major, a supported epilogue with homogeneous I/O types, TMA-compatible
+// output / side-input pitches, and enough 256 x 256 tiles to fill the 74 CTA pairs reasonably.
+extern "C" int mma_gemm2_eligible(int a_mn, int b_mn, int M, int N, int K, const Epi* ep, int splits) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MMA_GEMM2");
+    enabled = e ? atoi(e) : 1;
+  }
+  if (!enabled || a_mn || splits > 1 || !ep) return 0;
+  auto ok16 = [](const void* p, long long ld, int f32) {
+    return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ((ld * (f32 ? 4 : 2)) & 15) == 0;
+  };
+  const int k = ep->kind;
+  // instantiated: forward STORE (bf16 / fp32), GELU (bf16), RESID (bf16 / fp32); dgrad STORE (bf16), DGELU (bf16), ACCUM
+  if (b_mn ? !(k == EPI_STORE || k == EPI_DGELU || k == EPI_ACCUM) : !(k == EPI_STORE || k == EPI_GELU || k == EPI_RESID))
+    return 0;
+  if (b_mn && (k == EPI_STORE || k == EPI_DGELU) && ep->out_f32) return 0;
+  if (k == EPI_STORE) {
+    if (!ok16(ep->out, ep->ldo, ep->out_f32)) return 0;
+  } else if (k == EPI_GELU) {
+    if (ep->out_f32 || !ok16(ep->out, ep->ldo, 0)) return 0;
+    if (ep->out2 && !ok16(ep->out2, ep->ldo2, 0)) return 0;
+  } else if (k == EPI_RESID) {
+    if (ep->out_f32 != ep->resid_f32 || !ok16(ep->out, ep->ldo, ep->out_f32) || !ok16(ep->resid, ep->ldr, ep->resid_f32))
+      return 0;
+  } else if (k == EPI_DGELU) {
+    if (ep->out_f32 != ep->aux_f32 || !ok16(ep->out, ep->ldo, ep->out_f32) || !ok16(ep->aux, ep->lda, ep->aux_f32)) return 0;
+  } else if (k == EPI_ACCUM) {
+    if (ep->accumulate == 2 || !ok16(ep->out, ep->ldo, 1)) return 0;
+  } else {
+    return 0;
+  }
+  if (N < 256 || M < 512) return 0;
+  const long long tiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
+  return tiles >= 48;
+}
+
+extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long long ldb, int b_mn, int M, int N, int K,
+                              const Epi* ep, cudaStream_t stream) {
+  using namespace tc2;
+  if (M <= 0 || N <= 0 || K <= 0 || !ep) return MMA_ERR_ARG;
+  static int swz = -1, dbg = 0;
+  if (swz < 0) {
+    const char* e = getenv("MMA_GEMM2_SWZ");
+    swz = e ? atoi(e) : 1;
+    const char* d = getenv("MMA_GEMM_DBG");
+    dbg = d ? atoi(d) : 0;
+  }
+  const int flags = (swz ? 1 : 0) | (dbg << 8);
+  const int box_swz = swz ? (int)CU_TENSOR_MAP_SWIZZLE_64B : (int)CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMap tmA, tmB, tmOut, tmOut2, tmIn;
+  int rc = make_map(&tmA, A, (unsigned long long)K, (unsigned long long)M, lda, BK, BM);
+  if (rc) return rc;
+  if (!b_mn) rc = make_map(&tmB, B, (unsigned long long)K, (unsigned long long)N, ldb, BK, BN / 2);
+  else rc = make_map(&tmB, B, (unsigned long long)N, (unsigned long long)K, ldb, 64, BK);
+  if (rc) return rc;
+  const int kind = ep->kind;
+  const int io32 = kind == EPI_ACCUM ? 1 : ep->out_f32;
+  const unsigned bc = io32 ? 16 : 32;
+  rc = make_map_ex(&tmOut, ep->out, (unsigned long long)N, (unsigned long long)M, ep->ldo, bc, 32, io32, box_swz);
+  if (rc) return rc;
+  tmOut2 = tmOut;
+  tmIn = tmOut;
+  if (kind == EPI_GELU && ep->out2) {
+    rc = make_map_ex(&tmOut2, ep->out2, (unsigned long long)N, (unsigned long long)M, ep->ldo2, bc, 32, io32, box_swz);
+    if (rc) return rc;
+  }
+  if (kind == EPI_RESID) rc = make_map_ex(&tmIn, ep->resid, (unsigned long long)N, (unsigned long long)M, ep->ldr, bc, 32, io32, box_swz);
+  if (kind == EPI_DGELU) rc = make_map_ex(&tmIn, ep->aux, (unsigned long long)N, (unsigned long long)M, ep->lda, bc, 32, io32, box_swz);
+  if (rc) return rc;
+#define MMA_L2(BMN, KD, IO) return launch<BMN, KD, IO>(tmA, tmB, tmOut, tmOut2, tmIn, M, N, K, flags, *ep, stream)
+  if (!b_mn) {
+    if (kind == EPI_STORE && !io32) MMA_L2(false, EPI_STORE, false);
+    if (kind == EPI_STORE && io32) MMA_L2(false, EPI_STORE, true);
+    if (kind == EPI_GELU && !io32) MMA_L2(false, EPI_GELU, false);
+    if (kind == EPI_RESID && io32) MMA_L2(false, EPI_RESID, true);
+    if (kind == EPI_RESID && !io32) MMA_L2(false, EPI_RESID, false);
+  } else {
+    if (kind == EPI_STORE && !io32) MMA_L2(true, EPI_STORE, false);
+    if (kind == EPI_DGELU && !io32) MMA_L2(true, EPI_DGELU, false);
+    if (kind == EPI_ACCUM) MMA_L2(true, EPI_ACCUM, true);
+  }
+#undef MMA_L2
+  return MMA_ERR_UNSUPPORTED;
+}

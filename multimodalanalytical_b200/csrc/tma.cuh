@@ -79,8 +79,9 @@ struct MapKey {
   const void* ptr;
   unsigned long long d0, d1, ld;
   unsigned int b0, b1;
+  unsigned int fmt;  // element type | swizzle mode << 8
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1 && fmt == o.fmt;
   }
 };
 struct MapKeyHash {
@@ -90,16 +91,19 @@ struct MapKeyHash {
     h = h * 1000003u ^ k.d1;
     h = h * 1000003u ^ k.ld;
     h = h * 1000003u ^ ((size_t)k.b0 << 16 | k.b1);
+    h = h * 1000003u ^ k.fmt;
     return h;
   }
 };
 
-// 2-D bf16 tensor map: inner extent d0 (contiguous), outer extent d1, row pitch ld elements.
-static int make_map(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1,
-                    unsigned long long ld, unsigned int b0, unsigned int b1) {
+// 2-D tensor map: inner extent d0 (contiguous), outer extent d1, row pitch ld elements, box b0 x b1 elements.
+// is_f32: element type float instead of bf16.  swizzle: 0 none, 1 32B, 2 64B, 3 128B (CUtensorMapSwizzle values).
+static int make_map_ex(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1,
+                       unsigned long long ld, unsigned int b0, unsigned int b1, int is_f32, int swizzle) {
   static std::mutex mu;
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, d0, d1, ld, b0, b1};
+  const unsigned long long es_bytes = is_f32 ? 4 : 2;
+  MapKey key{ptr, d0, d1, ld, b0, b1, (unsigned int)(is_f32 ? 1 : 0) | ((unsigned int)swizzle << 8)};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -110,19 +114,25 @@ static int make_map(CUtensorMap* out, const void* ptr, unsigned long long d0, un
   }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return MMA_ERR_DRIVER;
-  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return MMA_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * es_bytes) & 15)) return MMA_ERR_ARG;
   cuuint64_t dims[2] = {d0, d1};
-  cuuint64_t strides[1] = {ld * 2};
+  cuuint64_t strides[1] = {ld * es_bytes};
   cuuint32_t box[2] = {b0, b1};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  (CUtensorMapSwizzle)swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return MMA_ERR_DRIVER;
   std::lock_guard<std::mutex> g(mu);
   if (cache.size() > 65536) cache.clear();
   cache.emplace(key, *out);
   return MMA_OK;
+}
+
+// 2-D bf16 tensor map with the 128-byte swizzle the tcgen05 operand tiles use.
+static int make_map(CUtensorMap* out, const void* ptr, unsigned long long d0, unsigned long long d1,
+                    unsigned long long ld, unsigned int b0, unsigned int b1) {
+  return make_map_ex(out, ptr, d0, d1, ld, b0, b1, 0, (int)CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 

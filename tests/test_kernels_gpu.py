@@ -111,6 +111,64 @@ def test_gemm_epilogues(dtype):
     assert rel(o4, base + acc) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(16384, 512, 512), (12300, 1536, 512), (12416, 600, 200), (9216, 2048, 512),
+                                   (16384, 512, 2048)])
+def test_gemm_pair_kernel(M, N, K):
+    """The CTA-pair kernel (gemm_tc2.cu: cta_group::2, 256x256 tiles, TMA epilogue) takes the large products; every
+    instantiated epilogue against torch, and with dropout against the single-CTA kernel (max_ctas > 0 forces it)."""
+    dt, tol = torch.bfloat16, 1e-2
+    A, W, bias = _rand(M, K, dtype=dt), _rand(N, K, dtype=dt, scale=K ** -0.5), _rand(N)
+    acc = A.float() @ W.float().T
+    # forward STORE bf16 / fp32
+    o = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_STORE, o, bias=bias))
+    assert rel(o.float(), acc + bias) < tol
+    of = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_STORE, of, bias=bias))
+    assert rel(of, acc + bias) < 1e-5
+    # GELU + pre-activation copy
+    z, a = torch.empty(M, N, device=DEV, dtype=dt), torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_GELU, a, out2=z, bias=bias))
+    assert rel(z.float(), acc + bias) < tol
+    assert rel(a.float(), torch.nn.functional.gelu(acc + bias)) < tol
+    a1 = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_GELU, a1, bias=bias))
+    assert torch.equal(a1, a)
+    # residual, fp32 stream
+    resid = _rand(M, N)
+    r = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_RESID, r, bias=bias, resid=resid))
+    assert rel(r, resid + acc + bias) < 2e-5
+    # dgrad products: B is [K, N] row-major
+    Wt = W.t().contiguous()
+    d = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, Wt, M, N, K, ops.make_epi(EPI_STORE, d), b_mn=True)
+    assert rel(d.float(), acc) < tol
+    zz = _rand(M, N, dtype=dt, seed=5)
+    dg = torch.empty(M, N, device=DEV, dtype=dt)
+    ops.gemm(A, Wt, M, N, K, ops.make_epi(EPI_DGELU, dg, aux=zz), b_mn=True)
+    zf = zz.float().requires_grad_(True)
+    torch.nn.functional.gelu(zf).backward(acc)
+    assert rel(dg.float(), zf.grad) < tol
+    base = _rand(M, N, seed=9)
+    ac = base.clone()
+    ops.gemm(A, Wt, M, N, K, ops.make_epi(EPI_ACCUM, ac, accumulate=1), b_mn=True)
+    assert rel(ac, base + acc) < 2e-5
+    ops.gemm(A, Wt, M, N, K, ops.make_epi(EPI_ACCUM, ac, accumulate=0), b_mn=True)
+    assert rel(ac, acc) < 2e-5
+    # dropout: same masks and values as the single-CTA kernel
+    for kind, kw, bmn in ((EPI_GELU, dict(bias=bias), False), (EPI_RESID, dict(bias=bias, resid=resid), False),
+                          (EPI_DGELU, dict(aux=zz), True)):
+        odt = torch.float32 if kind == EPI_RESID else dt
+        x1, x2 = torch.empty(M, N, device=DEV, dtype=odt), torch.empty(M, N, device=DEV, dtype=odt)
+        Bm = Wt if bmn else W
+        ops.gemm(A, Bm, M, N, K, ops.make_epi(kind, x1, p_drop=0.1, seed=123, site=7, **kw), b_mn=bmn)
+        ops.gemm(A, Bm, M, N, K, ops.make_epi(kind, x2, p_drop=0.1, seed=123, site=7, **kw), b_mn=bmn, max_ctas=148)
+        assert rel(x1.float(), x2.float()) < 1e-2
+        if kind != EPI_RESID:
+            assert torch.equal(x1 == 0, x2 == 0)
+
+
 def test_gemm_dropout_mask_consistency():
     """RESID-epilogue dropout (forward) and ln_bwd's masked copy (backward) must use the same mask."""
     M, N, K, p = 256, 128, 64, 0.25
