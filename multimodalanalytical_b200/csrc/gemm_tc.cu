@@ -672,11 +672,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) wgrad_group_kernel(const __gri
 
 // Grouped wgrad (+ bias grad): for g < count:  out[g][Nout, Kin] += dy[g]^T x[g];  dbias[g][Nout] += colsum(dy[g]).
 // dy[g]: bf16 [R, Nout] pitch lddy;  x[g]: bf16 [R, Kin] pitch ldx.  Every output tile has one writer: no atomics.
+extern "C" int mma_wgrad2_group(int count, const void* const* dy, const long long* lddy, const void* const* x,
+                                const long long* ldx, float* const* out, const long long* ldo, float* const* dbias,
+                                const int* Nout, const int* Kin, const int* R, cudaStream_t stream);
+
 extern "C" int mma_wgrad_group(int count, const void* const* dy, const long long* lddy, const void* const* x,
                                const long long* ldx, float* const* out, const long long* ldo, float* const* dbias,
                                const int* Nout, const int* Kin, const int* R, cudaStream_t stream) {
   using namespace tc;
   if (count < 1 || count > 8) return MMA_ERR_ARG;
+  {
+    // CTA-pair kernel (gemm_tc2.cu) unless MMA_WGRAD2=0; it needs 16-byte aligned fp32 gradient rows
+    static int use2 = -1;
+    if (use2 < 0) {
+      const char* e = getenv("MMA_WGRAD2");
+      use2 = e ? atoi(e) : 1;
+    }
+    bool ok = use2 != 0;
+    for (int g = 0; g < count && ok; ++g)
+      ok = (reinterpret_cast<uintptr_t>(out[g]) & 15) == 0 && ((ldo[g] * 4) & 15) == 0;
+    if (ok) return mma_wgrad2_group(count, dy, lddy, x, ldx, out, ldo, dbias, Nout, Kin, R, stream);
+  }
   WgGroup grp{};
   int tiles = 0;
   for (int g = 0; g < count; ++g) {

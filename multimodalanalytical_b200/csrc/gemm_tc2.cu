@@ -538,6 +538,217 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   return MMA_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Grouped weight-gradient kernel, CTA-pair version:  dW_g[Nout_g, Kin_g] += dy_g^T x_g  (and db_g += colsum(dy_g)) for
+// up to 8 products (one backward layer) in ONE persistent launch.  Pair tiles are 256 x 256, both operands MN-major
+// (the rows of dy / x are the reduction dimension), every output tile has exactly one writer (no split-K, no atomics,
+// bit-reproducible).  The epilogue adds into the fp32 gradient buffer with TMA reduce-add stores
+// (cp.reduce.async.bulk.tensor ... add): no read-modify-write through the SM.  The bias gradient rides along on the
+// first tile column of every tile row: one extra N = 16 MMA per k-step multiplies the dy tile with an all-ones B tile
+// into 16 spare TMEM columns.
+// ------------------------------------------------------------------------------------------------------------------
+struct alignas(64) Wg2Problem {
+  CUtensorMap tmA;    // dy [R, Nout]: dims {Nout, R}, box {64, 64}
+  CUtensorMap tmB;    // x  [R, Kin] : dims {Kin, R},  box {64, 64}
+  CUtensorMap tmOut;  // dW [Nout, Kin] fp32: dims {Kin, Nout}, box {16, 32}, 64-byte swizzle
+  float* dbias;       // [Nout] fp32, accumulated (+=), may be null
+  int M, N, R;        // Nout, Kin, rows
+  int tiles_n, tile_begin;
+};
+struct Wg2Group {
+  Wg2Problem p[8];
+  int count, total_tiles, swz;
+};
+
+constexpr int WG2_STAGES = 5;
+constexpr uint32_t WG2_ONES_BYTES = 2048;
+constexpr uint32_t WG2_SMEM = 1024 + WG2_STAGES * (A_BYTES + B_BYTES) + WG2_ONES_BYTES + NUM_EPI_WARPS * BOX_BYTES + BAR_BYTES;
+static_assert(WG2_SMEM <= 232448, "shared memory budget");
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
+  pdl_trigger();
+  constexpr int ST = WG2_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + ST * A_BYTES;
+  uint8_t* sOnes = sB + ST * B_BYTES;
+  uint8_t* sEpi = sOnes + WG2_ONES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + NUM_EPI_WARPS * BOX_BYTES);
+  uint64_t* full = bars;            // [ST]  leader's are used
+  uint64_t* empty = bars + ST;      // [ST]
+  uint64_t* tfull = bars + 2 * ST;  // [1]
+  uint64_t* tempty = tfull + 1;     // [1]  leader's is used
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  for (int i = threadIdx.x; i < (int)(WG2_ONES_BYTES / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;  // bf16 1.0 pairs (swizzle-invariant: every element equal)
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < ST; ++i) {
+      mbar_init(smem_u32(&full[i]), 1);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    mbar_init(smem_u32(tfull), 1);
+    mbar_init(smem_u32(tempty), 2 * NUM_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();  // the ones tile is read by the tensor core
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  auto locate = [&](int tile, int& g, int& m0, int& n0) {
+    g = 0;
+#pragma unroll 1
+    for (int i = 1; i < grp.count; ++i)
+      if (tile >= grp.p[i].tile_begin) g = i;
+    const int t = tile - grp.p[g].tile_begin;
+    n0 = (t % grp.p[g].tiles_n) * BN;
+    m0 = (t / grp.p[g].tiles_n) * (2 * BM);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < grp.total_tiles; tile += npairs) {
+        int g, m0, n0;
+        locate(tile, g, m0, n0);
+        const Wg2Problem& P = grp.p[g];
+        const int num_kb = (P.R + BK - 1) / BK;
+        const int ma = m0 + (int)rank * BM, nb = n0 + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full[stage]);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + B_BYTES));
+          const uint32_t fb = mapa(fb_local, 0);
+          const uint32_t a_dst = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_dst = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+          for (int a = 0; a < BM / 64; ++a) tma_load_2d_2sm(a_dst + a * (BK * 128), &P.tmA, fb, ma + a * 64, kb * BK);
+#pragma unroll
+          for (int a = 0; a < (BN / 2) / 64; ++a) tma_load_2d_2sm(b_dst + a * (BK * 128), &P.tmB, fb, nb + a * 64, kb * BK);
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc_main = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                      ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      constexpr uint32_t idesc_bias = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (0u << 16) |
+                                      ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int tile = pair; tile < grp.total_tiles; tile += npairs) {
+        int g, m0, n0;
+        locate(tile, g, m0, n0);
+        const Wg2Problem& P = grp.p[g];
+        const int num_kb = (P.R + BK - 1) / BK;
+        const bool with_bias = n0 == 0 && P.dbias != nullptr;
+        mbar_wait(smem_u32(tempty), tphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc<true>(a_addr, k);
+            tc_mma2_bf16(tmem_base, ad, make_smem_desc<true>(b_addr, k), idesc_main, (kb > 0 || k > 0) ? 1u : 0u);
+            if (with_bias)
+              tc_mma2_bf16(tmem_base + BN, ad, make_smem_desc<false>(smem_u32(sOnes), k), idesc_bias,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit2_mc(smem_u32(&empty[stage]));
+          if (++stage == ST) { stage = 0; phase ^= 1; }
+        }
+        tc_commit2_mc(smem_u32(tfull));
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int ew = warp - 2, q = warp & 3, s = ew >> 2;
+    uint8_t* ob = sEpi + ew * BOX_BYTES;
+    const uint32_t ob_addr = smem_u32(ob);
+    const uint32_t tempty_leader = mapa(smem_u32(tempty), 0);
+    const int swz = grp.swz;
+    uint32_t tphase = 0;
+    for (int tile = pair; tile < grp.total_tiles; tile += npairs) {
+      int g, m0, n0;
+      locate(tile, g, m0, n0);
+      const Wg2Problem& P = grp.p[g];
+      const int r0 = m0 + (int)rank * BM + q * 32;
+      const int c0 = n0 + s * 64;
+      mbar_wait(smem_u32(tfull), tphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+      uint32_t raw[2][16];
+      tmem_ld16_nowait(t_row + (uint32_t)(s * 64), raw[0]);
+      float bias_v = 0.f;
+      const bool do_bias = s == 0 && n0 == 0 && P.dbias != nullptr;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_wait_ld();
+        if (c + 1 < 4) {
+          tmem_ld16_nowait(t_row + (uint32_t)(s * 64 + (c + 1) * 16), raw[(c + 1) & 1]);
+        } else if (do_bias) {
+          uint32_t rb[16];
+          tmem_ld16_nowait(t_row + (uint32_t)BN, rb);
+          tmem_wait_ld();
+          bias_v = __uint_as_float(rb[0]);
+        }
+        if (c == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader);
+        }
+        const bool live = r0 < P.M && c0 + c * 16 < P.N;
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<uint4*>(ob + box_off(lane, k, swz)) =
+              make_uint4(raw[c & 1][4 * k], raw[c & 1][4 * k + 1], raw[c & 1][4 * k + 2], raw[c & 1][4 * k + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && live) {
+          tma_reduce_add_2d(&P.tmOut, ob_addr, c0 + c * 16, r0);
+          bulk_commit();
+        }
+      }
+      if (do_bias && r0 + lane < P.M) P.dbias[r0 + lane] += bias_v;
+      tphase ^= 1;
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace tc2
 
 // Which products go to the pair kernel: A K-major, a supported epilogue with homogeneous I/O types, TMA-compatible
@@ -624,4 +835,65 @@ extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long 
   }
 #undef MMA_L2
   return MMA_ERR_UNSUPPORTED;
+}
+
+// Grouped wgrad (+ bias grad), CTA-pair kernel: same contract as mma_wgrad_group (gemm_tc.cu), which forwards here.
+extern "C" int mma_wgrad2_group(int count, const void* const* dy, const long long* lddy, const void* const* x,
+                                const long long* ldx, float* const* out, const long long* ldo, float* const* dbias,
+                                const int* Nout, const int* Kin, const int* R, cudaStream_t stream) {
+  using namespace tc2;
+  if (count < 1 || count > 8) return MMA_ERR_ARG;
+  static int swz = -1;
+  if (swz < 0) {
+    const char* e = getenv("MMA_GEMM2_SWZ");
+    swz = e ? atoi(e) : 1;
+  }
+  Wg2Group grp{};
+  int tiles = 0;
+  for (int g = 0; g < count; ++g) {
+    Wg2Problem& P = grp.p[g];
+    if (Nout[g] <= 0 || Kin[g] <= 0 || R[g] <= 0) return MMA_ERR_ARG;
+    int rc = make_map(&P.tmA, dy[g], (unsigned long long)Nout[g], (unsigned long long)R[g], lddy[g], 64, BK);
+    if (rc) return rc;
+    rc = make_map(&P.tmB, x[g], (unsigned long long)Kin[g], (unsigned long long)R[g], ldx[g], 64, BK);
+    if (rc) return rc;
+    rc = make_map_ex(&P.tmOut, out[g], (unsigned long long)Kin[g], (unsigned long long)Nout[g], ldo[g], 16, 32, 1,
+                     swz ? (int)CU_TENSOR_MAP_SWIZZLE_64B : (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc) return rc;
+    P.dbias = dbias ? dbias[g] : nullptr;
+    P.M = Nout[g];
+    P.N = Kin[g];
+    P.R = R[g];
+    P.tiles_n = (Kin[g] + BN - 1) / BN;
+    P.tile_begin = tiles;
+    tiles += ((Nout[g] + 2 * BM - 1) / (2 * BM)) * P.tiles_n;
+  }
+  grp.count = count;
+  grp.total_tiles = tiles;
+  grp.swz = swz ? 1 : 0;
+  static int max_pairs = 0;
+  if (!max_pairs) {
+    if (cudaFuncSetAttribute(wgrad2_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM) != cudaSuccess)
+      return MMA_ERR_LAUNCH;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(2 * (num_sms() / 2));
+    q.blockDim = dim3(NUM_THREADS);
+    q.dynamicSmemBytes = WG2_SMEM;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, wgrad2_group_kernel, &q) != cudaSuccess || n <= 0) n = num_sms() / 2;
+    max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+  }
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = WG2_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, wgrad2_group_kernel, grp) != cudaSuccess) return MMA_ERR_LAUNCH;
+  return MMA_OK;
 }
