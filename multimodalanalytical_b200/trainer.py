@@ -9,6 +9,7 @@ Lightning itself still works with the module (wrapper.py); this loop is what ben
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, Dict, Optional
 
 import torch
@@ -103,6 +104,9 @@ class FusedTrainer:
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.norm_ws = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.bucketer = GradBucketer(self.ps.g, self.BUCKET_ELEMS, process_group) if self.world > 1 else None
+        # multi-GPU: the bucketed NCCL all-reduces (forked onto the side stream) are captured into the step's CUDA
+        # graph together with the kernels; MMA_DDP_GRAPH=0 falls back to eager launches
+        self.graph_ddp = os.environ.get("MMA_DDP_GRAPH", "1") != "0"
         self._sync_now = False
         self.eng.grad_ready_hook = self._on_grads_ready
 
@@ -154,7 +158,7 @@ class FusedTrainer:
         if self.bucketer is not None:
             self.bucketer.reset()
         inputs = self._prepare(batch)
-        if self.use_graph and self.acc == 1 and self.bucketer is None:
+        if self.use_graph and self.acc == 1 and (self.bucketer is None or self.graph_ddp):
             return self._graphed_step(inputs)
         loss = self._step_body(inputs)
         if self._sync_now:
