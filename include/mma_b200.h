@@ -98,6 +98,22 @@ int mma_colsum(const void* in, int in_f32, long long ld, float* out, int rows, i
 int mma_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 int mma_cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t stream);
 
+/* ---- encoder-alignment head (custom_modeling.py:363-396 networks, :453-475 masked mean pool + loss; LOSS_FACTORY
+ * :15; modeling/utils.py:8-22 kl_div / sid).  The MLP / centre-tap conv products run on the GEMM entry points.  */
+/* pooled[b,:] = sum_s mask[b,s] mem[b,s,:] / sum_s mask[b,s]   (mask 1 = real token) */
+int mma_masked_mean_fwd(const void* mem, int mem_f32, long long ld, const unsigned char* mask, float* pooled, int B,
+                        int S, int d, cudaStream_t stream);
+/* dmem[b,s,:] += mask[b,s] dpooled[b,:] / count_b */
+int mma_masked_mean_bwd(const float* dpooled, const unsigned char* mask, float* dmem, long long ld, int B, int S,
+                        int d, cudaStream_t stream);
+/* pred = sigmoid(z); kind 0 mae, 1 mse, 2 sid; out[0] = loss, out[1] = *lm_loss + lambda * loss;
+ * dz (optional) = dscale * lambda * dloss/dz */
+int mma_align_loss(const float* z, long long ldz, const float* target, long long ldt, int rows, int cols, int kind,
+                   float lambda, const float* lm_loss, float* out, float* dz, long long lddz, float dscale,
+                   cudaStream_t stream);
+/* dst[i * stride] += src[i] */
+int mma_add_strided(float* dst, long long stride, const float* src, long long n, cudaStream_t stream);
+
 /* ---- attention (F.scaled_dot_product_attention inside nn.MultiheadAttention; masks custom_modeling.py:233-234,
  * 299-318).  q/k/v/o are [B*L, ld] with head h at columns [h*dh, (h+1)*dh); kmask[B,Lk] 1 = real token.         */
 int mma_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,

@@ -410,9 +410,10 @@ class Engine:
         return hT
 
     # ------------------------------------------------------------------------------------ forward
-    def forward(self, enc_inputs, enc_mask, dec_ids, dec_mask, labels=None, train=False):
+    def forward(self, enc_inputs, enc_mask, dec_ids, dec_mask, labels=None, train=False, align_target=None):
         """enc_mask/dec_mask: uint8 [B, L], 1 = real token.  labels: int64 [B, T], -100 = ignore.
-        Returns dict(logits=[B, T, V] fp32 view, loss=device scalar or None)."""
+        align_target: fp32 [B, output_dimension] (models with an align head, custom_modeling.py:453-475).
+        Returns dict(logits=[B, T, V] fp32 view, loss=device scalar or None, lm_loss, align_loss)."""
         cfg = self.cfg
         self.sync_weights()
         if train:
@@ -433,10 +434,84 @@ class Engine:
             row_lse = self.buf("ce.row_lse", (M,), torch.float32)
             stats = self.buf("ce.stats", (2,), torch.float32)
             ops.ce_fwd(logits, labels, V, row_loss, row_lse, stats, smoothing=cfg.label_smoothing)
-            out["loss"] = stats[0]
+            out["loss"] = out["lm_loss"] = stats[0]
+            out["align_loss"] = None
             if train:
                 self.saved["ce"] = dict(logits=logits, labels=labels, row_lse=row_lse, stats=stats, M=M)
+            if cfg.align_config and align_target is not None:
+                al = self._align_fwd(mem, enc_mask, align_target, stats[0:1], train)
+                out["align_loss"], out["loss"] = al[0], al[1]
         return out
+
+    # ------------------------------------------------------------------------------- align head
+    def _align_layers(self):
+        """[(weight view [out, in], bias, grad-weight view, grad bias, relu?)] of the align network; the Conv1d layers
+        act on a length-1 sequence, so only the centre tap (k // 2) of `4.weight` contributes."""
+        ac, p = self.cfg.align_config, "hf_model.align_network."
+        names = [("0", True)]
+        names += [("2", False), ("4", True), ("6", False)] if ac["align_network"] == "convolutional" else [("2", False)]
+        out = []
+        for n, relu in names:
+            W, G = self.P(f"{p}{n}.weight"), self.G(f"{p}{n}.weight")
+            if W.dim() == 3:
+                c = W.shape[2] // 2
+                W, G = W[:, :, c], G[:, :, c]
+            out.append((W, self.P(f"{p}{n}.bias"), G, self.G(f"{p}{n}.bias"), relu))
+        return out
+
+    def _align_fwd(self, mem, enc_mask, target, lm_loss, train):
+        ac = self.cfg.align_config
+        if ac["align_network"] not in ("convolutional", "mlp"):
+            raise ValueError(f"unknown align network {ac['align_network']}")
+        if ac["loss_function"] not in ops.ALIGN_LOSS_KINDS:
+            raise ValueError(f"Loss function {ac['loss_function']} not supported for alignment!")
+        B, S = enc_mask.shape
+        d = self.cfg.d_model
+        pooled = self.buf("al.pooled", (B, d), torch.float32)
+        ops.masked_mean_fwd(mem, enc_mask, pooled, B, S)
+        acts = [pooled]
+        h = pooled
+        layers = self._align_layers()
+        for li, (W, b, _, _, relu) in enumerate(layers):
+            o, i = W.shape
+            y = self.buf(f"al.h{li}", (B, o), torch.float32)
+            ops.gemm(h, W, B, o, i, ops.make_epi(EPI_RELU if relu else EPI_STORE, y, bias=b), force_simt=True)
+            acts.append(y)
+            h = y
+        target = target.contiguous().float()
+        res = self.buf("al.loss", (2,), torch.float32)
+        ops.align_loss(h, target, ac["loss_function"], ac["loss_lambda"], lm_loss, res)
+        if train:
+            self.saved["align"] = dict(acts=acts, target=target, mask=enc_mask, B=B, S=S)
+        return res
+
+    def _align_bwd(self, dmem, gscale):
+        """Weight / bias gradients of the align network and its contribution to d(memory)."""
+        s = self.saved["align"]
+        acts, B = s["acts"], s["B"]
+        ac = self.cfg.align_config
+        z = acts[-1]
+        dy = self.buf("al.dz", tuple(z.shape), torch.float32)
+        ops.align_loss(z, s["target"], ac["loss_function"], ac["loss_lambda"], None, self.buf("al.loss_bw", (2,), torch.float32),
+                       dz=dy, dscale=gscale)
+        layers = self._align_layers()
+        for li in reversed(range(len(layers))):
+            W, _, G, Gb, relu = layers[li]
+            o, i = W.shape
+            x = acts[li]
+            if G.stride(1) == 1:
+                ops.gemm(dy, x, o, i, B, ops.make_epi(EPI_ACCUM, G, accumulate=1), a_mn=True, b_mn=True, force_simt=True)
+            else:  # centre tap of a Conv1d weight: accumulate through a contiguous scratch
+                tmp = self.buf(f"al.dw{li}", (o, i), torch.float32)
+                ops.gemm(dy, x, o, i, B, ops.make_epi(EPI_ACCUM, tmp, accumulate=0), a_mn=True, b_mn=True, force_simt=True)
+                ops.add_strided(G.as_strided((o * i,), (G.stride(1),), G.storage_offset()), tmp.view(-1))
+            ops.colsum(dy, Gb, rows=B, cols=o)
+            dx = self.buf(f"al.dx{li}", (B, i), torch.float32)
+            prev_relu = li > 0 and layers[li - 1][4]
+            epi = ops.make_epi(EPI_DRELU, dx, aux=x) if prev_relu else ops.make_epi(EPI_STORE, dx)
+            ops.gemm(dy, W, B, i, o, epi, b_mn=True, force_simt=True)
+            dy = dx
+        ops.masked_mean_bwd(dy, s["mask"], dmem, B, s["S"])
 
     # ----------------------------------------------------------------------------------- backward
     def backward(self, gscale: float = 1.0):
@@ -485,6 +560,8 @@ class Engine:
             self._flush_wgrads()
             notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
         self._embed_bwd(dx, dec["recs"], T_, "dec", B)
+        if "align" in self.saved:
+            self._align_bwd(dmem, gscale)
 
         # encoder: d(mem) arrives in fp32 from the cross-attention K/V projections
         He = cfg.encoder_attention_heads

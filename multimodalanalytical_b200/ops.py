@@ -93,8 +93,8 @@ def gemm(A, B, M, N, K, epi, a_mn=False, b_mn=False, splits=1, force_simt=False,
             if tiles < 148 and K >= 1024:
                 ssplit = max(1, min(64, K // 256, 296 // tiles))
             epi.accumulate = 2 if ssplit > 1 else 1
-        sam, sak = (1, A.stride(0)) if a_mn else (A.stride(0), 1)
-        sbn, sbk = (1, B.stride(0)) if b_mn else (B.stride(0), 1)
+        sam, sak = (A.stride(1), A.stride(0)) if a_mn else (A.stride(0), A.stride(1))
+        sbn, sbk = (B.stride(1), B.stride(0)) if b_mn else (B.stride(0), B.stride(1))
         rc = lib.mma_gemm_simt(A.data_ptr(), _ty(A), sam, sak, B.data_ptr(), _ty(B), sbn, sbk, M, N, K, C.byref(epi),
                                ssplit, _stream())
         check(rc, "mma_gemm_simt")
@@ -175,6 +175,46 @@ def colsum(x, out, rows=None, cols=None):
     cols = x.shape[1] if cols is None else cols
     check(_lib.load().mma_colsum(x.data_ptr(), _ty(x), x.stride(0), out.data_ptr(), rows, cols, _stream()),
           "mma_colsum")
+    _count()
+
+
+ALIGN_LOSS_KINDS = {"mae": 0, "mse": 1, "sid": 2}
+
+
+def masked_mean_fwd(mem, mask, pooled, B, S):
+    _need_cuda(mem, mask, pooled)
+    assert mask.dtype == torch.uint8 and mask.is_contiguous() and pooled.dtype == torch.float32 and pooled.is_contiguous()
+    check(_lib.load().mma_masked_mean_fwd(mem.data_ptr(), _ty(mem), mem.stride(0), mask.data_ptr(), pooled.data_ptr(),
+                                          B, S, mem.shape[1], _stream()), "mma_masked_mean_fwd")
+    _count()
+
+
+def masked_mean_bwd(dpooled, mask, dmem, B, S):
+    _need_cuda(dpooled, mask, dmem)
+    assert dmem.dtype == torch.float32 and dpooled.dtype == torch.float32 and dpooled.is_contiguous()
+    check(_lib.load().mma_masked_mean_bwd(dpooled.data_ptr(), mask.data_ptr(), dmem.data_ptr(), dmem.stride(0), B, S,
+                                          dmem.shape[1], _stream()), "mma_masked_mean_bwd")
+    _count()
+
+
+def align_loss(z, target, kind, lam, lm_loss, out, dz=None, dscale=1.0):
+    """out[0] = loss(sigmoid(z), target), out[1] = lm_loss + lam * out[0]; dz = dscale * lam * dloss/dz."""
+    _need_cuda(z, target, out)
+    assert z.dtype == torch.float32 and target.dtype == torch.float32 and out.dtype == torch.float32
+    check(_lib.load().mma_align_loss(z.data_ptr(), z.stride(0), target.data_ptr(), target.stride(0), z.shape[0],
+                                     z.shape[1], ALIGN_LOSS_KINDS[kind], float(lam), _p(lm_loss), out.data_ptr(),
+                                     _p(dz), 0 if dz is None else dz.stride(0), float(dscale), _stream()),
+          "mma_align_loss")
+    _count()
+
+
+def add_strided(dst, src):
+    """dst (a 1-D strided fp32 view) += src (contiguous, same element count)."""
+    _need_cuda(dst, src)
+    assert dst.dim() == 1 and dst.dtype == torch.float32 and src.dtype == torch.float32 and src.is_contiguous()
+    assert dst.numel() == src.numel()
+    check(_lib.load().mma_add_strided(dst.data_ptr(), dst.stride(0), src.data_ptr(), src.numel(), _stream()),
+          "mma_add_strided")
     _count()
 
 

@@ -127,23 +127,29 @@ class FusedTrainer:
         dec_mask = (~m._to_dev(batch["decoder_pad_mask"])).T.to(torch.uint8).contiguous()
         labels = m._to_dev(batch["target"]).T.contiguous().clone()
         labels[labels == m.target_tokenizer.pad_token_id] = -100
+        if m.engine.cfg.align_config and "encoder_alignment_input" in batch:
+            return (input_ids, attention_mask, dec_in, dec_mask, labels,
+                    m._to_dev(batch["encoder_alignment_input"]).float().contiguous())
         return input_ids, attention_mask, dec_in, dec_mask, labels
 
     @staticmethod
     def _flat(inputs):
-        ids, am, di, dm, lb = inputs
+        ids, am, di, dm, lb = inputs[:5]
         out = []
         for k, v in ids.items():
             if isinstance(v, dict):
                 out += [(f"{k}.{kk}", t) for kk, t in v.items()]
             else:
                 out.append((k, v))
-        return out + [("enc_mask", am), ("dec_in", di), ("dec_mask", dm), ("labels", lb)]
+        out += [("enc_mask", am), ("dec_in", di), ("dec_mask", dm), ("labels", lb)]
+        if len(inputs) > 5:
+            out.append(("align_target", inputs[5]))
+        return out
 
     def _step_body(self, inputs):
-        ids, am, di, dm, lb = inputs
+        ids, am, di, dm, lb = inputs[:5]
         self.eng.next_seed()
-        out = self.eng.forward(ids, am, di, dm, labels=lb, train=True)
+        out = self.eng.forward(ids, am, di, dm, labels=lb, train=True, align_target=inputs[5] if len(inputs) > 5 else None)
         self.eng.backward(gscale=1.0)
         return out["loss"]
 

@@ -112,7 +112,9 @@ def load_custom_model(model_name: str, target_tokenizer, target_modality: str, d
     if kwargs.get("post_layer_normalisation", True) is not True:
         raise NotImplementedError("post_layer_normalisation=False (post-LN) is not on the accelerated path")
     if cfg.align_config:
-        raise NotImplementedError("align head (custom_model_align) is not on the accelerated path yet")
+        ac = cfg.align_config = dict(cfg.align_config)
+        if ac.get("align_network") not in ("convolutional", "mlp"):
+            raise ValueError(f"unknown align network {ac.get('align_network')}")
     store = ParamStore(cfg, device=device, seed=seed)
     engine = Engine(cfg, store, precision=precision)
     return B200CustomModel(cfg, store, engine), store
@@ -243,11 +245,16 @@ class HFWrapper(_Base):
         labels = self._to_dev(batch["target"]).T.contiguous().clone()
         labels[labels == self.target_tokenizer.pad_token_id] = -100
         train = self.training and torch.is_grad_enabled()
-        out = self.engine.forward(input_ids, attention_mask, dec_in, dec_mask, labels=labels, train=train)
+        # wrapper.py:394-396: the align target rides along when the collator provides it
+        align_target = None
+        if self.engine.cfg.align_config and "encoder_alignment_input" in batch:
+            align_target = self._to_dev(batch["encoder_alignment_input"]).float().contiguous()
+        out = self.engine.forward(input_ids, attention_mask, dec_in, dec_mask, labels=labels, train=train,
+                                  align_target=align_target)
         loss = out["loss"]
         if train:
             loss = _EngineLoss.apply(self._anchor, loss, self.engine)
-        loss_dict = {"model_only_loss": out["loss"], "alignment_loss": None}
+        loss_dict = {"model_only_loss": out["lm_loss"], "alignment_loss": out["align_loss"]}
         return CustomLMOutput(loss=loss, logits=out["logits"], loss_dict=loss_dict,
                               encoder_hidden_states=out["memory"])
 

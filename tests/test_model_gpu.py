@@ -53,7 +53,7 @@ def oracle_grads(fx):
     return out, {k: v.grad for k, v in leaves.items() if v.grad is not None}
 
 
-CASES = ("c1_ir_tiny", "mm_gated_learned")
+CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv")
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -182,7 +182,55 @@ def test_midsize_random_model_against_oracle():
         assert worst[0][0] < tol_g, (precision, worst[:5])
 
 
-def test_align_head_is_rejected_loudly():
+def test_align_head_losses_match_reference_and_oracle():
+    """custom_model_align: total = lm + lambda * align (golden from the reference: convolutional head + MAE); the MLP
+    head and the MSE / SID losses against the oracle (loss and every gradient)."""
     fx = load_case("align_conv")
-    with pytest.raises(NotImplementedError):
-        build(fx, "fp32")
+    m = build(fx, "fp32")
+    m.eval()
+    with torch.no_grad():
+        out = m.forward(fx["batch"])
+    ref = fx["ref"]
+    assert abs(float(out.loss_dict["alignment_loss"]) - float(ref["alignment_loss"])) < 1e-5 * abs(float(ref["alignment_loss"]))
+    assert abs(float(out.loss_dict["model_only_loss"]) - float(ref["model_only_loss"])) < 1e-5 * abs(float(ref["model_only_loss"]))
+    assert abs(float(out.loss) - float(ref["loss"])) < 1e-5 * abs(float(ref["loss"]))
+    for network, loss_fn in (("convolutional", "mse"), ("convolutional", "sid"), ("mlp", "mae"), ("mlp", "sid")):
+        fy = copy.deepcopy(fx)
+        ac = dict(fy["model_kwargs"]["align_config"], align_network=network, loss_function=loss_fn, loss_lambda=3.0)
+        fy["model_kwargs"]["align_config"] = ac
+        if loss_fn == "sid":  # a spectrum-like positive target
+            fy["batch"]["encoder_alignment_input"] = fy["batch"]["encoder_alignment_input"].abs() + 0.05
+        if network == "mlp":
+            sd = {k: v for k, v in fy["state_dict"].items() if ".align_network." not in k or ".0." in k}
+            g = torch.Generator().manual_seed(5)
+            sd["hf_model.align_network.2.weight"] = torch.randn(ac["output_dimension"], ac["hidden_dimension"], generator=g) * 0.2
+            sd["hf_model.align_network.2.bias"] = torch.randn(ac["output_dimension"], generator=g) * 0.1
+            fy["state_dict"] = sd
+        want_out, want_g = oracle_grads(fy)
+        mm = build(fy, "fp32", dropout=0.0)
+        mm.train()
+        mm.store.g.zero_()
+        o = mm.forward(fy["batch"])
+        o.loss.backward()
+        torch.cuda.synchronize()
+        assert abs(float(o.loss) - float(want_out["loss"])) < 2e-5 * abs(float(want_out["loss"])), (network, loss_fn)
+        assert abs(float(o.loss_dict["alignment_loss"]) - float(want_out["alignment_loss"])) < 2e-5 * abs(float(want_out["alignment_loss"]))
+        worst = sorted(((rel_err(mm.store.G(k).cpu(), g), k) for k, g in want_g.items()), reverse=True)
+        assert worst[0][0] < 3e-4, (network, loss_fn, worst[:5])
+
+
+def test_align_model_trains_with_fused_trainer_and_generates():
+    """The C5 model (align weights) through FusedTrainer (graph-captured step incl. the align target) and generate()
+    (the head is skipped when generating, custom_modeling.py:447)."""
+    from multimodalanalytical_b200.trainer import FusedTrainer
+    fx = load_case("align_conv")
+    m = build(fx, "bf16", dropout=0.0)
+    tr = FusedTrainer(m)
+    l0 = float(tr.train_step(fx["batch"]))
+    want = float(fx["ref"]["loss"])
+    assert abs(l0 - want) < 2e-2 * abs(want)
+    losses = [float(tr.train_step(fx["batch"])) for _ in range(4)]
+    assert all(torch.isfinite(torch.tensor(losses)))
+    m.eval()
+    got = m.generate(fx["batch"], n_beams=3).cpu()
+    assert got.shape[0] == fx["ref"]["gen_beam3"].shape[0]
