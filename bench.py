@@ -23,6 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 3247
+PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 C2 = dict(B=256, S_formula=15, P=21, ps=75, T=64, V=200, d=512, layers=6, heads=8, ffn=2048)
 
 
@@ -281,6 +282,7 @@ def run_ours(args):
         peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
         peak_src = "fallback"
 
+    PEAKS.update(peaks)
     mk = model_kwargs(c)
     total_steps = args.steps + args.warmup + 8
     model = HFWrapper(data_config=data_config(c), target_tokenizer=Tok(c["V"]), num_steps=2 * total_steps + 16,
@@ -361,23 +363,45 @@ def run_ours(args):
 
 
 def bench_decode(model, c, args):
-    """Secondary metric: beam-10 molecules/s (KV-cached, CUDA-graph replayed step), random-init weights never emit
-    EOS early so every hypothesis runs the full 127 steps."""
-    B, K = args.decode_batch, 10
-    batch = map_batch(synth_batch(c, B, SEED + 7), lambda x: x.cuda())
+    """Secondary metric: beam-10 molecules/s (KV-cached, CUDA-graph replayed step); random-init weights never emit
+    EOS early, so every hypothesis runs the full 127 steps.  Headline at --decode-batch spectra per GPU plus the C5
+    batch-size sweep; `hbm_roofline_frac` compares the measured time with the cached-decode byte floor
+    (weights once per step + self-attention K/V history per row + cross K/V per spectrum + logits)."""
+    K = 10
     model.eval()
-    model.generate(batch, n_beams=K)  # warm-up + graph capture
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 2
-    e0.record()
-    for _ in range(reps):
-        out = model.generate(batch, n_beams=K)
-    e1.record()
-    torch.cuda.synchronize()
-    t = e0.elapsed_time(e1) * 1e-3 / reps
-    return {"metric": "beam-10 decode molecules/s", "value": B / t, "unit": "molecules/s", "batch": B, "beams": K,
-            "steps": int(out.shape[1]) - 1, "ms_per_batch": t * 1e3, "dtype": "bf16"}
+
+    def run(B, reps):
+        batch = map_batch(synth_batch(c, B, SEED + 7), lambda x: x.cuda())
+        out = model.generate(batch, n_beams=K)  # warm-up + graph capture
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = model.generate(batch, n_beams=K)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps, int(out.shape[1]) - 1
+
+    def floor_s(B, steps):
+        d, f, Ld, S, V = c["d"], c["ffn"], c["layers"], c["S_formula"] + c["P"], c["V"]
+        R = B * K
+        w = Ld * (6 * d * d + 2 * d * f) * 2 + d * V * 2
+        tot = 0.0
+        for t in range(1, steps + 1):
+            by = w + R * Ld * 2 * t * d * 2 + R * Ld * 2 * d * 2 + B * Ld * 2 * S * d * 2 + R * V * 4
+            fl = 2.0 * R * (Ld * (6 * d * d + 2 * d * f + 2 * (t + S) * d) + d * V)
+            tot += max(by / (PEAKS["hbm_gbs"] * 1e9), fl / (PEAKS["bf16_tflops_sustained"] * 1e12))
+        return tot
+
+    t, steps = run(args.decode_batch, 2)
+    res = {"metric": "beam-10 decode molecules/s", "value": args.decode_batch / t, "unit": "molecules/s",
+           "batch": args.decode_batch, "beams": K, "steps": steps, "ms_per_batch": t * 1e3, "dtype": "bf16",
+           "roofline_frac": floor_s(args.decode_batch, steps) / t, "sweep": []}
+    for B in (1, 64, 1024):
+        tb, sb = run(B, 1)
+        res["sweep"].append({"batch": B, "molecules_per_s": B / tb, "ms_per_step": tb * 1e3 / sb,
+                             "roofline_frac": floor_s(B, sb) / tb})
+    return res
 
 
 def main():
@@ -387,7 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0)
-    ap.add_argument("--decode-batch", type=int, default=64)
+    ap.add_argument("--decode-batch", type=int, default=256)
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -115,7 +115,9 @@ class Generator:
             ops.gemm(h, eng.W(p + "multihead_attn.in_proj_weight")[:d], R, d, d,
                      ops.make_epi(EPI_STORE, q, bias=eng.P(p + "multihead_attn.in_proj_bias")[:d]))
             kv = ctx["kvmem"][i]
-            ops.decode_cross_attn(q, kv[:, :d], kv[:, d:], ctx["enc_mask"], st.cur_len, att, R, H, dh, ctx["S"], K)
+            # the K beams of a spectrum attend over the same memory: one (spectrum, head) problem with K queries on
+            # the tensor-core forward-attention kernel (K/V are read once per spectrum, not once per beam)
+            ops.attn_fwd(q, kv[:, :d], kv[:, d:], att, None, st.B, H, K, ctx["S"], dh, kmask=ctx["enc_mask"])
             ops.gemm(att, eng.W(p + "multihead_attn.out_proj.weight"), R, d, d,
                      ops.make_epi(EPI_RESID, xb, bias=eng.P(p + "multihead_attn.out_proj.bias"), resid=xa))
             ops.ln_fwd(xb, eng.P(p + "norm3.weight"), eng.P(p + "norm3.bias"), h)

@@ -29,10 +29,11 @@ if what == "train":
 else:
     model.eval()
     batch = bench.map_batch(bench.synth_batch(c, B, 1), lambda x: x.cuda())
-    model.generator.generate(*model._relayout(batch, False), n_beams=10, max_length=24, use_graph=False)
+    L = int(sys.argv[3]) if len(sys.argv) > 3 else 24
+    model.generator.generate(*model._relayout(batch, False), n_beams=10, max_length=L, use_graph=False)
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
-    model.generator.generate(*model._relayout(batch, False), n_beams=10, max_length=24, use_graph=False)
+    model.generator.generate(*model._relayout(batch, False), n_beams=10, max_length=L, use_graph=False)
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
 print("done")
