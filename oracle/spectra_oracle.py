@@ -466,6 +466,21 @@ def init_state_dict(cfg: OracleConfig, vocab: int, enc_ffn: int, dec_ffn: int, s
         ln(p + "norm1.")
         ln(p + "norm2.")
     ln("hf_model.encoder.norm.")
+    if cfg.align_config:  # custom_modeling.py:363-396
+        ac, p = cfg.align_config, "hf_model.align_network."
+        hd = ac["hidden_dimension"]
+        lin(p + "0.", hd, d)
+        if ac["align_network"] == "convolutional":
+            lin(p + "2.", hd, hd)
+            ks, cc = ac["kernel_size"], ac["conv_channels"]
+            a = math.sqrt(6.0 / (hd * ks + cc * ks))
+            sd[p + "4.weight"] = (torch.rand(cc, hd, ks, generator=g) * 2 - 1) * a
+            sd[p + "4.bias"] = bias(cc, hd * ks)
+            a = math.sqrt(6.0 / (cc + ac["output_dimension"]))
+            sd[p + "6.weight"] = (torch.rand(ac["output_dimension"], cc, 1, generator=g) * 2 - 1) * a
+            sd[p + "6.bias"] = bias(ac["output_dimension"], cc)
+        else:
+            lin(p + "2.", ac["output_dimension"], hd)
     for i in range(cfg.decoder_layers):
         p = f"hf_model.decoder.layers.{i}."
         attn(p + "self_attn.")
