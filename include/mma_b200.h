@@ -98,6 +98,12 @@ int mma_colsum(const void* in, int in_f32, long long ld, float* out, int rows, i
 int mma_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);
 int mma_cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t stream);
 
+/* PatchPreprocessor on the device (data/preprocessing/patches.py:54-107): standardise, (interpolation == slice,
+ * see rowops.cu), trim, patch.  out [B, P, ps] batch-first; pad [B, P] (optional): patch-sum == 0 when masking,
+ * else missing[b].  hop = ps / overlap.                                                                          */
+int mma_patchify(const float* raw, long long ld, int offset, float mean, float std, float* out, unsigned char* pad,
+                 const unsigned char* missing, int masking, int B, int P, int ps, int hop, cudaStream_t stream);
+
 /* ---- encoder-alignment head (custom_modeling.py:363-396 networks, :453-475 masked mean pool + loss; LOSS_FACTORY
  * :15; modeling/utils.py:8-22 kl_div / sid).  The MLP / centre-tap conv products run on the GEMM entry points.  */
 /* pooled[b,:] = sum_s mask[b,s] mem[b,s,:] / sum_s mask[b,s]   (mask 1 = real token) */

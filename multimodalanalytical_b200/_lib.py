@@ -96,6 +96,7 @@ _SIGS = {
     "mma_colsum": [_vp, _i, _ll, _vp, _i, _i, _vp],
     "mma_cast_f32_bf16": [_vp, _vp, _ll, _vp],
     "mma_cast_bf16_f32": [_vp, _vp, _ll, _vp],
+    "mma_patchify": [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mma_masked_mean_fwd": [_vp, _i, _ll, _vp, _vp, _i, _i, _i, _vp],
     "mma_masked_mean_bwd": [_vp, _vp, _vp, _ll, _i, _i, _i, _vp],
     "mma_align_loss": [_vp, _ll, _vp, _ll, _i, _i, _i, _f, _vp, _vp, _vp, _ll, _f, _vp],

@@ -423,3 +423,48 @@ extern "C" int mma_cast_bf16_f32(const void* in, float* out, long long n, cudaSt
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// PatchPreprocessor on the device (reference: data/preprocessing/patches.py:54-107).  The reference's optional
+// interpolation maps the 400..3980 cm^-1 grid (step 2) onto 650..3898 (step 2): every new abscissa IS an old knot, so
+// the linear interpolation is the slice [125, 125 + 1625) of the input - `offset` / `n_use` express that.
+//   out[b, p, k] = (raw[b, offset + p * hop + k] - mean) / std          p < P, k < ps,  hop = ps / overlap
+//   pad[b, p]    = (sum_k out[b, p, k] == 0)   when `masking`, else the caller's per-sample "spectrum missing" flag
+// Output is batch-first [B, P, ps] - the layout the embedding GEMM consumes - so the seq-first host tensor and its
+// transpose never exist.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) patchify_kernel(const float* __restrict__ raw, long long ld, int offset,
+                                                       float mean, float std, float* __restrict__ out,
+                                                       unsigned char* __restrict__ pad,
+                                                       const unsigned char* __restrict__ missing, int masking, int P,
+                                                       int ps, int hop) {
+  pdl_trigger();
+  const int b = blockIdx.y, p = blockIdx.x;
+  const float* src = raw + (long long)b * ld + offset + (long long)p * hop;
+  float* dst = out + ((long long)b * P + p) * ps;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < ps; k += blockDim.x) {
+    const float v = (src[k] - mean) / std;  // exact division: bit-identical to the reference's fp32 arithmetic
+    dst[k] = v;
+    s += v;
+  }
+  if (pad) {
+    __shared__ float red[4];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float tot = red[0] + red[1] + red[2] + red[3];
+      pad[(long long)b * P + p] = masking ? (tot == 0.f) : (missing ? missing[b] : 0);
+    }
+  }
+}
+
+extern "C" int mma_patchify(const float* raw, long long ld, int offset, float mean, float std, float* out,
+                            unsigned char* pad, const unsigned char* missing, int masking, int B, int P, int ps,
+                            int hop, cudaStream_t stream) {
+  if (B <= 0 || P <= 0 || ps <= 0 || hop <= 0 || std == 0.f) return MMA_ERR_ARG;
+  patchify_kernel<<<dim3(P, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, P, ps, hop);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}

@@ -178,6 +178,18 @@ def colsum(x, out, rows=None, cols=None):
     _count()
 
 
+def patchify(raw, out, mean, std, offset=0, hop=None, pad=None, missing=None, masking=False):
+    """raw fp32 [B, n_points] -> out fp32 [B, P, ps] standardised patches (PatchPreprocessor.__call__ on the device)."""
+    _need_cuda(raw, out)
+    assert raw.dtype == torch.float32 and raw.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
+    B, P, ps = out.shape
+    hop = ps if hop is None else hop
+    assert offset + (P - 1) * hop + ps <= raw.shape[1], "patches run past the spectrum"
+    check(_lib.load().mma_patchify(raw.data_ptr(), raw.stride(0), int(offset), float(mean), float(std), out.data_ptr(),
+                                   _p(pad), _p(missing), int(masking), B, P, ps, hop, _stream()), "mma_patchify")
+    _count()
+
+
 ALIGN_LOSS_KINDS = {"mae": 0, "mse": 1, "sid": 2}
 
 

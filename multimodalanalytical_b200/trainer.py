@@ -255,3 +255,26 @@ def predict(module: HFWrapper, batches, n_beams: Optional[int] = None):
     for i, batch in enumerate(batches):
         outs.append(module.predict_step(batch, i))
     return outs
+
+
+@torch.no_grad()
+def validate(module: HFWrapper, batches, limit_batches: Optional[int] = None) -> Dict[str, float]:
+    """One validation epoch: what Lightning runs around `validation_step` / `on_validation_epoch_end`
+    (wrapper.py:491-530): per batch the teacher-forced loss, token accuracy, a KV-cached greedy decode and its Top-1
+    molecular accuracy; returns the epoch means.  Host syncs happen once per batch (string comparison of the decoded
+    SMILES), never per decode step."""
+    was_training = module.training
+    sums: Dict[str, float] = {}
+    n = 0
+    for i, batch in enumerate(batches):
+        if limit_batches is not None and i >= limit_batches:
+            break
+        out = module.validation_step(batch, i)
+        for k, v in out.items():
+            if v is not None:
+                sums[k] = sums.get(k, 0.0) + float(v)
+        n += 1
+    module.on_validation_epoch_end()
+    if was_training:
+        module.train()
+    return {k: v / max(n, 1) for k, v in sums.items()}

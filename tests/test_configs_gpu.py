@@ -237,3 +237,15 @@ def test_fused_trainer_loss_decreases_on_c3():
     tr = FusedTrainer(m)
     losses = [float(tr.train_step(fx["batch"], i)) for i in range(12)]
     assert losses[-1] < losses[0] - 0.2, losses
+
+
+def test_validation_epoch_runs_greedy_decode_and_token_accuracy():
+    """N4: trainer.validate = the reference's validation loop (loss, token accuracy, greedy Top-1) over batches."""
+    from multimodalanalytical_b200.trainer import validate
+    fx = make_case("c3", 16)
+    m = build(fx, "bf16")
+    m.generation_config["max_length"] = 32
+    res = validate(m, [fx["batch"], fx["batch"]])
+    assert set(res) >= {"val_loss", "val_token_acc", "val_molecular_accuracy"}
+    assert res["val_loss"] > 0 and 0.0 <= res["val_token_acc"] <= 1.0 and 0.0 <= res["val_molecular_accuracy"] <= 1.0
+    assert m.validation_step_outputs == []

@@ -1,0 +1,79 @@
+"""PatchPreprocessor: the numpy oracle against golden vectors produced by the reference class, and the
+device kernel (`DevicePatchPreprocessor`) against both."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import patch_oracle as po
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "patches.pt")
+
+
+def cases():
+    return torch.load(GOLDEN, weights_only=False)
+
+
+def test_patch_oracle_matches_reference_golden():
+    for c in cases():
+        live = [s for s in c["spectra"] if s is not None]
+        mean, std = po.statistics(live)
+        assert abs(mean - c["mean"]) <= 1e-12 and abs(std - c["std"]) <= 1e-12, c["name"]
+        p, m = po.patch_preprocess(c["spectra"], c["mean"], c["std"], **c["kwargs"])
+        want = c["patches"].numpy()
+        assert p.shape == want.shape, c["name"]
+        np.testing.assert_allclose(p, want, rtol=0, atol=2e-6 * np.abs(want).max(), err_msg=c["name"])
+        assert np.array_equal(m, c["mask"].numpy()), c["name"]
+
+
+def test_interpolation_is_a_slice():
+    """Both wavenumber grids share their knots, so the reference's interp1d is x[125 : 125 + 1625]."""
+    rng = np.random.default_rng(0)
+    for n in (1791, 1800):
+        x = rng.random(n)
+        got = po.interpolate(x)
+        assert got.shape == (1625,)
+        np.testing.assert_allclose(got, x[125:125 + 1625], rtol=1e-14)
+
+
+@pytest.mark.gpu
+def test_device_patch_preprocessor_matches_reference_golden():
+    from multimodalanalytical_b200.preprocess import DevicePatchPreprocessor
+    for c in cases():
+        pp = DevicePatchPreprocessor(**c["kwargs"])
+        pp.initialise(np.array([s for s in c["spectra"] if s is not None]))
+        assert abs(pp.mean - c["mean"]) <= 1e-12 and abs(pp.std - c["std"]) <= 1e-12
+        patches, mask = pp([None if s is None else list(s) for s in c["spectra"]])
+        want = c["patches"]
+        assert tuple(patches.shape) == tuple(want.shape), c["name"]
+        err = (patches.cpu() - want).abs().max() / want.abs().max()
+        assert float(err) < 2e-6, (c["name"], float(err))
+        assert torch.equal(mask.cpu(), c["mask"]), c["name"]
+
+
+@pytest.mark.gpu
+def test_device_patches_feed_the_model_like_collator_patches():
+    """C2 at full batch: raw spectra -> device patches -> HFWrapper.forward equals the host-patched batch."""
+    import bench
+    from multimodalanalytical_b200.preprocess import DevicePatchPreprocessor
+    from multimodalanalytical_b200.wrapper import HFWrapper
+    c = dict(bench.C2)
+    B = 256
+    g = torch.Generator().manual_seed(1)
+    raw = torch.rand(B, 1791, generator=g)
+    pp = DevicePatchPreprocessor(patch_size=75, interpolation=True)
+    pp.initialise(raw.numpy())
+    dev_patches, _ = pp(raw)
+    host_patches, _ = po.patch_preprocess(raw.numpy().tolist(), pp.mean, pp.std, 75, interpolation=True)
+    batch = bench.synth_batch(c, B, 5)
+    batch["encoder_input"]["IR"] = torch.from_numpy(host_patches).transpose(0, 1).contiguous()  # collator: [P, B, ps]
+    m = HFWrapper(data_config=bench.data_config(c), target_tokenizer=bench.Tok(c["V"]), num_steps=10, precision="bf16",
+                  seed=2, **bench.model_kwargs(c, dropout=0.0))
+    m.eval()
+    with torch.no_grad():
+        a = m.forward(batch)
+        la = float(a.loss)
+        batch["encoder_input"]["IR"] = dev_patches.transpose(0, 1)  # device tensor, seq-first view
+        b = m.forward(batch)
+    assert abs(la - float(b.loss)) < 1e-5 * abs(la)
