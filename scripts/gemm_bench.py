@@ -11,7 +11,33 @@ from multimodalanalytical_b200._lib import EPI_ACCUM, EPI_DGELU, EPI_GELU, EPI_R
 dev = "cuda"
 
 
+def timeit_graph(fn, n=10, inner=20):
+    """us per launch with `inner` launches captured in ONE CUDA graph (no host launch path at all: what the kernel
+    costs inside the captured training step, PDL overlap included)."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(inner):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3 / inner)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
 def timeit(fn, n=10, inner=10):
+    if os.environ.get("BENCH_GRAPH", "1") != "0":
+        return timeit_graph(fn, n=n)
     """us per launch: `inner` back-to-back launches per event pair (the GPU queue never drains, so the Python /
     launch path is not part of the measurement), median over `n` repeats."""
     for _ in range(3):
