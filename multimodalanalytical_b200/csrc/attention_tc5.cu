@@ -11,6 +11,8 @@
 // keys 0-63 = problem A, rows 64-127 / keys 64-127 = problem B; the off-diagonal blocks of P / dS are written as
 // zeros so the packed products stay block-diagonal).  PACK = 1 is one problem with <= 128 queries and keys.
 // Longer sequences use the streaming mma.sync kernels (attention_mma.cu).  Masks / dropout stream: as everywhere.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -80,9 +82,9 @@ struct RowMap {
   int prob, b, h, i;   // problem index, batch, head, local row index
   bool exists;
   int key_col0;        // first score column of this row's problem
-  __device__ RowMap(const Args& a, int row) {
+  __device__ RowMap(const Args& a, int row, int tile = blockIdx.x) {
     const int sub = PACK == 2 ? (row >> 6) : 0;
-    prob = blockIdx.x * PACK + sub;
+    prob = tile * PACK + sub;
     exists = prob < a.nprob;
     const int pp = exists ? prob : 0;
     b = pp / a.H;
@@ -93,11 +95,12 @@ struct RowMap {
 };
 
 template <int PACK>
-__device__ __forceinline__ void issue_tile_loads(const Args& a, const CUtensorMap* tm, uint32_t dst, uint32_t bar, int L) {
+__device__ __forceinline__ void issue_tile_loads(const Args& a, const CUtensorMap* tm, uint32_t dst, uint32_t bar, int L,
+                                                 int tile = blockIdx.x) {
   // two 64-row boxes: rows [0,64) and [64,128) of the tile
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    int prob = PACK == 2 ? blockIdx.x * 2 + s : blockIdx.x;
+    int prob = PACK == 2 ? tile * 2 + s : tile;
     if (prob >= a.nprob) prob = a.nprob - 1;  // dummy (masked) when the pair is incomplete
     const int b = prob / a.H, h = prob % a.H;
     const int row0 = b * L + (PACK == 2 ? 0 : s * 64);
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(128) fwd_kernel(const __grid_constant__ CUtens
 template <int PACK>
 __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                                                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
-                                                  Args a) {
+                                                  const __grid_constant__ CUtensorMap to, Args a) {
   pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem[];  // no static smem in this kernel: the window starts 1024-aligned
   // layout (ascending): Pd atom 0 | dS atom 0 | dS atom 1 | Q | K | dO | V (= Pd atom 1 once dP has retired)
@@ -304,11 +307,12 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
   pdl_wait();
   if (threadIdx.x == 0) {
     const uint32_t bar = smem_u32(&bars[0]);
-    mbar_expect_tx(bar, 4 * TILE);
+    mbar_expect_tx(bar, 5 * TILE);
     issue_tile_loads<PACK>(a, &tq, smem_u32(sQ), bar, a.Lq);
     issue_tile_loads<PACK>(a, &tk, smem_u32(sK), bar, a.Lk);
     issue_tile_loads<PACK>(a, &tv, smem_u32(sV), bar, a.Lk);
     issue_tile_loads<PACK>(a, &tdo, smem_u32(sDO), bar, a.Lq);
+    issue_tile_loads<PACK>(a, &to, smem_u32(sdS), bar, a.Lq);  // O parks in dS atom 0 until D_i is formed
     mbar_wait(bar, 0);
     tc_fence_after();
 #pragma unroll
@@ -323,14 +327,19 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
   const RowMap<PACK> rm(a, row);
   const bool qvalid = rm.exists && rm.i < a.Lq;
   const unsigned char* km = a.kmask ? a.kmask + (long long)rm.b * a.Lk : nullptr;
-  // D_i = sum_c dO[i,c] O[i,c] and lse_i while the tensor core works
+  // D_i = sum_c dO[i,c] O[i,c] and lse_i while the tensor core works.  Both rows come from the TMA-loaded shared
+  // tiles (a thread owns one row: read from global that is 16 scattered 16-byte loads per thread)
   float Di = 0.f, lse2 = 0.f;
-  if (qvalid) {
-    const uint4* po = reinterpret_cast<const uint4*>(a.o_in + ((long long)rm.b * a.Lq + rm.i) * a.ldo + rm.h * 64);
-    const uint4* pd = reinterpret_cast<const uint4*>(a.dout + ((long long)rm.b * a.Lq + rm.i) * a.lddo + rm.h * 64);
+  if (qvalid) lse2 = a.lse[((long long)rm.b * a.H + rm.h) * a.Lq + rm.i] * LOG2E;
+  if (lane == 0) mbar_wait(smem_u32(&bars[0]), 0);
+  __syncwarp();
+  {
+    const uint8_t* orow = sdS + row * 128;
+    const uint8_t* drow = sDO + row * 128;
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const uint4 x = po[u], y = pd[u];
+      const int sw = (u ^ (row & 7)) << 4;
+      const uint4 x = *reinterpret_cast<const uint4*>(orow + sw), y = *reinterpret_cast<const uint4*>(drow + sw);
       const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&x);
       const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&y);
 #pragma unroll
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
         Di += xf.x * yf.x + xf.y * yf.y;
       }
     }
-    lse2 = a.lse[((long long)rm.b * a.H + rm.h) * a.Lq + rm.i] * LOG2E;
+    if (!qvalid) Di = 0.f;
   }
   const float sl2 = a.scale * LOG2E;
   const bool drop = a.p_drop > 0.f;
@@ -459,6 +468,278 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
   }
 }
 
+// ------------------------------------------------------------------------------------------------ backward, pipelined
+// Persistent, warp-specialised version of bwd_kernel: one CTA per SM walks over tiles; a TMA warp prefetches the next
+// tile's five operand tiles (Q K V dO O) into a 2-stage ring, one thread issues the MMAs, a SOFTMAX group (4 warps)
+// turns S / dP into P~ / dS, an EPILOGUE group (4 warps) drains dV / dK / dQ.  S | dP and the three outputs live in
+// disjoint TMEM columns, so MMA-1 of tile i+1, the softmax of tile i+1 and the epilogue of tile i overlap; the
+// single-shot kernel paid the whole load -> MMA -> softmax -> MMA -> store latency chain per CTA with only two CTAs
+// per SM to hide it.  Math identical to bwd_kernel.
+constexpr int PIPE_THREADS = 448;  // warp 0 TMA, warp 1 MMA, warps 2-9 softmax (two per row quarter), warps 10-13 epilogue
+constexpr uint32_t PIPE_STAGE = 5 * TILE;
+constexpr uint32_t PIPE_SMEM = 2 * PIPE_STAGE + 4 * TILE + 256;
+
+template <int PACK>
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+bwd_pipe_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                const __grid_constant__ CUtensorMap to, Args a, int ntiles) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem[];  // no static smem: the window starts 1024-aligned
+  uint8_t* sIn = smem;                    // [2 stages][Q | K | V | dO | O]
+  uint8_t* sPd = smem + 2 * PIPE_STAGE;   // P~ (dropout applied), two 64-key atoms
+  uint8_t* sdS = sPd + 2 * TILE;          // dS, two 64-key atoms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 2 * TILE);
+  uint64_t* in_full = bars;        // [2]
+  uint64_t* in_empty = bars + 2;   // [2]
+  uint64_t* sdp_full = bars + 4;   // S | dP of the current tile are in TMEM
+  uint64_t* sdp_free = bars + 5;   // the softmax group has read them
+  uint64_t* pds_full = bars + 6;   // P~ | dS are in shared memory
+  uint64_t* pd_free = bars + 7;    // the MMAs reading them have retired
+  uint64_t* out_full = bars + 8;   // dV | dK | dQ are in TMEM
+  uint64_t* out_free = bars + 9;   // the epilogue group has read them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&in_full[i]), 1);
+      mbar_init(smem_u32(&in_empty[i]), 1);
+    }
+    mbar_init(smem_u32(sdp_full), 1);
+    mbar_init(smem_u32(sdp_free), 8);
+    mbar_init(smem_u32(pds_full), 8);
+    mbar_init(smem_u32(pd_free), 1);
+    mbar_init(smem_u32(out_full), 1);
+    mbar_init(smem_u32(out_free), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ================= TMA loader =================
+      int i = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int s = i & 1;
+        mbar_wait(smem_u32(&in_empty[s]), ((i >> 1) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&in_full[s]);
+        const uint32_t base = smem_u32(sIn + s * PIPE_STAGE);
+        mbar_expect_tx(bar, 5 * TILE);
+        issue_tile_loads<PACK>(a, &tq, base, bar, a.Lq, tile);
+        issue_tile_loads<PACK>(a, &tk, base + TILE, bar, a.Lk, tile);
+        issue_tile_loads<PACK>(a, &tv, base + 2 * TILE, bar, a.Lk, tile);
+        issue_tile_loads<PACK>(a, &tdo, base + 3 * TILE, bar, a.Lq, tile);
+        issue_tile_loads<PACK>(a, &to, base + 4 * TILE, bar, a.Lq, tile);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ================= MMA issuer =================
+      auto mma1 = [&](int s) {  // S = Q K^T -> cols [0,128);  dP = dO V^T -> cols [128,256)
+        const uint32_t base = smem_u32(sIn + s * PIPE_STAGE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tm, desc_kmajor(base + k * 32), desc_kmajor(base + TILE + k * 32), idesc(128, false, false), k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc_mma_bf16(tm + 128, desc_kmajor(base + 3 * TILE + k * 32), desc_kmajor(base + 2 * TILE + k * 32),
+                      idesc(128, false, false), k > 0);
+        tc_commit(smem_u32(sdp_full));
+      };
+      int n_my = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++n_my;
+      if (n_my > 0) {
+        mbar_wait(smem_u32(&in_full[0]), 0);
+        tc_fence_after();
+        mma1(0);
+      }
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i & 1;
+        if (i + 1 < n_my) {
+          mbar_wait(smem_u32(&in_full[s ^ 1]), ((i + 1) >> 1) & 1);
+          mbar_wait(smem_u32(sdp_free), i & 1);  // the softmax group holds S | dP of tile i in registers
+          tc_fence_after();
+          mma1(s ^ 1);
+        }
+        mbar_wait(smem_u32(pds_full), i & 1);
+        mbar_wait(smem_u32(out_free), (i & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(sIn + s * PIPE_STAGE);
+        const uint32_t q_a = base, k_a = base + TILE, do_a = base + 3 * TILE;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV[keys x 64] = P~^T dO     -> cols [256,320)
+          tc_mma_bf16(tm + 256, desc_mnmajor(smem_u32(sPd) + k * 2048, TILE), desc_mnmajor(do_a + k * 2048, TILE),
+                      idesc(64, true, true), k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK[keys x 64] = dS^T Q      -> cols [320,384)
+          tc_mma_bf16(tm + 320, desc_mnmajor(smem_u32(sdS) + k * 2048, TILE), desc_mnmajor(q_a + k * 2048, TILE),
+                      idesc(64, true, true), k > 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ[q x 64] = dS K           -> cols [384,448)
+          tc_mma_bf16(tm + 384, desc_kmajor(smem_u32(sdS) + (k >> 2) * TILE + (k & 3) * 32),
+                      desc_mnmajor(k_a + k * 2048, TILE), idesc(64, false, true), k > 0);
+        tc_commit(smem_u32(out_full));
+        tc_commit(smem_u32(pd_free));
+        tc_commit(smem_u32(&in_empty[s]));
+      }
+    }
+  } else if (warp < 10) {
+    // ================= softmax group: S, dP -> P~, dS  (warps w and w+4 share a row quarter and split its columns) ====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const float sl2 = a.scale * LOG2E;
+    const bool drop = a.p_drop > 0.f;
+    const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+    const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+    const uint32_t dkey = drop_key(a.seed, a.site);
+    constexpr int NCH = PACK == 2 ? 2 : 4;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const int s = i & 1;
+      const RowMap<PACK> rm(a, row, tile);
+      const bool qvalid = rm.exists && rm.i < a.Lq;
+      const unsigned char* km = a.kmask ? a.kmask + (long long)rm.b * a.Lk : nullptr;
+      const float lse2 = qvalid ? a.lse[((long long)rm.b * a.H + rm.h) * a.Lq + rm.i] * LOG2E : 0.f;
+      const unsigned long long ebase =
+          (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)((a.Lk + 1) & ~1);
+      const uint32_t ebase32 = (uint32_t)ebase;
+      uint32_t vbits[NCH];
+      key_valid_bits<NCH>(vbits, km, a.Lk, a.causal, rm.i, lane);
+      // D_i = sum_c dO[i,c] O[i,c] from the staged tiles
+      mbar_wait(smem_u32(&in_full[s]), (i >> 1) & 1);
+      float Di = 0.f;
+      {
+        const uint8_t* orow = sIn + s * PIPE_STAGE + 4 * TILE + row * 128;
+        const uint8_t* drow = sIn + s * PIPE_STAGE + 3 * TILE + row * 128;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int sw = (u ^ (row & 7)) << 4;
+          const uint4 x = *reinterpret_cast<const uint4*>(orow + sw), y = *reinterpret_cast<const uint4*>(drow + sw);
+          const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&x);
+          const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const float2 xf = __bfloat1622float2(xb[w]), yf = __bfloat1622float2(yb[w]);
+            Di += xf.x * yf.x + xf.y * yf.y;
+          }
+        }
+        if (!qvalid) Di = 0.f;
+      }
+      const uint32_t t_row = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)rm.key_col0;
+      mbar_wait(smem_u32(sdp_full), i & 1);
+      tc_fence_after();
+      constexpr int CPW = NCH / 2;  // chunks per warp
+#pragma unroll 1
+      for (int ch = half * CPW; ch < (half + 1) * CPW; ++ch) {
+        float sv[32], dp[32];
+        tmem_ld32f(t_row + ch * 32, sv);
+        tmem_ld32f(t_row + 128 + ch * 32, dp);
+        if (ch == (half + 1) * CPW - 1) {  // S | dP of this tile are in registers: MMA-1 of the next tile may overwrite them
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(sdp_free));
+        }
+        const uint32_t vb = qvalid ? vbits[ch] : 0u;
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = (vb >> c) & 1u ? ex2_approx(sv[c] * sl2 - lse2) : 0.f;
+          const float p1 = (vb >> (c + 1)) & 1u ? ex2_approx(sv[c + 1] * sl2 - lse2) : 0.f;
+          float k0 = 1.f, k1 = 1.f;
+          if (drop) {
+            const uint32_t r = drop_pair(dkey, (ebase32 + (uint32_t)(ch * 32 + c)) >> 1);
+            k0 = (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+            k1 = (r >> 16) >= thr ? inv_keep : 0.f;
+          }
+          sv[c] = p0 * k0;
+          sv[c + 1] = p1 * k1;
+          dp[c] = p0 * (dp[c] * k0 - Di);
+          dp[c + 1] = p1 * (dp[c + 1] * k1 - Di);
+        }
+        if (ch == half * CPW) mbar_wait(smem_u32(pd_free), (i & 1) ^ 1);  // MMA-2 of the previous tile has read P~ | dS
+        const int kcol = rm.key_col0 + ch * 32;
+        uint8_t* pa = sPd + (kcol >> 6) * TILE;
+        uint8_t* da = sdS + (kcol >> 6) * TILE;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 u, w;
+          u.x = pack2(sv[c], sv[c + 1]); u.y = pack2(sv[c + 2], sv[c + 3]);
+          u.z = pack2(sv[c + 4], sv[c + 5]); u.w = pack2(sv[c + 6], sv[c + 7]);
+          w.x = pack2(dp[c], dp[c + 1]); w.y = pack2(dp[c + 2], dp[c + 3]);
+          w.z = pack2(dp[c + 4], dp[c + 5]); w.w = pack2(dp[c + 6], dp[c + 7]);
+          st_chunk(pa, row, (kcol & 63) + c, u);
+          st_chunk(da, row, (kcol & 63) + c, w);
+        }
+      }
+      if (PACK == 2) {
+        const int other = (rm.key_col0 >> 6) ^ 1;
+#pragma unroll
+        for (int c = half * 32; c < half * 32 + 32; c += 8) {
+          st_chunk(sPd + other * TILE, row, c, make_uint4(0, 0, 0, 0));
+          st_chunk(sdS + other * TILE, row, c, make_uint4(0, 0, 0, 0));
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(pds_full));
+    }
+  } else {
+    // ================= epilogue group: dV, dK, dQ -> global =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const RowMap<PACK> rm(a, row, tile);
+      const bool qvalid = rm.exists && rm.i < a.Lq;
+      const bool kvalid = rm.exists && rm.i < a.Lk;
+      bf16* dqrow = a.dq + ((long long)rm.b * a.Lq + rm.i) * a.lddq + rm.h * 64;
+      bf16* dkrow = a.dk + ((long long)rm.b * a.Lk + rm.i) * a.lddk + rm.h * 64;
+      bf16* dvrow = a.dv + ((long long)rm.b * a.Lk + rm.i) * a.lddv + rm.h * 64;
+      const uint32_t tl = tm + ((uint32_t)(q * 32) << 16) + 256;
+      mbar_wait(smem_u32(out_full), i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int part = 0; part < 6; ++part) {  // dV lo/hi, dK lo/hi, dQ lo/hi
+        float v[32];
+        tmem_ld32f(tl + part * 32, v);
+        if (part == 5) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(out_free));
+        }
+        const int which = part >> 1, half = part & 1;
+        const bool wr = which == 2 ? qvalid : kvalid;
+        const float sc = which == 0 ? 1.f : a.scale;
+        bf16* dst = (which == 0 ? dvrow : which == 1 ? dkrow : dqrow) + half * 32;
+        if (wr) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 u;
+            u.x = pack2(v[c] * sc, v[c + 1] * sc); u.y = pack2(v[c + 2] * sc, v[c + 3] * sc);
+            u.z = pack2(v[c + 4] * sc, v[c + 5] * sc); u.w = pack2(v[c + 6] * sc, v[c + 7] * sc);
+            *reinterpret_cast<uint4*>(dst + c) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+  }
+}
+
 static int map64(CUtensorMap* m, const void* p, int H, long long rows, long long ld) {
   return make_map(m, p, (unsigned long long)H * 64, (unsigned long long)rows, (unsigned long long)ld, 64, 64);
 }
@@ -506,26 +787,53 @@ extern "C" int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long
   using namespace at5;
   if (B <= 0 || Lq <= 0 || Lk <= 0) return MMA_OK;
   if (Lq > 128 || Lk > 128 || ((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 7)) return MMA_ERR_UNSUPPORTED;
-  CUtensorMap tq, tk, tv, tdo;
+  CUtensorMap tq, tk, tv, tdo, to;
   int rc;
   if ((rc = map64(&tq, q, H, (long long)B * Lq, ldq))) return rc;
   if ((rc = map64(&tk, k, H, (long long)B * Lk, ldk))) return rc;
   if ((rc = map64(&tv, v, H, (long long)B * Lk, ldv))) return rc;
   if ((rc = map64(&tdo, dout, H, (long long)B * Lq, lddo))) return rc;
+  if ((rc = map64(&to, o, H, (long long)B * Lq, ldo))) return rc;
   Args a{};
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nprob = B * H; a.scale = scale; a.p_drop = p_drop;
   a.seed = seed; a.site = site; a.kmask = kmask; a.lse = const_cast<float*>(lse);
   a.o_in = (const bf16*)o; a.ldo = ldo; a.dout = (const bf16*)dout; a.lddo = lddo;
   a.dq = (bf16*)dq; a.dk = (bf16*)dk; a.dv = (bf16*)dv; a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
+  static int pipe = -1;
+  if (pipe < 0) {
+    const char* e = getenv("MMA_ATTN_PIPE");
+    pipe = e ? atoi(e) : 1;
+  }
+  if (pipe) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const bool pack2 = Lq <= 64 && Lk <= 64;
+    const int ntiles = pack2 ? (a.nprob + 1) / 2 : a.nprob;
+    const int grid = ntiles < sms ? ntiles : sms;
+    static bool set2 = false, set1 = false;
+    if (pack2) {
+      if (!set2) { cudaFuncSetAttribute(bwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM); set2 = true; }
+      if (launch_pdl(bwd_pipe_kernel<2>, dim3(grid), dim3(PIPE_THREADS), PIPE_SMEM, stream, tq, tk, tv, tdo, to, a, ntiles) != cudaSuccess) return MMA_ERR_LAUNCH;
+    } else {
+      if (!set1) { cudaFuncSetAttribute(bwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM); set1 = true; }
+      if (launch_pdl(bwd_pipe_kernel<1>, dim3(grid), dim3(PIPE_THREADS), PIPE_SMEM, stream, tq, tk, tv, tdo, to, a, ntiles) != cudaSuccess) return MMA_ERR_LAUNCH;
+    }
+    MMA_CHECK_LAUNCH();
+    return MMA_OK;
+  }
   const int smem = 7 * TILE + 64;  // 2 CTAs per SM
   if (Lq <= 64 && Lk <= 64) {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    if (launch_pdl(bwd_kernel<2>, dim3((a.nprob + 1) / 2), dim3(128), smem, stream, tq, tk, tv, tdo, a) != cudaSuccess) return MMA_ERR_LAUNCH;
+    if (launch_pdl(bwd_kernel<2>, dim3((a.nprob + 1) / 2), dim3(128), smem, stream, tq, tk, tv, tdo, to, a) != cudaSuccess) return MMA_ERR_LAUNCH;
   } else {
     static bool set = false;
     if (!set) { cudaFuncSetAttribute(bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
-    if (launch_pdl(bwd_kernel<1>, dim3(a.nprob), dim3(128), smem, stream, tq, tk, tv, tdo, a) != cudaSuccess) return MMA_ERR_LAUNCH;
+    if (launch_pdl(bwd_kernel<1>, dim3(a.nprob), dim3(128), smem, stream, tq, tk, tv, tdo, to, a) != cudaSuccess) return MMA_ERR_LAUNCH;
   }
   MMA_CHECK_LAUNCH();
   return MMA_OK;
