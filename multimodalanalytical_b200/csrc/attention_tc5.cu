@@ -75,6 +75,18 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 
 // which (batch, head, local row) a tile row belongs to
 template <int PACK>
@@ -468,6 +480,243 @@ __global__ void __launch_bounds__(128) bwd_kernel(const __grid_constant__ CUtens
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward, pipelined
+// Persistent, warp-specialised version of fwd_kernel (same structure as bwd_pipe_kernel below): TMA warp with a 2-stage
+// (Q K V) ring, one MMA thread, an 8-warp softmax group (warps w and w+4 share a row quarter and split its key
+// columns; the row maximum is exchanged through shared memory), a 4-warp epilogue group.  S is double-buffered in
+// TMEM, so S of tile i+1 is computed while tile i is still in the softmax.
+constexpr int FPIPE_THREADS = 448;
+constexpr uint32_t FPIPE_STAGE = 3 * TILE;
+constexpr int FST = 3;  // operand ring depth
+constexpr uint32_t FPIPE_SMEM = FST * FPIPE_STAGE + 2 * TILE + 4 * 128 * 4 /*row max*/ + 2 * 2 * 128 * 4 /*sums*/ + 2 * 128 * 4 + 256;
+
+template <int PACK>
+__global__ void __launch_bounds__(FPIPE_THREADS, 1)
+fwd_pipe_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                const __grid_constant__ CUtensorMap tv, Args a, int ntiles) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sIn = smem;                     // [FST stages][Q | K | V]
+  uint8_t* sP = smem + FST * FPIPE_STAGE;  // P (dropout applied), two 64-key atoms
+  float* s_hmax = reinterpret_cast<float*>(sP + 2 * TILE);  // [2 tile parities][2 halves][128] partial row maxima
+  float* s_sum = s_hmax + 4 * 128;                          // [2 tile parities][2 halves][128] partial row sums
+  float* s_max = s_sum + 4 * 128;                           // [2 tile parities][128] row maxima (log2 domain)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_max + 2 * 128);
+  uint64_t* in_full = bars;       // [FST]
+  uint64_t* in_empty = bars + 4;  // [FST]
+  uint64_t* s_full = bars + 8;    // [2]  S buffer b holds the scores of a tile
+  uint64_t* s_free = bars + 10;   // [2]  the softmax group has read it
+  uint64_t* p_full = bars + 12;
+  uint64_t* p_free = bars + 13;
+  uint64_t* o_full = bars + 14;
+  uint64_t* o_free = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FST; ++i) {
+      mbar_init(smem_u32(&in_full[i]), 1);
+      mbar_init(smem_u32(&in_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 8);
+    }
+    mbar_init(smem_u32(p_full), 8);
+    mbar_init(smem_u32(p_free), 1);
+    mbar_init(smem_u32(o_full), 1);
+    mbar_init(smem_u32(o_free), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;  // S0 [0,128)  S1 [128,256)  O [256,320)
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int i = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        const int s = i % FST;
+        mbar_wait(smem_u32(&in_empty[s]), ((i / FST) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&in_full[s]);
+        const uint32_t base = smem_u32(sIn + s * FPIPE_STAGE);
+        mbar_expect_tx(bar, 3 * TILE);
+        issue_tile_loads<PACK>(a, &tq, base, bar, a.Lq, tile);
+        issue_tile_loads<PACK>(a, &tk, base + TILE, bar, a.Lk, tile);
+        issue_tile_loads<PACK>(a, &tv, base + 2 * TILE, bar, a.Lk, tile);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // Both products are issued as soon as their inputs are ready (non-blocking polls): S of tile t+1 must not wait
+      // for the softmax of tile t, and O of tile t must not wait for the operands of tile t+1.
+      int n_my = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++n_my;
+      int t1 = 0, t2 = 0;  // next tile for MMA-1 (S = Q K^T) / MMA-2 (O = P V)
+      const long long t0 = clock64();
+      while (t2 < n_my) {
+        if (t1 < n_my && t1 < t2 + 2) {
+          const int st = t1 % FST, sb = t1 & 1;
+          if (mbar_test(smem_u32(&in_full[st]), (t1 / FST) & 1) && mbar_test(smem_u32(&s_free[sb]), ((t1 >> 1) & 1) ^ 1)) {
+            tc_fence_after();
+            const uint32_t base = smem_u32(sIn + st * FPIPE_STAGE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_bf16(tm + sb * 128, desc_kmajor(base + k * 32), desc_kmajor(base + TILE + k * 32), idesc(128, false, false), k > 0);
+            tc_commit(smem_u32(&s_full[sb]));
+            ++t1;
+          }
+        }
+        if (t2 < t1 && mbar_test(smem_u32(p_full), t2 & 1) && mbar_test(smem_u32(o_free), (t2 & 1) ^ 1)) {
+          tc_fence_after();
+          const int st = t2 % FST;
+          const uint32_t v_a = smem_u32(sIn + st * FPIPE_STAGE + 2 * TILE);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)  // O[128 x 64] = P[128 x 128] V[128 x 64]
+            tc_mma_bf16(tm + 256, desc_kmajor(smem_u32(sP) + (k >> 2) * TILE + (k & 3) * 32),
+                        desc_mnmajor(v_a + k * 2048, TILE), idesc(64, false, true), k > 0);
+          tc_commit(smem_u32(o_full));
+          tc_commit(smem_u32(p_free));
+          tc_commit(smem_u32(&in_empty[st]));
+          ++t2;
+        }
+        if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must trap, never hang
+      }
+    }
+  } else if (warp < 10) {
+    // ================= softmax group =================
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const float sl2 = a.scale * LOG2E;
+    const bool drop = a.p_drop > 0.f;
+    const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+    const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+    const uint32_t dkey = drop_key(a.seed, a.site);
+    constexpr int NCH = PACK == 2 ? 2 : 4;
+    constexpr int CPW = NCH / 2;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const int sb = i & 1;
+      const RowMap<PACK> rm(a, row, tile);
+      const unsigned char* km = a.kmask ? a.kmask + (long long)rm.b * a.Lk : nullptr;
+      const unsigned long long ebase =
+          (((unsigned long long)rm.b * a.H + rm.h) * a.Lq + rm.i) * (unsigned long long)((a.Lk + 1) & ~1);
+      const uint32_t ebase32 = (uint32_t)ebase;
+      uint32_t vbits[NCH];
+      key_valid_bits<NCH>(vbits, km, a.Lk, a.causal, rm.i, lane);
+      const uint32_t t_row = tm + ((uint32_t)(q * 32) << 16) + (uint32_t)(sb * 128 + rm.key_col0);
+      mbar_wait(smem_u32(&s_full[sb]), (i >> 1) & 1);
+      tc_fence_after();
+      float sv[CPW][32];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int ch = half * CPW + cc;
+        tmem_ld32f(t_row + ch * 32, sv[cc]);
+        const uint32_t vb = vbits[ch];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (vb >> c) & 1u ? sv[cc][c] * sl2 : -INFINITY);
+      }
+      // the scores are in registers: the S buffer may be overwritten by the tile after next
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[sb]));
+      // exchange the partial maxima with the warp that owns the other half of this row quarter's columns
+      s_hmax[(sb * 2 + half) * 128 + row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, s_hmax[(sb * 2 + (half ^ 1)) * 128 + row]);
+      float l = 0.f;
+      mbar_wait(smem_u32(p_free), (i & 1) ^ 1);  // MMA-2 of the previous tile has read P
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int ch = half * CPW + cc;
+        const uint32_t vb = vbits[ch];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = (vb >> c) & 1u ? ex2_approx(sv[cc][c] * sl2 - mx) : 0.f;
+          float p1 = (vb >> (c + 1)) & 1u ? ex2_approx(sv[cc][c + 1] * sl2 - mx) : 0.f;
+          l += p0 + p1;
+          if (drop) {
+            const uint32_t r = drop_pair(dkey, (ebase32 + (uint32_t)(ch * 32 + c)) >> 1);
+            p0 *= (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+            p1 *= (r >> 16) >= thr ? inv_keep : 0.f;
+          }
+          sv[cc][c] = p0;
+          sv[cc][c + 1] = p1;
+        }
+        const int kcol = rm.key_col0 + ch * 32;
+        uint8_t* atom = sP + (kcol >> 6) * TILE;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 u;
+          u.x = pack2(sv[cc][c], sv[cc][c + 1]); u.y = pack2(sv[cc][c + 2], sv[cc][c + 3]);
+          u.z = pack2(sv[cc][c + 4], sv[cc][c + 5]); u.w = pack2(sv[cc][c + 6], sv[cc][c + 7]);
+          st_chunk(atom, row, (kcol & 63) + c, u);
+        }
+      }
+      if (PACK == 2) {  // zero this warp's share of the other problem's key block of this row
+        uint8_t* atom = sP + ((rm.key_col0 >> 6) ^ 1) * TILE;
+#pragma unroll
+        for (int c = half * 32; c < half * 32 + 32; c += 8) st_chunk(atom, row, c, make_uint4(0, 0, 0, 0));
+      }
+      s_sum[(sb * 2 + half) * 128 + row] = l;
+      if (half == 0) s_max[sb * 128 + row] = mx;
+      fence_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(p_full));
+    }
+  } else {
+    // ================= epilogue group =================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int i = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+      const int sb = i & 1;
+      const RowMap<PACK> rm(a, row, tile);
+      const bool wr = rm.exists && rm.i < a.Lq;
+      bf16* orow = a.o + ((long long)rm.b * a.Lq + rm.i) * a.ldo + rm.h * 64;
+      mbar_wait(smem_u32(o_full), i & 1);
+      tc_fence_after();
+      const float l = s_sum[(sb * 2) * 128 + row] + s_sum[(sb * 2 + 1) * 128 + row];
+      const float mx = s_max[sb * 128 + row];
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 2; ++ch) {
+        float v[32];
+        tmem_ld32f(tm + ((uint32_t)(q * 32) << 16) + 256 + ch * 32, v);
+        if (ch == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(o_free));
+        }
+        if (wr) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 u;
+            u.x = pack2(v[c] * inv, v[c + 1] * inv); u.y = pack2(v[c + 2] * inv, v[c + 3] * inv);
+            u.z = pack2(v[c + 4] * inv, v[c + 5] * inv); u.w = pack2(v[c + 6] * inv, v[c + 7] * inv);
+            *reinterpret_cast<uint4*>(orow + ch * 32 + c) = u;
+          }
+        }
+      }
+      if (wr && a.lse) a.lse[((long long)rm.b * a.H + rm.h) * a.Lq + rm.i] = l > 0.f ? mx / LOG2E + logf(l) : -INFINITY;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(512) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ backward, pipelined
 // Persistent, warp-specialised version of bwd_kernel: one CTA per SM walks over tiles; a TMA warp prefetches the next
 // tile's five operand tiles (Q K V dO O) into a 2-stage ring, one thread issues the MMAs, a SOFTMAX group (4 warps)
@@ -554,41 +803,42 @@ bwd_pipe_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                       idesc(128, false, false), k > 0);
         tc_commit(smem_u32(sdp_full));
       };
+      // Both product groups are issued as soon as their inputs are ready (non-blocking polls): MMA-2 of tile t must
+      // not wait for the operands of tile t+1, MMA-1 of tile t+1 must not wait for the softmax of tile t to finish.
       int n_my = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) ++n_my;
-      if (n_my > 0) {
-        mbar_wait(smem_u32(&in_full[0]), 0);
-        tc_fence_after();
-        mma1(0);
-      }
-      for (int i = 0; i < n_my; ++i) {
-        const int s = i & 1;
-        if (i + 1 < n_my) {
-          mbar_wait(smem_u32(&in_full[s ^ 1]), ((i + 1) >> 1) & 1);
-          mbar_wait(smem_u32(sdp_free), i & 1);  // the softmax group holds S | dP of tile i in registers
+      int t1 = 0, t2 = 0;
+      const long long t0 = clock64();
+      while (t2 < n_my) {
+        if (t1 < n_my && t1 < t2 + 2 && mbar_test(smem_u32(&in_full[t1 & 1]), (t1 >> 1) & 1) &&
+            mbar_test(smem_u32(sdp_free), (t1 & 1) ^ 1)) {
           tc_fence_after();
-          mma1(s ^ 1);
+          mma1(t1 & 1);
+          ++t1;
         }
-        mbar_wait(smem_u32(pds_full), i & 1);
-        mbar_wait(smem_u32(out_free), (i & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t base = smem_u32(sIn + s * PIPE_STAGE);
-        const uint32_t q_a = base, k_a = base + TILE, do_a = base + 3 * TILE;
+        if (t2 < t1 && mbar_test(smem_u32(pds_full), t2 & 1) && mbar_test(smem_u32(out_free), (t2 & 1) ^ 1)) {
+          tc_fence_after();
+          const int s = t2 & 1;
+          const uint32_t base = smem_u32(sIn + s * PIPE_STAGE);
+          const uint32_t q_a = base, k_a = base + TILE, do_a = base + 3 * TILE;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dV[keys x 64] = P~^T dO     -> cols [256,320)
-          tc_mma_bf16(tm + 256, desc_mnmajor(smem_u32(sPd) + k * 2048, TILE), desc_mnmajor(do_a + k * 2048, TILE),
-                      idesc(64, true, true), k > 0);
+          for (int k = 0; k < 8; ++k)  // dV[keys x 64] = P~^T dO     -> cols [256,320)
+            tc_mma_bf16(tm + 256, desc_mnmajor(smem_u32(sPd) + k * 2048, TILE), desc_mnmajor(do_a + k * 2048, TILE),
+                        idesc(64, true, true), k > 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dK[keys x 64] = dS^T Q      -> cols [320,384)
-          tc_mma_bf16(tm + 320, desc_mnmajor(smem_u32(sdS) + k * 2048, TILE), desc_mnmajor(q_a + k * 2048, TILE),
-                      idesc(64, true, true), k > 0);
+          for (int k = 0; k < 8; ++k)  // dK[keys x 64] = dS^T Q      -> cols [320,384)
+            tc_mma_bf16(tm + 320, desc_mnmajor(smem_u32(sdS) + k * 2048, TILE), desc_mnmajor(q_a + k * 2048, TILE),
+                        idesc(64, true, true), k > 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)  // dQ[q x 64] = dS K           -> cols [384,448)
-          tc_mma_bf16(tm + 384, desc_kmajor(smem_u32(sdS) + (k >> 2) * TILE + (k & 3) * 32),
-                      desc_mnmajor(k_a + k * 2048, TILE), idesc(64, false, true), k > 0);
-        tc_commit(smem_u32(out_full));
-        tc_commit(smem_u32(pd_free));
-        tc_commit(smem_u32(&in_empty[s]));
+          for (int k = 0; k < 8; ++k)  // dQ[q x 64] = dS K           -> cols [384,448)
+            tc_mma_bf16(tm + 384, desc_kmajor(smem_u32(sdS) + (k >> 2) * TILE + (k & 3) * 32),
+                        desc_mnmajor(k_a + k * 2048, TILE), idesc(64, false, true), k > 0);
+          tc_commit(smem_u32(out_full));
+          tc_commit(smem_u32(pd_free));
+          tc_commit(smem_u32(&in_empty[s]));
+          ++t2;
+        }
+        if (clock64() - t0 > 8000000000LL) __trap();  // a protocol bug must trap, never hang
       }
     }
   } else if (warp < 10) {
@@ -764,6 +1014,34 @@ extern "C" int mma_attn_fwd_t5(const void* q, long long ldq, const void* k, long
   Args a{};
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nprob = B * H; a.scale = scale; a.p_drop = p_drop;
   a.seed = seed; a.site = site; a.kmask = kmask; a.o = (bf16*)o; a.ldo = ldo; a.lse = lse;
+  static int pipe = -1;
+  if (pipe < 0) {
+    // measured on B200: the 4-CTA/SM single-shot forward kernel already overlaps its latency chain (and wins
+    // clearly when there are few tiles, e.g. the decode cross-attention); the persistent variant is opt-in
+    const char* e = getenv("MMA_ATTN_FWD_PIPE");
+    pipe = e ? atoi(e) : 0;
+  }
+  if (pipe) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const bool pack2 = Lq <= 64 && Lk <= 64;
+    const int ntiles = pack2 ? (a.nprob + 1) / 2 : a.nprob;
+    const int grid = ntiles < sms ? ntiles : sms;
+    static bool set2 = false, set1 = false;
+    if (pack2) {
+      if (!set2) { cudaFuncSetAttribute(fwd_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FPIPE_SMEM); set2 = true; }
+      if (launch_pdl(fwd_pipe_kernel<2>, dim3(grid), dim3(FPIPE_THREADS), FPIPE_SMEM, stream, tq, tk, tv, a, ntiles) != cudaSuccess) return MMA_ERR_LAUNCH;
+    } else {
+      if (!set1) { cudaFuncSetAttribute(fwd_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FPIPE_SMEM); set1 = true; }
+      if (launch_pdl(fwd_pipe_kernel<1>, dim3(grid), dim3(FPIPE_THREADS), FPIPE_SMEM, stream, tq, tk, tv, a, ntiles) != cudaSuccess) return MMA_ERR_LAUNCH;
+    }
+    MMA_CHECK_LAUNCH();
+    return MMA_OK;
+  }
   const int smem = 3 * TILE + 64;
   if (Lq <= 64 && Lk <= 64) {
     static bool set = false;
