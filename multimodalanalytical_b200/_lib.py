@@ -134,7 +134,8 @@ def load():
         return _lib
     with _lock:
         if _lib is None:
-            path = build()
+            # MMA_B200_LIB: load a prebuilt library instead (A/B measurements of two builds on one box)
+            path = os.environ.get("MMA_B200_LIB") or build()
             lib = C.CDLL(path)
             for name, sig in _SIGS.items():
                 fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly

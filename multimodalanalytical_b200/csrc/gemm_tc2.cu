@@ -215,8 +215,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty = bars + STAGES;             // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;         // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;    // [2]       (only the leader's are used)
-  uint64_t* inbar = bars + 2 * STAGES + 4;     // [NUM_EPI_WARPS][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 2 * NUM_EPI_WARPS);
+  uint64_t* inbar = bars + 2 * STAGES + 4;     // [NUM_EPI_WARPS][3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 3 * NUM_EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -234,7 +234,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(smem_u32(&tfull[i]), 1);
       mbar_init(smem_u32(&tempty[i]), 2 * NUM_EPI_WARPS);  // the epilogue warps of BOTH CTAs
     }
-    for (int i = 0; i < 2 * NUM_EPI_WARPS; ++i) mbar_init(smem_u32(&inbar[i]), 1);
+    for (int i = 0; i < 3 * NUM_EPI_WARPS; ++i) mbar_init(smem_u32(&inbar[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -334,11 +334,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool has_in = IN_KIND && (KIND != EPI_ACCUM || ep.accumulate == 1) && !(dbg & 1);
     const bool has_out2 = KIND == EPI_GELU && ep.out2 != nullptr;
     const bool has_bias = ep.bias != nullptr && (KIND == EPI_STORE || KIND == EPI_GELU || KIND == EPI_RESID);
+    // Three 2 KB boxes X[0..2] per warp, used in rotation by the running box index g:
+    //   kinds with a side input: box g's input is TMA-loaded into X[g % 3] two boxes ahead; its results are written
+    //     IN PLACE over the input and stored from there, so a load never waits for the store that precedes it by
+    //     one box and a store's shared-memory read has a whole box of math to drain;
+    //   kinds without: outputs rotate through the three boxes (two per box for GELU + pre-activation copy).
     uint8_t* myb = sEpi + ew * EPI_WARP_BYTES;
-    // box roles: kinds with a side input: [0], [1] = input ring, [2] = output; otherwise [0] = output, [1] = output 2
-    const uint32_t b_in0 = smem_u32(myb), b_out = smem_u32(myb + (IN_KIND ? 2 : 0) * BOX_BYTES);
-    const uint32_t b_out2 = smem_u32(myb + BOX_BYTES);
-    const uint32_t ibar0 = smem_u32(&inbar[2 * ew]);
+    const uint32_t myb_a = smem_u32(myb);
+    const uint32_t ibar0 = smem_u32(&inbar[3 * ew]);
     const uint32_t tempty_leader0 = mapa(smem_u32(&tempty[0]), 0);
 
     DropCtx dc;
@@ -350,21 +353,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // coordinates of this warp's rows / columns in tile `tile`
     auto rows_of = [&](int tile) { return (tile / tiles_n) * (2 * BM) + (int)rank * BM + q * 32; };
     auto cols_of = [&](int tile) { return (tile % tiles_n) * BN + s * 64; };
-    // side-input boxes: load number n goes to ring slot n & 1 and completes phase (n >> 1) & 1 of that slot's
-    // barrier.  Boxes entirely outside the output (tail rows / columns) are neither loaded nor waited for, so only
-    // live boxes are counted; every lane keeps the same counters.
-    uint32_t issued = 0, consumed = 0;
-    auto issue_in = [&](int tile, int box) {
+    // side-input load of the box `ahead` boxes after (tile, box) into X[k]; boxes entirely outside the output (tail
+    // rows / columns) are neither loaded nor waited for
+    auto issue_in = [&](int tile, int box, int ahead, int k) {
+      box += ahead;
+      while (box >= NBOX) {
+        box -= NBOX;
+        tile += npairs;
+      }
+      if (tile >= total) return;
       const int r0 = rows_of(tile), c = cols_of(tile) + box * BOXCOLS;
       if (r0 >= M || c >= N) return;
       if (lane == 0) {
-        const uint32_t bar = ibar0 + (issued & 1u) * 8u;
+        const uint32_t bar = ibar0 + (uint32_t)k * 8u;
         mbar_expect_tx(bar, BOX_BYTES);
-        tma_load_2d(b_in0 + (issued & 1u) * BOX_BYTES, &tmIn, bar, c, r0);
+        tma_load_2d(myb_a + (uint32_t)k * BOX_BYTES, &tmIn, bar, c, r0);
       }
-      ++issued;
     };
-    if (has_in && pair < total) issue_in(pair, 0);
+    if (has_in && pair < total) {
+      issue_in(pair, 0, 0, 0);
+      issue_in(pair, 0, 1, 1);
+    }
+    uint32_t ph = 0;  // bit k: parity of the next completion of X[k]'s load barrier
+    int gk = 0;       // g % 3 (kinds with a side input, STORE, ACCUM) or (2 g) % 3 (GELU with two outputs)
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -389,11 +400,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool first = (c % CPB) == 0, last = (c % CPB) == CPB - 1;
         const int bcol = c0 + box * BOXCOLS;            // first column of this box
         const bool live = r0 < M && bcol < N && !(dbg & 1);  // warp-uniform: the box touches the output at all
-        if (first && has_in) {
-          __syncwarp();  // every lane is done reading the ring slot the next load overwrites
-          if (box + 1 < NBOX) issue_in(tile, box + 1);
-          else if (tile + npairs < total) issue_in(tile + npairs, 0);
-          if (live) mbar_wait(ibar0 + (consumed & 1u) * 8u, (consumed >> 1) & 1u);
+        const int k1 = gk;                               // box of output 1 (and of the side input)
+        const int k2 = gk == 2 ? 0 : gk + 1;             // box of output 2
+        if (first && has_in && live) {
+          mbar_wait(ibar0 + (uint32_t)k1 * 8u, (ph >> k1) & 1u);
+          ph ^= 1u << k1;
         }
         tmem_wait_ld();
         if (c + 1 < 4) {
@@ -407,18 +418,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float v[16], o2[16], in[16], bv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
+        uint8_t* x1 = myb + k1 * BOX_BYTES;
         if (has_in && live) {
-          const uint8_t* ib = myb + (consumed & 1u) * BOX_BYTES;
           if (IO32) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float4 f = *reinterpret_cast<const float4*>(ib + box_off(lane, k, swz));
+              const float4 f = *reinterpret_cast<const float4*>(x1 + box_off(lane, k, swz));
               in[4 * k] = f.x; in[4 * k + 1] = f.y; in[4 * k + 2] = f.z; in[4 * k + 3] = f.w;
             }
           } else {
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              const uint4 u = *reinterpret_cast<const uint4*>(ib + box_off(lane, 2 * (c % CPB) + k, swz));
+              const uint4 u = *reinterpret_cast<const uint4*>(x1 + box_off(lane, 2 * (c % CPB) + k, swz));
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
@@ -438,27 +449,36 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         chunk_math<KIND>(ep, dc, row, c0 + c * 16, v, o2, in, bv, has_bias);
         if (first) {
-          // the TMA store that last read the output box(es) must have finished reading shared memory
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
+          if (IN_KIND) {
+            // the store issued one box ago has had this box's math to drain: its box becomes the landing zone of the
+            // input two boxes ahead
+            if (lane == 0) bulk_wait_read0();
+            if (has_in) issue_in(tile, box, 2, gk == 0 ? 2 : gk - 1);
+            __syncwarp();
+          } else {
+            // the stores that last read the box(es) written next must have finished reading shared memory
+            if (lane == 0) {
+              if (has_out2) bulk_wait_read0();
+              else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+            }
+            __syncwarp();
+          }
         }
         if (IO32) {
-          uint8_t* ob = myb + (IN_KIND ? 2 : 0) * BOX_BYTES;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            *reinterpret_cast<float4*>(ob + box_off(lane, k, swz)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            *reinterpret_cast<float4*>(x1 + box_off(lane, k, swz)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         } else {
-          uint8_t* ob = myb + (IN_KIND ? 2 : 0) * BOX_BYTES;
 #pragma unroll
           for (int k = 0; k < 2; ++k)
-            *reinterpret_cast<uint4*>(ob + box_off(lane, 2 * (c % CPB) + k, swz)) =
+            *reinterpret_cast<uint4*>(x1 + box_off(lane, 2 * (c % CPB) + k, swz)) =
                 make_uint4(pack2_bf16(v[8 * k], v[8 * k + 1]), pack2_bf16(v[8 * k + 2], v[8 * k + 3]),
                            pack2_bf16(v[8 * k + 4], v[8 * k + 5]), pack2_bf16(v[8 * k + 6], v[8 * k + 7]));
           if (has_out2) {
-            uint8_t* ob2 = myb + BOX_BYTES;
+            uint8_t* x2 = myb + k2 * BOX_BYTES;
 #pragma unroll
             for (int k = 0; k < 2; ++k)
-              *reinterpret_cast<uint4*>(ob2 + box_off(lane, 2 * (c % CPB) + k, swz)) =
+              *reinterpret_cast<uint4*>(x2 + box_off(lane, 2 * (c % CPB) + k, swz)) =
                   make_uint4(pack2_bf16(o2[8 * k], o2[8 * k + 1]), pack2_bf16(o2[8 * k + 2], o2[8 * k + 3]),
                              pack2_bf16(o2[8 * k + 4], o2[8 * k + 5]), pack2_bf16(o2[8 * k + 6], o2[8 * k + 7]));
           }
@@ -466,12 +486,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (last) {
           fence_async_smem();  // generic-proxy writes -> visible to the TMA engine
           __syncwarp();
-          if (lane == 0 && live) {
-            tma_store_2d(&tmOut, b_out, bcol, r0);
-            if (has_out2) tma_store_2d(&tmOut2, b_out2, bcol, r0);
-            bulk_commit();
+          if (lane == 0) {
+            if (live) {
+              tma_store_2d(&tmOut, myb_a + (uint32_t)k1 * BOX_BYTES, bcol, r0);
+              if (has_out2) tma_store_2d(&tmOut2, myb_a + (uint32_t)k2 * BOX_BYTES, bcol, r0);
+            }
+            bulk_commit();  // one group per box, live or not: wait_group counts stay aligned with the rotation
           }
-          if (has_in && live) ++consumed;
+          gk += has_out2 ? 2 : 1;
+          if (gk >= 3) gk -= 3;
         }
       }
       if (++acc == 2) {
