@@ -13,6 +13,7 @@ Precision modes
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Callable, Dict, List, Optional
 
 import torch
@@ -43,6 +44,17 @@ class Engine:
         self.ldv = (cfg.vocab_size + 7) // 8 * 8
         self._wq: List[Any] = []  # weight / bias gradient products deferred to one grouped launch per layer
         self.group_wgrad = True
+        # The grouped weight-gradient launch of a layer is off the critical path of backward (nothing but the
+        # optimiser reads its output), so it CAN run on a side stream next to the memory-bound LayerNorm / attention
+        # kernels of the next layer down (MMA_WGRAD_STREAM=1).  Measured on B200: no gain - the persistent 200 KB CTAs
+        # leave no room for co-resident blocks - so the default keeps everything on one stream.  Its `dy` operands live in one of three rotating buffer sets (`wbuf`), so
+        # the layer after next may overwrite them only once that launch is done (`_begin_group`).
+        self.wgrad_stream = None
+        if self.dev.type == "cuda" and os.environ.get("MMA_WGRAD_STREAM", "0") != "0":
+            self.wgrad_stream = torch.cuda.Stream(device=self.dev)
+        self._wev: Dict[int, Any] = {}
+        self._bset = 0
+        self.last_wgrad_event = None
 
     # ------------------------------------------------------------------------------------- utils
     def buf(self, name, shape, dtype):
@@ -101,10 +113,39 @@ class Engine:
                  splits=self._splits(n_out, k_in, rows))
         ops.colsum(dy, Gb, rows=rows, cols=n_out)
 
+    def wbuf(self, name, shape, dtype, ahead=0):
+        """Buffer read by the grouped wgrad launch of backward group `_bset + ahead` (three rotating sets)."""
+        return self.buf(f"{name}.s{(self._bset + ahead) % 3}", shape, dtype)
+
+    def _begin_group(self, b: int):
+        """Backward group b (LM head = 0, then one per layer) starts: its buffer set (and, at its end, the next one)
+        is rewritten, so the wgrad launch of group b - 2 must have finished reading."""
+        self._bset = b
+        ev = self._wev.pop(b - 2, None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
     def _flush_wgrads(self):
-        if self._wq:
+        if not self._wq:
+            return
+        if self.wgrad_stream is None:
             ops.wgrad_group(self._wq)
-            self._wq = []
+        else:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            self.wgrad_stream.wait_event(ready)
+            with torch.cuda.stream(self.wgrad_stream):
+                ops.wgrad_group(self._wq)
+                done = torch.cuda.Event()
+                done.record(self.wgrad_stream)
+            self._wev[self._bset] = done
+            self.last_wgrad_event = done
+        self._wq = []
+
+    def _join_wgrads(self):
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+            self._wev.clear()
 
     # --------------------------------------------------------------------------------- embedding
     def _pos_rows(self, L, tag):
@@ -232,9 +273,9 @@ class Engine:
         dh = d // heads
         T = self.adt
         s = self.saved[tag]
-        dctx = self.buf("bw.dctx", (M, d), T)
+        dctx = self.wbuf("bw.dctx", (M, d), T)
         self._lin_bwd(dyb, s["ctx"], wp["out_w"], wp["out_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dctx))
-        dqkv = self.buf("bw.dqkv", (M, 3 * d), T)
+        dqkv = self.wbuf("bw.dqkv", (M, 3 * d), T)
         qkv = s["qkv"]
         ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], s["ctx"], s["lse"], dctx, dqkv[:, :d],
                      dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, heads, L, L, dh, kmask=kmask, causal=causal, p_drop=p,
@@ -242,7 +283,7 @@ class Engine:
         dh_ = self.buf("bw.dh", (M, d), T)
         self._lin_bwd(dqkv, s["h"], wp["in_w"], wp["in_b"], M, 3 * d, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
         dx_in = self._other_dx(dx, M)
-        dyb_in = None if first else self.buf(f"bw.dyb.{out_tag}", (M, d), T)
+        dyb_in = None if first else self.wbuf("bw.dyb.x", (M, d), T, ahead=1)  # read by the next group down
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
@@ -276,14 +317,14 @@ class Engine:
         d = self.cfg.d_model
         T = self.adt
         s = self.saved[tag]
-        dz = self.buf("bw.dz", (M, f), T)
+        dz = self.wbuf("bw.dz", (M, f), T)
         dh_ = self.buf("bw.dh", (M, d), T)
         if not self.cfg.gated_linear:
             self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
                           dx_epi=ops.make_epi(EPI_DGELU, dz, aux=s["z"], p_drop=p, seed=self.seed_arg, site=site_i, drop_ld=f))
             self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
         else:
-            dz2 = self.buf("bw.dz2", (M, f), T)
+            dz2 = self.wbuf("bw.dz2", (M, f), T)
             self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
                           dx_epi=ops.make_epi(EPI_DGLU, dz, out2=dz2, aux=s["z"], aux2=s["z2"], p_drop=p,
                                               seed=self.seed_arg, site=site_i, drop_ld=f))
@@ -292,7 +333,7 @@ class Engine:
             self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=0))
             self._lin_bwd(dz2, s["h"], wp["wg"], wp["bg"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=1))
         dx_in = self._other_dx(dx, M)
-        dyb_in = self.buf("bw.dyb.ffn_in", (M, d), T)
+        dyb_in = self.wbuf("bw.dyb.ffn_in", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
@@ -345,10 +386,10 @@ class Engine:
         dh = d // heads
         T = self.adt
         s = self.saved[tag]
-        dctx = self.buf("bw.dctx", (M, d), T)
+        dctx = self.wbuf("bw.dctx", (M, d), T)
         self._lin_bwd(dyb, s["ctx"], wp["out_w"], wp["out_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dctx))
-        dq = self.buf("bw.dq", (M, d), T)
-        dkv = self.buf("bw.dkv", (Me, 2 * d), T)
+        dq = self.wbuf("bw.dq", (M, d), T)
+        dkv = self.wbuf("bw.dkv", (Me, 2 * d), T)
         kv = s["kv"]
         ops.attn_bwd(s["q"], kv[:, :d], kv[:, d:], s["ctx"], s["lse"], dctx, dq, dkv[:, :d], dkv[:, d:], B, heads, T_,
                      S, dh, kmask=kmask, causal=False, p_drop=p, seed=self.seed_arg, site=site_a,
@@ -360,7 +401,7 @@ class Engine:
                       dx_epi=ops.make_epi(EPI_ACCUM, dmem, accumulate=0 if first_mem else 1),
                       row_slice=slice(d, 3 * d))
         dx_in = self._other_dx(dx, M)
-        dyb_in = self.buf("bw.dyb.ca_in", (M, d), T)
+        dyb_in = self.wbuf("bw.dyb.ca_in", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
@@ -526,7 +567,9 @@ class Engine:
         H = cfg.decoder_attention_heads
         notify = self.grad_ready_hook or (lambda off: None)
 
-        dlogits = self.buf("bw.dlogits", (M, self.ldv), T)
+        self._wev.clear()
+        self._begin_group(0)
+        dlogits = self.wbuf("bw.dlogits", (M, self.ldv), T)
         ops.ce_bwd(ce["logits"], ce["labels"], V, ce["row_lse"], ce["stats"], dlogits, gscale=gscale,
                    smoothing=cfg.label_smoothing)
         dl = dlogits[:, :V]
@@ -536,9 +579,9 @@ class Engine:
         self._flush_wgrads()
         last_site = self._site(True, cfg.decoder_layers - 1, 3)
         dx = self._other_dx(None, M)
-        # the masked low-precision gradient handed to the layer below alternates between two buffers: it must stay
-        # alive until that layer's grouped weight-gradient launch
-        dyb = self.buf(f"bw.dyb.x{cfg.decoder_layers % 2}", (M, d), T)
+        # the masked low-precision gradient handed to the layer below lives in the buffer set of the group that reads
+        # it (it must stay alive until that group's weight-gradient launch is done)
+        dyb = self.wbuf("bw.dyb.x", (M, d), T, ahead=1)
         ops.ln_bwd(dhT, dec["xL"], self.P("hf_model.decoder.norm.weight"), dx=dx, dxb=dyb,
                    dgamma=self.G("hf_model.decoder.norm.weight"), dbeta=self.G("hf_model.decoder.norm.bias"),
                    p_drop=p, seed=self.seed_arg, site=last_site)
@@ -546,6 +589,7 @@ class Engine:
 
         dmem = self.buf("bw.dmem", (Me, d), torch.float32)
         for i in reversed(range(cfg.decoder_layers)):
+            self._begin_group(cfg.decoder_layers - i)
             pre = f"hf_model.decoder.layers.{i}."
             tg = f"dec{i}"
             dx, dyb = self._ffn_block_bwd(tg + ".ff", dx, dyb, M, cfg.decoder_ffn_dim, self._wp_ffn(pre, "norm3"), p,
@@ -566,12 +610,13 @@ class Engine:
         # encoder: d(mem) arrives in fp32 from the cross-attention K/V projections
         He = cfg.encoder_attention_heads
         dxe = self._other_dx(None, Me)
-        dybe = self.buf(f"bw.dyb.x{cfg.encoder_layers % 2}", (Me, d), T)
+        dybe = self.wbuf("bw.dyb.x", (Me, d), T, ahead=1)
         ops.ln_bwd(dmem, enc["xL"], self.P("hf_model.encoder.norm.weight"), dx=dxe, dxb=dybe,
                    dgamma=self.G("hf_model.encoder.norm.weight"), dbeta=self.G("hf_model.encoder.norm.bias"),
                    p_drop=p, seed=self.seed_arg, site=self._site(False, cfg.encoder_layers - 1, 3))
         notify(ps.offsets["hf_model.encoder.norm.weight"][0])
         for i in reversed(range(cfg.encoder_layers)):
+            self._begin_group(cfg.decoder_layers + cfg.encoder_layers - i)
             pre = f"hf_model.encoder.layers.{i}."
             tg = f"enc{i}"
             dxe, dybe = self._ffn_block_bwd(tg + ".ff", dxe, dybe, Me, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"),
@@ -584,3 +629,4 @@ class Engine:
             notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
         self._embed_bwd(dxe, enc["recs"], S, "enc", B)
         notify(0)
+        self._join_wgrads()

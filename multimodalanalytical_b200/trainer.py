@@ -55,27 +55,31 @@ class GradBucketer:
         self.hi = self.g.numel()
         self.launched = []
 
-    def on_ready(self, off: int):
+    def on_ready(self, off: int, also_wait=None):
+        """`also_wait`: an event of another producer stream (the engine's weight-gradient side stream) that must
+        have completed before the reduced range is read."""
         while self.hi - off >= self.bucket or (off == 0 and self.hi > 0):
             lo = max(off, self.hi - self.bucket)
-            self._allreduce(lo, self.hi)
+            self._allreduce(lo, self.hi, also_wait)
             self.hi = lo
 
-    def _allreduce(self, lo, hi):
+    def _allreduce(self, lo, hi, also_wait=None):
         g = self.g[lo:hi]
         self.launched.append((lo, hi))
         if self.comm_stream is not None:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             self.comm_stream.wait_event(ev)
+            if also_wait is not None:
+                self.comm_stream.wait_event(also_wait)
             with torch.cuda.stream(self.comm_stream):
                 torch.distributed.all_reduce(g, group=self.pg)
         else:
             torch.distributed.all_reduce(g, group=self.pg)
 
-    def finish(self):
+    def finish(self, also_wait=None):
         if self.hi > 0:
-            self.on_ready(0)
+            self.on_ready(0, also_wait)
         if self.comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
@@ -117,7 +121,7 @@ class FusedTrainer:
     # gradient buckets complete back to front; reduce each as soon as it is final
     def _on_grads_ready(self, off: int):
         if self._sync_now and self.bucketer is not None:
-            self.bucketer.on_ready(off)
+            self.bucketer.on_ready(off, also_wait=self.eng.last_wgrad_event)
 
     def _prepare(self, batch):
         """Collator dict -> device tensors in the engine's layout (what HFWrapper.forward does, wrapper.py:356-389)."""
@@ -221,7 +225,7 @@ class FusedTrainer:
     def _optimizer_kernels(self):
         ps = self.ps
         if self.bucketer is not None:
-            self.bucketer.finish()
+            self.bucketer.finish(also_wait=self.eng.last_wgrad_event)
         norm = None
         if self.clip_grad:
             ops.grad_norm(ps.g, self.norm_ws, self.norm)
