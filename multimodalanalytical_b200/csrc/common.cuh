@@ -128,8 +128,16 @@ __device__ __forceinline__ uint32_t drop_key(unsigned long long seed, unsigned i
   }
   return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + 0x9E3779B9u) ^ (site * 0x85EBCA77u + 0x165667B1u));
 }
-// one 32-bit hash serves two neighbouring elements (16 random bits each; p is quantised to 1/65536)
-__device__ __forceinline__ uint32_t drop_pair(uint32_t key, uint32_t pair_idx) { return mix32((pair_idx * 0x9E3779B1u) ^ key); }
+// one 32-bit hash serves two neighbouring elements (16 random bits each; p is quantised to 1/65536).
+// Two rounds of a 32 x 32 -> 64 bit multiply folded by xor (5 instructions; the lowbias32 finaliser this replaces took
+// 10, and the hash sits in the ALU-bound GELU / dGELU GEMM epilogues): the first round turns consecutive counters
+// into a Weyl-like sequence, the second destroys its regular spacing.
+__device__ __forceinline__ uint32_t drop_pair(uint32_t key, uint32_t pair_idx) {
+  unsigned long long t = (unsigned long long)(pair_idx ^ key) * 0x9E3779B1ull;
+  uint32_t r = (uint32_t)t ^ (uint32_t)(t >> 32);
+  t = (unsigned long long)r * 0x85EBCA77ull;
+  return (uint32_t)t ^ (uint32_t)(t >> 32);
+}
 __device__ __forceinline__ uint32_t drop_threshold(float p) {
   const float t = p * 65536.0f + 0.5f;
   return t >= 65535.0f ? 65535u : (uint32_t)t;
@@ -155,14 +163,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // rcp.approx / ex2.approx - used when the result is rounded to bf16 anyway; the fp32 parity path keeps erff().
 template <bool FAST> __device__ __forceinline__ void normal_cdf_exp(float x, float& cdf, float& e) {
   if (FAST) {
-    const float u = fabsf(x) * 0.70710678118654752440f;
-    const float t = rcp_approx(fmaf(0.3275911f, u, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    e = ex2_approx(-0.72134752044448170368f * x * x);
-    const float half_erfc = 0.5f * p * t * e;
+    // u = |x| / sqrt(2);  t = 1 / (1 + 0.3275911 u);  erfc(u) ~ t (a1 + t (a2 + ...)) exp(-u^2)   (A&S 7.1.26)
+    // constants folded: w = |x| sqrt(log2(e) / 2) so that exp(-u^2) = 2^(-w^2), 0.3275911 u = 0.27279 w, and the
+    // polynomial coefficients carry the factor 1/2 of Phi = erfc / 2
+    const float w = fabsf(x) * 0.84932180028801904272f;
+    const float t = rcp_approx(fmaf(0.27273748f, w, 1.0f));
+    float p = fmaf(0.5307027145f, t, -0.7265760135f);
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    e = ex2_approx(-w * w);
+    const float half_erfc = p * t * e;
     cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   } else {
     cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
