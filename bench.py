@@ -374,13 +374,15 @@ def bench_decode(model, c, args):
         batch = map_batch(synth_batch(c, B, SEED + 7), lambda x: x.cuda())
         out = model.generate(batch, n_beams=K)  # warm-up + graph capture
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
+        ts = []
+        for _ in range(reps):  # each call timed on its own; the median is reported
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             out = model.generate(batch, n_beams=K)
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) * 1e-3 / reps, int(out.shape[1]) - 1
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return sorted(ts)[len(ts) // 2], int(out.shape[1]) - 1
 
     def floor_s(B, steps):
         d, f, Ld, S, V = c["d"], c["ffn"], c["layers"], c["S_formula"] + c["P"], c["V"]
@@ -393,12 +395,12 @@ def bench_decode(model, c, args):
             tot += max(by / (PEAKS["hbm_gbs"] * 1e9), fl / (PEAKS["bf16_tflops_sustained"] * 1e12))
         return tot
 
-    t, steps = run(args.decode_batch, 2)
+    t, steps = run(args.decode_batch, 3)
     res = {"metric": "beam-10 decode molecules/s", "value": args.decode_batch / t, "unit": "molecules/s",
            "batch": args.decode_batch, "beams": K, "steps": steps, "ms_per_batch": t * 1e3, "dtype": "bf16",
            "roofline_frac": floor_s(args.decode_batch, steps) / t, "sweep": []}
     for B in (1, 64, 1024):
-        tb, sb = run(B, 1)
+        tb, sb = run(B, 3)
         res["sweep"].append({"batch": B, "molecules_per_s": B / tb, "ms_per_step": tb * 1e3 / sb,
                              "roofline_frac": floor_s(B, sb) / tb})
     return res
