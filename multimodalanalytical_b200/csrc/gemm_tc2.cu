@@ -807,8 +807,13 @@ extern "C" int mma_gemm2_eligible(int a_mn, int b_mn, int M, int N, int K, const
     return 0;
   }
   if (N < 256 || M < 512) return 0;
+  static int min_tiles = -1;
+  if (min_tiles < 0) {
+    const char* e = getenv("MMA_GEMM2_MIN_TILES");
+    min_tiles = e ? atoi(e) : 48;
+  }
   const long long tiles = (long long)((M + 255) / 256) * ((N + 255) / 256);
-  return tiles >= 48;
+  return tiles >= min_tiles;
 }
 
 extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long long ldb, int b_mn, int M, int N, int K,

@@ -260,10 +260,19 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdArgs a) {
         if (a.dxb) {
           if (drop) {
             const unsigned long long e = (unsigned long long)r * d + c;
-            o.x *= drop_scale1(dkey, e, thr, inv_keep);
-            o.y *= drop_scale1(dkey, e + 1, thr, inv_keep);
-            o.z *= drop_scale1(dkey, e + 2, thr, inv_keep);
-            o.w *= drop_scale1(dkey, e + 3, thr, inv_keep);
+            if ((e & 1ull) == 0) {  // one hash per pair of neighbouring elements (the usual case: d and c are even)
+              const uint32_t e32 = (uint32_t)e;
+              const uint32_t r0 = drop_pair(dkey, e32 >> 1), r1 = drop_pair(dkey, (e32 >> 1) + 1u);
+              o.x *= (r0 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+              o.y *= (r0 >> 16) >= thr ? inv_keep : 0.f;
+              o.z *= (r1 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+              o.w *= (r1 >> 16) >= thr ? inv_keep : 0.f;
+            } else {
+              o.x *= drop_scale1(dkey, e, thr, inv_keep);
+              o.y *= drop_scale1(dkey, e + 1, thr, inv_keep);
+              o.z *= drop_scale1(dkey, e + 2, thr, inv_keep);
+              o.w *= drop_scale1(dkey, e + 3, thr, inv_keep);
+            }
           }
           st4_any(a.dxb, r * a.lddxb + c, a.dxb_f32, o);
         }
