@@ -93,6 +93,12 @@ int mma_ln_bwd(const void* dy, int dy_f32, long long lddy, int group, int in_gro
                long long lddres, float* dx, long long lddx, void* dxb, int dxb_f32, long long lddxb, float p_drop,
                unsigned long long seed, unsigned int site, float* dgamma, float* dbeta, int rows, int d,
                cudaStream_t stream);
+/* Residual product fused with the LayerNorm that follows it (d_model = N = 512, CTA-pair tcgen05 kernel):
+ *   ep->out (fp32) = ep->resid + drop(A W^T + bias);   h (bf16) = LayerNorm(ep->out) * gamma + beta.
+ * Replaces nn.Linear + dropout + residual add + the next sub-layer's nn.LayerNorm (custom_modeling.py:129-152,176-199).
+ * MMA_ERR_UNSUPPORTED (-3) outside that envelope: run mma_gemm_bf16 and mma_ln_fwd instead.                      */
+int mma_gemm2_resid_ln(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K, const Epi* ep,
+                       const float* gamma, const float* beta, float eps, void* h, long long ldh, cudaStream_t stream);
 /* out[c] += sum_r in[r,c]  (bias gradients) */
 int mma_colsum(const void* in, int in_f32, long long ld, float* out, int rows, int cols, cudaStream_t stream);
 int mma_cast_f32_bf16(const float* in, void* out, long long n, cudaStream_t stream);

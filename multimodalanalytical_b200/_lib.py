@@ -86,6 +86,7 @@ _lib = None
 _vp, _i, _ll, _f, _ull, _u = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_uint
 _SIGS = {
     "mma_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, C.POINTER(Epi), _i, _i, _vp],
+    "mma_gemm2_resid_ln": [_vp, _ll, _vp, _ll, _i, _i, _i, C.POINTER(Epi), _vp, _vp, _f, _vp, _ll, _vp],
     "mma_wgrad_group": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mma_gemm_simt": [_vp, _i, _ll, _ll, _vp, _i, _ll, _ll, _i, _i, _i, C.POINTER(Epi), _i, _vp],
     "mma_gather_rows": [_vp, _vp, _vp, _vp, _i, _i, _vp],

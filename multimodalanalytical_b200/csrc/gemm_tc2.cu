@@ -563,6 +563,314 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
 
 
 // ------------------------------------------------------------------------------------------------------------------
+// Residual product fused with the LayerNorm that follows it (d_model = 512 only):
+//   x_new[M,512] = resid + drop(A[M,K] W[512,K]^T + bias)            fp32 residual stream
+//   h[M,512]     = LayerNorm(x_new) * gamma + beta                   bf16 operand of the next product
+// Every out-projection / FFN-2 of the pre-LN layers is followed by exactly one LayerNorm of its result (the next
+// sub-layer's, or the stack's final norm), which used to be a separate pass over x_new (read 4 B + write 2 B per
+// element and a launch).  Here a CTA pair owns 256 rows x ALL 512 columns: each CTA's 128 x 512 fp32 accumulator
+// fills its TMEM (two N = 256 MMAs per k-step); a thread owns one row of its warp's 128-column slice, so the row
+// statistics are thread-local sums plus one exchange between the four warps of a row quarter.  Pass 1 forms x_new,
+// stores it (TMA boxes, as in gemm2_kernel) and parks it back in TMEM; pass 2 re-reads it, normalises and stores h.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LN_N = 512;
+constexpr int LN_STAGES = 2;
+constexpr uint32_t LNB_BYTES = 256 * BK * 2;  // per-CTA B tile: 256 of the 512 weight rows
+constexpr uint32_t LN_STATS_BYTES = 4 * 128 * 8;
+constexpr uint32_t LN_SMEM = 1024 + LN_STAGES * (A_BYTES + LNB_BYTES) + NUM_EPI_WARPS * EPI_WARP_BYTES + LN_STATS_BYTES + BAR_BYTES;
+static_assert(LN_SMEM <= 232448, "shared memory budget");
+
+struct LnExtra {
+  const float* gamma;
+  const float* beta;
+  float eps;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm2_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmIn,
+                const __grid_constant__ CUtensorMap tmH, int M, int K, int swz, Epi ep, LnExtra ln) {
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + LN_STAGES * A_BYTES;
+  uint8_t* sEpi = sB + LN_STAGES * LNB_BYTES;
+  float2* sStats = reinterpret_cast<float2*>(sEpi + NUM_EPI_WARPS * EPI_WARP_BYTES);  // [4 slices][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStats) + LN_STATS_BYTES);
+  uint64_t* full = bars;                      // [LN_STAGES] (leader's are used)
+  uint64_t* empty = bars + LN_STAGES;         // [LN_STAGES]
+  uint64_t* tfull = bars + 2 * LN_STAGES;     // [1]
+  uint64_t* tempty = tfull + 1;               // [1] (leader's is used)
+  uint64_t* inbar = tempty + 1;               // [NUM_EPI_WARPS][3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(inbar + 3 * NUM_EPI_WARPS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < LN_STAGES; ++i) {
+      mbar_init(smem_u32(&full[i]), 1);
+      mbar_init(smem_u32(&empty[i]), 1);
+    }
+    mbar_init(smem_u32(tfull), 1);
+    mbar_init(smem_u32(tempty), 2 * NUM_EPI_WARPS);
+    for (int i = 0; i < 3 * NUM_EPI_WARPS; ++i) mbar_init(smem_u32(&inbar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  const int total = (M + 2 * BM - 1) / (2 * BM);
+  const int num_kb = (K + BK - 1) / BK;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total; tile += npairs) {
+        const int m0 = tile * (2 * BM) + (int)rank * BM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          const uint32_t fb_local = smem_u32(&full[stage]);
+          if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + LNB_BYTES));
+          const uint32_t fb = mapa(fb_local, 0);
+          tma_load_2d_2sm(smem_u32(sA + stage * A_BYTES), &tmA, fb, kb * BK, m0);
+          // this CTA's weight rows: [128 r, 128 r + 128) feed output columns [0, 256), [256 + 128 r, ...) feed [256, 512)
+          const uint32_t b_dst = smem_u32(sB + stage * LNB_BYTES);
+          tma_load_2d_2sm(b_dst, &tmB, fb, kb * BK, (int)rank * 128);
+          tma_load_2d_2sm(b_dst + 128 * 128, &tmB, fb, kb * BK, 256 + (int)rank * 128);
+          if (++stage == LN_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0, tphase = 0;
+      for (int tile = pair; tile < total; tile += npairs) {
+        mbar_wait(smem_u32(tempty), tphase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * LNB_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_smem_desc<false>(a_addr, k);
+            tc_mma2_bf16(tmem_base, ad, make_smem_desc<false>(b_addr, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma2_bf16(tmem_base + 256, ad, make_smem_desc<false>(b_addr + 128 * 128, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit2_mc(smem_u32(&empty[stage]));
+          if (++stage == LN_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit2_mc(smem_u32(tfull));
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int ew = warp - 2, q = warp & 3, s = ew >> 2;  // rows [32 q, +32) of the CTA tile, columns [128 s, +128)
+    uint8_t* myb = sEpi + ew * EPI_WARP_BYTES;
+    const uint32_t myb_a = smem_u32(myb);
+    const uint32_t ibar0 = smem_u32(&inbar[3 * ew]);
+    const uint32_t tempty_leader = mapa(smem_u32(tempty), 0);
+    const int c0 = s * 128;
+    // per-lane copies of this warp's 128 bias / gamma / beta values (column c0 + 32 j + lane), read back with shuffles
+    float bias_r[4], gam_r[4], bet_r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bias_r[j] = ep.bias ? ep.bias[c0 + 32 * j + lane] : 0.f;
+      gam_r[j] = ln.gamma[c0 + 32 * j + lane];
+      bet_r[j] = ln.beta[c0 + 32 * j + lane];
+    }
+    DropCtx dc;
+    dc.on = ep.p_drop > 0.0f;
+    dc.thr = dc.on ? drop_threshold(ep.p_drop) : 0u;
+    dc.inv_keep = dc.on ? 1.0f / (1.0f - ep.p_drop) : 1.0f;
+    dc.key = dc.on ? drop_key(ep.seed, ep.site) : 0u;
+
+    auto rows_of = [&](int tile) { return tile * (2 * BM) + (int)rank * BM + q * 32; };
+    // residual box `ahead` chunks after (tile, chunk) into X[k]
+    auto issue_in = [&](int tile, int chunk, int ahead, int k) {
+      chunk += ahead;
+      while (chunk >= 8) {
+        chunk -= 8;
+        tile += npairs;
+      }
+      if (tile >= total) return;
+      const int r0 = rows_of(tile);
+      if (r0 >= M) return;
+      if (lane == 0) {
+        const uint32_t bar = ibar0 + (uint32_t)k * 8u;
+        mbar_expect_tx(bar, BOX_BYTES);
+        tma_load_2d(myb_a + (uint32_t)k * BOX_BYTES, &tmIn, bar, c0 + chunk * 16, r0);
+      }
+    };
+    if (pair < total) {
+      issue_in(pair, 0, 0, 0);
+      issue_in(pair, 0, 1, 1);
+    }
+    uint32_t ph = 0;
+    int gk = 0;
+    uint32_t tphase = 0;
+    for (int tile = pair; tile < total; tile += npairs) {
+      const int r0 = rows_of(tile);
+      const long long row = (long long)r0 + lane;
+      const bool live = r0 < M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      mbar_wait(smem_u32(tfull), tphase);
+      tc_fence_after();
+      // ---------------- pass 1: x_new = resid + drop(acc + bias); row statistics; x_new -> global and back to TMEM
+      float sum = 0.f, sumsq = 0.f;
+      uint32_t raw[2][16];
+      tmem_ld16_nowait(t_row, raw[0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int k1 = gk;
+        if (live) {
+          mbar_wait(ibar0 + (uint32_t)k1 * 8u, (ph >> k1) & 1u);
+          ph ^= 1u << k1;
+        }
+        tmem_wait_ld();
+        if (c + 1 < 8) tmem_ld16_nowait(t_row + (uint32_t)((c + 1) * 16), raw[(c + 1) & 1]);
+        uint8_t* x1 = myb + k1 * BOX_BYTES;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          v[j] = __uint_as_float(raw[c & 1][j]) + __shfl_sync(0xffffffffu, bias_r[c >> 1], (16 * (c & 1) + j) & 31);
+        if (dc.on) {
+          const uint32_t e0 = (uint32_t)((unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)(c0 + c * 16));
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {  // e0 is even: drop_ld and the column are
+            const uint32_t r = drop_pair(dc.key, (e0 + j) >> 1);
+            v[j] *= (r & 0xFFFFu) >= dc.thr ? dc.inv_keep : 0.f;
+            v[j + 1] *= (r >> 16) >= dc.thr ? dc.inv_keep : 0.f;
+          }
+        }
+        if (live) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 f = *reinterpret_cast<const float4*>(x1 + box_off(lane, k, swz));
+            v[4 * k] += f.x; v[4 * k + 1] += f.y; v[4 * k + 2] += f.z; v[4 * k + 3] += f.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          sum += v[j];
+          sumsq = fmaf(v[j], v[j], sumsq);
+        }
+        tmem_st16(t_row + (uint32_t)(c * 16), v);
+        // the store issued one chunk ago has drained behind this chunk's math: reuse its box for the residual two ahead
+        if (lane == 0) bulk_wait_read0();
+        issue_in(tile, c, 2, gk == 0 ? 2 : gk - 1);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          *reinterpret_cast<float4*>(x1 + box_off(lane, k, swz)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (live) tma_store_2d(&tmOut, myb_a + (uint32_t)k1 * BOX_BYTES, c0 + c * 16, r0);
+          bulk_commit();
+        }
+        gk = gk == 2 ? 0 : gk + 1;
+      }
+      tmem_wait_st();
+      // ---------------- row statistics across the four column slices of this row quarter
+      sStats[s * 128 + q * 32 + lane] = make_float2(sum, sumsq);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");
+      float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 p = sStats[j * 128 + q * 32 + lane];
+        tsum += p.x;
+        tsq += p.y;
+      }
+      const float mean = tsum * (1.0f / LN_N);
+      const float rstd = rsqrtf(fmaxf(tsq * (1.0f / LN_N) - mean * mean, 0.f) + ln.eps);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory");  // sStats may be rewritten by the next tile
+      // ---------------- pass 2: h = (x_new - mean) rstd gamma + beta  -> bf16, 32 columns per box
+      tmem_ld16_nowait(t_row, raw[0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        tmem_wait_ld();
+        if (c + 1 < 8) {
+          tmem_ld16_nowait(t_row + (uint32_t)((c + 1) * 16), raw[(c + 1) & 1]);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader);
+        }
+        float hreg[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float g = __shfl_sync(0xffffffffu, gam_r[c >> 1], (16 * (c & 1) + j) & 31);
+          const float b = __shfl_sync(0xffffffffu, bet_r[c >> 1], (16 * (c & 1) + j) & 31);
+          hreg[j] = fmaf((__uint_as_float(raw[c & 1][j]) - mean) * rstd, g, b);
+        }
+        uint8_t* xb = myb + gk * BOX_BYTES;
+        if ((c & 1) == 0) {
+          // the box written next was last read by the store three boxes ago (pass-1 stores included)
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          *reinterpret_cast<uint4*>(xb + box_off(lane, 2 * (c & 1) + k, swz)) =
+              make_uint4(pack2_bf16(hreg[8 * k], hreg[8 * k + 1]), pack2_bf16(hreg[8 * k + 2], hreg[8 * k + 3]),
+                         pack2_bf16(hreg[8 * k + 4], hreg[8 * k + 5]), pack2_bf16(hreg[8 * k + 6], hreg[8 * k + 7]));
+        if (c & 1) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (live) tma_store_2d(&tmH, myb_a + (uint32_t)gk * BOX_BYTES, c0 + (c - 1) * 16, r0);
+            bulk_commit();
+          }
+          gk = gk == 2 ? 0 : gk + 1;
+        }
+      }
+      tphase ^= 1;
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Grouped weight-gradient kernel, CTA-pair version:  dW_g[Nout_g, Kin_g] += dy_g^T x_g  (and db_g += colsum(dy_g)) for
 // up to 8 products (one backward layer) in ONE persistent launch.  Pair tiles are 256 x 256, both operands MN-major
 // (the rows of dy / x are the reduction dimension), every output tile has exactly one writer (no split-K, no atomics,
@@ -923,5 +1231,62 @@ extern "C" int mma_wgrad2_group(int count, const void* const* dy, const long lon
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (cudaLaunchKernelEx(&cfg, wgrad2_group_kernel, grp) != cudaSuccess) return MMA_ERR_LAUNCH;
+  return MMA_OK;
+}
+
+// x_new = resid + drop(A W^T + bias)  (fp32, ep->out)  and  h = LayerNorm(x_new) gamma + beta  (bf16), d_model = 512.
+// ep: kind EPI_RESID with fp32 out / resid; everything else as in mma_gemm_bf16.  Returns MMA_ERR_UNSUPPORTED for
+// shapes / layouts outside that envelope (the caller then runs the product and the LayerNorm separately).
+extern "C" int mma_gemm2_resid_ln(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                                  const Epi* ep, const float* gamma, const float* beta, float eps, void* h,
+                                  long long ldh, cudaStream_t stream) {
+  using namespace tc2;
+  if (M <= 0 || K <= 0 || !ep || !gamma || !beta || !h) return MMA_ERR_ARG;
+  auto ok16 = [](const void* p, long long ld, int esz) {
+    return p && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && ((ld * esz) & 15) == 0;
+  };
+  if (N != LN_N || ep->kind != EPI_RESID || !ep->out_f32 || !ep->resid_f32 || !ok16(ep->out, ep->ldo, 4) ||
+      !ok16(ep->resid, ep->ldr, 4) || !ok16(h, ldh, 2) || (ep->p_drop > 0.f && (ep->drop_ld & 1)))
+    return MMA_ERR_UNSUPPORTED;
+  static int swz = -1;
+  if (swz < 0) {
+    const char* e = getenv("MMA_GEMM2_SWZ");
+    swz = e ? atoi(e) : 1;
+  }
+  const int box_swz = swz ? (int)CU_TENSOR_MAP_SWIZZLE_64B : (int)CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUtensorMap tmA, tmB, tmOut, tmIn, tmH;
+  int rc = make_map(&tmA, A, (unsigned long long)K, (unsigned long long)M, lda, BK, BM);
+  if (rc) return rc;
+  if ((rc = make_map(&tmB, W, (unsigned long long)K, (unsigned long long)N, ldw, BK, 128))) return rc;
+  if ((rc = make_map_ex(&tmOut, ep->out, (unsigned long long)N, (unsigned long long)M, ep->ldo, 16, 32, 1, box_swz))) return rc;
+  if ((rc = make_map_ex(&tmIn, ep->resid, (unsigned long long)N, (unsigned long long)M, ep->ldr, 16, 32, 1, box_swz))) return rc;
+  if ((rc = make_map_ex(&tmH, h, (unsigned long long)N, (unsigned long long)M, ldh, 32, 32, 0, box_swz))) return rc;
+  static int max_pairs = 0;
+  if (!max_pairs) {
+    if (cudaFuncSetAttribute(gemm2_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_SMEM) != cudaSuccess)
+      return MMA_ERR_LAUNCH;
+    cudaLaunchConfig_t q{};
+    q.gridDim = dim3(2 * (num_sms() / 2));
+    q.blockDim = dim3(NUM_THREADS);
+    q.dynamicSmemBytes = LN_SMEM;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm2_ln_kernel, &q) != cudaSuccess || n <= 0) n = num_sms() / 2;
+    max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+  }
+  const int total = (M + 2 * BM - 1) / (2 * BM);
+  const int pairs = total < max_pairs ? total : max_pairs;
+  LnExtra ln{gamma, beta, eps};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = LN_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cudaLaunchKernelEx(&cfg, gemm2_ln_kernel, tmA, tmB, tmOut, tmIn, tmH, M, K, swz ? 1 : 0, *ep, ln) != cudaSuccess)
+    return MMA_ERR_LAUNCH;
   return MMA_OK;
 }

@@ -243,15 +243,34 @@ class Engine:
             ops.ln_bwd(dpos.view(L_total, d), self.P(pe + "pos_encodings.weight")[:L_total], self.P(pe + "norm.weight"),
                        dx=gtab, dres=gtab, dgamma=self.G(pe + "norm.weight"), dbeta=self.G(pe + "norm.bias"))
 
+    def _resid_gemm(self, a, wname, bname, M, n_out, k_in, xo, x, p, site_r, nxt):
+        """xo = x + drop(a W^T + b).  `nxt` = (gamma, beta, h buffer) of the LayerNorm that consumes xo next: when the
+        fused CTA-pair kernel applies (d_model 512, bf16), h = LN(xo) comes out of the same launch.  Returns h or None."""
+        epi = ops.make_epi(EPI_RESID, xo, bias=self.P(bname), resid=x, p_drop=p, seed=self.seed_arg, site=site_r)
+        if nxt is not None and self.precision == "bf16" and ops.FUSE_LN:
+            gam, bet, hbuf = nxt
+            if ops.gemm_resid_ln(a, self.W(wname), M, n_out, k_in, epi, gam, bet, hbuf):
+                return hbuf
+        ops.gemm(a, self.W(wname), M, n_out, k_in, epi)
+        return None
+
+    def _next_norm(self, wname, bname, tag, M):
+        """(gamma, beta, output buffer) for the LayerNorm that opens the block `tag`."""
+        return self.P(wname), self.P(bname), self.buf(tag + ".h", (M, self.cfg.d_model), self.adt)
+
     # ----------------------------------------------------------------------------- layer forward
-    def _attn_block_fwd(self, tag, x, B, L, heads, wp, kmask, causal, p, site_a, site_r, train):
-        """x -> x + drop(out_proj(attn(LN(x))))  (self-attention).  Returns the new residual stream."""
+    def _attn_block_fwd(self, tag, x, B, L, heads, wp, kmask, causal, p, site_a, site_r, train, h_pre=None, nxt=None):
+        """x -> x + drop(out_proj(attn(LN(x))))  (self-attention).  `h_pre`: LN(x) if the previous block's fused
+        product already made it; `nxt`: the LayerNorm that follows.  Returns (new residual stream, LN of it or None)."""
         d = self.cfg.d_model
         M = B * L
         dh = d // heads
         T = self.adt
         h = self.buf(tag + ".h", (M, d), T)
-        ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        if h_pre is None:
+            ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        else:
+            assert h_pre.data_ptr() == h.data_ptr()
         qkv = self.buf(tag + ".qkv", (M, 3 * d), T)
         ops.gemm(h, self.W(wp["in_w"]), M, 3 * d, d, ops.make_epi(EPI_STORE, qkv, bias=self.P(wp["in_b"])))
         ctx = self.buf(tag + ".ctx", (M, d), T)
@@ -259,11 +278,10 @@ class Engine:
         ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, lse, B, heads, L, L, dh, kmask=kmask,
                      causal=causal, p_drop=p, seed=self.seed_arg, site=site_a)
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
-        ops.gemm(ctx, self.W(wp["out_w"]), M, d, d,
-                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed_arg, site=site_r))
+        h_next = self._resid_gemm(ctx, wp["out_w"], wp["out_b"], M, d, d, xo, x, p, site_r, nxt)
         if train:
             self.saved[tag] = dict(x=x, h=h, qkv=qkv, ctx=ctx, lse=lse)
-        return xo
+        return xo, h_next
 
     def _attn_block_bwd(self, tag, dx, dyb, B, L, heads, wp, kmask, causal, p, site_a, prev_site, first=False,
                         out_tag="x"):
@@ -288,11 +306,14 @@ class Engine:
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
 
-    def _ffn_block_fwd(self, tag, x, M, f, wp, p, site_i, site_r, train):
+    def _ffn_block_fwd(self, tag, x, M, f, wp, p, site_i, site_r, train, h_pre=None, nxt=None):
         d = self.cfg.d_model
         T = self.adt
         h = self.buf(tag + ".h", (M, d), T)
-        ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        if h_pre is None:
+            ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        else:
+            assert h_pre.data_ptr() == h.data_ptr()
         a = self.buf(tag + ".a", (M, f), T)
         z = self.buf(tag + ".z", (M, f), T)
         z2 = None
@@ -307,11 +328,10 @@ class Engine:
                      ops.make_epi(EPI_GLU_MUL, a, out2=z2, bias=self.P(wp["bg"]), aux=z, p_drop=p, seed=self.seed_arg,
                                   site=site_i))
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
-        ops.gemm(a, self.W(wp["w2"]), M, d, f,
-                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["b2"]), resid=x, p_drop=p, seed=self.seed_arg, site=site_r))
+        h_next = self._resid_gemm(a, wp["w2"], wp["b2"], M, d, f, xo, x, p, site_r, nxt)
         if train:
             self.saved[tag] = dict(x=x, h=h, a=a, z=z, z2=z2)
-        return xo
+        return xo, h_next
 
     def _ffn_block_bwd(self, tag, dx, dyb, M, f, wp, p, site_i, prev_site):
         d = self.cfg.d_model
@@ -357,13 +377,16 @@ class Engine:
                     n_w=f"{prefix}{norm}.weight", n_b=f"{prefix}{norm}.bias")
 
     # -------------------------------------------------------------------------------- cross-attn
-    def _cross_block_fwd(self, tag, x, mem, B, T_, S, heads, wp, kmask, p, site_a, site_r, train):
+    def _cross_block_fwd(self, tag, x, mem, B, T_, S, heads, wp, kmask, p, site_a, site_r, train, h_pre=None, nxt=None):
         d = self.cfg.d_model
         M, Me = B * T_, B * S
         dh = d // heads
         T = self.adt
         h = self.buf(tag + ".h", (M, d), T)
-        ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        if h_pre is None:
+            ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        else:
+            assert h_pre.data_ptr() == h.data_ptr()
         q = self.buf(tag + ".q", (M, d), T)
         Win, bin_ = self.W(wp["in_w"]), self.P(wp["in_b"])
         ops.gemm(h, Win[:d], M, d, d, ops.make_epi(EPI_STORE, q, bias=bin_[:d]))
@@ -374,11 +397,10 @@ class Engine:
         ops.attn_fwd(q, kv[:, :d], kv[:, d:], ctx, lse, B, heads, T_, S, dh, kmask=kmask, causal=False, p_drop=p,
                      seed=self.seed_arg, site=site_a)
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
-        ops.gemm(ctx, self.W(wp["out_w"]), M, d, d,
-                 ops.make_epi(EPI_RESID, xo, bias=self.P(wp["out_b"]), resid=x, p_drop=p, seed=self.seed_arg, site=site_r))
+        h_next = self._resid_gemm(ctx, wp["out_w"], wp["out_b"], M, d, d, xo, x, p, site_r, nxt)
         if train:
             self.saved[tag] = dict(x=x, h=h, q=q, kv=kv, ctx=ctx, lse=lse)
-        return xo
+        return xo, h_next
 
     def _cross_block_bwd(self, tag, dx, dyb, mem, dmem, first_mem, B, T_, S, heads, wp, kmask, p, site_a, prev_site):
         d = self.cfg.d_model
@@ -413,16 +435,25 @@ class Engine:
         B, S = enc_mask.shape
         p = cfg.dropout if train else 0.0
         x, recs = self._embed(enc_inputs, S, "enc", B)
+        Me = B * S
+        mem = self.buf("enc.mem", (Me, cfg.d_model), self.adt)
+        h = None  # LN of x for the next block, when the previous block's fused product already produced it
         for i in range(cfg.encoder_layers):
             pre = f"hf_model.encoder.layers.{i}."
             tg = f"enc{i if train else ''}"
-            x = self._attn_block_fwd(tg + ".sa", x, B, S, cfg.encoder_attention_heads,
-                                     self._wp_attn(pre, "self_attn", "norm1"), enc_mask, False, p,
-                                     self._site(False, i, 0), self._site(False, i, 1), train)
-            x = self._ffn_block_fwd(tg + ".ff", x, B * S, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"), p,
-                                    self._site(False, i, 2), self._site(False, i, 3), train)
-        mem = self.buf("enc.mem", (B * S, cfg.d_model), self.adt)
-        ops.ln_fwd(x, self.P("hf_model.encoder.norm.weight"), self.P("hf_model.encoder.norm.bias"), mem)
+            x, h = self._attn_block_fwd(tg + ".sa", x, B, S, cfg.encoder_attention_heads,
+                                        self._wp_attn(pre, "self_attn", "norm1"), enc_mask, False, p,
+                                        self._site(False, i, 0), self._site(False, i, 1), train, h_pre=h,
+                                        nxt=self._next_norm(pre + "norm2.weight", pre + "norm2.bias", tg + ".ff", Me))
+            if i + 1 < cfg.encoder_layers:
+                npre = f"hf_model.encoder.layers.{i + 1}."
+                nxt = self._next_norm(npre + "norm1.weight", npre + "norm1.bias", f"enc{i + 1 if train else ''}.sa", Me)
+            else:
+                nxt = (self.P("hf_model.encoder.norm.weight"), self.P("hf_model.encoder.norm.bias"), mem)
+            x, h = self._ffn_block_fwd(tg + ".ff", x, Me, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"), p,
+                                       self._site(False, i, 2), self._site(False, i, 3), train, h_pre=h, nxt=nxt)
+        if h is None:
+            ops.ln_fwd(x, self.P("hf_model.encoder.norm.weight"), self.P("hf_model.encoder.norm.bias"), mem)
         if train:
             self.saved["enc"] = dict(recs=recs, xL=x, mem=mem, B=B, S=S, mask=enc_mask)
         return mem
@@ -435,17 +466,27 @@ class Engine:
         p = cfg.dropout if train else 0.0
         x, recs = self._embed({cfg.target_modality: dec_ids}, T_, "dec", B)
         H = cfg.decoder_attention_heads
+        M = B * T_
+        hT = self.buf("dec.hT", (M, cfg.d_model), self.adt)
+        h = None
         for i in range(cfg.decoder_layers):
             pre = f"hf_model.decoder.layers.{i}."
             tg = f"dec{i if train else ''}"
-            x = self._attn_block_fwd(tg + ".sa", x, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"), dec_mask, True,
-                                     p, self._site(True, i, 0), self._site(True, i, 1), train)
-            x = self._cross_block_fwd(tg + ".ca", x, mem, B, T_, S, H, self._wp_attn(pre, "multihead_attn", "norm2"),
-                                      enc_mask, p, self._site(True, i, 4), self._site(True, i, 5), train)
-            x = self._ffn_block_fwd(tg + ".ff", x, B * T_, cfg.decoder_ffn_dim, self._wp_ffn(pre, "norm3"), p,
-                                    self._site(True, i, 2), self._site(True, i, 3), train)
-        hT = self.buf("dec.hT", (B * T_, cfg.d_model), self.adt)
-        ops.ln_fwd(x, self.P("hf_model.decoder.norm.weight"), self.P("hf_model.decoder.norm.bias"), hT)
+            x, h = self._attn_block_fwd(tg + ".sa", x, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"), dec_mask,
+                                        True, p, self._site(True, i, 0), self._site(True, i, 1), train, h_pre=h,
+                                        nxt=self._next_norm(pre + "norm2.weight", pre + "norm2.bias", tg + ".ca", M))
+            x, h = self._cross_block_fwd(tg + ".ca", x, mem, B, T_, S, H, self._wp_attn(pre, "multihead_attn", "norm2"),
+                                         enc_mask, p, self._site(True, i, 4), self._site(True, i, 5), train, h_pre=h,
+                                         nxt=self._next_norm(pre + "norm3.weight", pre + "norm3.bias", tg + ".ff", M))
+            if i + 1 < cfg.decoder_layers:
+                npre = f"hf_model.decoder.layers.{i + 1}."
+                nxt = self._next_norm(npre + "norm1.weight", npre + "norm1.bias", f"dec{i + 1 if train else ''}.sa", M)
+            else:
+                nxt = (self.P("hf_model.decoder.norm.weight"), self.P("hf_model.decoder.norm.bias"), hT)
+            x, h = self._ffn_block_fwd(tg + ".ff", x, M, cfg.decoder_ffn_dim, self._wp_ffn(pre, "norm3"), p,
+                                       self._site(True, i, 2), self._site(True, i, 3), train, h_pre=h, nxt=nxt)
+        if h is None:
+            ops.ln_fwd(x, self.P("hf_model.decoder.norm.weight"), self.P("hf_model.decoder.norm.bias"), hT)
         if train:
             self.saved["dec"] = dict(recs=recs, xL=x, hT=hT, B=B, T=T_, mask=dec_mask)
         return hT

@@ -101,6 +101,33 @@ def gemm(A, B, M, N, K, epi, a_mn=False, b_mn=False, splits=1, force_simt=False,
     _count()
 
 
+# Engine-level switch for the fused residual-product + LayerNorm kernel.  Measured on B200 at the C2 shapes (CUDA-graph
+# timing, scripts/ln_fuse_bench.py): 26.9 vs 33.1 us for the decoder out-projection, but 43.2 vs 28.5 us for the
+# encoder FFN-2 - a CTA pair owns 256 rows x all 512 columns, so M = 9216 fills only 36 of the 74 pairs - and the
+# training step as a whole is 2.5 % slower with it.  Off by default; it pays from M ~ 32k rows upwards.
+FUSE_LN = os.environ.get("MMA_FUSE_LN", "0") != "0"
+
+
+def gemm_resid_ln(A, W, M, N, K, epi, gamma, beta, h, eps=1e-5):
+    """epi.out = epi.resid + drop(A W^T + bias) and h = LayerNorm(epi.out) * gamma + beta in ONE launch (CTA-pair
+    tcgen05 kernel, N == 512).  Returns False (nothing launched) when the shape / layout is outside the fused
+    kernel's envelope - the caller then runs `gemm` and `ln_fwd`."""
+    _need_cuda(A, W, h)
+    if not (N == 512 and M >= 512 and epi.kind == EPI_RESID and epi.out_f32 and epi.resid_f32
+            and h.dtype == torch.bfloat16 and _tc_ok(A, False, M, K) and _tc_ok(W, False, N, K)):
+        return False
+    if epi.p_drop > 0 and epi.drop_ld == 0:
+        epi.drop_ld = N
+    rc = _lib.load().mma_gemm2_resid_ln(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K, C.byref(epi),
+                                        gamma.data_ptr(), beta.data_ptr(), float(eps), h.data_ptr(), h.stride(0),
+                                        _stream())
+    if rc == -3:
+        return False
+    check(rc, "mma_gemm2_resid_ln")
+    _count()
+    return True
+
+
 def wgrad_group_ok(dy, x, n_out, k_in):
     return (_tc_ok(dy, True, 0, 0) and _tc_ok(x, True, 0, 0) and n_out % 8 == 0 and k_in % 8 == 0)
 

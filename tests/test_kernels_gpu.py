@@ -169,6 +169,40 @@ def test_gemm_pair_kernel(M, N, K):
             assert torch.equal(x1 == 0, x2 == 0)
 
 
+@pytest.mark.parametrize("M,K", [(16384, 512), (9216, 2048), (12300, 512), (640, 512)])
+def test_gemm_resid_layernorm_fused(M, K):
+    """x_new = resid + drop(A W^T + b) and h = LN(x_new) in one launch (gemm2_ln_kernel) against torch; with dropout
+    against the unfused pair of launches (same mask)."""
+    N = 512
+    A, W, bias = _rand(M, K, dtype=torch.bfloat16), _rand(N, K, dtype=torch.bfloat16, scale=K ** -0.5), _rand(N)
+    resid = _rand(M, N, seed=3)
+    gamma, beta = _rand(N, seed=4) * 0.5 + 1.0, _rand(N, seed=5) * 0.1
+    x = torch.empty(M, N, device=DEV)
+    h = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ok = ops.gemm_resid_ln(A, W, M, N, K, ops.make_epi(EPI_RESID, x, bias=bias, resid=resid), gamma, beta, h)
+    if M < 512:
+        assert not ok
+        return
+    assert ok
+    ref_x = resid + A.float() @ W.float().T + bias
+    assert rel(x, ref_x) < 2e-5
+    ref_h = torch.nn.functional.layer_norm(ref_x, (N,), gamma, beta, 1e-5)
+    assert rel(h.float(), ref_h) < 1e-2
+    # dropout: same mask / values as gemm (RESID epilogue) + ln_fwd
+    x1, x2 = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    h1, h2 = torch.empty_like(h), torch.empty_like(h)
+    assert ops.gemm_resid_ln(A, W, M, N, K, ops.make_epi(EPI_RESID, x1, bias=bias, resid=resid, p_drop=0.1, seed=11, site=5),
+                             gamma, beta, h1)
+    ops.gemm(A, W, M, N, K, ops.make_epi(EPI_RESID, x2, bias=bias, resid=resid, p_drop=0.1, seed=11, site=5))
+    ops.ln_fwd(x2, gamma, beta, h2)
+    assert rel(x1, x2) < 1e-5
+    assert rel(h1.float(), h2.float()) < 1e-2
+    # in place on the residual stream (out == resid) must work too
+    x3 = resid.clone()
+    assert ops.gemm_resid_ln(A, W, M, N, K, ops.make_epi(EPI_RESID, x3, bias=bias, resid=x3), gamma, beta, h1)
+    assert rel(x3, ref_x) < 2e-5
+
+
 def test_gemm_dropout_mask_consistency():
     """RESID-epilogue dropout (forward) and ln_bwd's masked copy (backward) must use the same mask."""
     M, N, K, p = 256, 128, 64, 0.25
