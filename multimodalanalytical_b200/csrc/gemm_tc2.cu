@@ -890,6 +890,7 @@ struct alignas(64) Wg2Problem {
 struct Wg2Group {
   Wg2Problem p[8];
   int count, total_tiles, swz;
+  int segs;  // every tile's reduction range is cut into `segs` work items (all land with TMA reduce-add / atomics)
 };
 
 constexpr int WG2_STAGES = 5;
@@ -946,7 +947,11 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
   pdl_wait();
 
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  auto locate = [&](int tile, int& g, int& m0, int& n0) {
+  const int segs = grp.segs;
+  const int total_items = grp.total_tiles * segs;
+  // work item -> problem, tile origin, k-block range [kb0, kb1) of the rows-of-dy reduction
+  auto locate = [&](int item, int& g, int& m0, int& n0, int& kb0, int& kb1) {
+    const int tile = item / segs, seg = item % segs;
     g = 0;
 #pragma unroll 1
     for (int i = 1; i < grp.count; ++i)
@@ -954,19 +959,21 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
     const int t = tile - grp.p[g].tile_begin;
     n0 = (t % grp.p[g].tiles_n) * BN;
     m0 = (t / grp.p[g].tiles_n) * (2 * BM);
+    const int num_kb = (grp.p[g].R + BK - 1) / BK;
+    kb0 = (int)((long long)seg * num_kb / segs);
+    kb1 = (int)((long long)(seg + 1) * num_kb / segs);
   };
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < grp.total_tiles; tile += npairs) {
-        int g, m0, n0;
-        locate(tile, g, m0, n0);
+      for (int item = pair; item < total_items; item += npairs) {
+        int g, m0, n0, kb0, kb1;
+        locate(item, g, m0, n0, kb0, kb1);
         const Wg2Problem& P = grp.p[g];
-        const int num_kb = (P.R + BK - 1) / BK;
         const int ma = m0 + (int)rank * BM, nb = n0 + (int)rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + B_BYTES));
@@ -989,15 +996,14 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
                                       ((uint32_t)(16 >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
-      for (int tile = pair; tile < grp.total_tiles; tile += npairs) {
-        int g, m0, n0;
-        locate(tile, g, m0, n0);
+      for (int item = pair; item < total_items; item += npairs) {
+        int g, m0, n0, kb0, kb1;
+        locate(item, g, m0, n0, kb0, kb1);
         const Wg2Problem& P = grp.p[g];
-        const int num_kb = (P.R + BK - 1) / BK;
         const bool with_bias = n0 == 0 && P.dbias != nullptr;
         mbar_wait(smem_u32(tempty), tphase ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&full[stage]), phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
@@ -1005,10 +1011,10 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = make_smem_desc<true>(a_addr, k);
-            tc_mma2_bf16(tmem_base, ad, make_smem_desc<true>(b_addr, k), idesc_main, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma2_bf16(tmem_base, ad, make_smem_desc<true>(b_addr, k), idesc_main, (kb > kb0 || k > 0) ? 1u : 0u);
             if (with_bias)
               tc_mma2_bf16(tmem_base + BN, ad, make_smem_desc<false>(smem_u32(sOnes), k), idesc_bias,
-                           (kb > 0 || k > 0) ? 1u : 0u);
+                           (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit2_mc(smem_u32(&empty[stage]));
           if (++stage == ST) { stage = 0; phase ^= 1; }
@@ -1024,9 +1030,9 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
     const uint32_t tempty_leader = mapa(smem_u32(tempty), 0);
     const int swz = grp.swz;
     uint32_t tphase = 0;
-    for (int tile = pair; tile < grp.total_tiles; tile += npairs) {
-      int g, m0, n0;
-      locate(tile, g, m0, n0);
+    for (int item = pair; item < total_items; item += npairs) {
+      int g, m0, n0, kb0, kb1;
+      locate(item, g, m0, n0, kb0, kb1);
       const Wg2Problem& P = grp.p[g];
       const int r0 = m0 + (int)rank * BM + q * 32;
       const int c0 = n0 + s * 64;
@@ -1067,7 +1073,10 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
           bulk_commit();
         }
       }
-      if (do_bias && r0 + lane < P.M) P.dbias[r0 + lane] += bias_v;
+      if (do_bias && r0 + lane < P.M) {
+        if (segs > 1) atomicAdd(P.dbias + r0 + lane, bias_v);  // several k-segments add into the same entry
+        else P.dbias[r0 + lane] += bias_v;
+      }
       tphase ^= 1;
     }
     if (lane == 0) bulk_wait_all();
@@ -1207,6 +1216,7 @@ extern "C" int mma_wgrad2_group(int count, const void* const* dy, const long lon
   grp.count = count;
   grp.total_tiles = tiles;
   grp.swz = swz ? 1 : 0;
+  grp.segs = 1;
   static int max_pairs = 0;
   if (!max_pairs) {
     if (cudaFuncSetAttribute(wgrad2_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM) != cudaSuccess)
@@ -1219,7 +1229,33 @@ extern "C" int mma_wgrad2_group(int count, const void* const* dy, const long lon
     if (cudaOccupancyMaxActiveClusters(&n, wgrad2_group_kernel, &q) != cudaSuccess || n <= 0) n = num_sms() / 2;
     max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
   }
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  // Split the reduction (rows of dy) of every tile into `segs` work items when that fills the CTA pairs better: the
+  // encoder layers have 48 tiles for 74 pairs, the LM head 2.  Each item adds into the gradient with TMA reduce-add
+  // (fp32 add order then depends on the schedule; the unsplit case keeps one writer per tile).  MMA_WGRAD_SPLIT=0: off.
+  static int allow_split = -1;
+  if (allow_split < 0) {
+    const char* e = getenv("MMA_WGRAD_SPLIT");
+    allow_split = e ? atoi(e) : 1;
+  }
+  if (allow_split) {
+    int min_kb = 1 << 30;
+    for (int g = 0; g < count; ++g) {
+      const int kb = (R[g] + BK - 1) / BK;
+      if (kb < min_kb) min_kb = kb;
+    }
+    double best = (double)((tiles + max_pairs - 1) / max_pairs);  // rounds of full-length tiles
+    const int cand[] = {2, 3, 4, 6, 8, 12, 16};
+    for (int c : cand) {
+      if (min_kb / c < 16) break;  // keep every item at least 16 k-blocks long
+      const double cost = (double)((tiles * c + max_pairs - 1) / max_pairs) / c + 0.02 * c;  // + epilogue overhead
+      if (cost < best - 1e-9) {
+        best = cost;
+        grp.segs = c;
+      }
+    }
+  }
+  const int items = tiles * grp.segs;
+  const int pairs = items < max_pairs ? items : max_pairs;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(NUM_THREADS);

@@ -516,3 +516,25 @@ def test_grouped_wgrad_with_fused_bias_grad():
     for it, (rw, rb) in zip(items, refs):
         assert rel(it[2], rw) < 3e-5, it[4:]
         assert rel(it[3], rb) < 3e-5, it[4:]
+
+
+@pytest.mark.parametrize("specs", [
+    [(9216, 1536, 512), (9216, 512, 512), (9216, 2048, 512), (9216, 512, 2048)],   # encoder layer: 48 tiles -> 3 k-segments
+    [(16384, 200, 512)],                                                           # LM head: 2 tiles -> 8 k-segments
+])
+def test_grouped_wgrad_split_reduction(specs):
+    """Few output tiles + a long reduction: the grouped kernel cuts every tile's row range into work items that add into
+    the gradient with TMA reduce-add (bias gradients with atomics)."""
+    dt = torch.bfloat16
+    items, refs = [], []
+    for i, (R, n_out, k_in) in enumerate(specs):
+        dy = _rand(R, n_out, dtype=dt, scale=R ** -0.5, seed=i)
+        x = _rand(R, k_in, dtype=dt, seed=100 + i)
+        dw0, db0 = _rand(n_out, k_in, seed=200 + i), _rand(n_out, seed=300 + i)
+        dw, db = dw0.clone(), db0.clone()
+        items.append((dy, x, dw, db, n_out, k_in, R))
+        refs.append((dw0 + dy.float().T @ x.float(), db0 + dy.float().sum(0)))
+    ops.wgrad_group(items)
+    for it, (rw, rb) in zip(items, refs):
+        assert rel(it[2], rw) < 3e-5, it[4:]
+        assert rel(it[3], rb) < 3e-5, it[4:]
