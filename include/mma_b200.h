@@ -195,6 +195,29 @@ int mma_greedy_step(const float* logits, long long ldl, const float* extra_bias,
                     cudaStream_t stream);
 int mma_advance(int* cur_len, cudaStream_t stream);
 
+/* ---- logits processors inside generate (wrapper.py:443-451 `logits_processor=`) ---------------
+ * `_ex` steps: prenorm != 0 -> `logits` already holds the processed scores (log_softmax -> ForcedEOS -> processors),
+ * the step only adds the running score and selects.  g_cur != NULL fuses GuidedFormulaProcessor.__call__
+ * (generation/logit_processors.py:89-152) into the step: g_cur [rows][n_atoms] = atom counts of each running
+ * hypothesis (host chemistry), g_tgt [spectra][n_atoms] = target formula, g_tok_atoms [V] = bit e set when the token
+ * adds an atom of element e (logit_processors.py:46-62); <eos> := 0 when all n_atoms counts match, := -inf while any
+ * is short, and a token := -inf when it would push one of the first n_check elements over its target. */
+int mma_beam_step_ex(const float* logits, long long ldl, const float* extra_bias, int B, int K, int V, int L,
+                     int pad_id, int eos_id, const int* cur_len, int* run_seq, int* fin_seq, float* run_score,
+                     float* fin_score, unsigned char* fin_flag, int* fin_len, unsigned char* improvable,
+                     unsigned char* all_hit, int* anc, int* next_tok, int* parent_row, int prenorm, const int* g_cur,
+                     const int* g_tgt, const unsigned* g_tok_atoms, int n_atoms, int n_check, cudaStream_t stream);
+int mma_greedy_step_ex(const float* logits, long long ldl, const float* extra_bias, int R, int V, int L, int pad_id,
+                       int eos_id, const int* cur_len, int* seq, unsigned char* unfinished, int* next_tok, int prenorm,
+                       const int* g_cur, const int* g_tgt, const unsigned* g_tok_atoms, int n_atoms, int n_check,
+                       cudaStream_t stream);
+/* dense scores handed to host-visible processors: log_softmax (beam) or raw logits (greedy), then ForcedEOS */
+int mma_score_rows(const float* logits, long long ldl, float* out, long long ldo, int R, int V, int L, int eos_id,
+                   const int* cur_len, int log_softmax, cudaStream_t stream);
+/* GuidedFormulaProcessor.__call__ on a dense [R, V] score matrix, in place; target row = r / beams */
+int mma_guided_mask(float* scores, long long lds, int R, int V, int eos_id, int beams, const int* g_cur,
+                    const int* g_tgt, const unsigned* g_tok_atoms, int n_atoms, int n_check, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

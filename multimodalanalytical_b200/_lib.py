@@ -124,6 +124,11 @@ _SIGS = {
                       _vp, _vp],
     "mma_greedy_step": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "mma_advance": [_vp, _vp],
+    "mma_beam_step_ex": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                         _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "mma_greedy_step_ex": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "mma_score_rows": [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _i, _vp],
+    "mma_guided_mask": [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
 }
 EXPORTS = tuple(_SIGS)
 

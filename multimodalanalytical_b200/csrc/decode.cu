@@ -219,7 +219,40 @@ struct BeamArgs {
   int* anc;          // [2][B*K][L]
   int* next_tok;     // [B*K]
   int* parent_row;   // [B*K]
+  // processed-score mode: `logits` already holds log_softmax -> forced EOS -> processors (skip stages 1 + forced EOS)
+  int prenorm;
+  // formula-guided decoding (GuidedFormulaProcessor, generation/logit_processors.py:89-152), nullptr = off
+  const int* g_cur;        // [B*K][g_na] atom counts of each running hypothesis (host chemistry, refreshed per step)
+  const int* g_tgt;        // [B][g_na] atom counts of the target formula
+  const unsigned* g_tok;   // [V] bit a set: the token adds one atom of element a
+  int g_na, g_ncheck;      // elements compared for <eos> (14) / for the look-ahead (9: H and rarer elements skipped)
 };
+
+// Row verdict of the formula guide: bit 31 = formula matches (force <eos> to 0), bit 30 = some element still short
+// (ban <eos>), bit 29 = an element already over target (ban everything), bits 0..g_ncheck-1 = elements at their
+// target count (ban tokens that add one).  Order of the writes follows logit_processors.py:122-150.
+__device__ __forceinline__ unsigned guide_row(const int* cur, const int* tgt, int na, int ncheck) {
+  bool match = true, small = false, over = false;
+  unsigned full = 0u;
+  for (int e = 0; e < na; ++e) {
+    const int c = cur[e], t = tgt[e];
+    match = match && (c == t);
+    small = small || (c < t);
+    if (e < ncheck) {
+      over = over || (c > t);
+      if (c >= t) full |= 1u << e;
+    }
+  }
+  return full | (match ? 0x80000000u : 0u) | (small ? 0x40000000u : 0u) | (over ? 0x20000000u : 0u);
+}
+__device__ __forceinline__ float guide_apply(float lp, unsigned verdict, unsigned tok_bits, bool is_eos) {
+  if (is_eos) {
+    if (verdict & 0x80000000u) lp = 0.f;
+    if (verdict & 0x40000000u) lp = -INFINITY;
+  }
+  if ((verdict & 0x20000000u) || (tok_bits & verdict & 0x1fffffffu)) lp = -INFINITY;
+  return lp;
+}
 
 constexpr int MAXK = 64;  // beams (2K candidates <= 128)
 
@@ -239,6 +272,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
   __shared__ unsigned char n_fin_flag[MAXK];
   __shared__ int n_fin_len[MAXK];
   __shared__ float n_run_score[MAXK];
+  __shared__ unsigned s_guide[MAXK];
 
   const int b = blockIdx.x;
   const int K = a.K, V = a.V, L = a.L;
@@ -248,8 +282,11 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const bool force_eos = cur == L - 1;
 
+  if (a.g_cur && threadIdx.x < K)
+    s_guide[threadIdx.x] = guide_row(a.g_cur + (long long)(b * K + threadIdx.x) * a.g_na, a.g_tgt + (long long)b * a.g_na,
+                                     a.g_na, a.g_ncheck);
   // 1. log-softmax statistics per beam row (one warp per row)
-  for (int k = warp; k < K; k += nwarp) {
+  for (int k = warp; k < K && !a.prenorm; k += nwarp) {
     const float* x = a.logits + (long long)(b * K + k) * a.ldl;
     float mx = -INFINITY;
     for (int c = lane; c < V; c += 32) mx = fmaxf(mx, x[c]);
@@ -263,9 +300,13 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
   // 2. accumulated scores of the K*V continuations
   for (int i = threadIdx.x; i < K * V; i += blockDim.x) {
     const int k = i / V, c = i % V;
-    float lp = a.logits[(long long)(b * K + k) * a.ldl + c] - s_lse[k];
-    if (force_eos) lp = c == a.eos_id ? 0.f : -INFINITY;
+    float lp = a.logits[(long long)(b * K + k) * a.ldl + c];
+    if (!a.prenorm) {
+      lp -= s_lse[k];
+      if (force_eos) lp = c == a.eos_id ? 0.f : -INFINITY;
+    }
     if (a.extra_bias) lp += a.extra_bias[(long long)(b * K + k) * V + c];
+    if (a.g_cur) lp = guide_apply(lp, s_guide[k], a.g_tok[c], c == a.eos_id);
     cand[i] = f2ord(lp + a.run_score[b * K + k]);
   }
   __syncthreads();
@@ -442,17 +483,22 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
                                                           const float* __restrict__ extra_bias, int R, int V, int L,
                                                           int pad_id, int eos_id, const int* __restrict__ cur_len,
                                                           int* __restrict__ seq, unsigned char* __restrict__ unfinished,
-                                                          int* __restrict__ next_tok) {
+                                                          int* __restrict__ next_tok, int prenorm,
+                                                          const int* __restrict__ g_cur, const int* __restrict__ g_tgt,
+                                                          const unsigned* __restrict__ g_tok, int g_na, int g_ncheck) {
   pdl_trigger();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= R) return;
   const int cur = *cur_len;
   const float* x = logits + (long long)r * ldl;
   unsigned long long best = 0ull;
+  // processor order of transformers' merged list: ForcedEOS first, then the caller's processors
+  const unsigned verdict = g_cur ? guide_row(g_cur + (long long)r * g_na, g_tgt + (long long)r * g_na, g_na, g_ncheck) : 0u;
   for (int c = lane; c < V; c += 32) {
     float v = x[c];
+    if (!prenorm && cur == L - 1) v = c == eos_id ? 0.f : -INFINITY;
     if (extra_bias) v += extra_bias[(long long)r * V + c];
-    if (cur == L - 1) v = c == eos_id ? 0.f : -INFINITY;
+    if (g_cur) v = guide_apply(v, verdict, g_tok[c], c == eos_id);
     const unsigned long long key = ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)c);
     best = key > best ? key : best;
   }
@@ -469,6 +515,44 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
     next_tok[r] = tok;
     unfinished[r] = (unf && tok != eos_id) ? 1 : 0;
   }
+}
+
+// Dense processed scores for host-visible logits processors: beam search sees log_softmax(logits) then ForcedEOS,
+// greedy sees the raw logits then ForcedEOS (transformers `_beam_search` / `_sample`).  One warp per row.
+__global__ void __launch_bounds__(256) score_rows_kernel(const float* __restrict__ logits, long long ldl,
+                                                         float* __restrict__ out, long long ldo, int R, int V, int L,
+                                                         int eos_id, const int* __restrict__ cur_len, int log_softmax) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int cur = *cur_len;
+  const float* x = logits + (long long)r * ldl;
+  float* o = out + (long long)r * ldo;
+  if (cur == L - 1) {
+    for (int c = lane; c < V; c += 32) o[c] = c == eos_id ? 0.f : -INFINITY;
+    return;
+  }
+  float lse = 0.f;
+  if (log_softmax) {
+    float mx = -INFINITY;
+    for (int c = lane; c < V; c += 32) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int c = lane; c < V; c += 32) s += expf(x[c] - mx);
+    lse = mx + logf(warp_sum(s));
+  }
+  for (int c = lane; c < V; c += 32) o[c] = x[c] - lse;
+}
+
+// GuidedFormulaProcessor.__call__ on a dense score matrix (in place); tgt row = r / beams.
+__global__ void __launch_bounds__(256) guided_mask_kernel(float* __restrict__ scores, long long lds, int R, int V,
+                                                          int eos_id, int beams, const int* __restrict__ g_cur,
+                                                          const int* __restrict__ g_tgt,
+                                                          const unsigned* __restrict__ g_tok, int g_na, int g_ncheck) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const unsigned verdict = guide_row(g_cur + (long long)r * g_na, g_tgt + (long long)(r / beams) * g_na, g_na, g_ncheck);
+  float* x = scores + (long long)r * lds;
+  for (int c = lane; c < V; c += 32) x[c] = guide_apply(x[c], verdict, g_tok[c], c == eos_id);
 }
 
 __global__ void advance_kernel(int* cur_len) {
@@ -522,13 +606,18 @@ extern "C" int mma_decode_cross_attn(const void* q, long long ldq, const void* k
   return type == MMA_F32 ? launch_attn<float>(a, dh, stream) : launch_attn<bf16>(a, dh, stream);
 }
 
-extern "C" int mma_beam_step(const float* logits, long long ldl, const float* extra_bias, int B, int K, int V, int L,
-                             int pad_id, int eos_id, const int* cur_len, int* run_seq, int* fin_seq, float* run_score,
-                             float* fin_score, unsigned char* fin_flag, int* fin_len, unsigned char* improvable,
-                             unsigned char* all_hit, int* anc, int* next_tok, int* parent_row, cudaStream_t stream) {
+extern "C" int mma_beam_step_ex(const float* logits, long long ldl, const float* extra_bias, int B, int K, int V, int L,
+                                int pad_id, int eos_id, const int* cur_len, int* run_seq, int* fin_seq,
+                                float* run_score, float* fin_score, unsigned char* fin_flag, int* fin_len,
+                                unsigned char* improvable, unsigned char* all_hit, int* anc, int* next_tok,
+                                int* parent_row, int prenorm, const int* g_cur, const int* g_tgt,
+                                const unsigned* g_tok_atoms, int n_atoms, int n_check, cudaStream_t stream) {
   if (K > MAXK || K < 1 || B < 1) return MMA_ERR_ARG;
+  if (g_cur && (!g_tgt || !g_tok_atoms || n_atoms < 1 || n_atoms > 29 || n_check < 0 || n_check > n_atoms))
+    return MMA_ERR_ARG;
   BeamArgs a{logits, ldl, extra_bias, B, K, V, L, pad_id, eos_id, cur_len, run_seq, fin_seq, run_score, fin_score,
-             fin_flag, fin_len, improvable, all_hit, anc, next_tok, parent_row};
+             fin_flag, fin_len, improvable, all_hit, anc, next_tok, parent_row, prenorm, g_cur, g_tgt, g_tok_atoms,
+             n_atoms, n_check};
   const size_t smem = sizeof(uint32_t) * (size_t)K * V;
   if (smem > 200 * 1024) return MMA_ERR_UNSUPPORTED;
   if (smem > 40 * 1024) cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -537,12 +626,52 @@ extern "C" int mma_beam_step(const float* logits, long long ldl, const float* ex
   return MMA_OK;
 }
 
+extern "C" int mma_beam_step(const float* logits, long long ldl, const float* extra_bias, int B, int K, int V, int L,
+                             int pad_id, int eos_id, const int* cur_len, int* run_seq, int* fin_seq, float* run_score,
+                             float* fin_score, unsigned char* fin_flag, int* fin_len, unsigned char* improvable,
+                             unsigned char* all_hit, int* anc, int* next_tok, int* parent_row, cudaStream_t stream) {
+  return mma_beam_step_ex(logits, ldl, extra_bias, B, K, V, L, pad_id, eos_id, cur_len, run_seq, fin_seq, run_score,
+                          fin_score, fin_flag, fin_len, improvable, all_hit, anc, next_tok, parent_row, 0, nullptr,
+                          nullptr, nullptr, 0, 0, stream);
+}
+
+extern "C" int mma_greedy_step_ex(const float* logits, long long ldl, const float* extra_bias, int R, int V, int L,
+                                  int pad_id, int eos_id, const int* cur_len, int* seq, unsigned char* unfinished,
+                                  int* next_tok, int prenorm, const int* g_cur, const int* g_tgt,
+                                  const unsigned* g_tok_atoms, int n_atoms, int n_check, cudaStream_t stream) {
+  if (R < 1) return MMA_ERR_ARG;
+  if (g_cur && (!g_tgt || !g_tok_atoms || n_atoms < 1 || n_atoms > 29 || n_check < 0 || n_check > n_atoms))
+    return MMA_ERR_ARG;
+  greedy_step_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, ldl, extra_bias, R, V, L, pad_id, eos_id, cur_len, seq,
+                                                      unfinished, next_tok, prenorm, g_cur, g_tgt, g_tok_atoms,
+                                                      n_atoms, n_check);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
 extern "C" int mma_greedy_step(const float* logits, long long ldl, const float* extra_bias, int R, int V, int L,
                                int pad_id, int eos_id, const int* cur_len, int* seq, unsigned char* unfinished,
                                int* next_tok, cudaStream_t stream) {
-  if (R < 1) return MMA_ERR_ARG;
-  greedy_step_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, ldl, extra_bias, R, V, L, pad_id, eos_id, cur_len, seq,
-                                                      unfinished, next_tok);
+  return mma_greedy_step_ex(logits, ldl, extra_bias, R, V, L, pad_id, eos_id, cur_len, seq, unfinished, next_tok, 0,
+                            nullptr, nullptr, nullptr, 0, 0, stream);
+}
+
+extern "C" int mma_score_rows(const float* logits, long long ldl, float* out, long long ldo, int R, int V, int L,
+                              int eos_id, const int* cur_len, int log_softmax, cudaStream_t stream) {
+  if (R < 1 || V < 1) return MMA_ERR_ARG;
+  score_rows_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, ldl, out, ldo, R, V, L, eos_id, cur_len, log_softmax);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_guided_mask(float* scores, long long lds, int R, int V, int eos_id, int beams, const int* g_cur,
+                               const int* g_tgt, const unsigned* g_tok_atoms, int n_atoms, int n_check,
+                               cudaStream_t stream) {
+  if (R < 1 || V < 1 || beams < 1 || !g_cur || !g_tgt || !g_tok_atoms || n_atoms < 1 || n_atoms > 29 || n_check < 0 ||
+      n_check > n_atoms)
+    return MMA_ERR_ARG;
+  guided_mask_kernel<<<(R + 7) / 8, 256, 0, stream>>>(scores, lds, R, V, eos_id, beams, g_cur, g_tgt, g_tok_atoms,
+                                                      n_atoms, n_check);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

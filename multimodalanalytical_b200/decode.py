@@ -81,6 +81,18 @@ class Generator:
 
     # one decoder step for R rows; every shape is static and cur_len lives on the device
     def _step(self, st: BeamState, ctx: Dict[str, Any], extra_bias=None):
+        logits = self._forward_logits(st, ctx)
+        self._select(st, logits, extra_bias)
+
+    def _select(self, st: BeamState, scores, extra_bias=None, prenorm=False, guide=None):
+        V = self.eng.cfg.vocab_size
+        if st.K == 1:
+            ops.greedy_step(scores, V, st, extra_bias, prenorm=prenorm, guide=guide)
+        else:
+            ops.beam_step(scores, V, st, extra_bias, prenorm=prenorm, guide=guide)
+        ops.advance(st.cur_len)
+
+    def _forward_logits(self, st: BeamState, ctx: Dict[str, Any]):
         eng, cfg = self.eng, self.eng.cfg
         d, H = cfg.d_model, cfg.decoder_attention_heads
         dh = d // H
@@ -134,16 +146,15 @@ class Generator:
         logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
         ops.gemm(h, eng.W("hf_model.token_ff.weight"), R, V, d,
                  ops.make_epi(EPI_STORE, logits, bias=eng.P("hf_model.token_ff.bias")))
-        if K == 1:
-            ops.greedy_step(logits, V, st, extra_bias)
-        else:
-            ops.beam_step(logits, V, st, extra_bias)
-        ops.advance(st.cur_len)
+        return logits
 
     @torch.no_grad()
     def generate(self, enc_inputs, enc_mask, n_beams: int = 1, max_length: Optional[int] = None, extra_bias=None,
-                 use_graph: bool = True, check_every: int = 8, return_scores: bool = False):
+                 use_graph: bool = True, check_every: int = 8, return_scores: bool = False, processors=None):
         """enc_inputs: {modality: batch-first tensor}; enc_mask: uint8 [B, S] (1 = real token).
+        processors: list of `(input_ids, scores) -> scores` callables on CUDA tensors (transformers' LogitsProcessor
+        protocol, applied after ForcedEOS as transformers orders them); a single `GuidedFormulaProcessor` is fused
+        into the step kernel.
         Returns int64 [B * n_beams, L <= max_length]; row b*K + r is the r-th best hypothesis of spectrum b."""
         eng, cfg = self.eng, self.eng.cfg
         eng.sync_weights()
@@ -173,26 +184,16 @@ class Generator:
         pos = eng._pos_rows(L, "g")
         ctx = dict(kvmem=kvmem, kc=kc, vc=vc, pos=pos, enc_mask=mask_buf, S=S)
 
+        if processors:
+            self._run_processed(st, ctx, list(processors), extra_bias, use_graph, (B, K, L, S))
+            return self._collect(st, return_scores)
+
         graph = None
         if use_graph:
             # every buffer touched by a step (workspace, caches, search state) is cached by shape, so the captured
             # step is reusable across calls of the same (B, K, L, S)
             gkey = (B, K, L, S, 0 if extra_bias is None else extra_bias.data_ptr())
-            graph = self._graphs.get(gkey)
-            if graph is None:
-                torch.cuda.synchronize()
-                side = torch.cuda.Stream()
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
-                    self._step(st, ctx, extra_bias)  # warm-up: builds tensor maps, sets kernel attributes
-                torch.cuda.current_stream().wait_stream(side)
-                torch.cuda.synchronize()
-                st.reset()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    self._step(st, ctx, extra_bias)
-                st.reset()
-                self._graphs[gkey] = graph
+            graph = self._capture(gkey, st, lambda: self._step(st, ctx, extra_bias))
 
         steps = 0
         max_steps = L - 1
@@ -210,6 +211,87 @@ class Generator:
             else:
                 if not (bool(st.improvable.any().item()) and not bool(st.all_hit.all().item())):
                     break
+        return self._collect(st, return_scores)
+
+    def _capture(self, gkey, st: BeamState, fn):
+        graph = self._graphs.get(gkey)
+        if graph is None:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()  # warm-up: builds tensor maps, sets kernel attributes
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            st.reset()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fn()
+            st.reset()
+            self._graphs[gkey] = graph
+        return graph
+
+    def _run_processed(self, st: BeamState, ctx, processors, extra_bias, use_graph, shape_key):
+        """Decode loop with logits processors (wrapper.py:443-451 `logits_processor=`).  The decoder forward of a
+        step is one graph replay; while it runs, the host reads the running hypotheses of that step (copied to
+        pinned memory before the replay was queued) and does the processors' host work, so e.g. the chemistry of
+        formula-guided decoding overlaps the GPU instead of serialising with it.  Selection follows un-captured."""
+        from .guided import GuidedFormulaProcessor
+
+        eng, cfg = self.eng, self.eng.cfg
+        B, K, L = st.B, st.K, st.L
+        R, V = B * K, cfg.vocab_size
+        fused = len(processors) == 1 and isinstance(processors[0], GuidedFormulaProcessor)
+        graph = self._capture(shape_key + ("fwd",), st, lambda: self._forward_logits(st, ctx)) if use_graph else None
+        logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
+        seq_host = torch.empty(R, L, dtype=torch.int32).pin_memory()
+        nflag = B if K == 1 else 2 * B
+        flag_dev = eng.buf("g.flags", (nflag,), torch.uint8)
+        flag_host = torch.ones(nflag, dtype=torch.uint8).pin_memory()
+        cnt_host = torch.zeros(R, 14, dtype=torch.int32).pin_memory()
+        cnt_dev = eng.buf("g.guide_counts", (R, 14), torch.int32)
+        scores = None if fused else eng.buf("g.scores", (R, V), torch.float32)
+        ev = torch.cuda.Event()
+        for cur in range(1, L):
+            running = st.run_seq if K == 1 else st.run_seq[cur & 1].view(R, L)
+            seq_host.copy_(running, non_blocking=True)
+            if K == 1:
+                flag_dev.copy_(st.unfinished)
+            else:
+                flag_dev[:B].copy_(st.improvable)
+                flag_dev[B:].copy_(st.all_hit)
+            flag_host.copy_(flag_dev, non_blocking=True)
+            ev.record()
+            if graph is not None:
+                graph.replay()
+            else:
+                self._forward_logits(st, ctx)
+            ev.synchronize()
+            if cur > 1:  # stop tests of transformers' `_sample` / `_beam_search` on the state after the last step
+                if K == 1:
+                    if not bool(flag_host.any()):
+                        break
+                elif not (bool(flag_host[:B].any()) and not bool(flag_host[B:].all())):
+                    break
+            ids_host = seq_host[:, :cur]
+            if fused:
+                processors[0].counts(ids_host, out=cnt_host)
+                cnt_dev.copy_(cnt_host, non_blocking=True)
+                self._select(st, logits, extra_bias, guide=processors[0].guide(cnt_dev))
+            else:
+                ops.score_rows(logits, scores, V, L, cfg.eos_token_id, st.cur_len, log_softmax=K > 1)
+                ids_dev = running[:, :cur].to(torch.int64)
+                sc = scores
+                for proc in processors:
+                    sc = proc(ids_dev, sc)
+                if sc.data_ptr() != scores.data_ptr():
+                    scores.copy_(sc)
+                self._select(st, scores, extra_bias, prenorm=True)
+        torch.cuda.current_stream().synchronize()
+
+    def _collect(self, st: BeamState, return_scores: bool = False):
+        cfg = self.eng.cfg
+        K, L, R = st.K, st.L, st.B * st.K
         cur = int(st.cur_len.item())
         if K == 1:
             seq = st.run_seq.to(torch.int64)

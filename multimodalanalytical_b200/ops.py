@@ -391,22 +391,51 @@ def decode_cross_attn(q, kmem, vmem, kmask, cur_len, o, R, H, dh, S, beams):
     _count()
 
 
-def beam_step(logits, V, st, extra_bias=None):
-    """st: decode.BeamState (device buffers)."""
-    check(_lib.load().mma_beam_step(
+def _guide_args(guide):
+    """guide: None or (cur_counts int32 [rows, NA], target_counts int32 [spectra, NA], tok_atoms int32 [V], n_check)."""
+    if guide is None:
+        return 0, 0, 0, 0, 0
+    cur, tgt, tok, n_check = guide
+    _need_cuda(cur, tgt, tok)
+    assert cur.dtype == torch.int32 and tgt.dtype == torch.int32 and tok.dtype == torch.int32
+    assert cur.is_contiguous() and tgt.is_contiguous() and cur.shape[1] == tgt.shape[1]
+    return cur.data_ptr(), tgt.data_ptr(), tok.data_ptr(), cur.shape[1], int(n_check)
+
+
+def beam_step(logits, V, st, extra_bias=None, prenorm=False, guide=None):
+    """st: decode.BeamState (device buffers).  prenorm: `logits` already holds processed log-probabilities."""
+    check(_lib.load().mma_beam_step_ex(
         logits.data_ptr(), logits.stride(0), _p(extra_bias), st.B, st.K, V, st.L, st.pad_id, st.eos_id,
         st.cur_len.data_ptr(), st.run_seq.data_ptr(), st.fin_seq.data_ptr(), st.run_score.data_ptr(),
         st.fin_score.data_ptr(), st.fin_flag.data_ptr(), st.fin_len.data_ptr(), st.improvable.data_ptr(),
-        st.all_hit.data_ptr(), st.anc.data_ptr(), st.next_tok.data_ptr(), st.parent_row.data_ptr(), _stream()),
-        "mma_beam_step")
+        st.all_hit.data_ptr(), st.anc.data_ptr(), st.next_tok.data_ptr(), st.parent_row.data_ptr(),
+        1 if prenorm else 0, *_guide_args(guide), _stream()), "mma_beam_step_ex")
     _count()
 
 
-def greedy_step(logits, V, st, extra_bias=None):
-    check(_lib.load().mma_greedy_step(
+def greedy_step(logits, V, st, extra_bias=None, prenorm=False, guide=None):
+    check(_lib.load().mma_greedy_step_ex(
         logits.data_ptr(), logits.stride(0), _p(extra_bias), st.B, V, st.L, st.pad_id, st.eos_id,
-        st.cur_len.data_ptr(), st.run_seq.data_ptr(), st.unfinished.data_ptr(), st.next_tok.data_ptr(), _stream()),
-        "mma_greedy_step")
+        st.cur_len.data_ptr(), st.run_seq.data_ptr(), st.unfinished.data_ptr(), st.next_tok.data_ptr(),
+        1 if prenorm else 0, *_guide_args(guide), _stream()), "mma_greedy_step_ex")
+    _count()
+
+
+def score_rows(logits, out, V, L, eos_id, cur_len, log_softmax):
+    """Dense scores for host-visible logits processors (log_softmax or raw logits, then ForcedEOS)."""
+    _need_cuda(logits, out)
+    check(_lib.load().mma_score_rows(logits.data_ptr(), logits.stride(0), out.data_ptr(), out.stride(0),
+                                     logits.shape[0], V, L, eos_id, cur_len.data_ptr(), 1 if log_softmax else 0,
+                                     _stream()), "mma_score_rows")
+    _count()
+
+
+def guided_mask(scores, eos_id, beams, guide):
+    """GuidedFormulaProcessor.__call__ on a dense fp32 [R, V] matrix, in place."""
+    _need_cuda(scores)
+    assert scores.dtype == torch.float32 and scores.stride(1) == 1
+    check(_lib.load().mma_guided_mask(scores.data_ptr(), scores.stride(0), scores.shape[0], scores.shape[1], eos_id,
+                                      beams, *_guide_args(guide), _stream()), "mma_guided_mask")
     _count()
 
 

@@ -153,6 +153,8 @@ class HFWrapper(_Base):
         self.multimodal_norm = multimodal_norm
         self.modality_dropout = modality_dropout
         self.guided_generation = kwargs.get("guided_generation", False)
+        # chemistry of guided decoding (rdkit in the reference); None -> rdkit, imported when first needed
+        self.chem_backend = kwargs.pop("chem_backend", None)
         self.target_modality = ""
         for modality, modality_config in self.data_config.items():
             if modality_config["target"]:
@@ -259,14 +261,22 @@ class HFWrapper(_Base):
                               encoder_hidden_states=out["memory"])
 
     def generate(self, batch: Dict[str, Any], n_beams: int = 1, logits_processor=None, **kw) -> torch.Tensor:
-        """wrapper.py:409-453.  `logits_processor`: optional additive fp32 [B*n_beams, V] device tensor applied to the
-        log-probabilities every step (host-side HF LogitsProcessor objects are not on the accelerated path)."""
-        if logits_processor is not None and not isinstance(logits_processor, torch.Tensor):
-            raise NotImplementedError("only additive device-tensor processors are supported on the accelerated path")
+        """wrapper.py:409-453.  `logits_processor`: None; a processor or a list of processors with transformers'
+        protocol `(input_ids [rows, cur_len] int64, scores [rows, V] fp32) -> scores` on CUDA tensors, applied after
+        ForcedEOS exactly where transformers applies them (a lone `guided.GuidedFormulaProcessor` is fused into the
+        step kernel); or an additive fp32 [B*n_beams, V] device tensor."""
         input_ids, attention_mask = self._relayout(batch, training=False)
+        extra_bias, processors = None, None
+        if isinstance(logits_processor, torch.Tensor):
+            extra_bias = logits_processor
+        elif logits_processor is not None:
+            processors = list(logits_processor) if isinstance(logits_processor, (list, tuple)) else [logits_processor]
+            for proc in processors:
+                if not callable(proc):
+                    raise TypeError(f"logits processor {type(proc).__name__} is not callable")
         return self.generator.generate(input_ids, attention_mask, n_beams=n_beams,
-                                       max_length=self.generation_config["max_length"], extra_bias=logits_processor,
-                                       **kw)
+                                       max_length=self.generation_config["max_length"], extra_bias=extra_bias,
+                                       processors=processors, **kw)
 
     # ---------------------------------------------------------------------------------------- hooks
     def training_step(self, batch: Dict[str, Any], batch_idx: int) -> torch.Tensor:
@@ -319,9 +329,15 @@ class HFWrapper(_Base):
         self.eval()
         model_output = self.forward(batch)
         loss = model_output.loss
-        if self.guided_generation:
-            raise NotImplementedError("guided generation needs rdkit (SURVEY.md §2: out of scope)")
-        generated = self.generate(batch, n_beams=self.n_beams)
+        if self.guided_generation:  # wrapper.py:546-556
+            from .guided import GuidedFormulaProcessor, RDKitChem
+
+            chem = self.chem_backend if self.chem_backend is not None else RDKitChem()
+            target_formula = [chem.formula(smiles) for smiles in batch["target_smiles"]]
+            processor = GuidedFormulaProcessor(self.n_beams, target_formula, self.target_tokenizer, chem=chem)
+            generated = self.generate(batch, n_beams=self.n_beams, logits_processor=[processor])
+        else:
+            generated = self.generate(batch, n_beams=self.n_beams)
         decoded = self.target_tokenizer.batch_decode(generated, skip_special_tokens=True)
         extra = {k: v for k, v in batch.items()
                  if not k.startswith("encoder_") and not k.startswith("decoder_") and not k.startswith("target_")}

@@ -297,6 +297,15 @@ def _force_eos(scores, cur_len, cfg):
     return scores
 
 
+def _apply_hooks(hooks, seqs, scores):
+    """`logits_processor=` of wrapper.py:443-451: one callable or a list, `(input_ids, scores) -> scores`, in order."""
+    if hooks is None:
+        return scores
+    for h in (hooks if isinstance(hooks, (list, tuple)) else [hooks]):
+        scores = h(seqs, scores)
+    return scores
+
+
 def generate(sd, cfg: OracleConfig, batch, n_beams: int = 1, logits_hook=None, return_scores=False):
     """Greedy (n_beams=1) or beam search with num_return_sequences = n_beams.
     Output: int64 [B*n_beams, L<=max_length]; row b*K+r is the r-th best hypothesis of sample b."""
@@ -315,9 +324,10 @@ def _greedy(sd, cfg, memory, am, logits_hook):
     while seqs.shape[1] < cfg.max_length and unfinished.any():
         cur_len = seqs.shape[1]
         scores = _next_logits(sd, cfg, seqs, memory, am)
-        if logits_hook is not None:
-            scores = logits_hook(seqs, scores)
+        # transformers merges the caller's processors AFTER its own (ForcedEOS first): generation/utils.py
+        # `_get_logits_processor` -> `_merge_criteria_processor_list`
         scores = _force_eos(scores, cur_len, cfg)
+        scores = _apply_hooks(logits_hook, seqs, scores)
         nxt = scores.argmax(dim=-1)
         nxt = torch.where(unfinished, nxt, torch.full_like(nxt, cfg.pad_token_id))
         seqs = torch.cat([seqs, nxt[:, None]], dim=1)
@@ -353,9 +363,8 @@ def _beam(sd, cfg, memory, am, K, logits_hook, return_scores):
         flat = run_seq[:, :, :cur_len].reshape(B * K, cur_len)
         logits = _next_logits(sd, cfg, flat, mem, mmask)
         logp = torch.log_softmax(logits, dim=-1)
-        if logits_hook is not None:
-            logp = logits_hook(flat, logp)
         logp = _force_eos(logp, cur_len, cfg)
+        logp = _apply_hooks(logits_hook, flat, logp)
         acc = (logp.view(B, K, V) + run_score[:, :, None]).reshape(B, K * V)
         cand_score, cand_idx = torch.topk(acc, k=keep)
         cand_beam = cand_idx // V
