@@ -109,6 +109,26 @@ int mma_cast_bf16_f32(const void* in, float* out, long long n, cudaStream_t stre
  * else missing[b].  hop = ps / overlap.                                                                          */
 int mma_patchify(const float* raw, long long ld, int offset, float mean, float std, float* out, unsigned char* pad,
                  const unsigned char* missing, int masking, int B, int P, int ps, int hop, cudaStream_t stream);
+/* same, for spectra resident in HBM as a dataset table: batch element b reads row rows[b] of raw / missing */
+int mma_patchify_rows(const float* raw, long long ld, const int* rows, int offset, float mean, float std, float* out,
+                      unsigned char* pad, const unsigned char* missing, int masking, int B, int P, int ps, int hop,
+                      cudaStream_t stream);
+
+/* ---- batch assembly from an HBM-resident pre-tokenised dataset (replaces the host collator,
+ * data/datamodules.py:140-351).  Ragged storage: flat values + int64 row offsets [N+1]; rows [B] are
+ * the sample indices of the batch; rows longer than max_len are truncated (tokenizer truncation=True).          */
+/* ids int64 [B, L] (pad_id beyond the row), mask u8 [B, L] = position < length and row_valid[row] (optional)    */
+int mma_collate_tokens(const int* flat, const long long* offsets, const unsigned char* row_valid, const int* rows,
+                       int B, int L, int pad_id, int max_len, long long* ids, unsigned char* mask,
+                       cudaStream_t stream);
+/* teacher forcing (datamodules.py:178-206, wrapper.py:365,389): dec_in = tokens[:-1], labels = tokens[1:] with
+ * pad -> -100, dec_mask = position < length; all [B, T], T = padded length - 1                                   */
+int mma_collate_target(const int* flat, const long long* offsets, const int* rows, int B, int T, int pad_id,
+                       int max_len, long long* dec_in, unsigned char* dec_mask, long long* labels,
+                       cudaStream_t stream);
+/* fp32 rows of `width` values per position -> out [B, L, width] (pad_value beyond the row), mask u8 [B, L] opt.  */
+int mma_collate_values(const float* flat, const long long* offsets, const int* rows, int B, int L, int width,
+                       float pad_value, int max_len, float* out, unsigned char* mask, cudaStream_t stream);
 
 /* ---- encoder-alignment head (custom_modeling.py:363-396 networks, :453-475 masked mean pool + loss; LOSS_FACTORY
  * :15; modeling/utils.py:8-22 kl_div / sid).  The MLP / centre-tap conv products run on the GEMM entry points.  */

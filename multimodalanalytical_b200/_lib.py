@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu", "align.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu", "align.cu", "collate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -98,6 +98,10 @@ _SIGS = {
     "mma_cast_f32_bf16": [_vp, _vp, _ll, _vp],
     "mma_cast_bf16_f32": [_vp, _vp, _ll, _vp],
     "mma_patchify": [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "mma_patchify_rows": [_vp, _ll, _vp, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "mma_collate_tokens": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+    "mma_collate_target": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "mma_collate_values": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp],
     "mma_masked_mean_fwd": [_vp, _i, _ll, _vp, _vp, _i, _i, _i, _vp],
     "mma_masked_mean_bwd": [_vp, _vp, _vp, _ll, _i, _i, _i, _vp],
     "mma_align_loss": [_vp, _ll, _vp, _ll, _i, _i, _i, _f, _vp, _vp, _vp, _ll, _f, _vp],

@@ -446,10 +446,11 @@ __global__ void __launch_bounds__(128) patchify_kernel(const float* __restrict__
                                                        float mean, float std, float* __restrict__ out,
                                                        unsigned char* __restrict__ pad,
                                                        const unsigned char* __restrict__ missing, int masking, int P,
-                                                       int ps, int hop) {
+                                                       int ps, int hop, const int* __restrict__ rows) {
   pdl_trigger();
   const int b = blockIdx.y, p = blockIdx.x;
-  const float* src = raw + (long long)b * ld + offset + (long long)p * hop;
+  const long long r = rows ? rows[b] : b;  // dataset-resident spectra: batch element b is row rows[b] of `raw`
+  const float* src = raw + r * ld + offset + (long long)p * hop;
   float* dst = out + ((long long)b * P + p) * ps;
   float s = 0.f;
   for (int k = threadIdx.x; k < ps; k += blockDim.x) {
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(128) patchify_kernel(const float* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
       const float tot = red[0] + red[1] + red[2] + red[3];
-      pad[(long long)b * P + p] = masking ? (tot == 0.f) : (missing ? missing[b] : 0);
+      pad[(long long)b * P + p] = masking ? (tot == 0.f) : (missing ? missing[r] : 0);
     }
   }
 }
@@ -473,7 +474,18 @@ extern "C" int mma_patchify(const float* raw, long long ld, int offset, float me
                             unsigned char* pad, const unsigned char* missing, int masking, int B, int P, int ps,
                             int hop, cudaStream_t stream) {
   if (B <= 0 || P <= 0 || ps <= 0 || hop <= 0 || std == 0.f) return MMA_ERR_ARG;
-  patchify_kernel<<<dim3(P, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, P, ps, hop);
+  patchify_kernel<<<dim3(P, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, P, ps, hop,
+                                                  nullptr);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+extern "C" int mma_patchify_rows(const float* raw, long long ld, const int* rows, int offset, float mean, float std,
+                                 float* out, unsigned char* pad, const unsigned char* missing, int masking, int B,
+                                 int P, int ps, int hop, cudaStream_t stream) {
+  if (B <= 0 || P <= 0 || ps <= 0 || hop <= 0 || std == 0.f || !rows) return MMA_ERR_ARG;
+  patchify_kernel<<<dim3(P, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, P, ps, hop,
+                                                  rows);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

@@ -205,15 +205,65 @@ def colsum(x, out, rows=None, cols=None):
     _count()
 
 
-def patchify(raw, out, mean, std, offset=0, hop=None, pad=None, missing=None, masking=False):
-    """raw fp32 [B, n_points] -> out fp32 [B, P, ps] standardised patches (PatchPreprocessor.__call__ on the device)."""
+def patchify(raw, out, mean, std, offset=0, hop=None, pad=None, missing=None, masking=False, rows=None):
+    """raw fp32 [B, n_points] -> out fp32 [B, P, ps] standardised patches (PatchPreprocessor.__call__ on the device).
+    rows (int32 [B]): `raw` / `missing` are a dataset table and batch element b reads row rows[b]."""
     _need_cuda(raw, out)
     assert raw.dtype == torch.float32 and raw.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
     B, P, ps = out.shape
     hop = ps if hop is None else hop
     assert offset + (P - 1) * hop + ps <= raw.shape[1], "patches run past the spectrum"
-    check(_lib.load().mma_patchify(raw.data_ptr(), raw.stride(0), int(offset), float(mean), float(std), out.data_ptr(),
-                                   _p(pad), _p(missing), int(masking), B, P, ps, hop, _stream()), "mma_patchify")
+    if rows is None:
+        check(_lib.load().mma_patchify(raw.data_ptr(), raw.stride(0), int(offset), float(mean), float(std),
+                                       out.data_ptr(), _p(pad), _p(missing), int(masking), B, P, ps, hop, _stream()),
+              "mma_patchify")
+    else:
+        _need_cuda(rows)
+        assert rows.dtype == torch.int32 and rows.numel() == B
+        check(_lib.load().mma_patchify_rows(raw.data_ptr(), raw.stride(0), rows.data_ptr(), int(offset), float(mean),
+                                            float(std), out.data_ptr(), _p(pad), _p(missing), int(masking), B, P, ps,
+                                            hop, _stream()), "mma_patchify_rows")
+    _count()
+
+
+def _ragged_ok(flat, offsets, rows):
+    _need_cuda(flat, offsets, rows)
+    assert offsets.dtype == torch.int64 and rows.dtype == torch.int32 and flat.is_contiguous()
+
+
+def collate_tokens(flat, offsets, row_valid, rows, pad_id, max_len, ids, mask):
+    """Ragged int32 token rows -> ids int64 [B, L] + validity mask u8 [B, L] for the samples `rows` (int32 [B])."""
+    _ragged_ok(flat, offsets, rows)
+    assert flat.dtype == torch.int32 and ids.dtype == torch.int64 and ids.is_contiguous()
+    assert mask is None or (mask.dtype == torch.uint8 and mask.shape == ids.shape and mask.is_contiguous())
+    B, L = ids.shape
+    check(_lib.load().mma_collate_tokens(flat.data_ptr(), offsets.data_ptr(), _p(row_valid), rows.data_ptr(), B, L,
+                                         int(pad_id), int(max_len), ids.data_ptr(), _p(mask), _stream()),
+          "mma_collate_tokens")
+    _count()
+
+
+def collate_target(flat, offsets, rows, pad_id, max_len, dec_in, dec_mask, labels):
+    """Ragged target rows -> teacher-forcing tensors [B, T]: dec_in = tokens[:-1], labels = tokens[1:] (pad -> -100)."""
+    _ragged_ok(flat, offsets, rows)
+    assert flat.dtype == torch.int32 and dec_in.dtype == torch.int64 and labels.dtype == torch.int64
+    assert dec_mask.dtype == torch.uint8 and dec_in.shape == labels.shape == dec_mask.shape
+    B, T = dec_in.shape
+    check(_lib.load().mma_collate_target(flat.data_ptr(), offsets.data_ptr(), rows.data_ptr(), B, T, int(pad_id),
+                                         int(max_len), dec_in.data_ptr(), dec_mask.data_ptr(), labels.data_ptr(),
+                                         _stream()), "mma_collate_target")
+    _count()
+
+
+def collate_values(flat, offsets, rows, pad_value, max_len, out, mask):
+    """Ragged fp32 rows [n, width] -> out [B, L, width] (+ validity mask u8 [B, L])."""
+    _ragged_ok(flat, offsets, rows)
+    assert flat.dtype == torch.float32 and flat.dim() == 2 and out.dtype == torch.float32 and out.is_contiguous()
+    B, L, width = out.shape
+    assert width == flat.shape[1]
+    check(_lib.load().mma_collate_values(flat.data_ptr(), offsets.data_ptr(), rows.data_ptr(), B, L, width,
+                                         float(pad_value), int(max_len), out.data_ptr(), _p(mask), _stream()),
+          "mma_collate_values")
     _count()
 
 

@@ -167,7 +167,8 @@ class FusedTrainer:
         self._sync_now = (self.micro % self.acc) == 0
         if self.bucketer is not None:
             self.bucketer.reset()
-        inputs = self._prepare(batch)
+        # a tuple is a batch already in the engine's layout (pipeline.DeviceDataset.collate)
+        inputs = batch if isinstance(batch, tuple) else self._prepare(batch)
         if self.use_graph and self.acc == 1 and (self.bucketer is None or self.graph_ddp):
             return self._graphed_step(inputs)
         loss = self._step_body(inputs)
