@@ -288,7 +288,7 @@ def run_ours(args):
     PEAKS.update(peaks)
     mk = model_kwargs(c)
     total_steps = args.steps + args.warmup + 8
-    model = HFWrapper(data_config=data_config(c), target_tokenizer=Tok(c["V"]), num_steps=2 * total_steps + 16,
+    model = HFWrapper(data_config=data_config(c), target_tokenizer=Tok(c["V"]), num_steps=4 * total_steps + 16,
                       precision="bf16", seed=SEED, **mk)
     trainer = FusedTrainer(model, clip_grad=1.0, acc_batches=1)
     nb = 4
@@ -347,6 +347,8 @@ def run_ours(args):
         line["step_roofline"] = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16_tflops_sustained"],
                                  "unit": "TFLOP/s", "frac": step_tflops / peaks["bf16_tflops_sustained"],
                                  "flops_per_sample": fl, "peak_source": f"{peak_src} sustained"}
+        if world == 1:
+            line["pipeline"] = bench_pipeline(trainer, c, B, args.steps)
         if not args.no_decode:
             line["decode"] = bench_decode(model, c, args)
         if world == 1 and not args.no_cpu:
@@ -363,6 +365,57 @@ def run_ours(args):
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)
+
+
+def bench_pipeline(trainer, c, B, steps):
+    """the batch is assembled on the device from an HBM-resident pre-tokenised dataset; the host only
+    sends B sample indices.  Synthetic set in the C2 raw format (1791-point spectra, interpolation + 21 patches of 75
+    on the device; 15 formula tokens; 65 target tokens).  Reports the collate time alone and the training throughput
+    when every step's batch comes from `DeviceDataset.collate` (H2D per step = B int32 indices)."""
+    import numpy as np
+    from multimodalanalytical_b200.pipeline import Column, DeviceDataset, HostDataset, IndexSampler, Ragged
+
+    n = 8192
+    rng = np.random.default_rng(SEED)
+    raw = rng.standard_normal((n, 1791), dtype=np.float32)
+    ftok = rng.integers(4, 64, size=(n, c["S_formula"]), dtype=np.int32)
+    ttok = rng.integers(4, c["V"], size=(n, c["T"] + 1), dtype=np.int32)
+    ttok[:, 0] = 2
+    cols = {
+        "Formula": Column("tokens", pad_len=c["S_formula"], max_len=c["S_formula"], pad_id=0,
+                          tokens=Ragged.from_rows(list(ftok), np.int32)),
+        "IR": Column("patches", raw=raw, missing=np.zeros(n, dtype=np.uint8),
+                     patch=dict(patch_size=c["ps"], mean=0.0, std=1.0, interpolation=True, overlap=1, masking=False)),
+    }
+    target = Column("tokens", pad_len=None, max_len=c["T"] + 1, pad_id=0, tokens=Ragged.from_rows(list(ttok), np.int32))
+    ds = DeviceDataset(HostDataset(cols, "Smiles", target, n))
+    batches = list(IndexSampler(n, B, shuffle=True, seed=SEED, drop_last=True))
+    for i in range(3):
+        ds.collate(batches[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = min(len(batches), 32)
+    e0.record()
+    for i in range(reps):
+        ds.collate(batches[i])
+    e1.record()
+    torch.cuda.synchronize()
+    t_col = e0.elapsed_time(e1) * 1e-3 / reps
+    for i in range(4):
+        trainer.train_step(ds.collate(batches[i]), i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        loss = trainer.train_step(ds.collate(batches[i % len(batches)]), i)
+    float(loss)
+    e1.record()
+    torch.cuda.synchronize()
+    t_step = e0.elapsed_time(e1) * 1e-3 / steps
+    out_bytes = B * (c["P"] * c["ps"] * 4 + c["P"] + 2 * c["S_formula"] * 8 + c["S_formula"] + c["T"] * (8 + 8 + 1))
+    in_bytes = B * (c["P"] * c["ps"] * 4 + (c["S_formula"] + c["T"] + 1) * 4)
+    return {"dataset_samples": n, "resident_mb": ds.bytes_resident() / 1e6, "collate_us_per_batch": t_col * 1e6,
+            "collate_spectra_per_s": B / t_col, "collate_algorithmic_gbs": (in_bytes + out_bytes) / t_col / 1e9,
+            "train_spectra_per_s_index_fed": B / t_step, "h2d_bytes_per_step": B * 4}
 
 
 def bench_decode(model, c, args):

@@ -272,3 +272,61 @@ def test_side_stream_weight_gradients_match_single_stream(monkeypatch):
     tr = FusedTrainer(m)
     losses = [float(tr.train_step(fx["batch"], i)) for i in range(4)]  # step 2+ replays the captured graph
     assert all(l == l for l in losses) and losses[-1] < losses[0]
+
+
+def _width_case(d, heads, ffn, layers, B, seed=5):
+    """IR + formula -> SMILES at the widths of configs/model/custom_model_base.yaml (768 / 12 heads / 3072) and
+    custom_model_large.yaml (1024 / 16 / 4096); fewer layers than the yaml so the oracle stays in seconds."""
+    g = torch.Generator().manual_seed(seed)
+    dc = {"Formula": _tok(64), "IR": {"type": "1D_patches", "target": False, "preprocessor_arguments": {"patch_size": 75}},
+          "Smiles": _tok(200, True)}
+    f, fpad = _ragged_tokens(g, 15, B, 64, 6)
+    enc = {"Formula": f, "IR": torch.randn(21, B, 75, generator=g)}
+    epad = torch.cat([fpad, torch.zeros(21, B, dtype=torch.bool)], 0)
+    T, V = 40, 200
+    t, tpad = _ragged_tokens(g, T + 1, B, V, T // 2)
+    t[0] = 2
+    batch = {"encoder_input": enc, "encoder_pad_mask": epad, "decoder_input": {"Smiles": t[:-1].contiguous()},
+             "decoder_pad_mask": tpad[:-1].contiguous(), "target": t[1:].contiguous()}
+    mk = _mk(d_model=d, num_heads=heads, encoder_attention_heads=heads, decoder_attention_heads=heads,
+             encoder_layers=layers, decoder_layers=layers, encoder_ffn_dim=ffn, decoder_ffn_dim=ffn)
+    fx = {"model_kwargs": mk, "data_config": dc, "batch": batch}
+    fx["state_dict"] = orc.init_state_dict(oracle_cfg(fx), vocab=V, enc_ffn=ffn, dec_ffn=ffn, seed=seed)
+    return fx
+
+
+@pytest.mark.parametrize("d,heads,ffn,layers", [(768, 12, 3072, 2), (1024, 16, 4096, 2)])
+def test_base_and_large_widths_match_oracle(d, heads, ffn, layers):
+    """custom_model_base / custom_model_large widths: fp32 logits + loss at 1e-5, bf16 train step (loss, logits, every
+    gradient) at the bf16 bounds, greedy + beam-4 decode token-identical in fp32."""
+    fx = _width_case(d, heads, ffn, layers, B=24)
+    want_out, want_g = oracle_grads(fx)
+    m32 = build(fx, "fp32")
+    m32.eval()
+    with torch.no_grad():
+        out32 = m32.forward(fx["batch"])
+    assert rel_err(out32.logits.cpu(), want_out["logits"].detach()) < 1e-5
+    assert abs(float(out32.loss) - float(want_out["loss"])) < 1e-5 * abs(float(want_out["loss"]))
+    m = build(fx, "bf16")
+    m.train()
+    m.store.g.zero_()
+    out = m.forward(fx["batch"])
+    out.loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(out.logits.float().cpu(), want_out["logits"].detach()) < 1e-2
+    assert abs(float(out.loss) - float(want_out["loss"])) < 1e-2 * abs(float(want_out["loss"]))
+    worst = sorted(((rel_err(m.store.G(k).cpu(), g), k) for k, g in want_g.items()), reverse=True)
+    assert worst[0][0] < 8e-2, worst[:5]
+    # decode on 3 spectra, short horizon (the oracle re-decodes the whole prefix every step)
+    sub = {"encoder_input": {k: v[:, :3] for k, v in fx["batch"]["encoder_input"].items()},
+           "encoder_pad_mask": fx["batch"]["encoder_pad_mask"][:, :3],
+           "decoder_input": {"Smiles": fx["batch"]["decoder_input"]["Smiles"][:, :3]},
+           "decoder_pad_mask": fx["batch"]["decoder_pad_mask"][:, :3], "target": fx["batch"]["target"][:, :3]}
+    cfg = oracle_cfg(fx)
+    cfg.max_length = 24
+    m32.generation_config["max_length"] = 24
+    for k in (1, 4):
+        got = m32.generate(sub, n_beams=k).cpu()
+        with torch.no_grad():
+            want = orc.generate(fx["state_dict"], cfg, sub, n_beams=k)
+        assert got.shape == want.shape and torch.equal(got, want), (d, k)
