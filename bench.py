@@ -337,6 +337,11 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "last_loss": last_loss,
     }
+    dec = None
+    if not args.no_decode:
+        # inference shards independent spectra over the ranks with no collective: every rank decodes its
+        # own --decode-batch spectra; the aggregate is all molecules / the slowest rank's time
+        dec = bench_decode(model, c, args, world, rank, dist if world > 1 else None)
     if rank == 0:
         line["clocks"] = clocks
         tf, t_k, shape = time_dominant_gemm(model.engine, c, B)
@@ -349,8 +354,8 @@ def run_ours(args):
                                  "flops_per_sample": fl, "peak_source": f"{peak_src} sustained"}
         if world == 1:
             line["pipeline"] = bench_pipeline(trainer, c, B, args.steps)
-        if not args.no_decode:
-            line["decode"] = bench_decode(model, c, args)
+        if dec is not None:
+            line["decode"] = dec
         if world == 1 and not args.no_cpu:
             cb = 64
             cv, cs = cpu_train_baseline(c, cb, steps=3, warmup=1)
@@ -418,7 +423,7 @@ def bench_pipeline(trainer, c, B, steps):
             "train_spectra_per_s_index_fed": B / t_step, "h2d_bytes_per_step": B * 4}
 
 
-def bench_decode(model, c, args):
+def bench_decode(model, c, args, world=1, rank=0, dist=None):
     """Secondary metric: beam-10 molecules/s (KV-cached, CUDA-graph replayed step); random-init weights never emit
     EOS early, so every hypothesis runs the full 127 steps.  Headline at --decode-batch spectra per GPU plus the C5
     batch-size sweep; `hbm_roofline_frac` compares the measured time with the cached-decode byte floor
@@ -426,19 +431,27 @@ def bench_decode(model, c, args):
     K = 10
     model.eval()
 
-    def run(B, reps):
-        batch = map_batch(synth_batch(c, B, SEED + 7), lambda x: x.cuda())
+    def run(B, reps, sync_ranks=False):
+        batch = map_batch(synth_batch(c, B, SEED + 7 + 100 * rank), lambda x: x.cuda())
         out = model.generate(batch, n_beams=K)  # warm-up + graph capture
         torch.cuda.synchronize()
         ts = []
         for _ in range(reps):  # each call timed on its own; the median is reported
+            if sync_ranks and dist is not None:
+                dist.barrier()
+                torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = model.generate(batch, n_beams=K)
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)
-        return sorted(ts)[len(ts) // 2], int(out.shape[1]) - 1
+        t = sorted(ts)[len(ts) // 2]
+        if sync_ranks and dist is not None:  # slowest rank
+            tt = torch.tensor([t], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt)
+        return t, int(out.shape[1]) - 1
 
     def floor_s(B, steps):
         d, f, Ld, S, V = c["d"], c["ffn"], c["layers"], c["S_formula"] + c["P"], c["V"]
@@ -451,10 +464,13 @@ def bench_decode(model, c, args):
             tot += max(by / (PEAKS["hbm_gbs"] * 1e9), fl / (PEAKS["bf16_tflops_sustained"] * 1e12))
         return tot
 
-    t, steps = run(args.decode_batch, 3)
-    res = {"metric": "beam-10 decode molecules/s", "value": args.decode_batch / t, "unit": "molecules/s",
-           "batch": args.decode_batch, "beams": K, "steps": steps, "ms_per_batch": t * 1e3, "dtype": "bf16",
+    t, steps = run(args.decode_batch, 3, sync_ranks=True)
+    res = {"metric": "beam-10 decode molecules/s", "value": world * args.decode_batch / t, "unit": "molecules/s",
+           "n_gpus": world, "batch_per_gpu": args.decode_batch, "beams": K, "steps": steps, "ms_per_batch": t * 1e3,
+           "dtype": "bf16", "sharding": "independent spectra per rank, no collective",
            "roofline_frac": floor_s(args.decode_batch, steps) / t, "sweep": []}
+    if rank != 0 or world > 1:
+        return res  # the batch-size sweep is a single-GPU curve
     for B in (1, 64, 1024):
         tb, sb = run(B, 3)
         res["sweep"].append({"batch": B, "molecules_per_s": B / tb, "ms_per_step": tb * 1e3 / sb,
