@@ -6,6 +6,7 @@ PyTorch fallback: if the library is missing or a launch fails, the caller gets a
 """
 import ctypes as C
 import os
+import shutil
 import subprocess
 import threading
 from concurrent.futures import ThreadPoolExecutor
@@ -52,11 +53,26 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu -> lib/libmma_b200.so (sm_100a, -lineinfo).  Cross-compiles without a GPU."""
+    """Compile csrc/*.cu -> lib/libmma_b200.so (sm_100a, -lineinfo).  Cross-compiles without a GPU.
+    Safe under concurrent callers (one process per GPU under torchrun): the staleness check and the build run under an
+    exclusive file lock, so one rank compiles and the others wait and then find the library fresh."""
     if not force and not _stale():
         return LIBPATH
+    import fcntl
+
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIBPATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose=False):
+    objdir = os.path.join(LIBDIR, f"obj.{os.getpid()}")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
@@ -72,11 +88,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    tmp = LIBPATH + ".tmp"
+    tmp = f"{LIBPATH}.{os.getpid()}.tmp"
     r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     os.replace(tmp, LIBPATH)
+    shutil.rmtree(objdir, ignore_errors=True)
     return LIBPATH
 
 
