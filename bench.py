@@ -206,7 +206,7 @@ def run_reference(args):
                          "sample": f"{args.steps} timed train steps (fwd+bwd+clip+AdamW) of batch {B}, C2 shapes, fp32"},
         "e2e": {"value": val, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(c, B):
@@ -270,9 +270,6 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     c = dict(C2)
     B = args.batch or c["B"]
@@ -361,7 +358,7 @@ def run_ours(args):
             cv, cs = cpu_train_baseline(c, cb, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": cv, "unit": "spectra/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"3 timed train steps of batch {cb} (C2 shapes, fp32, oracle port)"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         # the captured step graphs hold NCCL work; tearing the communicator down underneath them can block, so leave
         # without the teardown once every rank is done
@@ -478,7 +475,27 @@ def bench_decode(model, c, args, world=1, rank=0, dist=None):
     return res
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: keep a private duplicate of fd 1 for it and point fd 1 at stderr, so that
+    nothing a library prints (NCCL's version banner goes to stdout at every NCCL_DEBUG level >= VERSION) can land there."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

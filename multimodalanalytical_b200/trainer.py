@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import math
 import os
-from typing import Any, Dict, Optional
+from typing import Any, Dict, Optional, List
 
 import torch
 
@@ -260,6 +260,61 @@ def predict(module: HFWrapper, batches, n_beams: Optional[int] = None):
     for i, batch in enumerate(batches):
         outs.append(module.predict_step(batch, i))
     return outs
+
+
+def shard_indices(n: int, rank: int, world: int, contiguous: bool = False):
+    """Sample indices of `rank` for sharded inference (independent spectra per GPU, no data-path
+    collective).  Strided by default (rank r takes r, r + world, ...: DistributedSampler order without padding, so
+    no sample is decoded twice); `contiguous=True` gives rank r the r-th block."""
+    if not 0 <= rank < world:
+        raise ValueError("rank must be in [0, world)")
+    if contiguous:
+        per = -(-n // world)
+        return list(range(min(n, rank * per), min(n, (rank + 1) * per)))
+    return list(range(rank, n, world))
+
+
+def gather_outputs(local: List[Any], indices: List[int], n: int, process_group=None) -> Optional[List[Any]]:
+    """Reassemble per-sample outputs of a sharded predict in dataset order.  Host objects only (decoded strings,
+    losses), exchanged once at the end with `all_gather_object` - nothing on the decode path waits on another rank
+    (the reference writes one pickle per rank instead, cli/training.py:230-240).  Every rank returns the full list."""
+    if len(local) != len(indices):
+        raise ValueError("one output per local index expected")
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        parts = [(indices, local)]
+    else:
+        world = torch.distributed.get_world_size(process_group)
+        parts = [None] * world
+        torch.distributed.all_gather_object(parts, (indices, local), group=process_group)
+    out: List[Any] = [None] * n
+    seen = 0
+    for idx, vals in parts:
+        for i, v in zip(idx, vals):
+            if out[i] is not None:
+                raise ValueError(f"sample {i} was produced by two ranks")
+            out[i] = v
+            seen += 1
+    if seen != n:
+        raise ValueError(f"{n - seen} samples were not produced by any rank")
+    return out
+
+
+@torch.no_grad()
+def predict_sharded(module: HFWrapper, dataset, batch_size: int, rank: int = 0, world: int = 1,
+                    n_beams: Optional[int] = None, process_group=None) -> List[List[str]]:
+    """Beam-search prediction of a `pipeline.DeviceDataset` split over `world` GPUs: each rank decodes its own
+    samples (wire batches assembled on its device), then the decoded hypotheses are exchanged once.  Returns, on every
+    rank, `n_beams` strings per sample in dataset order."""
+    K = n_beams if n_beams is not None else module.n_beams
+    mine = shard_indices(len(dataset), rank, world)
+    local: List[List[str]] = []
+    module.eval()
+    for lo in range(0, len(mine), batch_size):
+        batch = dataset.wire_batch(mine[lo: lo + batch_size])
+        seqs = module.generate(batch, n_beams=K)
+        dec = module.target_tokenizer.batch_decode(seqs, skip_special_tokens=True)
+        local += [dec[i * K: (i + 1) * K] for i in range(len(dec) // K)]
+    return gather_outputs(local, mine, len(dataset), process_group)
 
 
 @torch.no_grad()

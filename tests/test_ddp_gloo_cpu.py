@@ -51,3 +51,47 @@ def test_bucketed_allreduce_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(nb >= 3 for _, _, nb in res)
+
+
+def _shard_worker(rank, world, port, n, q):
+    from multimodalanalytical_b200.trainer import gather_outputs, shard_indices
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard_indices(n, rank, world)
+    local = [[f"mol{i}-beam{k}" for k in range(3)] for i in mine]  # what a rank's decode would return
+    full = gather_outputs(local, mine, n)
+    ok = full == [[f"mol{i}-beam{k}" for k in range(3)] for i in range(n)]
+    # a sample decoded twice, or never, is an error - not a silent overwrite
+    try:
+        gather_outputs(local, [0] * len(mine), n)
+        dup = False
+    except ValueError:
+        dup = True
+    q.put((rank, ok, dup, len(mine)))
+    dist.destroy_process_group()
+
+
+def test_sharded_inference_partition_and_gather_world2():
+    """Inference shards independent spectra over the ranks with no data-path collective; the decoded strings are
+    exchanged once at the end."""
+    from multimodalanalytical_b200.trainer import shard_indices
+
+    for n, world in ((11, 2), (8, 4), (3, 4), (0, 2)):
+        for contiguous in (False, True):
+            parts = [shard_indices(n, r, world, contiguous) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(n))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= (1 if not contiguous else -(-n // world))
+    world, n = 2, 11
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok and dup for _, ok, dup, _ in res), res
+    assert sorted(m for *_, m in res) == [5, 6]

@@ -244,3 +244,29 @@ def test_gpu_fused_trainer_takes_device_batches():
         for batch in loader:
             losses.append(float(tr.train_step(batch)))
     assert losses[-1] < losses[0]  # same shape every step: eager, capture, then graph replays; the loss goes down
+
+
+@gpu
+def test_gpu_predict_sharded_equals_one_big_batch():
+    """Sharded prediction (strided shard, device-assembled wire batches of 4) returns, in dataset order, the same
+    hypotheses as one batch holding the whole set."""
+    from multimodalanalytical_b200.pipeline import DeviceDataset
+    from multimodalanalytical_b200.trainer import predict_sharded, shard_indices
+    from multimodalanalytical_b200.wrapper import HFWrapper
+    from tests.test_guided import VocabTokenizer
+
+    fx, cx = fixture()["c1"], load_case("c1_ir_tiny")
+    tok = VocabTokenizer(cx["smiles_vocab"])
+    m = HFWrapper(data_config=cx["data_config"], target_tokenizer=tok, num_steps=100, precision="fp32",
+                  **cx["model_kwargs"])
+    m.load_state_dict(cx["state_dict"])
+    m.eval()
+    ds = DeviceDataset(fx["host"])
+    n, K = len(ds), 3
+    got = predict_sharded(m, ds, batch_size=4, n_beams=K)
+    seqs = m.generate(ds.wire_batch(list(range(n))), n_beams=K)
+    dec = tok.batch_decode(seqs, skip_special_tokens=True)
+    assert got == [dec[i * K: (i + 1) * K] for i in range(n)]
+    # and the reference's own golden beam-3 ids for this set (make_golden.case_c1 used the same rows in order)
+    assert torch.equal(seqs.cpu(), cx["ref"]["gen_beam3"])
+    assert shard_indices(n, 1, 2) == list(range(1, n, 2))
