@@ -57,8 +57,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a peer CTA's mbarrier.  CTA-scope release (the PTX default, what CUTLASS' ClusterBarrier::arrive issues):
+// the only work this hand-off orders is the warp's TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+// have already retired.  A cluster-scope release made ptxas emit MEMBAR.ALL.GPU + CGAERRBAR in front of every arrive
+// (10 % of the epilogue warps' stall samples in the GELU kernel).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load of one CTA of a pair: data lands in this CTA's shared memory, the bytes are counted on the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
