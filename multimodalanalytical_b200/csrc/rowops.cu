@@ -3,6 +3,7 @@
 // dropout-masked low-precision copy on the way back), column sums (bias gradients), casts.
 // One warp per row, float4-vectorised lanes, warp-shuffle reductions; fp32 statistics throughout.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace rowops {
 
@@ -294,6 +295,167 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(LnBwdArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// LayerNorm backward, prefetching variant (same math and outputs as ln_bwd_kernel).
+// ncu on the plain kernel: 44 % of the stall samples are long-scoreboard waits on the row's first use - a warp
+// issues the loads of ONE row, waits for DRAM, computes, stores, and only then asks for its next row; with 16 warps
+// per SM that leaves the memory system idle most of the time (31 % of DRAM peak).  Here every warp owns two
+// shared-memory stages: while row i is being reduced, the x / dy / dres rows of row i + stride are already in flight
+// as 1-D bulk copies (cp.async.bulk -> mbarrier complete_tx), issued by lane 0.  dgamma / dbeta partial sums live in
+// registers instead of a read-modify-write through shared memory.  Requires d == NI * 128 and 16-byte aligned rows.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int NI>
+__global__ void __launch_bounds__(256, 2) ln_bwd_pipe_kernel(LnBwdArgs a) {
+  pdl_trigger();
+  constexpr int D = NI * 128;
+  constexpr int STAGE_FLOATS = 3 * D;           // x | dy | dres, each sized for fp32
+  extern __shared__ __align__(128) float s_buf[];  // [warp][2 stages][3 * D] then the mbarriers
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* my = s_buf + (size_t)wib * 2 * STAGE_FLOATS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_buf + (size_t)wpb * 2 * STAGE_FLOATS);
+  const uint32_t bar0 = tma::smem_u32(bars + 2 * wib);
+  if (lane == 0) {
+    tma::mbar_init(bar0, 1);
+    tma::mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
+  const bool acc_params = a.gamma && a.dgamma;
+  const uint32_t xb = (uint32_t)D * (a.x_f32 ? 4u : 2u), yb = (uint32_t)D * (a.dy_f32 ? 4u : 2u);
+  const uint32_t rb = a.dres ? (uint32_t)D * 4u : 0u;
+  const long long stride = (long long)gridDim.x * wpb;
+
+  auto issue = [&](long long r, int st) {
+    const long long irow = (r / a.group) * (long long)a.in_group_stride + a.in_offset + (r % a.group);
+    const uint32_t bar = bar0 + 8u * (uint32_t)st;
+    float* base = my + (size_t)st * STAGE_FLOATS;
+    tma::mbar_expect_tx(bar, xb + yb + rb);
+    bulk_load_1d(tma::smem_u32(base), reinterpret_cast<const char*>(a.x) + (r * a.ldx) * (a.x_f32 ? 4 : 2), xb, bar);
+    bulk_load_1d(tma::smem_u32(base + D), reinterpret_cast<const char*>(a.dy) + (irow * a.lddy) * (a.dy_f32 ? 4 : 2), yb, bar);
+    if (rb) bulk_load_1d(tma::smem_u32(base + 2 * D), a.dres + r * a.lddres, rb, bar);
+  };
+
+  float4 ag[NI], ab[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  long long r = (long long)blockIdx.x * wpb + wib;
+  if (r < a.rows && lane == 0) issue(r, 0);
+  int k = 0;
+  for (; r < a.rows; r += stride, ++k) {
+    const int st = k & 1;
+    if (lane == 0 && r + stride < a.rows) issue(r + stride, st ^ 1);  // that stage was drained one iteration ago
+    tma::mbar_wait(bar0 + 8u * (uint32_t)st, (uint32_t)(k >> 1) & 1u);
+    const float* sx = my + (size_t)st * STAGE_FLOATS;
+    const float* sy = sx + D;
+    const float* sr = sx + 2 * D;
+    float4 xv[NI], gv[NI];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int c = lane * 4 + i * 128;
+      xv[i] = ld4_any(sx, c, a.x_f32);
+      gv[i] = ld4_any(sy, c, a.dy_f32);
+      sum += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (a.gamma) {
+      mean = warp_sum(sum) / D;
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const float e0 = xv[i].x - mean, e1 = xv[i].y - mean, e2 = xv[i].z - mean, e3 = xv[i].w - mean;
+        sq += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+      }
+      rstd = rsqrtf(warp_sum(sq) / D + a.eps);
+    }
+    float sg = 0.f, sgx = 0.f;
+    if (a.gamma) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int c = lane * 4 + i * 128;
+        const float4 gm = *reinterpret_cast<const float4*>(a.gamma + c);
+        float4 xh;
+        xh.x = (xv[i].x - mean) * rstd; xh.y = (xv[i].y - mean) * rstd;
+        xh.z = (xv[i].z - mean) * rstd; xh.w = (xv[i].w - mean) * rstd;
+        const float4 dy = gv[i];
+        if (acc_params) {
+          ag[i].x += dy.x * xh.x; ag[i].y += dy.y * xh.y; ag[i].z += dy.z * xh.z; ag[i].w += dy.w * xh.w;
+          ab[i].x += dy.x; ab[i].y += dy.y; ab[i].z += dy.z; ab[i].w += dy.w;
+        }
+        float4 g;
+        g.x = dy.x * gm.x; g.y = dy.y * gm.y; g.z = dy.z * gm.z; g.w = dy.w * gm.w;
+        sg += g.x + g.y + g.z + g.w;
+        sgx += g.x * xh.x + g.y * xh.y + g.z * xh.z + g.w * xh.w;
+        gv[i] = g;
+        xv[i] = xh;
+      }
+      sg = warp_sum(sg) / D;
+      sgx = warp_sum(sgx) / D;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int c = lane * 4 + i * 128;
+      float4 o = gv[i];
+      if (a.gamma) {
+        o.x = rstd * (gv[i].x - sg - xv[i].x * sgx);
+        o.y = rstd * (gv[i].y - sg - xv[i].y * sgx);
+        o.z = rstd * (gv[i].z - sg - xv[i].z * sgx);
+        o.w = rstd * (gv[i].w - sg - xv[i].w * sgx);
+      }
+      if (rb) {
+        const float4 rv = *reinterpret_cast<const float4*>(sr + c);
+        o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+      }
+      if (a.dx) *reinterpret_cast<float4*>(a.dx + r * a.lddx + c) = o;
+      if (a.dxb) {
+        if (drop) {
+          const uint32_t e32 = (uint32_t)((unsigned long long)r * D + c);  // D and c are multiples of 4: pair-aligned
+          const uint32_t r0 = drop_pair(dkey, e32 >> 1), r1 = drop_pair(dkey, (e32 >> 1) + 1u);
+          o.x *= (r0 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+          o.y *= (r0 >> 16) >= thr ? inv_keep : 0.f;
+          o.z *= (r1 & 0xFFFFu) >= thr ? inv_keep : 0.f;
+          o.w *= (r1 >> 16) >= thr ? inv_keep : 0.f;
+        }
+        st4_any(a.dxb, r * a.lddxb + c, a.dxb_f32, o);
+      }
+    }
+    __syncwarp();  // every lane is done reading this stage before lane 0 re-arms it next iteration
+  }
+  if (acc_params) {
+    // block reduction of the per-warp register partials through the (now idle) stage buffers
+    __syncthreads();
+    float* red = s_buf + (size_t)wib * 2 * D;  // [warp][dgamma D | dbeta D], inside this warp's own stage memory
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int c = lane * 4 + i * 128;
+      *reinterpret_cast<float4*>(my + c) = ag[i];
+      *reinterpret_cast<float4*>(my + D + c) = ab[i];
+    }
+    (void)red;
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float sg = 0.f, sb = 0.f;
+      for (int w = 0; w < wpb; ++w) {
+        sg += s_buf[(size_t)w * 2 * STAGE_FLOATS + c];
+        sb += s_buf[(size_t)w * 2 * STAGE_FLOATS + D + c];
+      }
+      atomicAdd(a.dgamma + c, sg);
+      atomicAdd(a.dbeta + c, sb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // column sums: out[c] += sum_r in[r, c]      (bias gradients; batch-sum of the learned pos-enc gradient)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -385,6 +547,34 @@ extern "C" int mma_ln_bwd(const void* dy, int dy_f32, long long lddy, int group,
   int blocks = (rows + 31) / 32;  // >= 4 rows per warp: the dgamma/dbeta flush is amortised
   if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
+  // prefetching variant: full 128-column groups, every row 16-byte aligned, enough rows to fill the pipeline
+  {
+    static int use_pipe = -1;
+    if (use_pipe < 0) {
+      const char* e = getenv("MMA_LN_BWD_PIPE");
+      use_pipe = e ? atoi(e) : 1;
+    }
+    const long long xe = x_f32 ? 4 : 2, ye = dy_f32 ? 4 : 2;
+    const bool aligned = ((uintptr_t)x % 16 == 0) && ((ldx * xe) % 16 == 0) && ((uintptr_t)dy % 16 == 0) &&
+                         ((lddy * ye) % 16 == 0) && (!dres || (((uintptr_t)dres % 16 == 0) && ((lddres * 4) % 16 == 0)));
+    // d = 512 only: two 96 KB blocks per SM; wider rows would drop to one block per SM (and NI = 8 spills)
+    if (use_pipe && d == 512 && aligned && rows >= 1024) {
+      const size_t smem = sizeof(float) * 8 * 2 * 3 * d + 8 * 2 * sizeof(uint64_t);
+#define LN_BWD_PIPE(NI_)                                                                                     \
+  do {                                                                                                       \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      cudaFuncSetAttribute(ln_bwd_pipe_kernel<NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    ln_bwd_pipe_kernel<NI_><<<blocks, 256, smem, stream>>>(a);                                               \
+  } while (0)
+      LN_BWD_PIPE(4);
+#undef LN_BWD_PIPE
+      MMA_CHECK_LAUNCH();
+      return MMA_OK;
+    }
+  }
 #define LN_BWD_LAUNCH(NI_)                                                                                   \
   do {                                                                                                       \
     const size_t smem = sizeof(float) * 8 * 2 * (NI_) * 128;                                                 \

@@ -247,6 +247,48 @@ def test_layernorm_fwd_bwd(d, xdt):
     assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
 
 
+@pytest.mark.parametrize("xdt,dydt", [(torch.float32, torch.bfloat16), (torch.float32, torch.float32),
+                                      (torch.bfloat16, torch.bfloat16)])
+def test_layernorm_bwd_prefetching_variant(xdt, dydt):
+    """rows >= 1024 at d = 512 take the bulk-copy prefetching kernel: against torch's LayerNorm backward, and bit for
+    bit against the plain kernel (which rows < 1024 still use) on a prefix of the same data, in-place dres == dx,
+    dropout-masked low-precision copy and remapped dy rows included."""
+    rows, d, small = 5000, 512, 777
+    x = _rand(rows, d, dtype=xdt) * 2 + 0.5
+    gamma = _rand(d) + 1.0
+    dy = _rand(rows, d, seed=9, dtype=dydt)
+    dres = _rand(rows, d, seed=10)
+    xr = x.detach().clone().float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), torch.zeros(d, device=DEV, requires_grad=True)
+    torch.nn.functional.layer_norm(xr, (d,), gr, br).backward(dy.float())
+
+    def run(n):
+        dx = dres[:n].clone()  # in place: dres aliases dx, as the engine calls it
+        dxb = torch.empty(n, d, device=DEV, dtype=torch.bfloat16)
+        dg, db = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+        ops.ln_bwd(dy[:n], x[:n], gamma, dx=dx, dres=dx, dxb=dxb, dgamma=dg, dbeta=db, p_drop=0.1, seed=5, site=3)
+        return dx, dxb, dg, db
+
+    dx, dxb, dg, db = run(rows)
+    assert rel(dx, xr.grad + dres) < 2e-5
+    assert rel(dg, gr.grad) < 2e-4 and rel(db, br.grad) < 2e-4
+    keep = dxb != 0
+    assert abs(keep.float().mean().item() - 0.9) < 0.01
+    assert rel(dxb.float()[keep], (dx / 0.9)[keep]) < 1e-2
+    sdx, sdxb, _, _ = run(small)
+    assert torch.equal(sdx, dx[:small]) and torch.equal(sdxb, dxb[:small])
+    # dy read through the concat-by-offset row mapping (embedding backward): groups of 20 rows inside 36-row samples
+    B, S, S_tot, off = 250, 20, 36, 16
+    dyc = _rand(B * S_tot, d, seed=11, dtype=dydt)
+    xs = x[: B * S]
+    dx2 = torch.empty(B * S, d, device=DEV)
+    ops.ln_bwd(dyc, xs, gamma, dx=dx2, group=S, in_group_stride=S_tot, in_offset=off)
+    xr2 = xs.detach().clone().float().requires_grad_(True)
+    sel = dyc.view(B, S_tot, d)[:, off: off + S].reshape(B * S, d).float()
+    torch.nn.functional.layer_norm(xr2, (d,), gamma, None).backward(sel)
+    assert rel(dx2, xr2.grad) < 2e-5
+
+
 def test_embed_gather_ln_pos_concat_and_scatter():
     B, S1, S2, d, vocab = 5, 7, 4, 64, 30
     ids = torch.randint(0, vocab, (B, S1), device=DEV)
