@@ -11,3 +11,5 @@ echo "reference -> $?"; cat gpurun_out/bench_reference.json
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_train.csv python scripts/profile_step.py train > gpurun_out/prof_train.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_decode.csv python scripts/profile_step.py decode 256 > gpurun_out/prof_decode.log 2>&1
 echo done
+timeout 300 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:ln_bwd -s 4 -c 3 -o gpurun_out/ncu_ln_bwd_v6 -f python scripts/profile_step.py train > gpurun_out/ncu5.log 2>&1
+ls -la gpurun_out/ncu_ln_bwd_v6.ncu-rep
