@@ -353,6 +353,8 @@ def run_ours(args):
             line["pipeline"] = bench_pipeline(trainer, c, B, args.steps)
         if dec is not None:
             line["decode"] = dec
+            if world == 1:
+                line["guided_decode"] = bench_guided(model, c)
         if world == 1 and not args.no_cpu:
             cb = 64
             cv, cs = cpu_train_baseline(c, cb, steps=3, warmup=1)
@@ -418,6 +420,63 @@ def bench_pipeline(trainer, c, B, steps):
     return {"dataset_samples": n, "resident_mb": ds.bytes_resident() / 1e6, "collate_us_per_batch": t_col * 1e6,
             "collate_spectra_per_s": B / t_col, "collate_algorithmic_gbs": (in_bytes + out_bytes) / t_col / 1e9,
             "train_spectra_per_s_index_fed": B / t_step, "h2d_bytes_per_step": B * 4}
+
+
+def bench_guided(model, c, B=64, K=10):
+    """formula-guided beam-10 decode (guide fused into the step kernel, host chemistry overlapped with the
+    decoder forward).  Synthetic SMILES-like vocabulary; the chemistry backend is a plain element counter, so the number
+    shows the cost of the guided decode LOOP (per-step D2H of parent / token ids, host string bookkeeping + memo, one
+    chemistry call per NEW hypothesis, H2D of the counts), not of rdkit.  With random weights almost every hypothesis
+    of every step is new, so this is the memo's worst case: rows x chemistry calls per step on the host.  The search
+    also ends early here - the guide bans <eos> until the formula matches and beams that overshoot die."""
+    import re
+
+    from multimodalanalytical_b200.guided import ChemBackend, GuidedFormulaProcessor
+
+    pieces = ["C", "c", "N", "O", "(", ")", "=", "1", "Cl", "Br", "S", "n", "F", "#", "2", "o", "s", "P", "I"]
+    vocab = {"<pad>": 0, "<unk>": 1, "<bos>": 2, "<eos>": 3}
+    for i in range(4, c["V"]):
+        vocab[pieces[(i - 4) % len(pieces)] + ("" if i - 4 < len(pieces) else f"@{i}")] = i  # unique keys, same elements
+    elem = re.compile(r"Cl|Br|[CNOSPFI]|[cnosp]")
+
+    class Counter(ChemBackend):
+        def canonical(self, smiles):
+            return smiles
+
+        def formula(self, smiles):
+            n = {}
+            for t in elem.findall(smiles):
+                t = t if t[0].isupper() else t.upper()
+                n[t] = n.get(t, 0) + 1
+            return "".join(f"{k}{v}" for k, v in n.items())
+
+    class VTok:
+        vocab_size, pad_token_id, bos_token_id, eos_token_id = c["V"], 0, 2, 3
+
+        def __init__(self):
+            self.vocab = vocab
+
+    model.eval()
+    batch = map_batch(synth_batch(c, B, SEED + 11), lambda x: x.cuda())
+    formulas = ["C30N8O8S4P2F4Cl4Br4I2"] * B
+
+    def run(guided):
+        procs = [GuidedFormulaProcessor(K, formulas, VTok(), chem=Counter())] if guided else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = model.generate(batch, n_beams=K, logits_processor=procs)
+        e1.record()
+        torch.cuda.synchronize()
+        steps = model.generator.last_steps if guided else int(out.shape[1]) - 1
+        return e0.elapsed_time(e1) * 1e-3, steps
+
+    run(True)
+    run(False)
+    tg, sg = run(True)
+    tu, su = run(False)
+    return {"batch": B, "beams": K, "guided_molecules_per_s": B / tg, "guided_steps": sg, "guided_ms_per_step": tg * 1e3 / max(sg, 1),
+            "unguided_molecules_per_s": B / tu, "unguided_steps": su, "unguided_ms_per_step": tu * 1e3 / max(su, 1),
+            "chemistry": "element counter (no rdkit in the image)"}
 
 
 def bench_decode(model, c, args, world=1, rank=0, dist=None):

@@ -233,9 +233,12 @@ class Generator:
 
     def _run_processed(self, st: BeamState, ctx, processors, extra_bias, use_graph, shape_key):
         """Decode loop with logits processors (wrapper.py:443-451 `logits_processor=`).  The decoder forward of a
-        step is one graph replay; while it runs, the host reads the running hypotheses of that step (copied to
-        pinned memory before the replay was queued) and does the processors' host work, so e.g. the chemistry of
-        formula-guided decoding overlaps the GPU instead of serialising with it.  Selection follows un-captured."""
+        step is one graph replay.  A lone `GuidedFormulaProcessor` is fused: while the forward runs, the host reads
+        the previous step's `next_tok` / `parent_row` (2 ints per row, copied to pinned memory before the replay was
+        queued), extends its per-row strings, looks the element counts up in its memo and sends [rows, 14] counts
+        back - the chemistry overlaps the GPU instead of serialising with it - and the step kernel applies the guide.
+        Any other processor list gets dense scores (`mma_score_rows`) and CUDA `input_ids`, transformers' protocol.
+        Selection follows un-captured."""
         from .guided import GuidedFormulaProcessor
 
         eng, cfg = self.eng, self.eng.cfg
@@ -244,7 +247,7 @@ class Generator:
         fused = len(processors) == 1 and isinstance(processors[0], GuidedFormulaProcessor)
         graph = self._capture(shape_key + ("fwd",), st, lambda: self._forward_logits(st, ctx)) if use_graph else None
         logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
-        seq_host = torch.empty(R, L, dtype=torch.int32).pin_memory()
+        step_host = torch.empty(2, R, dtype=torch.int32).pin_memory()  # fused: next_tok | parent_row of the last step
         nflag = B if K == 1 else 2 * B
         flag_dev = eng.buf("g.flags", (nflag,), torch.uint8)
         flag_host = torch.ones(nflag, dtype=torch.uint8).pin_memory()
@@ -252,9 +255,15 @@ class Generator:
         cnt_dev = eng.buf("g.guide_counts", (R, 14), torch.int32)
         scores = None if fused else eng.buf("g.scores", (R, V), torch.float32)
         ev = torch.cuda.Event()
+        if fused:
+            processors[0].begin(R)
         for cur in range(1, L):
             running = st.run_seq if K == 1 else st.run_seq[cur & 1].view(R, L)
-            seq_host.copy_(running, non_blocking=True)
+            if fused:
+                # the fused guide follows the search incrementally: 2 ints per row per step instead of the sequences
+                if cur > 1:
+                    step_host[0].copy_(st.next_tok, non_blocking=True)
+                    step_host[1].copy_(st.parent_row, non_blocking=True)
             if K == 1:
                 flag_dev.copy_(st.unfinished)
             else:
@@ -273,9 +282,10 @@ class Generator:
                         break
                 elif not (bool(flag_host[:B].any()) and not bool(flag_host[B:].all())):
                     break
-            ids_host = seq_host[:, :cur]
             if fused:
-                processors[0].counts(ids_host, out=cnt_host)
+                if cur > 1:
+                    processors[0].advance(step_host[1].tolist(), step_host[0].tolist())
+                processors[0].counts_current(cnt_host)
                 cnt_dev.copy_(cnt_host, non_blocking=True)
                 self._select(st, logits, extra_bias, guide=processors[0].guide(cnt_dev))
             else:
@@ -288,6 +298,7 @@ class Generator:
                     scores.copy_(sc)
                 self._select(st, scores, extra_bias, prenorm=True)
         torch.cuda.current_stream().synchronize()
+        self.last_steps = cur  # search steps taken (diagnostics / benchmarks)
 
     def _collect(self, st: BeamState, return_scores: bool = False):
         cfg = self.eng.cfg

@@ -22,6 +22,7 @@ from __future__ import annotations
 import re
 from typing import Any, Dict, List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import ops
@@ -112,6 +113,11 @@ class GuidedFormulaProcessor:
         self.target_counts = torch.tensor([formula_counts(f) for f in chemical_formula], dtype=torch.int32)
         self._memo: Dict[str, List[int]] = {}
         self._dev: Dict[Any, Any] = {}
+        # incremental state of the fused decode loop: text of every running hypothesis, and the memo as an id -> counts
+        # table so a step's [rows, 14] matrix is one vectorised gather
+        self._texts: List[str] = []
+        self._ids: Dict[str, int] = {}
+        self._table = np.zeros((256, len(ATOM_LIST)), dtype=np.int32)
 
     # ---------------------------------------------------------------------------------------- host chemistry
     def _counts_of(self, text: str) -> List[int]:
@@ -134,6 +140,32 @@ class GuidedFormulaProcessor:
             out.copy_(res)
             return out
         return res
+
+    # ------------------------------------------------------------------ incremental form (fused decode loop)
+    def begin(self, rows: int) -> None:
+        """All hypotheses are `<bos>` (decodes to nothing)."""
+        self._texts = [""] * rows
+
+    def advance(self, parent_rows: Sequence[int], next_tokens: Sequence[int]) -> None:
+        """One search step: row r now continues row parent_rows[r] with token next_tokens[r] (what the step kernel
+        wrote to `parent_row` / `next_tok`).  O(rows) per step instead of re-decoding [rows, cur_len] ids."""
+        old, piece = self._texts, self._piece
+        self._texts = [old[p] + piece[t] for p, t in zip(parent_rows, next_tokens)]
+
+    def _row_id(self, text: str) -> int:
+        i = self._ids.get(text)
+        if i is None:
+            i = self._ids[text] = len(self._ids)
+            if i >= self._table.shape[0]:
+                self._table = np.concatenate([self._table, np.zeros_like(self._table)], axis=0)
+            self._table[i] = self._counts_of(text)
+        return i
+
+    def counts_current(self, out: torch.Tensor) -> torch.Tensor:
+        """Element counts of the current hypotheses -> `out` (host int32 [rows, 14], e.g. pinned)."""
+        idx = [self._row_id(t) for t in self._texts]
+        out.copy_(torch.from_numpy(self._table[idx]))
+        return out
 
     # --------------------------------------------------------------------------------------------- device side
     def _device_tables(self, device):

@@ -148,6 +148,29 @@ def test_host_counts_follow_the_oracle_and_are_memoised():
     assert Counting.calls == n  # second pass is served from the memo
 
 
+def test_incremental_host_state_equals_redecoding_the_sequences():
+    """The fused loop feeds the processor `parent_row` / `next_tok` per step; its counts must equal those obtained by
+    decoding the full [rows, cur_len] ids, for an arbitrary beam re-ordering."""
+    from multimodalanalytical_b200.guided import GuidedFormulaProcessor
+
+    g, fx = golden(), load_case("c1_ir_tiny")
+    vocab = fx["smiles_vocab"]
+    rows, K = 12, 3
+    proc = GuidedFormulaProcessor(K, g["formulas"][: rows // K], VocabTokenizer(vocab), chem=ToyChem())
+    gen = torch.Generator().manual_seed(4)
+    seqs = torch.full((rows, 1), 2, dtype=torch.long)
+    proc.begin(rows)
+    out = torch.zeros(rows, 14, dtype=torch.int32)
+    for step in range(25):
+        assert torch.equal(proc.counts_current(out), proc.counts(seqs))
+        parent = (torch.arange(rows) // K) * K + torch.randint(0, K, (rows,), generator=gen)  # beams stay in their spectrum
+        tok = torch.randint(0, len(vocab), (rows,), generator=gen)
+        seqs = torch.cat([seqs[parent], tok[:, None]], dim=1)
+        proc.advance(parent.tolist(), tok.tolist())
+    assert torch.equal(proc.counts_current(out), proc.counts(seqs))
+    assert len(proc._ids) < 25 * rows  # shared prefixes hit the memo
+
+
 def test_missing_rdkit_fails_loudly():
     from multimodalanalytical_b200.guided import RDKitChem
 
