@@ -13,6 +13,8 @@ rows = page("sass")
 print(rows[0][:2])
 hdr = rows[1]; ix = {h: i for i, h in enumerate(hdr)}
 data = [r for r in rows[2:] if len(r) == len(hdr)]
+rep = next((i for i in range(1, len(data)) if data[i][0] == data[0][0]), None)  # this ncu build prints the listing twice
+if rep: data = data[:rep]
 tot = sum(I(r[ix["# Samples"]]) for r in data)
 c = Counter(); ex = Counter()
 for r in data:
