@@ -270,3 +270,67 @@ def test_gpu_predict_sharded_equals_one_big_batch():
     # and the reference's own golden beam-3 ids for this set (make_golden.case_c1 used the same rows in order)
     assert torch.equal(seqs.cpu(), cx["ref"]["gen_beam3"])
     assert shard_indices(n, 1, 2) == list(range(1, n, 2))
+
+
+@gpu
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_gpu_collate_kernels_random_ragged(seed):
+    """Collate kernels against a numpy restatement on random ragged columns: empty rows, rows longer than the
+    truncation bound, rows flagged as missing, repeated and out-of-order indices, one-sample batches, width-2 values."""
+    from multimodalanalytical_b200 import ops
+    from multimodalanalytical_b200.pipeline import Ragged
+
+    rng = np.random.default_rng(seed)
+    N, pad_id, max_len = 57, 0, 19
+    lens = rng.integers(0, 30, size=N)
+    lens[3] = 0
+    rows = [rng.integers(4, 90, size=n).astype(np.int32) for n in lens]
+    valid = (rng.random(N) > 0.2).astype(np.uint8)
+    col = Ragged.from_rows(rows, np.int32, valid=valid)
+    vals = Ragged.from_rows([rng.standard_normal((n, 2)).astype(np.float32) for n in lens], np.float32, width=2)
+    dev = torch.device("cuda")
+    flat, off, vd = (torch.from_numpy(x).to(dev) for x in (col.flat, col.offsets, col.valid))
+    vflat, voff = torch.from_numpy(vals.flat).to(dev), torch.from_numpy(vals.offsets).to(dev)
+    for B in (1, 7, 64):
+        idx = rng.integers(0, N, size=B).astype(np.int32)
+        tl = np.minimum(lens[idx], max_len)
+        for L in (int(max(tl.max(), 1)), 24):
+            ids = torch.empty(B, L, dtype=torch.int64, device=dev)
+            mask = torch.empty(B, L, dtype=torch.uint8, device=dev)
+            r = torch.from_numpy(idx).to(dev)
+            ops.collate_tokens(flat, off, vd, r, pad_id, max_len, ids, mask)
+            want_ids = np.full((B, L), pad_id, dtype=np.int64)
+            want_mask = np.zeros((B, L), dtype=np.uint8)
+            for b, i in enumerate(idx):
+                n = min(tl[b], L)
+                want_ids[b, :n] = rows[i][:n]
+                want_mask[b, :n] = valid[i]
+            assert np.array_equal(ids.cpu().numpy(), want_ids) and np.array_equal(mask.cpu().numpy(), want_mask)
+            out = torch.empty(B, L, 2, device=dev)
+            vmask = torch.empty(B, L, dtype=torch.uint8, device=dev)
+            ops.collate_values(vflat, voff, r, -1.5, max_len, out, vmask)
+            want_v = np.full((B, L, 2), -1.5, dtype=np.float32)
+            want_vm = np.zeros((B, L), dtype=np.uint8)
+            for b, i in enumerate(idx):
+                n = min(tl[b], L)
+                want_v[b, :n] = vals.row(i)[:n]
+                want_vm[b, :n] = 1
+            assert np.array_equal(out.cpu().numpy(), want_v) and np.array_equal(vmask.cpu().numpy(), want_vm)
+        # teacher forcing: T = longest (truncated) row - 1, at least 1
+        T = int(max(tl.max() - 1, 1))
+        dec_in = torch.empty(B, T, dtype=torch.int64, device=dev)
+        dec_mask = torch.empty(B, T, dtype=torch.uint8, device=dev)
+        labels = torch.empty(B, T, dtype=torch.int64, device=dev)
+        ops.collate_target(flat, off, torch.from_numpy(idx).to(dev), pad_id, max_len, dec_in, dec_mask, labels)
+        w_in = np.full((B, T), pad_id, dtype=np.int64)
+        w_m = np.zeros((B, T), dtype=np.uint8)
+        w_l = np.full((B, T), -100, dtype=np.int64)
+        for b, i in enumerate(idx):
+            t = rows[i][: tl[b]]
+            n = min(len(t), T)
+            w_in[b, :n] = t[:n]
+            w_m[b, :n] = 1
+            m = min(max(len(t) - 1, 0), T)
+            w_l[b, :m] = t[1: 1 + m]
+        assert np.array_equal(dec_in.cpu().numpy(), w_in) and np.array_equal(dec_mask.cpu().numpy(), w_m)
+        assert np.array_equal(labels.cpu().numpy(), w_l)
