@@ -440,15 +440,21 @@ def bench_guided(model, c, B=64, K=10):
     elem = re.compile(r"Cl|Br|[CNOSPFI]|[cnosp]")
 
     class Counter(ChemBackend):
+        calls, seconds = 0, 0.0
+
         def canonical(self, smiles):
             return smiles
 
         def formula(self, smiles):
+            t0 = time.perf_counter()
             n = {}
             for t in elem.findall(smiles):
                 t = t if t[0].isupper() else t.upper()
                 n[t] = n.get(t, 0) + 1
-            return "".join(f"{k}{v}" for k, v in n.items())
+            out = "".join(f"{k}{v}" for k, v in n.items())
+            Counter.calls += 1
+            Counter.seconds += time.perf_counter() - t0
+            return out
 
     class VTok:
         vocab_size, pad_token_id, bos_token_id, eos_token_id = c["V"], 0, 2, 3
@@ -472,9 +478,11 @@ def bench_guided(model, c, B=64, K=10):
 
     run(True)
     run(False)
+    Counter.calls, Counter.seconds = 0, 0.0
     tg, sg = run(True)
     tu, su = run(False)
     return {"batch": B, "beams": K, "guided_molecules_per_s": B / tg, "guided_steps": sg, "guided_ms_per_step": tg * 1e3 / max(sg, 1),
+            "chemistry_calls_per_step": Counter.calls / max(sg, 1), "chemistry_ms_per_step": Counter.seconds * 1e3 / max(sg, 1),
             "unguided_molecules_per_s": B / tu, "unguided_steps": su, "unguided_ms_per_step": tu * 1e3 / max(su, 1),
             "chemistry": "element counter (no rdkit in the image)"}
 
