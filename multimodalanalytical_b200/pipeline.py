@@ -211,7 +211,10 @@ class DeviceDataset:
                 d["raw"], d["missing"] = up(col.raw), up(col.missing)
             self.dev[name] = d
         self.align = None if host.alignment is None else up(host.alignment)
-        self._idx_ring = [torch.empty(0, dtype=torch.int32).pin_memory() for _ in range(4)]
+        # pinned staging slots for the index vectors; a slot is rewritten only after the H2D copy that last read it has
+        # completed (the host may run many steps ahead of the GPU when the step is a graph replay)
+        self._idx_ring = [torch.empty(0, dtype=torch.int32).pin_memory() for _ in range(8)]
+        self._idx_done: List[Optional[torch.cuda.Event]] = [None] * len(self._idx_ring)
         self._ring_pos = 0
 
     def __len__(self):
@@ -228,11 +231,17 @@ class DeviceDataset:
         if idx.min() < 0 or idx.max() >= self.host.n:
             raise IndexError("sample index out of range")
         slot = self._ring_pos = (self._ring_pos + 1) % len(self._idx_ring)
+        if self._idx_done[slot] is not None:
+            self._idx_done[slot].synchronize()
         if self._idx_ring[slot].numel() < idx.size:
             self._idx_ring[slot] = torch.empty(max(idx.size, 1024), dtype=torch.int32).pin_memory()
         stage = self._idx_ring[slot][: idx.size]
         stage.copy_(torch.from_numpy(idx))
-        return idx, stage.to(self.device, non_blocking=True)
+        rows = stage.to(self.device, non_blocking=True)
+        ev = self._idx_done[slot] or torch.cuda.Event()
+        ev.record()
+        self._idx_done[slot] = ev
+        return idx, rows
 
     def collate(self, indices):
         idx, rows = self._indices(indices)
