@@ -243,6 +243,8 @@ class FusedTrainer:
     def fit(self, batches, epochs: int = 1, log_every: int = 10, log=print):
         step = 0
         for ep in range(epochs):
+            if hasattr(batches, "set_epoch"):  # pipeline.DeviceLoader / samplers: new shuffle per epoch
+                batches.set_epoch(ep)
             for i, batch in enumerate(batches):
                 loss = self.train_step(batch, i)
                 if log and step % log_every == 0:
