@@ -217,3 +217,27 @@ def reject_sample(predictions: Dict[str, Any], molecules: bool = True, chem: Opt
         predictions["predictions"][i] = kept + [""] * (n_beams - len(kept))
     assert len(predictions["predictions"]) == len(predictions["targets"])
     return predictions
+
+
+def calc_sampling_metrics(samples: List[Any], targets: List[str], classes: Optional[List[Any]] = None,
+                          molecules: bool = True, chem: Optional[ChemBackend] = None) -> Dict[Any, Any]:
+    """Top-N accuracies of ranked hypotheses (analytical_fm/utils.py:86-153): rank = position of the cleaned target
+    among the cleaned predictions (n_beams when absent), `Top-(i+1)` = share of samples with rank <= i; with `classes`
+    one such dict per class value.  `molecules=True` canonicalises both sides through the chemistry backend."""
+    n_beams = len(samples[0])
+    if molecules and chem is None:
+        chem = RDKitChem()
+    ranks = []
+    for preds, tgt in zip(samples, targets):
+        clean = [clean_sample(p, molecules, chem) for p in preds]
+        t = clean_sample(tgt, molecules, chem)
+        ranks.append(clean.index(t) if t in clean else n_beams)
+    metrics: Dict[Any, Any] = {}
+    for i in range(n_beams):
+        if classes:
+            for cl in dict.fromkeys(classes):
+                sel = [r for r, c in zip(ranks, classes) if c == cl]
+                metrics.setdefault(float(cl), {})[f"Top-{i + 1}"] = float(sum(r <= i for r in sel) / len(sel))
+        else:
+            metrics[f"Top-{i + 1}"] = float(sum(r <= i for r in ranks) / len(ranks))
+    return metrics

@@ -193,6 +193,30 @@ def test_reject_sample_semantics():
     assert clean_sample("<bos>C C<eos>", False) == "CC"
 
 
+def test_scoring_matches_the_reference_known_answers():
+    """The reference's own known-answer tests for this code (tests/test_scoring.py:19-48), replayed from
+    tests/golden/scoring.json: Top-1 = 0.2 and Top-10 = 0.6 on its pickled predictions, and the cleaned strings of
+    `test_clean_sample` (the fifth needs rdkit's aromatisation and is checked for cleaning only)."""
+    import json
+
+    from multimodalanalytical_b200.guided import calc_sampling_metrics, clean_sample
+    from multimodalanalytical_b200.wrapper import top_n_string_accuracy
+
+    fx = json.load(open(os.path.join(GOLDEN_DIR, "scoring.json")))
+    for m in (calc_sampling_metrics(fx["predictions"], fx["targets"], molecules=False),
+              calc_sampling_metrics(fx["predictions"], fx["targets"], molecules=True, chem=ToyChem()),
+              top_n_string_accuracy(fx["predictions"], fx["targets"])):
+        assert abs(m["Top-1"] - fx["expected"]["Top-1"]) < 1e-9 and abs(m["Top-10"] - fx["expected"]["Top-10"]) < 1e-9
+        assert all(m[f"Top-{i}"] <= m[f"Top-{i + 1}"] for i in range(1, 10))
+    cleaned = [clean_sample(x, False) for x in fx["samples_to_clean"]]
+    assert cleaned[:4] == fx["cleaned_samples_truth"][:4]
+    assert "<" not in cleaned[4] and " " not in cleaned[4]
+    by_class = calc_sampling_metrics(fx["predictions"], fx["targets"], classes=[0, 0, 1, 1, 1], molecules=False)
+    assert set(by_class) == {0.0, 1.0} and set(by_class[0.0]) == {f"Top-{i}" for i in range(1, 11)}
+    n0, n1 = 2, 3
+    assert abs(n0 * by_class[0.0]["Top-10"] + n1 * by_class[1.0]["Top-10"] - 5 * 0.6) < 1e-9
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 gpu = pytest.mark.gpu
 
