@@ -257,6 +257,7 @@ class Generator:
         ev = torch.cuda.Event()
         if fused:
             processors[0].begin(R)
+        steps = 0
         for cur in range(1, L):
             running = st.run_seq if K == 1 else st.run_seq[cur & 1].view(R, L)
             if fused:
@@ -297,8 +298,9 @@ class Generator:
                 if sc.data_ptr() != scores.data_ptr():
                     scores.copy_(sc)
                 self._select(st, scores, extra_bias, prenorm=True)
+            steps += 1
         torch.cuda.current_stream().synchronize()
-        self.last_steps = cur  # search steps taken (diagnostics / benchmarks)
+        self.last_steps = steps  # search steps taken (diagnostics / benchmarks)
 
     def _collect(self, st: BeamState, return_scores: bool = False):
         cfg = self.eng.cfg
