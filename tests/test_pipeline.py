@@ -24,6 +24,25 @@ def _pad_id(fx, m):
     return fx["data_config"][m].get("pad_token_id", 0)
 
 
+def _same(got, want, name):
+    if isinstance(want, dict):
+        assert set(got) == set(want), name
+        for k in want:
+            _same(got[k], want[k], f"{name}.{k}")
+        return
+    if isinstance(want, torch.Tensor):
+        got = got.cpu()
+        assert got.shape == want.shape, (name, got.shape, want.shape)
+        if want.is_floating_point():
+            assert torch.allclose(got, want.float(), atol=2e-6, rtol=0), name
+        else:
+            assert got.dtype == want.dtype, (name, got.dtype, want.dtype)
+            assert torch.equal(got, want), name
+        return
+    assert got == want, name
+
+
+
 # ------------------------------------------------------------------------------------------------------- CPU
 @pytest.mark.parametrize("case", ["c1", "multi"])
 def test_ragged_rows_are_the_valid_prefixes_of_the_reference_batch(case):
@@ -70,6 +89,22 @@ def test_ragged_rows_are_the_valid_prefixes_of_the_reference_batch(case):
         assert len(row) <= tgt.max_len
         assert np.array_equal(full_ids[: len(row), i].numpy(), row)
     assert host.passthrough["target_smiles"] == b["target_smiles"]
+
+
+@pytest.mark.parametrize("case", ["c1", "multi"])
+def test_collate_oracle_matches_reference_batches(case):
+    """oracle/collate_oracle.py (numpy restatement of the collator's padding / masking / shifting on the ragged columns)
+    reproduces every batch the reference collator produced, for every index list of the fixture."""
+    from oracle import collate_oracle
+
+    fx = fixture()[case]
+    for entry in fx["batches"]:
+        got = collate_oracle.collate(fx["host"], entry["indices"])
+        want = entry["batch"]
+        assert set(got) == set(want), set(got) ^ set(want)
+        assert list(got["encoder_input"]) == list(want["encoder_input"])
+        for k in want:
+            _same(got[k], want[k], f"{case}{entry['indices'][:4]}.{k}")
 
 
 def test_pretokenise_from_raw_rows_with_rebuilt_tokenizers():
@@ -149,24 +184,6 @@ def test_device_dataset_refuses_cpu():
 
 
 # ------------------------------------------------------------------------------------------------------- GPU
-def _same(got, want, name):
-    if isinstance(want, dict):
-        assert set(got) == set(want), name
-        for k in want:
-            _same(got[k], want[k], f"{name}.{k}")
-        return
-    if isinstance(want, torch.Tensor):
-        got = got.cpu()
-        assert got.shape == want.shape, (name, got.shape, want.shape)
-        if want.is_floating_point():
-            assert torch.allclose(got, want.float(), atol=2e-6, rtol=0), name
-        else:
-            assert got.dtype == want.dtype, (name, got.dtype, want.dtype)
-            assert torch.equal(got, want), name
-        return
-    assert got == want, name
-
-
 @gpu
 @pytest.mark.parametrize("case", ["c1", "multi"])
 def test_gpu_wire_batches_identical_to_reference_collator(case):
