@@ -95,3 +95,29 @@ def test_top_n_bookkeeping():
     targets = ["CCO", "CC", "S"]
     m = top_n_string_accuracy(samples, targets)
     assert m["Top-1"] == pytest.approx(1 / 3) and m["Top-2"] == pytest.approx(2 / 3)
+
+
+def test_product_code_never_imports_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke()/build() and bench.py's CPU-baseline legs
+    may import it; the package must not, and nothing shipped may reach into /root/reference at run time."""
+    import ast
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "multimodalanalytical_b200")
+    for fn in sorted(os.listdir(pkg)):
+        if not fn.endswith(".py"):
+            continue
+        src = open(os.path.join(pkg, fn)).read()
+        for node in ast.walk(ast.parse(src)):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                mods = [node.module or ""]
+            for m in mods:
+                assert not (m == "oracle" or m.startswith("oracle.")), (fn, m)
+                assert not m.startswith("analytical_fm"), (fn, m)
+        assert "/root/reference" not in src, fn
+    for fn in ("bench.py", "__graft_entry__.py"):
+        assert "/root/reference" not in open(os.path.join(root, fn)).read(), fn
