@@ -114,6 +114,21 @@ def main():
     out["call_scores_in"] = scores.clone()
     out["call_scores_out"] = proc(ids, scores.clone()).clone()
 
+    # the token -> element table on a realistic SMILES vocabulary (bracket atoms, two-letter elements, charges, ...):
+    # only the constructor of the reference processor runs here (logit_processors.py:42-62)
+    import types
+
+    big = ["<pad>", "<unk>", "<bos>", "<eos>", "C", "c", "N", "n", "O", "o", "S", "s", "P", "p", "F", "Cl", "Br", "I", "B",
+           "b", "(", ")", "[", "]", "=", "#", "-", "+", "/", "\\", ".", ":", "1", "2", "3", "%10", "%11", "[nH]", "[C@@H]",
+           "[C@H]", "[C@]", "[C@@]", "[N+]", "[O-]", "[n+]", "[S+]", "[Si]", "[Se]", "[se]", "[As]", "[B-]", "[2H]", "[13C]",
+           "[NH3+]", "[Cl-]", "[Br-]", "[I-]", "[Na+]", "[SiH]", "[PH]", "[te]", "[Te]", "[cH-]", "[Sn]", "[Cu]", "@", "H"]
+    big_vocab = {t: i for i, t in enumerate(big)}
+    fake = types.SimpleNamespace(vocab=big_vocab, eos_token_id=3, vocab_size=len(big))
+    bp = GuidedFormulaProcessor(1, ["C2H6O", "CCl4", "C6H5Br"], fake)
+    out["big_vocab"] = big_vocab
+    out["big_vocab_table"] = {a: sorted(v) for a, v in bp.atom_id_token_id_dict.items()}
+    out["big_vocab_formulas"] = torch.from_numpy(bp.chemical_formula_beams.copy())
+
     path = os.path.join(HERE, "guided_c1.pt")
     torch.save(out, path)
     for k, v in out.items():

@@ -124,6 +124,23 @@ def test_host_tables_match_oracle_and_reference():
     assert len(ATOM_LIST) == proc.target_counts.shape[1] == 14
 
 
+def test_token_element_table_on_a_realistic_vocabulary():
+    """Bracket atoms, two-letter elements, charges, isotopes: the substring rule has many side effects ("[Cl-]" counts
+    as carbon because only the bare token "Cl" is exempted, "[Na+]" / "[Sn]" as nitrogen, "[Si]" as sulfur and iodine,
+    ...).  Table and formula vectors from the reference processor's constructor (logit_processors.py:42-87)."""
+    from multimodalanalytical_b200.guided import formula_counts, token_atom_bits
+
+    g = golden()
+    vocab = g["big_vocab"]
+    bits = token_atom_bits(vocab, len(vocab))
+    mine = {a: sorted(t for t in range(len(vocab)) if bits[t] >> a & 1) for a in range(14)}
+    assert mine == g["big_vocab_table"]
+    assert {a: sorted(v) for a, v in token_atoms(vocab).items()} == g["big_vocab_table"]
+    assert vocab["[Cl-]"] in mine[0] and vocab["Cl"] not in mine[0] and vocab["[Si]"] in mine[8]
+    want = g["big_vocab_formulas"].long().tolist()
+    assert [formula_counts(f) for f in ("C2H6O", "CCl4", "C6H5Br")] == want
+
+
 def test_host_counts_follow_the_oracle_and_are_memoised():
     from multimodalanalytical_b200.guided import GuidedFormulaProcessor
 
