@@ -264,6 +264,16 @@ def predict(module: HFWrapper, batches, n_beams: Optional[int] = None):
     return outs
 
 
+def calculate_training_steps(n_train: int, batch_size: int, acc_batches: int = 1, epochs: int = 1, world: int = 1,
+                             reference_compat: bool = True) -> int:
+    """Optimiser steps of a run = OneCycleLR's `total_steps` (analytical_fm/utils.py:155-172).  The reference divides
+    by a hard-coded GPU count of 1, so under DDP its schedule is `world` times longer than the steps actually taken
+    (SURVEY App. A #10); `reference_compat=True` keeps that, False divides by the real world size."""
+    gpus = 1 if reference_compat else max(1, world)
+    batches_per_gpu = math.ceil((n_train / batch_size) / float(gpus))
+    return math.ceil(batches_per_gpu / acc_batches) * epochs
+
+
 def shard_indices(n: int, rank: int, world: int, contiguous: bool = False):
     """Sample indices of `rank` for sharded inference (independent spectra per GPU, no data-path
     collective).  Strided by default (rank r takes r, r + world, ...: DistributedSampler order without padding, so

@@ -121,3 +121,13 @@ def test_product_code_never_imports_the_oracle_or_the_reference():
         assert "/root/reference" not in src, fn
     for fn in ("bench.py", "__graft_entry__.py"):
         assert "/root/reference" not in open(os.path.join(root, fn)).read(), fn
+
+
+def test_calculate_training_steps_follows_the_reference_formula():
+    """analytical_fm/utils.py:155-172: ceil(ceil(n / batch) / acc) * epochs with a hard-coded GPU count of 1."""
+    from multimodalanalytical_b200.trainer import calculate_training_steps
+
+    assert calculate_training_steps(15, 128, 4, 1) == 1           # the tiny test run (tests/test_run.py)
+    assert calculate_training_steps(1000, 256, 4, 60) == math.ceil(math.ceil(1000 / 256) / 4) * 60
+    assert calculate_training_steps(100_000, 256, 4, 10, world=8) == calculate_training_steps(100_000, 256, 4, 10)
+    assert calculate_training_steps(100_000, 256, 4, 10, world=8, reference_compat=False) == math.ceil(49 / 4) * 10
