@@ -69,6 +69,28 @@ int mma_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
 int mma_wgrad_group(int count, const void* const* dy, const long long* lddy, const void* const* x,
                     const long long* ldx, float* const* out, const long long* ldo, float* const* dbias,
                     const int* Nout, const int* Kin, const int* R, cudaStream_t stream);
+/* One accumulation over two operand pairs, C[M,N] = epi(A1 B1_op^T + A2 B2_op^T) (reduction lengths K1, K2; A1/A2
+ * K-major, B1/B2 both K-major or both MN-major): the gated FFN's dh = dz1 W1 + dz2 Wg (backward of
+ * custom_modeling.py:137-152,184-199) without an fp32 accumulate round trip.  CTA-pair kernel only:
+ * MMA_ERR_UNSUPPORTED (-3) outside its envelope - run two mma_gemm_bf16 with EPI_ACCUM instead.                  */
+int mma_gemm2_dual(const void* A1, long long lda1, const void* B1, long long ldb1, const void* A2, long long lda2,
+                   const void* B2, long long ldb2, int b_mn, int M, int N, int K1, int K2, const Epi* ep,
+                   cudaStream_t stream);
+/* Gated FFN, forward (custom_modeling.py:137-152,184-199: `gelu(linear1(x)) * gate(x)` + dropout) as ONE CTA-pair
+ * tcgen05 launch over W1 and Wg: a[M,N] = drop(gelu(h W1^T + b1) * (h Wg^T + bg)); z1 / z2 (both or neither) receive
+ * the bf16 pre-activations for the backward.  h bf16 [M,K]; W1, Wg bf16 [N,K]; b1, bg fp32 [N].  Dropout stream index
+ * of element (row, col) = row * N + col.  MMA_ERR_UNSUPPORTED (-3) outside the envelope (alignment, N % 16, too few
+ * tiles): run mma_gemm_bf16 twice (EPI_STORE, then EPI_GLU_MUL).                                                  */
+int mma_ffn_glu_fwd(const void* h, long long ldh, const void* W1, long long ldw1, const void* Wg, long long ldwg,
+                    const float* b1, const float* bg, int M, int N, int K, void* a, long long lda, void* z1,
+                    long long ldz1, void* z2, long long ldz2, float p_drop, unsigned long long seed, unsigned int site,
+                    cudaStream_t stream);
+/* Gated FFN, backward through the gate: da = (dy W2) * dropmask with W2 = linear2.weight [K, N] as stored;
+ * dz1 = da * z2 * gelu'(z1), dz2 = da * gelu(z1)  (all bf16 [M,N]).  -3 outside the envelope: mma_gemm_bf16 + EPI_DGLU. */
+int mma_ffn_dglu(const void* dy, long long lddy, const void* W2, long long ldw2, int M, int N, int K, const void* z1,
+                 long long ldz1, const void* z2, long long ldz2, void* dz1, long long lddz1, void* dz2,
+                 long long lddz2, float p_drop, unsigned long long seed, unsigned int site, long long drop_ld,
+                 cudaStream_t stream);
 /* fp32 SIMT GEMM with arbitrary element strides (fp32 parity mode; patch embeddings with K = 75/125/1/2,
  * modeling/utils.py:119-134).  A(m,k) = A[m*sam + k*sak], B(n,k) = B[n*sbn + k*sbk].                          */
 int mma_gemm_simt(const void* A, int a_type, long long sam, long long sak, const void* B, int b_type,

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu", "align.cu", "collate.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_glu2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu", "align.cu", "collate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -104,6 +104,9 @@ _vp, _i, _ll, _f, _ull, _u = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_u
 _SIGS = {
     "mma_gemm_bf16": [_vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, C.POINTER(Epi), _i, _i, _vp],
     "mma_gemm2_resid_ln": [_vp, _ll, _vp, _ll, _i, _i, _i, C.POINTER(Epi), _vp, _vp, _f, _vp, _ll, _vp],
+    "mma_gemm2_dual": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _i, _i, C.POINTER(Epi), _vp],
+    "mma_ffn_glu_fwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _f, _ull, _u, _vp],
+    "mma_ffn_dglu": [_vp, _ll, _vp, _ll, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _f, _ull, _u, _ll, _vp],
     "mma_wgrad_group": [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "mma_gemm_simt": [_vp, _i, _ll, _ll, _vp, _i, _ll, _ll, _i, _i, _i, C.POINTER(Epi), _i, _vp],
     "mma_gather_rows": [_vp, _vp, _vp, _vp, _i, _i, _vp],

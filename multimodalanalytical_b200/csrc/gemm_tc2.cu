@@ -18,128 +18,12 @@
 //
 // Roles per CTA (576 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only; both CTAs allocate
 // TMEM), warps 2..17 = epilogue.  Two TMEM accumulator stages (2 x 256 columns) overlap epilogue and mainloop.
-#include <cstdio>
-#include <cstdlib>
-
-#include "common.cuh"
-#include "tma.cuh"
+#include "tc2.cuh"
 
 namespace tc2 {
-using namespace tma;
-
-constexpr int BM = 128;      // rows per CTA; the pair tile is 2 * BM x BN
-constexpr int BN = 256;      // pair-tile columns (each CTA loads BN / 2 rows of B)
-constexpr int BK = 64;       // 64 bf16 = one 128-byte swizzle row
-constexpr int STAGES = 4;
-constexpr int NUM_EPI_WARPS = 16;
-constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr uint32_t A_BYTES = BM * BK * 2;
-constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
-constexpr uint32_t BOX_BYTES = 32 * 64;                 // one epilogue box: 32 rows x 64 bytes
-constexpr uint32_t EPI_WARP_BYTES = 3 * BOX_BYTES;
-constexpr uint32_t BAR_BYTES = 512;
-constexpr uint32_t SMEM = 1024 /*align slack*/ + STAGES * (A_BYTES + B_BYTES) + NUM_EPI_WARPS * EPI_WARP_BYTES + BAR_BYTES;
-static_assert(SMEM <= 232448, "shared memory budget");
-
-// ---- PTX wrappers that only this kernel needs -----------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-// Arrive on a peer CTA's mbarrier.  CTA-scope release (the PTX default, what CUTLASS' ClusterBarrier::arrive issues):
-// the only work this hand-off orders is the warp's TMEM reads, which tcgen05.wait::ld + tcgen05.fence::before_thread_sync
-// have already retired.  A cluster-scope release made ptxas emit MEMBAR.ALL.GPU + CGAERRBAR in front of every arrive
-// (10 % of the epilogue warps' stall samples in the GELU kernel).
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load of one CTA of a pair: data lands in this CTA's shared memory, the bytes are counted on the LEADER's mbarrier
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_mma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// completion of all prior MMAs of the pair arrives on the mbarrier at this shared-memory offset in BOTH CTAs
-__device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, 128B swizzle (same layouts as gemm_tc.cu)
-template <bool MN_MAJOR>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t tile_addr, int k16) {
-  uint32_t addr, lbo, sbo;
-  if (!MN_MAJOR) {
-    addr = tile_addr + (uint32_t)k16 * 32u;
-    lbo = 16;
-    sbo = 1024;
-  } else {
-    addr = tile_addr + (uint32_t)k16 * 2048u;
-    lbo = BK * 128;
-    sbo = 1024;
-  }
-  uint64_t d = 0;
-  d |= (uint64_t)((addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 // ---- epilogue math on one 16-column chunk of one row ------------------------------------------------------------
 // Semantics identical to epilogue_store<16, KIND, true> (common.cuh); the dropout key / threshold are hoisted.
-struct DropCtx {
-  bool on;
-  uint32_t thr, key;
-  float inv_keep;
-};
 template <int KIND>
 __device__ __forceinline__ void chunk_math(const Epi& ep, const DropCtx& dc, long long row, int col, float (&v)[16],
                                            float (&o2)[16], const float (&in)[16], const float (&bv)[16], bool has_bias) {
@@ -193,17 +77,14 @@ __device__ __forceinline__ void chunk_math(const Epi& ep, const DropCtx& dc, lon
   }
 }
 
-// 16-byte piece `k` (0..3) of row `lane` inside a [32][64 B] box; swz = 1: CU_TENSOR_MAP_SWIZZLE_64B
-__device__ __forceinline__ uint32_t box_off(int lane, int k, int swz) {
-  return (uint32_t)(lane * 64 + ((k ^ (swz ? ((lane >> 1) & 3) : 0)) << 4));
-}
 
 // IO32: side input and outputs are fp32 (16 columns per box); otherwise bf16 (32 columns per box)
 template <bool B_MN, int KIND, bool IO32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
-             const __grid_constant__ CUtensorMap tmIn, int M, int N, int K, int flags, Epi ep) {
+             const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmA2,
+             const __grid_constant__ CUtensorMap tmB2, int M, int N, int K, int K2, int flags, Epi ep) {
   pdl_trigger();
   // flags: bit0 epilogue boxes use the 64-byte swizzle; diagnostics (MMA_GEMM_DBG): bit8 epilogue skips TMA loads /
   // stores, bit9 no operand loads and no MMAs, bit10 operand loads but no MMAs
@@ -255,7 +136,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int tiles_n = (N + BN - 1) / BN;
   const int tiles_m = (M + 2 * BM - 1) / (2 * BM);
   const int total = tiles_m * tiles_n;
-  const int num_kb = (K + BK - 1) / BK;
+  // K2 > 0: the reduction continues over a second operand pair, C = A B^T + A2 B2^T (dh = dz1 W1 + dz2 Wg of the gated FFN)
+  const int num_kb1 = (K + BK - 1) / BK;
+  const int num_kb = num_kb1 + (K2 + BK - 1) / BK;
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
 
@@ -274,12 +157,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint32_t fb = mapa(fb_local, 0);
           const uint32_t a_dst = smem_u32(sA + stage * A_BYTES);
           const uint32_t b_dst = smem_u32(sB + stage * B_BYTES);
-          tma_load_2d_2sm(a_dst, &tmA, fb, kb * BK, m0);
+          const bool second = kb >= num_kb1;
+          const CUtensorMap* ta = second ? &tmA2 : &tmA;
+          const CUtensorMap* tb = second ? &tmB2 : &tmB;
+          const int k0 = (second ? kb - num_kb1 : kb) * BK;
+          tma_load_2d_2sm(a_dst, ta, fb, k0, m0);
           if (!B_MN) {
-            tma_load_2d_2sm(b_dst, &tmB, fb, kb * BK, nb0);
+            tma_load_2d_2sm(b_dst, tb, fb, k0, nb0);
           } else {
 #pragma unroll
-            for (int a = 0; a < (BN / 2) / 64; ++a) tma_load_2d_2sm(b_dst + a * (BK * 128), &tmB, fb, nb0 + a * 64, kb * BK);
+            for (int a = 0; a < (BN / 2) / 64; ++a) tma_load_2d_2sm(b_dst + a * (BK * 128), tb, fb, nb0 + a * 64, k0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -517,19 +404,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
 template <bool B_MN, int KIND, bool IO32>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmOut2,
-                  const CUtensorMap& tmIn, int M, int N, int K, int flags, const Epi& ep, cudaStream_t stream) {
+                  const CUtensorMap& tmIn, const CUtensorMap& tmA2, const CUtensorMap& tmB2, int M, int N, int K, int K2,
+                  int flags, const Epi& ep, cudaStream_t stream) {
   auto kern = gemm2_kernel<B_MN, KIND, IO32>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -561,7 +439,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;  // the cluster shape is a compile-time attribute of the kernel (__cluster_dims__)
-  if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmOut2, tmIn, M, N, K, flags, ep) != cudaSuccess) return MMA_ERR_LAUNCH;
+  if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmOut2, tmIn, tmA2, tmB2, M, N, K, K2, flags, ep) != cudaSuccess)
+    return MMA_ERR_LAUNCH;
   return MMA_OK;
 }
 
@@ -1137,10 +1016,11 @@ extern "C" int mma_gemm2_eligible(int a_mn, int b_mn, int M, int N, int K, const
   return tiles >= min_tiles;
 }
 
-extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long long ldb, int b_mn, int M, int N, int K,
-                              const Epi* ep, cudaStream_t stream) {
+static int gemm2_run(const void* A, long long lda, const void* B, long long ldb, const void* A2, long long lda2,
+                     const void* B2, long long ldb2, int b_mn, int M, int N, int K, int K2, const Epi* ep,
+                     cudaStream_t stream) {
   using namespace tc2;
-  if (M <= 0 || N <= 0 || K <= 0 || !ep) return MMA_ERR_ARG;
+  if (M <= 0 || N <= 0 || K <= 0 || K2 < 0 || !ep) return MMA_ERR_ARG;
   static int swz = -1, dbg = 0;
   if (swz < 0) {
     const char* e = getenv("MMA_GEMM2_SWZ");
@@ -1156,6 +1036,14 @@ extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long 
   if (!b_mn) rc = make_map(&tmB, B, (unsigned long long)K, (unsigned long long)N, ldb, BK, BN / 2);
   else rc = make_map(&tmB, B, (unsigned long long)N, (unsigned long long)K, ldb, 64, BK);
   if (rc) return rc;
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (K2 > 0) {
+    rc = make_map(&tmA2, A2, (unsigned long long)K2, (unsigned long long)M, lda2, BK, BM);
+    if (rc) return rc;
+    if (!b_mn) rc = make_map(&tmB2, B2, (unsigned long long)K2, (unsigned long long)N, ldb2, BK, BN / 2);
+    else rc = make_map(&tmB2, B2, (unsigned long long)N, (unsigned long long)K2, ldb2, 64, BK);
+    if (rc) return rc;
+  }
   const int kind = ep->kind;
   const int io32 = kind == EPI_ACCUM ? 1 : ep->out_f32;
   const unsigned bc = io32 ? 16 : 32;
@@ -1170,7 +1058,8 @@ extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long 
   if (kind == EPI_RESID) rc = make_map_ex(&tmIn, ep->resid, (unsigned long long)N, (unsigned long long)M, ep->ldr, bc, 32, io32, box_swz);
   if (kind == EPI_DGELU) rc = make_map_ex(&tmIn, ep->aux, (unsigned long long)N, (unsigned long long)M, ep->lda, bc, 32, io32, box_swz);
   if (rc) return rc;
-#define MMA_L2(BMN, KD, IO) return launch<BMN, KD, IO>(tmA, tmB, tmOut, tmOut2, tmIn, M, N, K, flags, *ep, stream)
+#define MMA_L2(BMN, KD, IO) \
+  return launch<BMN, KD, IO>(tmA, tmB, tmOut, tmOut2, tmIn, tmA2, tmB2, M, N, K, K2, flags, *ep, stream)
   if (!b_mn) {
     if (kind == EPI_STORE && !io32) MMA_L2(false, EPI_STORE, false);
     if (kind == EPI_STORE && io32) MMA_L2(false, EPI_STORE, true);
@@ -1184,6 +1073,24 @@ extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long 
   }
 #undef MMA_L2
   return MMA_ERR_UNSUPPORTED;
+}
+
+extern "C" int mma_gemm2_bf16(const void* A, long long lda, const void* B, long long ldb, int b_mn, int M, int N, int K,
+                              const Epi* ep, cudaStream_t stream) {
+  return gemm2_run(A, lda, B, ldb, nullptr, 0, nullptr, 0, b_mn, M, N, K, 0, ep, stream);
+}
+
+// C[M,N] = epi(A1 B1_op^T + A2 B2_op^T): one accumulation over two operand pairs (reduction lengths K1, K2), e.g. the
+// gated FFN's dh = dz1 W1 + dz2 Wg.  CTA-pair kernel only: MMA_ERR_UNSUPPORTED when the product is outside its envelope
+// (mma_gemm2_eligible) - the caller then runs two products with the accumulate epilogue.
+extern "C" int mma_gemm2_dual(const void* A1, long long lda1, const void* B1, long long ldb1, const void* A2,
+                              long long lda2, const void* B2, long long ldb2, int b_mn, int M, int N, int K1, int K2,
+                              const Epi* ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K1 <= 0 || K2 <= 0 || !ep || !A2 || !B2) return MMA_ERR_ARG;
+  if (!mma_gemm2_eligible(0, b_mn, M, N, K1 + K2, ep, 1)) return MMA_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A2) & 15) || ((lda2 * 2) & 15) || (reinterpret_cast<uintptr_t>(B2) & 15) || ((ldb2 * 2) & 15))
+    return MMA_ERR_UNSUPPORTED;
+  return gemm2_run(A1, lda1, B1, ldb1, A2, lda2, B2, ldb2, b_mn, M, N, K1, K2, ep, stream);
 }
 
 // Grouped wgrad (+ bias grad), CTA-pair kernel: same contract as mma_wgrad_group (gemm_tc.cu), which forwards here.

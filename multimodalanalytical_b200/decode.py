@@ -78,6 +78,7 @@ class Generator:
         self.eng = engine
         self._graphs: Dict[Any, Any] = {}
         self._states: Dict[Any, BeamState] = {}
+        engine.on_release.append(self._graphs.clear)
 
     # one decoder step for R rows; every shape is static and cur_len lives on the device
     def _step(self, st: BeamState, ctx: Dict[str, Any], extra_bias=None):
@@ -136,9 +137,13 @@ class Generator:
             if not cfg.gated_linear:
                 ops.gemm(h, eng.W(p + "linear1.weight"), R, f, d, ops.make_epi(EPI_GELU, a, bias=eng.P(p + "linear1.bias")))
             else:
-                ops.gemm(h, eng.W(p + "linear1.weight"), R, f, d, ops.make_epi(EPI_STORE, z, bias=eng.P(p + "linear1.bias")))
-                ops.gemm(h, eng.W(p + "gate.weight"), R, f, d,
-                         ops.make_epi(EPI_GLU_MUL, a, bias=eng.P(p + "gate.bias"), aux=z))
+                if not (eng.precision == "bf16" and
+                        ops.ffn_glu_fwd(h, eng.W(p + "linear1.weight"), eng.W(p + "gate.weight"), eng.P(p + "linear1.bias"),
+                                        eng.P(p + "gate.bias"), R, f, d, a)):
+                    ops.gemm(h, eng.W(p + "linear1.weight"), R, f, d,
+                             ops.make_epi(EPI_STORE, z, bias=eng.P(p + "linear1.bias")))
+                    ops.gemm(h, eng.W(p + "gate.weight"), R, f, d,
+                             ops.make_epi(EPI_GLU_MUL, a, bias=eng.P(p + "gate.bias"), aux=z))
             ops.gemm(a, eng.W(p + "linear2.weight"), R, d, f,
                      ops.make_epi(EPI_RESID, x, bias=eng.P(p + "linear2.bias"), resid=xb))
         ops.ln_fwd(x, eng.P("hf_model.decoder.norm.weight"), eng.P("hf_model.decoder.norm.bias"), h)

@@ -34,6 +34,7 @@ class Engine:
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.dev = params.device
         self._bufs: Dict[Any, torch.Tensor] = {}
+        self.on_release: List[Callable[[], None]] = []
         self.seed = 0x5EED0001
         # dropout seed lives on the device: a captured CUDA graph advances it between replays (ops.add_u64) while its
         # launch parameters stay constant (kernels dereference it: MMA_SITE_SEED_INDIRECT)
@@ -65,6 +66,15 @@ class Engine:
             self._bufs[key] = t
         return t
 
+    def release_buffers(self):
+        """Drop every shape-keyed workspace.  Captured CUDA graphs hold raw pointers into them, so every graph owner
+        (trainer, generator) registered in `on_release` drops its graphs first."""
+        for fn in self.on_release:
+            fn()
+        self._bufs.clear()
+        self.saved = {}
+        self._wq = []
+
     def sync_weights(self):
         """Refresh the bf16 mirror of the master weights (after load_state_dict / an external optimiser)."""
         if self.precision == "bf16" and self.ps.bf16_dirty:
@@ -86,6 +96,14 @@ class Engine:
     @property
     def seed_arg(self) -> int:
         return self.seed_dev.data_ptr()
+
+    def set_seed(self, seed: Optional[int], rank: int = 0):
+        """Dropout stream of this process: a function of the user's seed and the rank, so DDP ranks draw different
+        masks and two runs with different seeds differ (the reference gets both from torch's per-process generator)."""
+        base = 0x5EED0001 if seed is None else (int(seed) * 0x9E3779B97F4A7C15 + 0x5EED0001)
+        self.seed = (base + (int(rank) << 40)) & 0x7FFFFFFFFFFFFFFF
+        if self.seed_dev is not None:
+            self.seed_dev.fill_(self.seed)
 
     def next_seed(self):
         """Fresh dropout masks for the next training step (stream-ordered, graph-capturable)."""
@@ -323,10 +341,16 @@ class Engine:
                                   seed=self.seed_arg, site=site_i))
         else:
             z2 = self.buf(tag + ".z2", (M, f), T)
-            ops.gemm(h, self.W(wp["w1"]), M, f, d, ops.make_epi(EPI_STORE, z, bias=self.P(wp["b1"])))
-            ops.gemm(h, self.W(wp["wg"]), M, f, d,
-                     ops.make_epi(EPI_GLU_MUL, a, out2=z2, bias=self.P(wp["bg"]), aux=z, p_drop=p, seed=self.seed_arg,
-                                  site=site_i))
+            # both products of the gate in one CTA-pair launch (h read once, z1 never re-read); small / fp32 shapes
+            # take the two single-CTA launches
+            if not (self.precision == "bf16" and
+                    ops.ffn_glu_fwd(h, self.W(wp["w1"]), self.W(wp["wg"]), self.P(wp["b1"]), self.P(wp["bg"]), M, f, d, a,
+                                    z1=z if train else None, z2=z2 if train else None, p_drop=p, seed=self.seed_arg,
+                                    site=site_i)):
+                ops.gemm(h, self.W(wp["w1"]), M, f, d, ops.make_epi(EPI_STORE, z, bias=self.P(wp["b1"])))
+                ops.gemm(h, self.W(wp["wg"]), M, f, d,
+                         ops.make_epi(EPI_GLU_MUL, a, out2=z2, bias=self.P(wp["bg"]), aux=z, p_drop=p,
+                                      seed=self.seed_arg, site=site_i))
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
         h_next = self._resid_gemm(a, wp["w2"], wp["b2"], M, d, f, xo, x, p, site_r, nxt)
         if train:
@@ -345,13 +369,24 @@ class Engine:
             self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_STORE, dh_))
         else:
             dz2 = self.wbuf("bw.dz2", (M, f), T)
-            self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
-                          dx_epi=ops.make_epi(EPI_DGLU, dz, out2=dz2, aux=s["z"], aux2=s["z2"], p_drop=p,
-                                              seed=self.seed_arg, site=site_i, drop_ld=f))
-            # dh = dz W1 + dz2 Wg: the second product lands through the accumulate epilogue (fp32)
-            dh_ = self.buf("bw.dhs", (M, d), torch.float32)
-            self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=0))
-            self._lin_bwd(dz2, s["h"], wp["wg"], wp["bg"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=1))
+            bf = self.precision == "bf16"
+            if bf and ops.ffn_dglu(dyb, self.W(wp["w2"]), M, f, d, s["z"], s["z2"], dz, dz2, p_drop=p,
+                                   seed=self.seed_arg, site=site_i, drop_ld=f):
+                self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f)  # weight / bias gradient only
+            else:
+                self._lin_bwd(dyb, s["a"], wp["w2"], wp["b2"], M, d, f,
+                              dx_epi=ops.make_epi(EPI_DGLU, dz, out2=dz2, aux=s["z"], aux2=s["z2"], p_drop=p,
+                                                  seed=self.seed_arg, site=site_i, drop_ld=f))
+            # dh = dz W1 + dz2 Wg: one accumulation over both reductions on the pair kernel, else the second product
+            # lands through the accumulate epilogue (fp32)
+            if bf and ops.gemm_dual(dz, self.W(wp["w1"]), dz2, self.W(wp["wg"]), M, d, f, f,
+                                    ops.make_epi(EPI_STORE, dh_), b_mn=True):
+                self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d)
+                self._lin_bwd(dz2, s["h"], wp["wg"], wp["bg"], M, f, d)
+            else:
+                dh_ = self.buf("bw.dhs", (M, d), torch.float32)
+                self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=0))
+                self._lin_bwd(dz2, s["h"], wp["wg"], wp["bg"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, dh_, accumulate=1))
         dx_in = self._other_dx(dx, M)
         dyb_in = self.wbuf("bw.dyb.ffn_in", (M, d), T)
         ops.ln_bwd(dh_, s["x"], self.P(wp["n_w"]), dx=dx_in, dres=dx, dxb=dyb_in, dgamma=self.G(wp["n_w"]),

@@ -101,7 +101,59 @@ def gemm(A, B, M, N, K, epi, a_mn=False, b_mn=False, splits=1, force_simt=False,
     _count()
 
 
-# Engine-level switch for the fused residual-product + LayerNorm kernel.  Measured on B200 at the C2 shapes (CUDA-graph
+def gemm_dual(A1, B1, A2, B2, M, N, K1, K2, epi, b_mn=False):
+    """C[M,N] = epi(A1 B1_op^T + A2 B2_op^T) in one CTA-pair launch (one accumulator over both reductions).
+    Returns False (nothing launched) outside the pair kernel's envelope."""
+    _need_cuda(A1, B1, A2, B2)
+    if not all(_tc_ok(t, False, 0, 0) for t in (A1, B1, A2, B2)):
+        return False
+    rc = _lib.load().mma_gemm2_dual(A1.data_ptr(), A1.stride(0), B1.data_ptr(), B1.stride(0), A2.data_ptr(),
+                                    A2.stride(0), B2.data_ptr(), B2.stride(0), int(b_mn), M, N, K1, K2, C.byref(epi),
+                                    _stream())
+    if rc == -3:
+        return False
+    check(rc, "mma_gemm2_dual")
+    _count()
+    return True
+
+
+def ffn_glu_fwd(h, W1, Wg, b1, bg, M, N, K, a, z1=None, z2=None, p_drop=0.0, seed=0, site=0):
+    """a = drop(gelu(h W1^T + b1) * (h Wg^T + bg)) (+ saved bf16 pre-activations z1, z2) in ONE tcgen05 launch.
+    Returns False (nothing launched) outside the fused kernel's envelope."""
+    _need_cuda(h, W1, Wg, a)
+    ts = (h, W1, Wg, a) + ((z1, z2) if z1 is not None else ())
+    if not all(_tc_ok(t, False, 0, 0) for t in ts):
+        return False
+    rc = _lib.load().mma_ffn_glu_fwd(h.data_ptr(), h.stride(0), W1.data_ptr(), W1.stride(0), Wg.data_ptr(),
+                                     Wg.stride(0), b1.data_ptr(), bg.data_ptr(), M, N, K, a.data_ptr(), a.stride(0),
+                                     _p(z1), z1.stride(0) if z1 is not None else 0, _p(z2),
+                                     z2.stride(0) if z2 is not None else 0, float(p_drop), int(seed), int(site),
+                                     _stream())
+    if rc == -3:
+        return False
+    check(rc, "mma_ffn_glu_fwd")
+    _count()
+    return True
+
+
+def ffn_dglu(dy, W2, M, N, K, z1, z2, dz1, dz2, p_drop=0.0, seed=0, site=0, drop_ld=0):
+    """dz1, dz2 of the gate from dy [M, K] and linear2.weight W2 [K, N] in one CTA-pair launch; False outside the
+    kernel's envelope."""
+    _need_cuda(dy, W2, z1, z2, dz1, dz2)
+    if not all(_tc_ok(t, False, 0, 0) for t in (dy, W2, z1, z2, dz1, dz2)):
+        return False
+    rc = _lib.load().mma_ffn_dglu(dy.data_ptr(), dy.stride(0), W2.data_ptr(), W2.stride(0), M, N, K, z1.data_ptr(),
+                                  z1.stride(0), z2.data_ptr(), z2.stride(0), dz1.data_ptr(), dz1.stride(0),
+                                  dz2.data_ptr(), dz2.stride(0), float(p_drop), int(seed), int(site), int(drop_ld or N),
+                                  _stream())
+    if rc == -3:
+        return False
+    check(rc, "mma_ffn_dglu")
+    _count()
+    return True
+
+
+# Engine-level switch for the fused residual-product + LayerNorm kernel. Measured on B200 at the C2 shapes (CUDA-graph
 # timing, scripts/ln_fuse_bench.py): 26.9 vs 33.1 us for the decoder out-projection, but 43.2 vs 28.5 us for the
 # encoder FFN-2 - a CTA pair owns 256 rows x all 512 columns, so M = 9216 fills only 36 of the 74 pairs - and the
 # training step as a whole is 2.5 % slower with it.  Off by default; it pays from M ~ 32k rows upwards.

@@ -93,8 +93,8 @@ def param_specs(cfg: ModelConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
     out: List[Tuple[str, Tuple[int, ...], str]] = []
     e = "hf_model.embedding."
     for m, mc in cfg.data_config.items():
-        if mc.get("alignment"):
-            continue
+        # an alignment-target modality (`alignment: true`) also gets its layer + norm: the reference builds one for every
+        # data_config entry (modeling/utils.py:73-77) and its checkpoints carry them, although no forward pass uses them
         base = f"{e}embedding_layer_dict.{m}."
         if mc["type"] in TOKEN_TYPES:
             out.append((base + "weight", (mc["vocab_size"], d), "xavier"))
@@ -197,6 +197,7 @@ class ParamStore:
                 cfg.d_model, cfg.max_position_embeddings).to(self.device)
         self._views: Dict[Tuple[str, str], torch.Tensor] = {}
         self.bf16_dirty = True
+        self.g_dirty = False  # the gradient buffer holds leftovers of a backward run outside FusedTrainer
         self.init_parameters(seed)
 
     # -- views ---------------------------------------------------------------------------------

@@ -86,6 +86,8 @@ class GradBucketer:
 
 class FusedTrainer:
     BUCKET_ELEMS = 8 * 1024 * 1024  # 32 MB of fp32 gradients per all-reduce
+    HYPER_SLOTS = 64
+    MAX_GRAPHS = 12  # distinct input-shape signatures kept as captured steps (each owns a step's worth of workspaces)
 
     def __init__(self, module: HFWrapper, clip_grad: float = 1.0, acc_batches: int = 1, process_group=None,
                  eps: float = 1e-8, use_graph: bool = True):
@@ -100,8 +102,11 @@ class FusedTrainer:
         self.micro = 0
         dev = self.ps.device
         self.ps.ensure_optimizer_state()
-        # ring of pinned staging rows: the async H2D of step i must not be overwritten by step i+1's host writes
-        self.hyper_ring = torch.zeros(64, 9, dtype=torch.float32)
+        # ring of pinned staging rows: the async H2D of step i must not be overwritten by a later step's host writes.
+        # Graph replay lets the host run far ahead of the GPU, so every slot carries an event recorded after its copy
+        # and is only rewritten once that event has completed.
+        self.hyper_ring = torch.zeros(self.HYPER_SLOTS, 9, dtype=torch.float32)
+        self._hyper_ev: List[Any] = [None] * self.HYPER_SLOTS
         if dev.type == "cuda":
             self.hyper_ring = self.hyper_ring.pin_memory()
         self.hyper = torch.zeros(9, dtype=torch.float32, device=dev)
@@ -112,7 +117,9 @@ class FusedTrainer:
         # graph together with the kernels; MMA_DDP_GRAPH=0 falls back to eager launches
         self.graph_ddp = os.environ.get("MMA_DDP_GRAPH", "1") != "0"
         self._sync_now = False
+        self._flush_next = False  # fit(): the last batch of an epoch steps the optimiser even inside a partial window
         self.eng.grad_ready_hook = self._on_grads_ready
+        self.eng.on_release.append(self._graphs.clear)
 
     def _dist(self):
         return torch.distributed.is_available() and torch.distributed.is_initialized() and \
@@ -163,8 +170,14 @@ class FusedTrainer:
         Adam) is captured once per input-shape signature and replayed."""
         m = self.m
         m.train()
+        if self.ps.g_dirty:  # a backward through the autograd path (HFWrapper.forward + loss.backward()) left gradients
+            self.ps.g.zero_()
+            self.ps.g_dirty = False
         self.micro += 1
-        self._sync_now = (self.micro % self.acc) == 0
+        self._sync_now = (self.micro % self.acc) == 0 or self._flush_next
+        self._flush_next = False
+        if self._sync_now:
+            self.micro = 0
         if self.bucketer is not None:
             self.bucketer.reset()
         # a tuple is a batch already in the engine's layout (pipeline.DeviceDataset.collate)
@@ -183,14 +196,21 @@ class FusedTrainer:
         key = tuple((n, tuple(t.shape), t.dtype) for n, t in flat)
         ent = self._graphs.get(key)
         if ent is None:
-            # first sight of this shape: run it eagerly (allocates workspaces, builds tensor maps), keep the inputs as
-            # the static buffers of the graph captured on the next step of this shape
-            loss = self._step_body(inputs)
+            # first sight of this shape: run it eagerly (allocates workspaces, builds tensor maps) on PRIVATE copies of
+            # the inputs, which become the static buffers of the graph captured on the next step of this shape (the
+            # caller's tensors are never adopted or written to)
+            if len(self._graphs) >= self.MAX_GRAPHS:
+                # captured graphs hold raw pointers into the engine's shape-keyed workspaces, so eviction is
+                # all-or-nothing: drop every graph, then every workspace
+                torch.cuda.synchronize()
+                self.eng.release_buffers()
+            static = self._clone_inputs(inputs)
+            loss = self._step_body(static)
             self._write_hyper()
             self._optimizer_kernels()
             self.opt_step += 1
-            self._graphs[key] = {"static": inputs, "graph": None, "loss": None}
-            return loss
+            self._graphs[key] = {"static": static, "graph": None, "loss": None}
+            return loss.clone()
         for (_, dst), (_, src) in zip(self._flat(ent["static"]), flat):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
@@ -207,7 +227,16 @@ class FusedTrainer:
         ent["graph"].replay()
         ops.LAUNCHES += ent["launches"]  # kernels executed by the replay
         self.opt_step += 1
-        return ent["loss"]
+        return ent["loss"].clone()  # the graph's loss buffer is overwritten by the next replay
+
+    @staticmethod
+    def _clone_inputs(inputs):
+        def cl(v):
+            if isinstance(v, dict):
+                return {k: cl(t) for k, t in v.items()}
+            return v.clone()
+
+        return tuple(cl(v) for v in inputs)
 
     def _write_hyper(self):
         """Stage this optimiser step's scalars (OneCycle lr / beta1, bias corrections, clip, grad scale) on the device."""
@@ -216,12 +245,19 @@ class FusedTrainer:
         if m.num_steps <= 0:
             lr, beta1 = m.lr, m.adam_beta1
         t = self.opt_step + 1
-        h = self.hyper_ring[self.opt_step % 64]
+        slot = self.opt_step % self.HYPER_SLOTS
+        if self._hyper_ev[slot] is not None:
+            self._hyper_ev[slot].synchronize()  # the copy that last read this slot has executed
+        h = self.hyper_ring[slot]
         h[0], h[1], h[2], h[3], h[4] = lr, beta1, m.adam_beta2, self.eps, m.weight_decay
         h[5], h[6] = 1.0 - beta1 ** t, 1.0 - m.adam_beta2 ** t
         h[7] = self.clip_grad if self.clip_grad else 0.0
         h[8] = 1.0 / (self.world * self.acc)
         self.hyper.copy_(h, non_blocking=True)
+        if self.hyper.is_cuda:
+            ev = self._hyper_ev[slot] or torch.cuda.Event()
+            ev.record()
+            self._hyper_ev[slot] = ev
 
     def _optimizer_kernels(self):
         ps = self.ps
@@ -245,11 +281,20 @@ class FusedTrainer:
         for ep in range(epochs):
             if hasattr(batches, "set_epoch"):  # pipeline.DeviceLoader / samplers: new shuffle per epoch
                 batches.set_epoch(ep)
-            for i, batch in enumerate(batches):
+            # Lightning steps the optimiser on the last batch of every epoch even when the accumulation window is not
+            # full (ceil(batches / acc) optimiser steps per epoch = what calculate_training_steps gives OneCycleLR):
+            # look one batch ahead so the last one is known
+            it = iter(batches)
+            nxt = next(it, None)
+            i = 0
+            while nxt is not None:
+                batch, nxt = nxt, next(it, None)
+                self._flush_next = nxt is None
                 loss = self.train_step(batch, i)
                 if log and step % log_every == 0:
                     log(f"epoch {ep} step {step} train_loss {float(loss):.4f}")
                 step += 1
+                i += 1
         return step
 
 

@@ -59,17 +59,38 @@ class CustomLMOutput:
 
 
 class _EngineLoss(torch.autograd.Function):
-    """Connects the engine's hand-scheduled backward to `loss.backward()` (what Lightning calls)."""
+    """Connects the engine's hand-scheduled backward to `loss.backward()` (what Lightning / a plain torch loop calls).
+
+    Every exposed `nn.Parameter` is an INPUT of this node, so autograd delivers one gradient per parameter through the
+    parameter's own AccumulateGrad node: `.grad` is populated / accumulated by autograd itself (it survives
+    `optimizer.zero_grad(set_to_none=True)`, which Lightning issues before every backward), gradient accumulation over
+    micro-batches adds up, and a stock `DistributedDataParallel` wrapper sees its per-parameter hooks fire and
+    all-reduces the gradients as it does for any module (reference: Lightning DDP, trainer/trainer.py:58-71).  The
+    engine writes into its (freshly zeroed) flat gradient buffer; the node returns views of ONE flat copy of it (a
+    177 MB device copy at d_model 512, ~0.05 ms)."""
 
     @staticmethod
-    def forward(ctx, anchor, loss_value, engine):
-        ctx.engine = engine
+    def forward(ctx, loss_value, module, *params):
+        ctx.module = module
         return loss_value.detach().clone().reshape(())
 
     @staticmethod
     def backward(ctx, grad_out):
-        ctx.engine.backward(gscale=float(grad_out))
-        return torch.zeros(1, device=grad_out.device), None, None
+        m = ctx.module
+        store = m.store
+        store.g.zero_()
+        m.engine.backward(gscale=float(grad_out))
+        flat = store.g.clone()
+        store.g_dirty = True  # holds this backward's gradients (read by tests / diagnostics); FusedTrainer re-zeroes
+        store.bf16_dirty = True  # an optimiser outside the engine is about to change the master weights
+        grads = []
+        for name in m._names:
+            off, shape = store.offsets[name]
+            n = 1
+            for x in shape:
+                n *= x
+            grads.append(flat[off: off + n].view(shape))
+        return (None, None, *grads)
 
 
 class B200CustomModel:
@@ -118,6 +139,14 @@ def load_custom_model(model_name: str, target_tokenizer, target_modality: str, d
     store = ParamStore(cfg, device=device, seed=seed)
     engine = Engine(cfg, store, precision=precision)
     return B200CustomModel(cfg, store, engine), store
+
+
+def _dist_rank() -> int:
+    import os
+
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank()
+    return int(os.environ.get("RANK", "0"))
 
 
 def _unsupported(name):
@@ -175,16 +204,15 @@ class HFWrapper(_Base):
             eos_token_id=target_tokenizer.eos_token_id, forced_eos_token_id=target_tokenizer.eos_token_id,
             max_length=128, pad_token_id=target_tokenizer.pad_token_id)
         self.n_beams = kwargs.get("n_beams", 10)
-        # parameters exposed to torch / Lightning are views of the flat master buffer; their .grad are views of
-        # the flat gradient buffer the engine's backward accumulates into
+        # parameters exposed to torch / Lightning / DDP are views of the flat master buffer; their gradients arrive
+        # through autograd (`_EngineLoss`)
         self._flat = nn.ParameterDict()
         self._names: List[str] = []
         for name, _, _ in self.store.specs:
-            prm = nn.Parameter(self.store.P(name), requires_grad=True)
-            prm.grad = self.store.G(name)
-            self._flat[name.replace(".", "|")] = prm
+            self._flat[name.replace(".", "|")] = nn.Parameter(self.store.P(name), requires_grad=True)
             self._names.append(name)
-        self._anchor = torch.zeros(1, device=self.store.device, requires_grad=True)
+        # dropout stream: a function of the user's seed and of the rank (DDP ranks must draw different masks)
+        self.engine.set_seed(kwargs.get("seed"), _dist_rank())
 
     # --------------------------------------------------------------------------- checkpoint layout
     def state_dict(self, *args, destination=None, prefix="", keep_vars=False, **kw):  # noqa: D401
@@ -212,6 +240,10 @@ class HFWrapper(_Base):
     def optimizer_step(self, *a, **k):  # Lightning hook: master weights changed -> bf16 mirror is stale
         self.store.bf16_dirty = True
         return super().optimizer_step(*a, **k) if hasattr(super(), "optimizer_step") else None
+
+    def named_gradients(self) -> Dict[str, Optional[torch.Tensor]]:
+        """{checkpoint name: .grad} of the exposed parameters (what a torch optimiser / DDP reducer sees)."""
+        return {n: self._flat[n.replace(".", "|")].grad for n in self._names}
 
     # -------------------------------------------------------------------------------------- forward
     def _to_dev(self, t):
@@ -255,7 +287,7 @@ class HFWrapper(_Base):
                                   align_target=align_target)
         loss = out["loss"]
         if train:
-            loss = _EngineLoss.apply(self._anchor, loss, self.engine)
+            loss = _EngineLoss.apply(loss, self, *[self._flat[n.replace(".", "|")] for n in self._names])
         loss_dict = {"model_only_loss": out["lm_loss"], "alignment_loss": out["align_loss"]}
         return CustomLMOutput(loss=loss, logits=out["logits"], loss_dict=loss_dict,
                               encoder_hidden_states=out["memory"])

@@ -6,7 +6,7 @@ import torch
 from oracle import spectra_oracle as orc
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv")
+CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality")
 
 
 def load_case(name):
@@ -15,7 +15,7 @@ def load_case(name):
 
 def oracle_cfg(fx):
     mk = fx["model_kwargs"]
-    target = [m for m, c in fx["data_config"].items() if c["target"]][0]
+    target = [m for m, c in fx["data_config"].items() if c["target"] and not c.get("alignment")][0]
     return orc.OracleConfig(
         d_model=mk["d_model"],
         encoder_layers=mk["encoder_layers"],

@@ -12,7 +12,7 @@ from tests.helpers import load_case
 
 def cfg_from(fx):
     mk = fx["model_kwargs"]
-    tgt = [m for m, c in fx["data_config"].items() if c["target"]][0]
+    tgt = [m for m, c in fx["data_config"].items() if c["target"] and not c.get("alignment")][0]
     return ModelConfig(data_config=fx["data_config"], vocab_size=fx["data_config"][tgt]["vocab_size"],
                        d_model=mk["d_model"], encoder_layers=mk["encoder_layers"], decoder_layers=mk["decoder_layers"],
                        encoder_attention_heads=mk["encoder_attention_heads"],
@@ -22,7 +22,7 @@ def cfg_from(fx):
                        max_position_embeddings=mk["max_position_embeddings"], align_config=mk.get("align_config"))
 
 
-@pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned", "align_conv"])
+@pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality"])
 def test_param_store_has_reference_checkpoint_layout(name):
     fx = load_case(name)
     ps = ParamStore(cfg_from(fx), device="cpu")

@@ -169,6 +169,74 @@ def test_gemm_pair_kernel(M, N, K):
             assert torch.equal(x1 == 0, x2 == 0)
 
 
+@pytest.mark.parametrize("M,N,K", [(16384, 2048, 512), (9216, 2048, 512), (12300, 1040, 200), (2560, 2048, 512),
+                                   (25472, 3072, 768)])
+def test_ffn_glu_pair_kernels(M, N, K):
+    """Gated FFN on the CTA-pair path (gemm_glu2.cu): the fused W1 | Wg forward, the DGLU dgrad and the two-reduction
+    dh product against torch autograd of gelu(h W1^T + b1) * (h Wg^T + bg); with dropout against the single-CTA
+    kernels' masks and values."""
+    dt, tol = torch.bfloat16, 1e-2
+    F = torch.nn.functional
+    h = _rand(M, K, dtype=dt)
+    W1, Wg = _rand(N, K, dtype=dt, scale=K ** -0.5, seed=1), _rand(N, K, dtype=dt, scale=K ** -0.5, seed=2)
+    b1, bg = _rand(N, seed=3), _rand(N, seed=4)
+    a, z1, z2 = (torch.empty(M, N, device=DEV, dtype=dt) for _ in range(3))
+    assert ops.ffn_glu_fwd(h, W1, Wg, b1, bg, M, N, K, a, z1=z1, z2=z2)
+    r1 = h.float() @ W1.float().T + b1
+    r2 = h.float() @ Wg.float().T + bg
+    assert rel(z1.float(), r1) < tol and rel(z2.float(), r2) < tol
+    assert rel(a.float(), F.gelu(r1) * r2) < tol
+    a_inf = torch.empty_like(a)
+    assert ops.ffn_glu_fwd(h, W1, Wg, b1, bg, M, N, K, a_inf)  # inference form: no saved pre-activations
+    assert torch.equal(a_inf, a)
+    # dropout: mask identical to the EPI_GLU_MUL epilogue of the single-CTA kernel (same seed / site / index)
+    ad, zs, ad2, z2b = (torch.empty(M, N, device=DEV, dtype=dt) for _ in range(4))
+    assert ops.ffn_glu_fwd(h, W1, Wg, b1, bg, M, N, K, ad, p_drop=0.1, seed=321, site=9)
+    ops.gemm(h, W1, M, N, K, ops.make_epi(EPI_STORE, zs, bias=b1), max_ctas=148)
+    ops.gemm(h, Wg, M, N, K, ops.make_epi(EPI_GLU_MUL, ad2, out2=z2b, bias=bg, aux=zs, p_drop=0.1, seed=321, site=9),
+             max_ctas=148)
+    assert torch.equal(ad == 0, ad2 == 0)
+    assert rel(ad.float(), ad2.float()) < 2e-2
+    keep = (ad != 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.01
+
+    # backward through the gate: dy [M, Kd] @ W2 [Kd, N]
+    Kd = K
+    dy = _rand(M, Kd, dtype=dt, seed=5)
+    W2 = _rand(Kd, N, dtype=dt, scale=N ** -0.5, seed=6)
+    dz1, dz2 = torch.empty(M, N, device=DEV, dtype=dt), torch.empty(M, N, device=DEV, dtype=dt)
+    assert ops.ffn_dglu(dy, W2, M, N, Kd, z1, z2, dz1, dz2)
+    da = dy.float() @ W2.float()
+    zf1, zf2 = z1.float().requires_grad_(True), z2.float().requires_grad_(True)
+    (F.gelu(zf1) * zf2).backward(da)
+    assert rel(dz1.float(), zf1.grad) < tol and rel(dz2.float(), zf2.grad) < tol
+    e1, e2, f1, f2 = (torch.empty(M, N, device=DEV, dtype=dt) for _ in range(4))
+    assert ops.ffn_dglu(dy, W2, M, N, Kd, z1, z2, e1, e2, p_drop=0.1, seed=321, site=9, drop_ld=N)
+    ops.gemm(dy, W2, M, N, Kd, ops.make_epi(EPI_DGLU, f1, out2=f2, aux=z1, aux2=z2, p_drop=0.1, seed=321, site=9,
+                                            drop_ld=N), b_mn=True, max_ctas=148)
+    assert torch.equal(e2 == 0, f2 == 0) and torch.equal(e2 == 0, ad == 0)  # backward mask == forward mask
+    assert rel(e1.float(), f1.float()) < 2e-2 and rel(e2.float(), f2.float()) < 2e-2
+
+    # dh = dz1 W1 + dz2 Wg in one accumulation (W1 / Wg are [N, K] = [reduction, out]: MN-major B operands)
+    dh = torch.empty(M, K, device=DEV, dtype=dt)
+    ok = ops.gemm_dual(dz1, W1, dz2, Wg, M, K, N, N, ops.make_epi(EPI_STORE, dh), b_mn=True)
+    tiles = ((M + 255) // 256) * ((K + 255) // 256)
+    assert ok == (K >= 256 and tiles >= 48)
+    if ok:
+        assert rel(dh.float(), dz1.float() @ W1.float() + dz2.float() @ Wg.float()) < tol
+
+
+def test_ffn_glu_pair_kernels_decline_small_or_misaligned():
+    dt = torch.bfloat16
+    h, W = _rand(64, 512, dtype=dt), _rand(2048, 512, dtype=dt)
+    b = _rand(2048)
+    a = torch.empty(64, 2048, device=DEV, dtype=dt)
+    assert not ops.ffn_glu_fwd(h, W, W, b, b, 64, 2048, 512, a)  # too few rows for the pair kernel
+    h2, W3 = _rand(4096, 512, dtype=dt), _rand(2040, 512, dtype=dt)
+    a2 = torch.empty(4096, 2040, device=DEV, dtype=dt)
+    assert not ops.ffn_glu_fwd(h2, W3, W3, b[:2040], b[:2040], 4096, 2040, 512, a2)  # N % 16 != 0
+
+
 @pytest.mark.parametrize("M,K", [(16384, 512), (9216, 2048), (12300, 512), (640, 512)])
 def test_gemm_resid_layernorm_fused(M, K):
     """x_new = resid + drop(A W^T + b) and h = LN(x_new) in one launch (gemm2_ln_kernel) against torch; with dropout

@@ -30,7 +30,7 @@ class FakeTokenizer:
 def build(fx, precision, **over):
     mk = dict(fx["model_kwargs"])
     mk.update(over)
-    tgt = [m for m, c in fx["data_config"].items() if c["target"]][0]
+    tgt = [m for m, c in fx["data_config"].items() if c["target"] and not c.get("alignment")][0]
     tok = FakeTokenizer(fx["data_config"][tgt]["vocab_size"])
     m = HFWrapper(data_config=fx["data_config"], target_tokenizer=tok, num_steps=100, precision=precision, **mk)
     m.load_state_dict(fx["state_dict"])
@@ -53,7 +53,7 @@ def oracle_grads(fx):
     return out, {k: v.grad for k, v in leaves.items() if v.grad is not None}
 
 
-CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv")
+CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality")
 
 
 @pytest.mark.parametrize("name", CASES)
