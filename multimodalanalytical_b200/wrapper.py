@@ -15,6 +15,7 @@ The module subclasses `pytorch_lightning.LightningModule` when Lightning is impo
 """
 from __future__ import annotations
 
+import dataclasses
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -44,15 +45,17 @@ except Exception:  # noqa: BLE001
         """Stand-in used when omegaconf is absent; pass `ListConfig([...])` to enable modality dropout."""
 
 
+@dataclasses.dataclass
 class CustomLMOutput:
-    """Same fields the callers read from the reference's CustomLMOutput (modeling/utils.py:25-30)."""
+    """Same fields the callers read from the reference's CustomLMOutput (modeling/utils.py:25-30).  A dataclass, so
+    that a DistributedDataParallel wrapper finds the loss tensor in the module's output (it walks lists, dicts and
+    dataclasses when `find_unused_parameters=True`, the reference's strategy) as it does in HF's ModelOutput."""
 
-    def __init__(self, loss, logits, loss_dict, encoder_hidden_states=None, decoder_hidden_states=None):
-        self.loss = loss
-        self.logits = logits
-        self.loss_dict = loss_dict
-        self.encoder_hidden_states = encoder_hidden_states
-        self.decoder_hidden_states = decoder_hidden_states
+    loss: Any = None
+    logits: Any = None
+    loss_dict: Any = None
+    encoder_hidden_states: Any = None
+    decoder_hidden_states: Any = None
 
     def __getitem__(self, k):
         return getattr(self, k)
@@ -213,6 +216,7 @@ class HFWrapper(_Base):
             self._names.append(name)
         # dropout stream: a function of the user's seed and of the rank (DDP ranks must draw different masks)
         self.engine.set_seed(kwargs.get("seed"), _dist_rank())
+        self.engine_seed_probe = self.engine.seed  # diagnostics / tests: differs across ranks
 
     # --------------------------------------------------------------------------- checkpoint layout
     def state_dict(self, *args, destination=None, prefix="", keep_vars=False, **kw):  # noqa: D401
