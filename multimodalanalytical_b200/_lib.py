@@ -48,7 +48,7 @@ def _stale():
     if not os.path.exists(LIBPATH):
         return True
     t = os.path.getmtime(LIBPATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
