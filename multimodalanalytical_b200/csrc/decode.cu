@@ -12,6 +12,8 @@
 //                       per spectrum; emits next tokens + parent rows and rewrites the ancestor table.
 //   * greedy_step       argmax decoding (n_beams == 1), transformers' `_sample` semantics.
 // All kernels read the current length from device memory so one CUDA graph replays for every step.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace dec {
@@ -23,6 +25,7 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict
                                                            const float* __restrict__ pos, const int* __restrict__ cur_len,
                                                            float* __restrict__ out, int rows, int d) {
   pdl_trigger();
+  pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const int t = *cur_len - 1;
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(256) decode_embed_kernel(const int* __restrict
 struct AttnArgs {
   const void* q; long long ldq;      // [R, ldq], head h at h*DH
   const void* knew; const void* vnew; long long ldkv;   // self: this step's K/V rows [R, ldkv]
-  void* kc; void* vc;                // self: cache [Lmax][R][d];  cross: memory K / V [B][S][ldm] (head offset applied)
+  void* kc; void* vc;                // self: cache [R][Lmax][d];  cross: memory K / V [B][S][ldm] (head offset applied)
   long long ldm;                     // cross: row pitch of memory K/V
   const int* anc;                    // self: [2][R][Lmax] ancestor rows, buffer cur_len&1 is live (nullptr: identity)
   const unsigned char* kmask;        // cross: [B][S]
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
     // append this step's K/V for (r, h) at position t, then attend over t+1 positions
     if (lane < G) {
       float tmp[8];
-      const long long dst = ((long long)t * a.R + r) * a.d + h * DH + lane * 8;
+      const long long dst = ((long long)r * a.Lmax + t) * a.d + h * DH + lane * 8;
       ld8(reinterpret_cast<const T*>(a.knew) + (long long)r * a.ldkv + h * DH + lane * 8, tmp);
       st8(reinterpret_cast<T*>(a.kc) + dst, tmp);
       ld8(reinterpret_cast<const T*>(a.vnew) + (long long)r * a.ldkv + h * DH + lane * 8, tmp);
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
     nkeys = t + 1;
     Kb = reinterpret_cast<const T*>(a.kc) + h * DH + sub * 8;
     Vb = reinterpret_cast<const T*>(a.vc) + h * DH + sub * 8;
-    pitch = (long long)a.R * a.d;  // per position
+    pitch = a.d;  // cache [R][Lmax][d]: a row's positions are contiguous (see decode_self_attn2_kernel)
     // the beam step ping-pongs the ancestor table on cur_len parity: [2][R][Lmax]
     anc = a.anc ? a.anc + ((long long)((t + 1) & 1) * a.R + r) * a.Lmax : nullptr;
   } else {
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(AttnArgs a) {
     if (j < nkeys) {
       if (!a.cross) {
         const int src = (j == t || !anc) ? r : anc[j];
-        off = (long long)j * pitch + (long long)src * a.d;
+        off = ((long long)src * a.Lmax + j) * pitch;
       } else {
         off = (long long)j * pitch;
       }
@@ -258,6 +261,7 @@ constexpr int MAXK = 64;  // beams (2K candidates <= 128)
 
 __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
   pdl_trigger();
+  pdl_wait();
   extern __shared__ uint32_t cand[];  // [K*V] ordered keys of accumulated log-probs
   __shared__ float s_lse[MAXK];
   __shared__ unsigned long long s_wkeys[8 * 2 * MAXK];  // per-warp top-2K keys
@@ -487,6 +491,7 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
                                                           const int* __restrict__ g_cur, const int* __restrict__ g_tgt,
                                                           const unsigned* __restrict__ g_tok, int g_na, int g_ncheck) {
   pdl_trigger();
+  pdl_wait();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= R) return;
   const int cur = *cur_len;
@@ -556,7 +561,149 @@ __global__ void __launch_bounds__(256) guided_mask_kernel(float* __restrict__ sc
 }
 
 __global__ void advance_kernel(int* cur_len) {
-  pdl_trigger(); *cur_len += 1; }
+  pdl_trigger();
+  pdl_wait();
+  *cur_len += 1;
+}
+
+// Self-attention of one decode step, bf16 / head dim 64: one CTA per (row, group of 4 heads).
+// A cached key row is gathered ONCE for the four heads (a 512-byte coalesced read, lane = (head, 16-byte chunk)): the
+// ancestor look-up and the address arithmetic - most of the instructions of the one-warp-per-(row, head) kernel above
+// (ncu: 2 500 warp instructions per (row, head) at 64 positions of which 256 were FMAs) - are shared by the heads.
+// The CTA's 4 warps walk interleaved chunks of 8 positions (split-K over the history) with a per-chunk online softmax:
+// the 8 key gathers of a chunk are independent loads in flight together, then its 8 value gathers; the partial
+// (max, sum, output) states of the warps are merged through shared memory.
+constexpr int SA_KC = 8;  // positions per chunk
+__global__ void __launch_bounds__(128) decode_self_attn2_kernel(AttnArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int DH = 64;
+  __shared__ float s_m[4][32], s_l[4][32], s_o[4][32][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x;
+  const int col = blockIdx.y * (4 * DH) + lane * 8;  // this lane's 8 columns: head = col / 64
+  const int t = *a.cur_len - 1;
+  const int nkeys = t + 1;
+  const bf16* kc = reinterpret_cast<const bf16*>(a.kc) + col;
+  const bf16* vc = reinterpret_cast<const bf16*>(a.vc) + col;
+  const bf16* knew = reinterpret_cast<const bf16*>(a.knew) + (long long)r * a.ldkv + col;
+  const bf16* vnew = reinterpret_cast<const bf16*>(a.vnew) + (long long)r * a.ldkv + col;
+  const long long rowpitch = (long long)a.Lmax * a.d;  // cache layout [R][Lmax][d]
+  if (warp == 0) {  // append this step's K / V of (r, these heads) at position t; position t is read from knew / vnew
+    const long long dst = (long long)r * rowpitch + (long long)t * a.d;
+    *reinterpret_cast<uint4*>(const_cast<bf16*>(kc) + dst) = *reinterpret_cast<const uint4*>(knew);
+    *reinterpret_cast<uint4*>(const_cast<bf16*>(vc) + dst) = *reinterpret_cast<const uint4*>(vnew);
+  }
+  float qreg[8];
+  ld8(reinterpret_cast<const bf16*>(a.q) + (long long)r * a.ldq + col, qreg);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) qreg[c] *= a.scale;
+  const int* anc = a.anc ? a.anc + ((long long)((t + 1) & 1) * a.R + r) * a.Lmax : nullptr;
+
+  float m = -INFINITY, l = 0.f, o[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) o[c] = 0.f;
+  if (warp == 3) {
+    // position t (this step's own key / value, still in registers of the projection output): the initial state of the
+    // warp that gets the fewest chunks
+    float kx[8];
+    ld8(knew, kx);
+    float sv = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sv = fmaf(qreg[c], kx[c], sv);
+    sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+    sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+    sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+    m = sv;
+    l = 1.f;
+    ld8(vnew, o);
+  }
+  // cached positions j < t; offsets are 32-bit element indices into one layer's cache (checked on the host)
+  const unsigned rp = (unsigned)a.Lmax * (unsigned)a.d, dd = (unsigned)a.d;
+  for (int j0 = warp * SA_KC; j0 < t; j0 += 4 * SA_KC) {
+    int src[SA_KC];
+    if (anc) {
+      const int4 a0 = *reinterpret_cast<const int4*>(anc + j0), a1 = *reinterpret_cast<const int4*>(anc + j0 + 4);
+      src[0] = a0.x; src[1] = a0.y; src[2] = a0.z; src[3] = a0.w;
+      src[4] = a1.x; src[5] = a1.y; src[6] = a1.z; src[7] = a1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < SA_KC; ++i) src[i] = r;
+    }
+    unsigned off[SA_KC];
+    uint4 raw[SA_KC];
+#pragma unroll
+    for (int i = 0; i < SA_KC; ++i) {
+      // positions past the history read the last cached one (always a valid address) and get weight 0 below
+      const int j = min(j0 + i, t - 1);
+      const int sr = j0 + i < t ? src[i] : r;
+      off[i] = (unsigned)sr * rp + (unsigned)j * dd;
+      raw[i] = *reinterpret_cast<const uint4*>(kc + off[i]);
+    }
+    float sc[SA_KC];
+    float cm = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < SA_KC; ++i) {
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float2 f = __bfloat1622float2(hp[w]);
+        s0 = fmaf(qreg[2 * w], f.x, s0);
+        s1 = fmaf(qreg[2 * w + 1], f.y, s1);
+      }
+      float sv = s0 + s1;
+      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+      sc[i] = j0 + i < t ? sv : -INFINITY;
+      cm = fmaxf(cm, sc[i]);
+    }
+    // value gathers of the chunk go out before the softmax arithmetic needs them
+#pragma unroll
+    for (int i = 0; i < SA_KC; ++i) raw[i] = *reinterpret_cast<const uint4*>(vc + off[i]);
+    const float mn = fmaxf(m, cm);  // finite: the chunk holds at least one valid position
+    const float corr = __expf(m - mn);
+    l *= corr;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] *= corr;
+#pragma unroll
+    for (int i = 0; i < SA_KC; ++i) {
+      const float pw = __expf(sc[i] - mn);  // exp(-inf) = 0 for positions past the history
+      l += pw;
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float2 f = __bfloat1622float2(hp[w]);
+        o[2 * w] = fmaf(pw, f.x, o[2 * w]);
+        o[2 * w + 1] = fmaf(pw, f.y, o[2 * w + 1]);
+      }
+    }
+    m = mn;
+  }
+  s_m[warp][lane] = m;
+  s_l[warp][lane] = l;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s_o[warp][lane][c] = o[c];
+  __syncthreads();
+  if (warp == 0) {
+    float M = fmaxf(fmaxf(s_m[0][lane], s_m[1][lane]), fmaxf(s_m[2][lane], s_m[3][lane]));
+    float L = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float f = __expf(s_m[w][lane] - M);  // a warp without chunks has m = -inf: weight 0
+      L = fmaf(s_l[w][lane], f, L);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = fmaf(s_o[w][lane][c], f, o[c]);
+    }
+    const float inv = L > 0.f ? 1.f / L : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] *= inv;
+    st8(reinterpret_cast<bf16*>(a.o) + (long long)r * a.ldo + col, o);
+  }
+}
 
 template <typename T>
 static int launch_attn(const AttnArgs& a, int dh, cudaStream_t s) {
@@ -580,7 +727,8 @@ extern "C" int mma_decode_embed(const int* tok, const float* table, const float*
                                 const float* pos, const int* cur_len, float* out, int rows, int d,
                                 cudaStream_t stream) {
   if (rows <= 0) return MMA_ERR_ARG;
-  decode_embed_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(tok, table, gamma, beta, eps, pos, cur_len, out, rows, d);
+  launch_rowop(decode_embed_kernel, dim3((rows + 7) / 8), dim3(256), 0, stream, tok, table, gamma, beta, eps, pos, cur_len, out,
+               rows, d);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }
@@ -593,6 +741,20 @@ extern "C" int mma_decode_self_attn(const void* q, long long ldq, const void* kn
   a.q = q; a.ldq = ldq; a.knew = knew; a.vnew = vnew; a.ldkv = ldkv; a.kc = kcache; a.vc = vcache; a.anc = anc;
   a.cur_len = cur_len; a.o = o; a.ldo = ldo; a.R = R; a.H = H; a.d = H * dh; a.Lmax = Lmax; a.scale = scale;
   a.cross = 0; a.beams = 1;
+  const bool anc_ok = !anc || (reinterpret_cast<uintptr_t>(anc) & 15) == 0;
+  static int v2 = -1;
+  if (v2 < 0) {
+    const char* e = getenv("MMA_DECODE_ATTN2");
+    v2 = e ? atoi(e) : 1;
+  }
+  if (v2 && type == MMA_BF16 && dh == 64 && (H % 4) == 0 && (Lmax % 8) == 0 && R > 0 && anc_ok &&
+      (unsigned long long)R * Lmax * H * dh < 4294967296ull && (ldq % 8) == 0 && (ldkv % 8) == 0 && (ldo % 8) == 0 &&
+      (reinterpret_cast<uintptr_t>(q) & 15) == 0 && (reinterpret_cast<uintptr_t>(knew) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(vnew) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    launch_rowop(decode_self_attn2_kernel, dim3(R, H / 4), dim3(128), 0, stream, a);
+    MMA_CHECK_LAUNCH();
+    return MMA_OK;
+  }
   return type == MMA_F32 ? launch_attn<float>(a, dh, stream) : launch_attn<bf16>(a, dh, stream);
 }
 
@@ -621,7 +783,7 @@ extern "C" int mma_beam_step_ex(const float* logits, long long ldl, const float*
   const size_t smem = sizeof(uint32_t) * (size_t)K * V;
   if (smem > 200 * 1024) return MMA_ERR_UNSUPPORTED;
   if (smem > 40 * 1024) cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  beam_step_kernel<<<B, 256, smem, stream>>>(a);
+  launch_rowop(beam_step_kernel, dim3(B), dim3(256), smem, stream, a);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }
@@ -642,9 +804,8 @@ extern "C" int mma_greedy_step_ex(const float* logits, long long ldl, const floa
   if (R < 1) return MMA_ERR_ARG;
   if (g_cur && (!g_tgt || !g_tok_atoms || n_atoms < 1 || n_atoms > 29 || n_check < 0 || n_check > n_atoms))
     return MMA_ERR_ARG;
-  greedy_step_kernel<<<(R + 7) / 8, 256, 0, stream>>>(logits, ldl, extra_bias, R, V, L, pad_id, eos_id, cur_len, seq,
-                                                      unfinished, next_tok, prenorm, g_cur, g_tgt, g_tok_atoms,
-                                                      n_atoms, n_check);
+  launch_rowop(greedy_step_kernel, dim3((R + 7) / 8), dim3(256), 0, stream, logits, ldl, extra_bias, R, V, L, pad_id, eos_id,
+               cur_len, seq, unfinished, next_tok, prenorm, g_cur, g_tgt, g_tok_atoms, n_atoms, n_check);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }
@@ -677,7 +838,7 @@ extern "C" int mma_guided_mask(float* scores, long long lds, int R, int V, int e
 }
 
 extern "C" int mma_advance(int* cur_len, cudaStream_t stream) {
-  advance_kernel<<<1, 1, 0, stream>>>(cur_len);
+  launch_rowop(advance_kernel, dim3(1), dim3(1), 0, stream, cur_len);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

@@ -92,6 +92,7 @@ struct LnFwdArgs {
 template <int NI>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(LnFwdArgs a) {
   pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.rows) return;
   const long long r = warp;
@@ -525,11 +526,11 @@ extern "C" int mma_ln_fwd(const void* x, int x_f32, long long ldx, const float* 
               rows, d, group > 0 ? group : rows, out_group_stride, out_offset};
   const int ni = (d + 127) / 128;
   const int blocks = (rows + 7) / 8;
-  if (ni <= 1) ln_fwd_kernel<1><<<blocks, 256, 0, stream>>>(a);
-  else if (ni <= 2) ln_fwd_kernel<2><<<blocks, 256, 0, stream>>>(a);
-  else if (ni <= 4) ln_fwd_kernel<4><<<blocks, 256, 0, stream>>>(a);
-  else if (ni <= 6) ln_fwd_kernel<6><<<blocks, 256, 0, stream>>>(a);
-  else ln_fwd_kernel<8><<<blocks, 256, 0, stream>>>(a);
+  if (ni <= 1) launch_rowop(ln_fwd_kernel<1>, dim3(blocks), dim3(256), 0, stream, a);
+  else if (ni <= 2) launch_rowop(ln_fwd_kernel<2>, dim3(blocks), dim3(256), 0, stream, a);
+  else if (ni <= 4) launch_rowop(ln_fwd_kernel<4>, dim3(blocks), dim3(256), 0, stream, a);
+  else if (ni <= 6) launch_rowop(ln_fwd_kernel<6>, dim3(blocks), dim3(256), 0, stream, a);
+  else launch_rowop(ln_fwd_kernel<8>, dim3(blocks), dim3(256), 0, stream, a);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

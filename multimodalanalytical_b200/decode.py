@@ -12,6 +12,7 @@ is captured once in a CUDA graph and replayed for all 127 steps.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, Optional
 
 import torch
@@ -19,6 +20,13 @@ import torch
 from . import ops
 from ._lib import EPI_GELU, EPI_GLU_MUL, EPI_RESID, EPI_STORE
 from .model import Engine
+
+
+# Residual products of the decode step fused with the LayerNorm that follows them (mma_gemm2_resid_ln): opt-in
+# (MMA_DECODE_FUSE_LN=1 every residual product, 2 only the K = d_model ones).  Measured on B200 at 2560 rows (256 spectra x
+# 10 beams): 1.75 ms / step fused against 1.58 ms with separate launches - a CTA pair owns 256 rows x all 512 columns, so
+# only 10 pairs work.
+FUSE_DECODE_LN = int(os.environ.get("MMA_DECODE_FUSE_LN", "0"))
 
 
 class BeamState:
@@ -115,38 +123,46 @@ class Generator:
         z = eng.buf("g.z", (R, f), T)
         xa = eng.buf("g.xa", (R, d), torch.float32)
         xb = eng.buf("g.xb", (R, d), torch.float32)
-        for i in range(cfg.decoder_layers):
+        bf = eng.precision == "bf16"
+
+        def resid_ln(a_in, wname, bname, k_in, resid, out, gname, bename):
+            """out = resid + a_in W^T + b and h = LayerNorm(out) with the NEXT sub-layer's norm: one CTA-pair launch when
+            the fused kernel applies (bf16, d_model 512, >= 256 rows), else the product followed by the LayerNorm."""
+            epi = ops.make_epi(EPI_RESID, out, bias=eng.P(bname), resid=resid)
+            if not (bf and (FUSE_DECODE_LN == 1 or (FUSE_DECODE_LN == 2 and k_in <= d)) and
+                    ops.gemm_resid_ln(a_in, eng.W(wname), R, d, k_in, epi, eng.P(gname), eng.P(bename), h)):
+                ops.gemm(a_in, eng.W(wname), R, d, k_in, epi)
+                ops.ln_fwd(out, eng.P(gname), eng.P(bename), h)
+
+        L_ = cfg.decoder_layers
+        ops.ln_fwd(x, eng.P("hf_model.decoder.layers.0.norm1.weight"), eng.P("hf_model.decoder.layers.0.norm1.bias"), h)
+        for i in range(L_):
             p = f"hf_model.decoder.layers.{i}."
-            ops.ln_fwd(x, eng.P(p + "norm1.weight"), eng.P(p + "norm1.bias"), h)
             ops.gemm(h, eng.W(p + "self_attn.in_proj_weight"), R, 3 * d, d,
                      ops.make_epi(EPI_STORE, qkv, bias=eng.P(p + "self_attn.in_proj_bias")))
             ops.decode_self_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx["kc"][i], ctx["vc"][i], st.anc,
                                  st.cur_len, att, R, H, dh, L)
-            ops.gemm(att, eng.W(p + "self_attn.out_proj.weight"), R, d, d,
-                     ops.make_epi(EPI_RESID, xa, bias=eng.P(p + "self_attn.out_proj.bias"), resid=x))
-            ops.ln_fwd(xa, eng.P(p + "norm2.weight"), eng.P(p + "norm2.bias"), h)
+            resid_ln(att, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", d, x, xa,
+                     p + "norm2.weight", p + "norm2.bias")
             ops.gemm(h, eng.W(p + "multihead_attn.in_proj_weight")[:d], R, d, d,
                      ops.make_epi(EPI_STORE, q, bias=eng.P(p + "multihead_attn.in_proj_bias")[:d]))
             kv = ctx["kvmem"][i]
             # the K beams of a spectrum attend over the same memory: one (spectrum, head) problem with K queries on
             # the tensor-core forward-attention kernel (K/V are read once per spectrum, not once per beam)
             ops.attn_fwd(q, kv[:, :d], kv[:, d:], att, None, st.B, H, K, ctx["S"], dh, kmask=ctx["enc_mask"])
-            ops.gemm(att, eng.W(p + "multihead_attn.out_proj.weight"), R, d, d,
-                     ops.make_epi(EPI_RESID, xb, bias=eng.P(p + "multihead_attn.out_proj.bias"), resid=xa))
-            ops.ln_fwd(xb, eng.P(p + "norm3.weight"), eng.P(p + "norm3.bias"), h)
+            resid_ln(att, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", d, xa, xb,
+                     p + "norm3.weight", p + "norm3.bias")
             if not cfg.gated_linear:
                 ops.gemm(h, eng.W(p + "linear1.weight"), R, f, d, ops.make_epi(EPI_GELU, a, bias=eng.P(p + "linear1.bias")))
             else:
-                if not (eng.precision == "bf16" and
-                        ops.ffn_glu_fwd(h, eng.W(p + "linear1.weight"), eng.W(p + "gate.weight"), eng.P(p + "linear1.bias"),
-                                        eng.P(p + "gate.bias"), R, f, d, a)):
+                if not (bf and ops.ffn_glu_fwd(h, eng.W(p + "linear1.weight"), eng.W(p + "gate.weight"),
+                                               eng.P(p + "linear1.bias"), eng.P(p + "gate.bias"), R, f, d, a)):
                     ops.gemm(h, eng.W(p + "linear1.weight"), R, f, d,
                              ops.make_epi(EPI_STORE, z, bias=eng.P(p + "linear1.bias")))
                     ops.gemm(h, eng.W(p + "gate.weight"), R, f, d,
                              ops.make_epi(EPI_GLU_MUL, a, bias=eng.P(p + "gate.bias"), aux=z))
-            ops.gemm(a, eng.W(p + "linear2.weight"), R, d, f,
-                     ops.make_epi(EPI_RESID, x, bias=eng.P(p + "linear2.bias"), resid=xb))
-        ops.ln_fwd(x, eng.P("hf_model.decoder.norm.weight"), eng.P("hf_model.decoder.norm.bias"), h)
+            nxt = f"hf_model.decoder.layers.{i + 1}.norm1." if i + 1 < L_ else "hf_model.decoder.norm."
+            resid_ln(a, p + "linear2.weight", p + "linear2.bias", f, xb, x, nxt + "weight", nxt + "bias")
         V = cfg.vocab_size
         logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
         ops.gemm(h, eng.W("hf_model.token_ff.weight"), R, V, d,
@@ -184,8 +200,8 @@ class Generator:
             p = f"hf_model.decoder.layers.{i}.multihead_attn."
             ops.gemm(mem, eng.W(p + "in_proj_weight")[d:], B * S, 2 * d, d,
                      ops.make_epi(EPI_STORE, kvmem[i], bias=eng.P(p + "in_proj_bias")[d:]))
-        kc = eng.buf("g.kc", (cfg.decoder_layers, L, R, d), T)
-        vc = eng.buf("g.vc", (cfg.decoder_layers, L, R, d), T)
+        kc = eng.buf("g.kc", (cfg.decoder_layers, R, L, d), T)
+        vc = eng.buf("g.vc", (cfg.decoder_layers, R, L, d), T)
         pos = eng._pos_rows(L, "g")
         ctx = dict(kvmem=kvmem, kc=kc, vc=vc, pos=pos, enc_mask=mask_buf, S=S)
 

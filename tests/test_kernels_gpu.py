@@ -214,7 +214,11 @@ def test_ffn_glu_pair_kernels(M, N, K):
     assert ops.ffn_dglu(dy, W2, M, N, Kd, z1, z2, e1, e2, p_drop=0.1, seed=321, site=9, drop_ld=N)
     ops.gemm(dy, W2, M, N, Kd, ops.make_epi(EPI_DGLU, f1, out2=f2, aux=z1, aux2=z2, p_drop=0.1, seed=321, site=9,
                                             drop_ld=N), b_mn=True, max_ctas=148)
-    assert torch.equal(e2 == 0, f2 == 0) and torch.equal(e2 == 0, ad == 0)  # backward mask == forward mask
+    assert torch.equal(e2 == 0, f2 == 0)
+    # backward mask == forward mask, wherever the un-dropped values are not exactly zero themselves (one fp32 sum in
+    # ~1e8 cancels its bias exactly)
+    nz = (a != 0) & (dz2 != 0)
+    assert torch.equal((e2 == 0) & nz, (ad == 0) & nz)
     assert rel(e1.float(), f1.float()) < 2e-2 and rel(e2.float(), f2.float()) < 2e-2
 
     # dh = dz1 W1 + dz2 Wg in one accumulation (W1 / Wg are [N, K] = [reduction, out]: MN-major B operands)

@@ -24,41 +24,79 @@ if torch.cuda.is_available():
     from tests.test_model_gpu import build, oracle_grads
 
 
-def _hyp_sets(seqs, K):
-    rows = [tuple(t for t in r if t not in (0, 3)) for r in seqs.tolist()]
-    return [rows[i * K:(i + 1) * K] for i in range(len(rows) // K)]
+def _teacher_forced_fp32_logits(m32, batch, seqs, K):
+    """fp32 logits [rows, L-1, V] of the fp32 engine for the given hypotheses (row b*K + r belongs to spectrum b)."""
+    def rep(t):
+        return t.repeat_interleave(K, dim=1) if K > 1 else t
+    enc = {k: ({kk: rep(vv) for kk, vv in v.items()} if isinstance(v, dict) else rep(v))
+           for k, v in batch["encoder_input"].items()}
+    seqs = seqs.cpu()
+    tb = {"encoder_input": enc, "encoder_pad_mask": rep(batch["encoder_pad_mask"]),
+          "decoder_input": {m32.target_modality: seqs[:, :-1].T.contiguous()},
+          "decoder_pad_mask": torch.zeros(seqs.shape[1] - 1, seqs.shape[0], dtype=torch.bool),
+          "target": seqs[:, 1:].T.contiguous()}
+    m32.eval()
+    with torch.no_grad():
+        return m32.forward(tb).logits.float().cpu()
 
 
 @pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned"])
-def test_bf16_decode_agrees_with_fp32_decode(name):
-    """bf16 decode kernels (decode_attn<bf16>, the bf16 GEMMs, tcgen05 cross-attention over the beams of a spectrum)
-    against the fp32 path with the same weights: greedy tokens, the beam hypothesis sets and their length-normalised
-    scores.  The fp32 path itself is token-identical to the reference (test_model_gpu.py)."""
+def test_bf16_decode_is_epsilon_optimal_under_fp32_scoring(name):
+    """bf16 decode kernels (decode self-attention over the K/V cache, the bf16 GEMMs, tcgen05 cross-attention over the beams
+    of a spectrum) judged by the fp32 engine, which is token-identical to the reference (test_model_gpu.py).  Sequences
+    cannot be compared token by token - one near-tie flips the rest of a greedy row - so the fp32 model re-scores what
+    bf16 decoded (teacher forcing): every greedy choice must be within the bf16 logit tolerance of the fp32 arg-max, every
+    beam hypothesis' kernel-reported score must equal its fp32 length-normalised log-probability, and the best bf16
+    hypothesis must score (in fp32) within tolerance of the best fp32 hypothesis."""
     fx = load_case(name)
     K = 10 if name == "c1_ir_tiny" else 4
+    eos = 3
     m32, m16 = build(fx, "fp32"), build(fx, "bf16")
     m32.eval()
     m16.eval()
-    g32 = m32.generate(fx["batch"], n_beams=1).cpu()
+    # ---- greedy
     g16 = m16.generate(fx["batch"], n_beams=1).cpu()
-    L = max(g32.shape[1], g16.shape[1])
-    pad = lambda t: torch.nn.functional.pad(t, (0, L - t.shape[1]))  # noqa: E731
-    same_rows = (pad(g32) == pad(g16)).all(dim=1).float().mean().item()
-    assert same_rows >= 0.75, f"greedy: only {same_rows:.2f} of the rows identical"
+    lg = _teacher_forced_fp32_logits(m32, fx["batch"], g16, 1)
+    worst, checked = 0.0, 0
+    forced = m16.generation_config["max_length"] - 2  # ForcedEOS: the token at max_length - 1 is not a choice
+    for r in range(g16.shape[0]):
+        for i in range(min(g16.shape[1] - 1, forced)):
+            tok = int(g16[r, i + 1])
+            row = lg[r, i]
+            worst = max(worst, float(row.max() - row[tok]) / float(row.abs().max()))
+            checked += 1
+            if tok == eos:
+                break
+    assert checked > g16.shape[0] and worst < 2e-2, f"greedy: a bf16 choice is {worst:.4f} (relative logit gap) below the fp32 arg-max"
+    # ---- beam search
     s32, sc32 = m32.generate(fx["batch"], n_beams=K, return_scores=True)
     s16, sc16 = m16.generate(fx["batch"], n_beams=K, return_scores=True)
-    h32, h16 = _hyp_sets(s32.cpu(), K), _hyp_sets(s16.cpu(), K)
-    sc32, sc16 = sc32.cpu().view(-1, K), sc16.cpu().view(-1, K)
-    top1 = sum(a[0] == b[0] for a, b in zip(h32, h16)) / len(h32)
-    overlap, dscore = [], []
-    for b, (a, c) in enumerate(zip(h32, h16)):
-        common = set(a) & set(c)
-        overlap.append(len(common) / K)
-        for hyp in common:
-            dscore.append(abs(float(sc32[b, a.index(hyp)]) - float(sc16[b, c.index(hyp)])))
-    assert top1 >= 0.75, f"best hypothesis identical for {top1:.2f} of the spectra"
-    assert sum(overlap) / len(overlap) >= 0.8, f"hypothesis-set overlap {sum(overlap) / len(overlap):.2f}"
-    assert max(dscore) < 2e-2, f"score of a shared hypothesis differs by {max(dscore):.4f}"
+    s16, sc16, sc32 = s16.cpu(), sc16.cpu(), sc32.cpu()
+    lp = torch.log_softmax(_teacher_forced_fp32_logits(m32, fx["batch"], s16, K), dim=-1)
+    fp32_score = torch.full((s16.shape[0],), float("nan"))
+    for r in range(s16.shape[0]):
+        tot, n = 0.0, 0
+        for i in range(s16.shape[1] - 1):
+            tok = int(s16[r, i + 1])
+            tot += float(lp[r, i, tok]) if i < forced else 0.0  # a forced <eos> scores log-probability 0
+            n += 1
+            if tok == eos:
+                fp32_score[r] = tot / n
+                break
+    fin = ~torch.isnan(fp32_score) & (sc16 > -1e8)
+    assert fin.float().mean() > 0.5, "too few finished hypotheses to compare"
+    dmax = float((fp32_score[fin] - sc16[fin]).abs().max())
+    assert dmax < 5e-2, f"kernel-reported bf16 score differs from the fp32 re-score by {dmax:.4f}"
+    best16 = fp32_score.view(-1, K)[:, 0]
+    best32 = sc32.view(-1, K)[:, 0]
+    ok = ~torch.isnan(best16)
+    gap = float((best32[ok] - best16[ok]).max())
+    assert gap < 5e-2, f"best bf16 hypothesis scores {gap:.4f} below the best fp32 hypothesis (fp32 scoring)"
+    same_best = sum(tuple(a) == tuple(b) for a, b in zip(s32.cpu().view(-1, K, s32.shape[1])[:, 0].tolist(),
+                                                         s16.view(-1, K, s16.shape[1])[:, 0].tolist())
+                    if len(a) == len(b))
+    print(f"{name}: greedy worst rel. logit gap {worst:.4f}; beam score |d| max {dmax:.4f}; best-hypothesis gap {gap:.4f}; "
+          f"identical best hypothesis for {same_best} spectra")
 
 
 def test_topk_accuracy_on_bundled_rows_unchanged_in_bf16():
