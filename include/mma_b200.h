@@ -217,6 +217,19 @@ int mma_adam_step(float* p, float* g, float* m, float* v, void* p_bf16, long lon
 
 int mma_add_u64(unsigned long long* p, unsigned long long inc, cudaStream_t stream);
 
+/* ---- data-parallel optimiser step over NVLink peer memory (replaces Lightning DDP's NCCL all-reduce + the replicated
+ * optimiser step, trainer/trainer.py:58-71, wrapper.py:329-344): reduce-scatter of the gradients by P2P loads, Adam on
+ * this rank's shard of the fp32 master weights / moments, bf16 weights written into every peer's mirror by P2P stores.
+ * The `peer_*` arguments are HOST arrays of `world` device pointers (symmetric allocations, index = rank); the barrier's
+ * flag arrays are int[16] per rank, zero-initialised, `epoch_ctr` a zero-initialised device int.  Sequence per step:
+ * barrier, reduce_shard, barrier, adam_shard, barrier.                                                              */
+int mma_p2p_barrier(const void* const* peer_flags, int* epoch_ctr, int world, int rank, cudaStream_t stream);
+int mma_p2p_reduce_shard(const void* const* peer_g, int world, int rank, long long lo, long long hi, float* workspace,
+                         float* sumsq_out, cudaStream_t stream);
+int mma_p2p_adam_shard(float* p, float* g, float* m, float* v, const void* const* peer_pb, const void* const* peer_sumsq,
+                       int world, int rank, long long n, long long lo, long long hi, const float* hyper, int decoupled,
+                       cudaStream_t stream);
+
 /* ---- KV-cached decoding (replaces transformers generate(use_cache=False), wrapper.py:443-451) ---------------- */
 int mma_decode_embed(const int* tok, const float* table, const float* gamma, const float* beta, float eps,
                      const float* pos, const int* cur_len, float* out, int rows, int d, cudaStream_t stream);

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_glu2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "decode.cu", "align.cu", "collate.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_glu2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "ddp_p2p.cu", "decode.cu", "align.cu", "collate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -141,6 +141,9 @@ _SIGS = {
     "mma_grad_norm": [_vp, _ll, _vp, _vp, _vp],
     "mma_adam_step": [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _vp],
     "mma_add_u64": [_vp, _ull, _vp],
+    "mma_p2p_barrier": [_vp, _vp, _i, _i, _vp],
+    "mma_p2p_reduce_shard": [_vp, _i, _i, _ll, _ll, _vp, _vp, _vp],
+    "mma_p2p_adam_shard": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp, _i, _vp],
     "mma_decode_embed": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp],
     "mma_decode_self_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
     "mma_decode_cross_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp],

@@ -462,6 +462,30 @@ def adam_step(p, g, m, v, p_bf16, hyper, norm=None, decoupled=True, zero_grad=Tr
     _count()
 
 
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(x) for x in ptrs])
+
+
+def p2p_barrier(peer_flags, epoch_ctr, world, rank):
+    """Cross-GPU barrier over flag words in symmetric memory (peer_flags: the ranks' device pointers)."""
+    check(_lib.load().mma_p2p_barrier(_ptr_array(peer_flags), epoch_ctr.data_ptr(), world, rank, _stream()),
+          "mma_p2p_barrier")
+    _count()
+
+
+def p2p_reduce_shard(peer_g, world, rank, lo, hi, workspace, sumsq_out):
+    check(_lib.load().mma_p2p_reduce_shard(_ptr_array(peer_g), world, rank, lo, hi, workspace.data_ptr(),
+                                           sumsq_out.data_ptr(), _stream()), "mma_p2p_reduce_shard")
+    _count(2)
+
+
+def p2p_adam_shard(p, g, m, v, peer_pb, peer_sumsq, world, rank, lo, hi, hyper, decoupled=True):
+    check(_lib.load().mma_p2p_adam_shard(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr_array(peer_pb),
+                                         _ptr_array(peer_sumsq), world, rank, p.numel(), lo, hi, hyper.data_ptr(),
+                                         int(decoupled), _stream()), "mma_p2p_adam_shard")
+    _count()
+
+
 def add_u64(t, inc=1):
     """t: int64 device scalar holding the dropout seed; advanced on the stream (graph-capturable)."""
     check(_lib.load().mma_add_u64(t.data_ptr(), int(inc), _stream()), "mma_add_u64")

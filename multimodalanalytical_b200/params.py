@@ -198,6 +198,7 @@ class ParamStore:
         self._views: Dict[Tuple[str, str], torch.Tensor] = {}
         self.bf16_dirty = True
         self.g_dirty = False  # the gradient buffer holds leftovers of a backward run outside FusedTrainer
+        self.shard: Optional[Tuple[int, int]] = None  # [lo, hi) of the master weights this rank's optimiser owns
         self.init_parameters(seed)
 
     # -- views ---------------------------------------------------------------------------------
@@ -221,6 +222,34 @@ class ParamStore:
 
     def has(self, name):
         return name in self.offsets
+
+    def rebind(self, g: Optional[torch.Tensor] = None, pb: Optional[torch.Tensor] = None):
+        """Move the gradient buffer / bf16 mirror into caller-provided storage of the same size (symmetric memory that
+        peer GPUs can address: trainer.PeerShardedStep).  Contents are carried over; cached views are rebuilt."""
+        for kind, new in (("g", g), ("pb", pb)):
+            if new is None:
+                continue
+            old = getattr(self, kind)
+            if new.numel() != old.numel() or new.dtype != old.dtype:
+                raise ValueError(f"rebind({kind}): expected {old.numel()} x {old.dtype}")
+            new.copy_(old)
+            setattr(self, kind, new)
+            for key in [k for k in self._views if k[0] == kind]:
+                del self._views[key]
+
+    def gather_master(self, process_group=None):
+        """Reassemble the fp32 master weights (and Adam moments) on every rank after rank-sharded optimiser steps
+        (`self.shard` = this rank's [lo, hi)): checkpoints / state_dict() need the full tensors."""
+        if self.shard is None:
+            return
+        lo, hi = self.shard
+        for buf in (self.p, self.m, self.v):
+            if buf is None:
+                continue
+            keep = buf[lo:hi].clone()
+            buf.zero_()
+            buf[lo:hi] = keep
+            torch.distributed.all_reduce(buf, group=process_group)
 
     def ensure_optimizer_state(self):
         if self.m is None:

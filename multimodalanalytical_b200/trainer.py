@@ -38,6 +38,9 @@ def one_cycle(step: int, total_steps: int, max_lr: float, pct_start: float = 0.3
     return cos(max_lr, min_lr, pct), cos(base_momentum, max_momentum, pct)
 
 
+DDP_DEFAULT = "nccl"
+
+
 class GradBucketer:
     """Back-to-front bucketed all-reduce of a flat gradient buffer.
 
@@ -84,6 +87,52 @@ class GradBucketer:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
 
 
+class PeerShardedStep:
+    """Gradient reduction + optimiser step over NVLink peer memory (csrc/ddp_p2p.cu): barrier -> each rank sums ITS shard
+    of the gradients from all peers -> barrier -> Adam on the shard, bf16 weights stored into every peer's mirror ->
+    barrier.  The gradient buffer, the bf16 mirror, the partial-norm slot and the barrier flags live in symmetric memory
+    (`torch.distributed._symmetric_memory`: torch allocates and exchanges the handles - plumbing; every byte on the data
+    path is moved by this repo's kernels).  Master weights and Adam moments are sharded by rank afterwards
+    (`ParamStore.gather_master` reassembles them for checkpoints)."""
+
+    def __init__(self, store, process_group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        pg = process_group if process_group is not None else torch.distributed.group.WORLD
+        self.pg = pg
+        self.world, self.rank = torch.distributed.get_world_size(pg), torch.distributed.get_rank(pg)
+        dev, n = store.device, store.numel
+        self.g = symm.empty(n, dtype=torch.float32, device=dev)
+        self.pb = symm.empty(n, dtype=torch.bfloat16, device=dev)
+        self.flags = symm.empty(16, dtype=torch.int32, device=dev).zero_()
+        self.sumsq = symm.empty(4, dtype=torch.float32, device=dev).zero_()
+        name = pg.group_name
+        self.peer_g = list(symm.rendezvous(self.g, name).buffer_ptrs)
+        self.peer_pb = list(symm.rendezvous(self.pb, name).buffer_ptrs)
+        self.peer_flags = list(symm.rendezvous(self.flags, name).buffer_ptrs)
+        self.peer_sumsq = list(symm.rendezvous(self.sumsq, name).buffer_ptrs)
+        store.rebind(g=self.g, pb=self.pb)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ws = torch.zeros(1024, dtype=torch.float32, device=dev)
+        per = -(-n // self.world)
+        per = (per + 127) // 128 * 128
+        self.lo, self.hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+        store.shard = (self.lo, self.hi)
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=pg)  # every rank's flags are zeroed before the first device-side barrier
+
+    def barrier(self):
+        ops.p2p_barrier(self.peer_flags, self.epoch, self.world, self.rank)
+
+    def step(self, store, hyper, decoupled: bool):
+        self.barrier()
+        ops.p2p_reduce_shard(self.peer_g, self.world, self.rank, self.lo, self.hi, self.ws, self.sumsq)
+        self.barrier()
+        ops.p2p_adam_shard(store.p, store.g, store.m, store.v, self.peer_pb, self.peer_sumsq, self.world, self.rank,
+                           self.lo, self.hi, hyper, decoupled=decoupled)
+        self.barrier()
+
+
 class FusedTrainer:
     BUCKET_ELEMS = 8 * 1024 * 1024  # 32 MB of fp32 gradients per all-reduce
     HYPER_SLOTS = 64
@@ -112,7 +161,16 @@ class FusedTrainer:
         self.hyper = torch.zeros(9, dtype=torch.float32, device=dev)
         self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.norm_ws = torch.zeros(1024, dtype=torch.float32, device=dev)
-        self.bucketer = GradBucketer(self.ps.g, self.BUCKET_ELEMS, process_group) if self.world > 1 else None
+        # multi-GPU gradient exchange: "p2p" = reduce-scatter + sharded Adam + bf16 all-gather by this repo's kernels over
+        # NVLink peer memory (bf16 engines; needs clipping semantics of the global norm: kept), "nccl" = bucketed NCCL
+        # all-reduce overlapped with backward + replicated Adam
+        self.ddp_mode = os.environ.get("MMA_DDP", DDP_DEFAULT)
+        if self.eng.precision != "bf16" or dev.type != "cuda":
+            self.ddp_mode = "nccl"
+        self.peer = None
+        if self.world > 1 and self.ddp_mode == "p2p":
+            self.peer = PeerShardedStep(self.ps, process_group)
+        self.bucketer = GradBucketer(self.ps.g, self.BUCKET_ELEMS, process_group) if self.world > 1 and self.peer is None else None
         # multi-GPU: the bucketed NCCL all-reduces (forked onto the side stream) are captured into the step's CUDA
         # graph together with the kernels; MMA_DDP_GRAPH=0 falls back to eager launches
         self.graph_ddp = os.environ.get("MMA_DDP_GRAPH", "1") != "0"
@@ -261,6 +319,10 @@ class FusedTrainer:
 
     def _optimizer_kernels(self):
         ps = self.ps
+        if self.peer is not None:
+            self.peer.step(ps, self.hyper, decoupled=(self.m.optimiser == "adamw"))
+            ps.bf16_dirty = False
+            return
         if self.bucketer is not None:
             self.bucketer.finish(also_wait=self.eng.last_wgrad_event)
         norm = None

@@ -220,6 +220,7 @@ class HFWrapper(_Base):
 
     # --------------------------------------------------------------------------- checkpoint layout
     def state_dict(self, *args, destination=None, prefix="", keep_vars=False, **kw):  # noqa: D401
+        self.store.gather_master()  # no-op unless the optimiser state is sharded by rank (trainer.PeerShardedStep)
         sd = self.store.state_dict(with_aliases=True)
         out = destination if destination is not None else {}
         for k, v in sd.items():
