@@ -24,6 +24,7 @@ sys.path.insert(0, ROOT)
 
 SEED = 3247
 PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+SWEEP_B, SWEEP_K = "1,8,32,128,256,512,1024", "10,30"
 C2 = dict(B=256, S_formula=15, P=21, ps=75, T=64, V=200, d=512, layers=6, heads=8, ffn=2048)
 
 
@@ -397,6 +398,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "last_loss": last_loss,
     }
+    if world > 1:
+        line["gradient_exchange"] = ("peer-memory reduce-scatter + rank-sharded Adam + bf16 all-gather (own kernels over NVLink)"
+                                     if trainer.peer is not None else "bucketed NCCL all-reduce overlapped with backward")
     # a >= 2.5 s leg: the 20-step headline lasts ~0.15 s, i.e. it runs in the GPU's burst regime
     n_long = max(args.steps, int(2.5 / (t_dev / args.steps)) + 1)
     t_long, _, clocks_long, _ = timed(dev_batches, n_long, 0, e2e=False)
@@ -412,8 +416,10 @@ def run_ours(args):
     if not args.no_configs:
         cfgs = bench_train_configs(["c2_paper", "c3", "c4"], min(args.steps, 10), world, rank, dd)
     if not args.no_decode and not args.no_sweep:
-        sweep = bench_decode_sweep(world, rank, dd, [int(x) for x in args.sweep_batches.split(",")],
-                                   [int(x) for x in args.sweep_beams.split(",")])
+        sb, sk = [int(x) for x in args.sweep_batches.split(",")], [int(x) for x in args.sweep_beams.split(",")]
+        if world > 1 and args.sweep_batches == SWEEP_B and args.sweep_beams == SWEEP_K:
+            sb, sk = [1, 256], [10]  # the full curve is a single-GPU measurement; N GPUs decode N independent shards
+        sweep = bench_decode_sweep(world, rank, dd, sb, sk)
     if rank == 0:
         line["clocks"] = clocks
         tf, t_k, shape = time_dominant_gemm(model.engine, c, B)
@@ -726,8 +732,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the C2-paper / C3 / C4 training legs")
     ap.add_argument("--no-sweep", action="store_true", help="skip the C5 decode batch x beams sweep")
-    ap.add_argument("--sweep-batches", default="1,8,32,128,256,512,1024")
-    ap.add_argument("--sweep-beams", default="10,30")
+    ap.add_argument("--sweep-batches", default=SWEEP_B)
+    ap.add_argument("--sweep-beams", default=SWEEP_K)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -161,10 +161,15 @@ __global__ void __launch_bounds__(256) adam_shard_kernel(float* __restrict__ p, 
     u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
     u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
     for (int q = 0; q < world; ++q) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(pb.p[q]) + e) = u;
+    // consumed: the next step accumulates into a clean gradient buffer
+    *reinterpret_cast<float4*>(g + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(g + e + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // next step accumulates into a clean gradient buffer (remote reads of it ended at the barrier before this kernel)
-  const long long n4 = n >> 2;
-  for (long long i = tid; i < n4; i += nth) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the rest of this rank's gradient buffer (the peers' shards; their remote reads ended at the barrier before this
+  // kernel).  Only OUTSIDE [lo, hi): other threads of this grid may still be reading shard elements.
+  const long long n4 = n >> 2, lo4 = lo >> 2, hi4 = hi >> 2;
+  for (long long i = tid; i < n4; i += nth)
+    if (i < lo4 || i >= hi4) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 static int fill(Peers& P, const void* const* ptrs, int world) {

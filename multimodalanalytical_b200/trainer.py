@@ -38,7 +38,7 @@ def one_cycle(step: int, total_steps: int, max_lr: float, pct_start: float = 0.3
     return cos(max_lr, min_lr, pct), cos(base_momentum, max_momentum, pct)
 
 
-DDP_DEFAULT = "nccl"
+DDP_DEFAULT = "p2p"  # MMA_DDP=nccl: bucketed NCCL all-reduce overlapped with backward + replicated Adam
 
 
 class GradBucketer:
@@ -107,10 +107,32 @@ class PeerShardedStep:
         self.flags = symm.empty(16, dtype=torch.int32, device=dev).zero_()
         self.sumsq = symm.empty(4, dtype=torch.float32, device=dev).zero_()
         name = pg.group_name
-        self.peer_g = list(symm.rendezvous(self.g, name).buffer_ptrs)
-        self.peer_pb = list(symm.rendezvous(self.pb, name).buffer_ptrs)
-        self.peer_flags = list(symm.rendezvous(self.flags, name).buffer_ptrs)
-        self.peer_sumsq = list(symm.rendezvous(self.sumsq, name).buffer_ptrs)
+        self._remote = []  # keeps the peers' mapped views alive
+
+        def peers(t):
+            hdl = symm.rendezvous(t, name)
+            out = []
+            for r in range(self.world):
+                if r == self.rank:
+                    out.append(t.data_ptr())
+                else:  # the peer's copy of THIS tensor (its offset inside the symmetric allocation included)
+                    rt = hdl.get_remote_tensor(r, tuple(t.shape), t.dtype)
+                    self._remote.append(rt)
+                    out.append(rt.data_ptr())
+            return out
+
+        self.peer_g, self.peer_pb = peers(self.g), peers(self.pb)
+        self.peer_flags, self.peer_sumsq = peers(self.flags), peers(self.sumsq)
+        # address check before any kernel trusts the table: every rank publishes its id, every rank reads every peer's
+        self.sumsq.fill_(float(self.rank + 1))
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=pg)
+        for rt_rank, rt in zip([r for r in range(self.world) if r != self.rank], self._remote[-(self.world - 1):]):
+            got = float(rt[0].item())
+            if got != float(rt_rank + 1):
+                raise RuntimeError(f"peer-memory address table is wrong: rank {rt_rank} slot reads {got}")
+        torch.distributed.barrier(group=pg)
+        self.sumsq.zero_()
         store.rebind(g=self.g, pb=self.pb)
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
         self.ws = torch.zeros(1024, dtype=torch.float32, device=dev)
@@ -169,7 +191,20 @@ class FusedTrainer:
             self.ddp_mode = "nccl"
         self.peer = None
         if self.world > 1 and self.ddp_mode == "p2p":
-            self.peer = PeerShardedStep(self.ps, process_group)
+            # every rank must take the same path: agree on whether the symmetric allocation + address exchange worked
+            ok = torch.ones(1, device=dev)
+            try:
+                self.peer = PeerShardedStep(self.ps, process_group)
+            except Exception as exc:  # noqa: BLE001  (no peer access / no symmetric-memory support on this system)
+                import warnings
+
+                warnings.warn(f"peer-memory optimiser step unavailable ({exc!r}); using the NCCL all-reduce path")
+                ok.zero_()
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=process_group)
+            if float(ok) == 0.0:
+                if self.peer is not None:
+                    self.ps.shard = None
+                self.peer, self.ddp_mode = None, "nccl"
         self.bucketer = GradBucketer(self.ps.g, self.BUCKET_ELEMS, process_group) if self.world > 1 and self.peer is None else None
         # multi-GPU: the bucketed NCCL all-reduces (forked onto the side stream) are captured into the step's CUDA
         # graph together with the kernels; MMA_DDP_GRAPH=0 falls back to eager launches

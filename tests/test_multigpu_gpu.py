@@ -9,6 +9,7 @@
 """
 import os
 import socket
+import time
 
 import pytest
 import torch
@@ -49,17 +50,22 @@ def _worker(rank, world, port, q, mode):
             loss = tr.train_step(mine, i)
         torch.cuda.synchronize()
         out = {"loss": float(loss), "m": m.store.m.cpu(), "p": m.store.p.cpu()}
-    elif mode in ("p2p", "nccl"):
-        os.environ["MMA_DDP"] = mode
-        m = _model("bf16", bench)
-        tr = FusedTrainer(m, clip_grad=1.0)
-        assert (tr.peer is not None) == (mode == "p2p")
-        for i in range(3):  # eager step, graph capture, one replay (device-side barriers inside the graph)
-            loss = tr.train_step(mine, i)
-        torch.cuda.synchronize()
-        sd = m.state_dict()  # p2p: reassembles the rank-sharded master weights
-        out = {"loss": float(loss), "m": m.store.m.cpu(), "p": m.store.p.cpu(), "pb": m.store.pb.float().cpu(),
-               "w": sd["hf_model.token_ff.weight"].float().cpu()}
+    elif mode == "p2p_vs_nccl":
+        for ddp_mode in ("nccl", "p2p"):  # both in one process pair: process start-up dominates the test's cost
+            os.environ["MMA_DDP"] = ddp_mode
+            m = _model("bf16", bench)
+            tr = FusedTrainer(m, clip_grad=1.0)
+            assert (tr.peer is not None) == (ddp_mode == "p2p")
+            for i in range(3):  # eager step, graph capture, one replay (device-side barriers inside the graph)
+                loss = tr.train_step(mine, i)
+                if i == 0:
+                    torch.cuda.synchronize()
+                    m.store.gather_master()
+                    m1 = m.store.m.cpu()
+            torch.cuda.synchronize()
+            sd = m.state_dict()  # p2p: reassembles the rank-sharded master weights
+            out[ddp_mode] = {"loss": float(loss), "m1": m1, "m": m.store.m.cpu(), "p": m.store.p.cpu(),
+                             "pb": m.store.pb.float().cpu(), "w": sd["hf_model.token_ff.weight"].float().cpu()}
     else:
         m = _model("bf16", bench)
         ddp = torch.nn.parallel.DistributedDataParallel(m, device_ids=[rank], find_unused_parameters=True)
@@ -76,7 +82,9 @@ def _worker(rank, world, port, q, mode):
         out = {"loss": float(res.loss), "g": g.cpu(), "same": all(torch.equal(ws[0], w) for w in ws)}
     q.put((rank, out))
     dist.barrier()
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    time.sleep(2.0)  # let the parent drain the queue
+    os._exit(0)  # captured graphs hold NCCL / symmetric-memory work: leave without the teardown (as bench.py does)
 
 
 def _spawn(mode, world=2):
@@ -142,12 +150,16 @@ def test_peer_memory_sharded_step_equals_nccl_allreduce_step():
     """MMA_DDP=p2p (reduce-scatter by P2P loads + rank-sharded Adam + bf16 weights stored into every peer's mirror, device
     barriers captured in the step graph) against MMA_DDP=nccl (bucketed all-reduce + replicated Adam) on the same two
     ranks and batches: same loss trajectory, same Adam moments and weights after three steps."""
-    a, b = _spawn("p2p"), _spawn("nccl")
+    res = _spawn("p2p_vs_nccl")
+    a, b = {r: res[r]["p2p"] for r in (0, 1)}, {r: res[r]["nccl"] for r in (0, 1)}
     for r in (0, 1):
         assert abs(a[r]["loss"] - b[r]["loss"]) < 1e-3 * abs(b[r]["loss"]), (a[r]["loss"], b[r]["loss"])
     assert torch.equal(a[0]["pb"], a[1]["pb"]), "bf16 mirrors differ between the ranks"
     assert torch.equal(a[0]["p"], a[1]["p"]), "gathered master weights differ between the ranks"
-    assert _rel(a[0]["m"], b[0]["m"]) < 1e-3
+    # after ONE step the Adam first moment is (1 - beta1) x the clipped world-averaged gradient: the two exchanges must
+    # agree to fp32 rounding; later steps drift apart through the bf16 rounding of the weights
+    assert _rel(a[0]["m1"], b[0]["m1"]) < 2e-5
+    assert _rel(a[0]["m"], b[0]["m"]) < 2e-2
     assert torch.equal(a[0]["w"], a[1]["w"]) and _rel(a[0]["w"], b[0]["w"]) < 1e-3  # state_dict(): gathered master
     d = (a[0]["pb"] - b[0]["pb"]).abs()
     assert float((d > 0).float().mean()) < 0.05, "more than 5 % of the bf16 weights differ from the NCCL path"
