@@ -399,8 +399,13 @@ def run_ours(args):
         "gpu_launches": launches, "last_loss": last_loss,
     }
     if world > 1:
-        line["gradient_exchange"] = ("peer-memory reduce-scatter + rank-sharded Adam + bf16 all-gather (own kernels over NVLink)"
-                                     if trainer.peer is not None else "bucketed NCCL all-reduce overlapped with backward")
+        if trainer.peer is not None:
+            nvls = any(trainer.peer.mc.values())
+            line["gradient_exchange"] = ("peer-memory reduce-scatter + rank-sharded Adam + bf16 all-gather, own kernels over "
+                                         + ("NVLink/NVSwitch multicast (multimem.ld_reduce / multimem.st)" if nvls
+                                            else "NVLink P2P loads / stores"))
+        else:
+            line["gradient_exchange"] = "bucketed NCCL all-reduce overlapped with backward"
     # a >= 2.5 s leg: the 20-step headline lasts ~0.15 s, i.e. it runs in the GPU's burst regime
     n_long = max(args.steps, int(2.5 / (t_dev / args.steps)) + 1)
     t_long, _, clocks_long, _ = timed(dev_batches, n_long, 0, e2e=False)

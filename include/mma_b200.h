@@ -203,6 +203,20 @@ int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long long ldk, 
                     int B, int H, int Lq, int Lk, int causal, float scale, float p_drop, unsigned long long seed,
                     unsigned int site, cudaStream_t stream);
 
+/* blocked tcgen05 / TMEM variants for 128 < L <= 512 (the multimodal encoder, S ~ 200-300): the score matrix is cut
+ * into 128 x 128 single-shot tile problems; forward merges the key blocks' (O, log-sum-exp), backward sums per-block fp32
+ * partial gradients (deterministic, no atomics).  Caller-owned fp32 workspaces with nqb = ceil(Lq/128), nkb = ceil(Lk/128):
+ * ws_o [nkb][B*Lq][H*64], ws_lse [nkb][B*H*Lq]; ws_dq [nkb][B*Lq][H*64], ws_dk / ws_dv [nqb][B*Lk][H*64].            */
+int mma_attn_fwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                     const unsigned char* kmask, void* o, long long ldo, float* lse, float* ws_o, float* ws_lse, int B,
+                     int H, int Lq, int Lk, int causal, float scale, float p_drop, unsigned long long seed,
+                     unsigned int site, cudaStream_t stream);
+int mma_attn_bwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                     const unsigned char* kmask, const void* o, long long ldo, const float* lse, const void* dout,
+                     long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
+                     float* ws_dq, float* ws_dk, float* ws_dv, int B, int H, int Lq, int Lk, int causal, float scale,
+                     float p_drop, unsigned long long seed, unsigned int site, cudaStream_t stream);
+
 /* ---- loss (nn.CrossEntropyLoss, custom_modeling.py:490-491; ignore_index -100 set at wrapper.py:389) --------- */
 int mma_ce_fwd(const float* logits, long long ld, const long long* labels, int rows, int V, float smoothing,
                long long ignore_index, float* row_loss, float* row_lse, float* stats, cudaStream_t stream);
@@ -222,13 +236,14 @@ int mma_add_u64(unsigned long long* p, unsigned long long inc, cudaStream_t stre
  * this rank's shard of the fp32 master weights / moments, bf16 weights written into every peer's mirror by P2P stores.
  * The `peer_*` arguments are HOST arrays of `world` device pointers (symmetric allocations, index = rank); the barrier's
  * flag arrays are int[16] per rank, zero-initialised, `epoch_ctr` a zero-initialised device int.  Sequence per step:
- * barrier, reduce_shard, barrier, adam_shard, barrier.                                                              */
+ * barrier, reduce_shard, barrier, adam_shard, barrier.  mc_g / mc_pb: NVLS multicast addresses of the gradient buffer /
+ * bf16 mirror (multimem.ld_reduce sums inside the NVSwitch, multimem.st is replicated by it) or NULL (explicit P2P).  */
 int mma_p2p_barrier(const void* const* peer_flags, int* epoch_ctr, int world, int rank, cudaStream_t stream);
-int mma_p2p_reduce_shard(const void* const* peer_g, int world, int rank, long long lo, long long hi, float* workspace,
-                         float* sumsq_out, cudaStream_t stream);
-int mma_p2p_adam_shard(float* p, float* g, float* m, float* v, const void* const* peer_pb, const void* const* peer_sumsq,
-                       int world, int rank, long long n, long long lo, long long hi, const float* hyper, int decoupled,
-                       cudaStream_t stream);
+int mma_p2p_reduce_shard(const void* const* peer_g, const void* mc_g, int world, int rank, long long lo, long long hi,
+                         float* workspace, float* sumsq_out, cudaStream_t stream);
+int mma_p2p_adam_shard(float* p, float* g, float* m, float* v, const void* const* peer_pb, void* mc_pb,
+                       const void* const* peer_sumsq, int world, int rank, long long n, long long lo, long long hi,
+                       const float* hyper, int decoupled, cudaStream_t stream);
 
 /* ---- KV-cached decoding (replaces transformers generate(use_cache=False), wrapper.py:443-451) ---------------- */
 int mma_decode_embed(const int* tok, const float* table, const float* gamma, const float* beta, float eps,

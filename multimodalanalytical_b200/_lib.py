@@ -134,6 +134,10 @@ _SIGS = {
     "mma_attn_fwd_t5": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
     "mma_attn_bwd_t5": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll,
                         _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
+    "mma_attn_fwd_t5b": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _ull, _u,
+                         _vp],
+    "mma_attn_bwd_t5b": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp,
+                         _vp, _i, _i, _i, _i, _i, _f, _f, _ull, _u, _vp],
     "mma_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _i, _i,
                      _i, _i, _i, _i, _f, _f, _ull, _u, _i, _vp],
     "mma_ce_fwd": [_vp, _ll, _vp, _i, _i, _f, _ll, _vp, _vp, _vp, _vp],
@@ -142,8 +146,8 @@ _SIGS = {
     "mma_adam_step": [_vp, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _i, _vp],
     "mma_add_u64": [_vp, _ull, _vp],
     "mma_p2p_barrier": [_vp, _vp, _i, _i, _vp],
-    "mma_p2p_reduce_shard": [_vp, _i, _i, _ll, _ll, _vp, _vp, _vp],
-    "mma_p2p_adam_shard": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp, _i, _vp],
+    "mma_p2p_reduce_shard": [_vp, _vp, _i, _i, _ll, _ll, _vp, _vp, _vp],
+    "mma_p2p_adam_shard": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp, _i, _vp],
     "mma_decode_embed": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp],
     "mma_decode_self_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
     "mma_decode_cross_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp],

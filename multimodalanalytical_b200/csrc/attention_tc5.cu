@@ -990,6 +990,444 @@ bwd_pipe_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Sequences longer than one tile (128 < L <= 512: the multimodal encoder, S ~ 200-300): BLOCKED attention.
+// The (Lq x Lk) score matrix of a (batch, head) is cut into 128 x 128 blocks; every block is one single-shot tcgen05
+// problem exactly like fwd_kernel<1> / bwd_kernel<1> above (same TMEM / shared-memory plan), addressed by block offsets:
+//   forward   block (qb, kb) -> O_kb = softmax_block(S) V_kb (normalised inside the block, fp32) and the block's
+//             log-sum-exp; merge_fwd combines the key blocks: lse = log sum_kb exp(lse_kb), O = sum_kb exp(lse_kb - lse) O_kb
+//   backward  with the MERGED lse and D_i = rowsum(dO o O) every block is independent: P = exp(S - lse), dS = P o (dP - D);
+//             block (qb, kb) contributes dQ_qb += dS K_kb, dK_kb += dS^T Q_qb, dV_kb += P^T dO_qb - written as fp32
+//             partials indexed by the OTHER block coordinate and summed by merge_bwd (no atomics: deterministic).
+// Masks (key padding, causal) and the dropout stream use GLOBAL (i, j), so results equal the single-tile / streaming
+// kernels' for the same seed.  The elementwise softmax / dropout work per score - not the MMA - bounds attention at
+// these sizes (ncu: the streaming mma.sync kernel issues ~40 instructions per score); the single-shot tile kernels do
+// it with one thread per row out of TMEM at ~3.6x the streaming kernel's rate per score.
+// ------------------------------------------------------------------------------------------------------------------
+struct BlkArgs {
+  int B, H, Lq, Lk, causal, nqb, nkb;
+  float scale, p_drop;
+  unsigned long long seed;
+  unsigned int site;
+  const unsigned char* kmask;
+  float* opart;     // fwd out: [nkb][B*Lq][H*64]
+  float* lsepart;   // fwd out: [nkb][B*H*Lq]
+  const float* lse; // bwd in: merged [B*H*Lq]
+  float* dqpart;    // bwd out: [nkb][B*Lq][H*64]
+  float* dkpart;    // bwd out: [nqb][B*Lk][H*64]
+  float* dvpart;    // bwd out: [nqb][B*Lk][H*64]
+};
+
+struct BlkMap {
+  int b, h, qb, kb;
+  __device__ BlkMap(const BlkArgs& a, int prob) {
+    kb = prob % a.nkb;
+    prob /= a.nkb;
+    qb = prob % a.nqb;
+    prob /= a.nqb;
+    h = prob % a.H;
+    b = prob / a.H;
+  }
+};
+
+// two 64-row boxes of the 128-row block `blk` of batch b (rows past the batch's length are masked by the callers)
+__device__ __forceinline__ void issue_blk_loads(const CUtensorMap* tm, uint32_t dst, uint32_t bar, int b, int h, int L, int blk) {
+#pragma unroll
+  for (int s = 0; s < 2; ++s) tma_load_2d(dst + s * 8192, tm, bar, h * 64, b * L + blk * 128 + s * 64);
+}
+
+// validity bits of the keys [k0 + ch*32, +32): global key < Lk, key-padding mask, causal j <= i
+__device__ __forceinline__ void key_valid_bits_blk(uint32_t (&bits)[4], const unsigned char* km, int Lk, int causal, int i,
+                                                   int k0, int lane) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const int j = k0 + ch * 32 + lane;
+    const bool ok = j < Lk && (!km || km[j] != 0);
+    uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if (causal) {
+      const int hi = i - (k0 + ch * 32);
+      m &= hi >= 31 ? 0xffffffffu : hi < 0 ? 0u : ((2u << hi) - 1u);
+    }
+    bits[ch] = m;
+  }
+}
+
+__global__ void __launch_bounds__(128) fwd_blk_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                                                      const __grid_constant__ CUtensorMap tv, BlkArgs a) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;  // after S is formed, sQ|sK is reused for P (two 64-key atoms)
+  uint8_t* sK = smem + TILE;
+  uint8_t* sV = smem + 2 * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BlkMap bm(a, blockIdx.x);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    const uint32_t bar = smem_u32(&bars[0]);
+    mbar_expect_tx(bar, 3 * TILE);
+    issue_blk_loads(&tq, smem_u32(sQ), bar, bm.b, bm.h, a.Lq, bm.qb);
+    issue_blk_loads(&tk, smem_u32(sK), bar, bm.b, bm.h, a.Lk, bm.kb);
+    issue_blk_loads(&tv, smem_u32(sV), bar, bm.b, bm.h, a.Lk, bm.kb);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // S[128 x 128] = Q K^T
+      tc_mma_bf16(tm, desc_kmajor(smem_u32(sQ) + k * 32), desc_kmajor(smem_u32(sK) + k * 32), idesc(128, false, false), k > 0);
+    tc_commit(smem_u32(&bars[1]));
+  }
+  const int row = warp * 32 + lane;
+  const int i = bm.qb * 128 + row;  // global query index
+  const int k0 = bm.kb * 128;
+  const unsigned char* km = a.kmask ? a.kmask + (long long)bm.b * a.Lk : nullptr;
+  const float sl2 = a.scale * LOG2E;
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
+  const unsigned long long ebase = (((unsigned long long)bm.b * a.H + bm.h) * a.Lq + i) * (unsigned long long)((a.Lk + 1) & ~1) + k0;
+  const uint32_t ebase32 = (uint32_t)ebase;  // even
+  const uint32_t t_row = tm + ((uint32_t)(warp * 32) << 16);
+  uint32_t vbits[4];
+  key_valid_bits_blk(vbits, km, a.Lk, a.causal, i, k0, lane);
+
+  if (lane == 0) mbar_wait(smem_u32(&bars[1]), 0);
+  __syncwarp();
+  tc_fence_after();
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    float s[32];
+    tmem_ld32f(t_row + ch * 32, s);
+    const uint32_t vb = vbits[ch];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (vb >> c) & 1u ? s[c] * sl2 : -INFINITY);
+  }
+  float l = 0.f;
+  uint8_t* sP = sQ;
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    float s[32];
+    tmem_ld32f(t_row + ch * 32, s);
+    const uint32_t vb = vbits[ch];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      float p0 = (vb >> c) & 1u ? ex2_approx(s[c] * sl2 - mx) : 0.f;
+      float p1 = (vb >> (c + 1)) & 1u ? ex2_approx(s[c + 1] * sl2 - mx) : 0.f;
+      l += p0 + p1;
+      if (drop) {
+        const uint32_t r = drop_pair(dkey, (ebase32 + (uint32_t)(ch * 32 + c)) >> 1);
+        p0 *= (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+        p1 *= (r >> 16) >= thr ? inv_keep : 0.f;
+      }
+      s[c] = p0;
+      s[c + 1] = p1;
+    }
+    const int kcol = ch * 32;
+    uint8_t* atom = sP + (kcol >> 6) * TILE;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      uint4 u;
+      u.x = pack2(s[c], s[c + 1]); u.y = pack2(s[c + 2], s[c + 3]);
+      u.z = pack2(s[c + 4], s[c + 5]); u.w = pack2(s[c + 6], s[c + 7]);
+      st_chunk(atom, row, (kcol & 63) + c, u);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // O[128 x 64] = P[128 x 128] V[128 x 64]
+      tc_mma_bf16(tm, desc_kmajor(smem_u32(sP) + (k >> 2) * TILE + (k & 3) * 32),
+                  desc_mnmajor(smem_u32(sV) + k * 2048, TILE), idesc(64, false, true), k > 0);
+    tc_commit(smem_u32(&bars[2]));
+  }
+  if (lane == 0) mbar_wait(smem_u32(&bars[2]), 0);
+  __syncwarp();
+  tc_fence_after();
+  {
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const bool wr = i < a.Lq;
+    const long long part = (long long)bm.kb * a.B * a.Lq;
+    float* orow = a.opart + (part + (long long)bm.b * a.Lq + i) * (a.H * 64) + bm.h * 64;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      float v[32];
+      tmem_ld32f(tm + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
+      if (wr) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(orow + ch * 32 + c) = make_float4(v[c] * inv, v[c + 1] * inv, v[c + 2] * inv, v[c + 3] * inv);
+      }
+    }
+    if (wr)
+      a.lsepart[(long long)bm.kb * a.B * a.H * a.Lq + ((long long)bm.b * a.H + bm.h) * a.Lq + i] =
+          l > 0.f ? mx / LOG2E + logf(l) : -INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(128) : "memory");
+  }
+}
+
+// one warp per (row, head): O = sum_kb w_kb O_kb, lse = m + log sum_kb exp(lse_kb - m)
+__global__ void __launch_bounds__(256) merge_fwd_kernel(const float* __restrict__ opart, const float* __restrict__ lsepart, bf16* o,
+                                                        long long ldo, float* __restrict__ lse, int B, int H, int Lq, int nkb) {
+  pdl_trigger();
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)B * Lq;
+  if (gw >= rows * H) return;
+  const long long r = gw / H;
+  const int h = (int)(gw % H);
+  const int b = (int)(r / Lq), i = (int)(r % Lq);
+  const long long li = ((long long)b * H + h) * Lq + i;
+  float lp[4], m = -INFINITY;
+  for (int kb = 0; kb < nkb; ++kb) {
+    lp[kb] = lsepart[(long long)kb * B * H * Lq + li];
+    m = fmaxf(m, lp[kb]);
+  }
+  float L = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const float w = lp[kb] == -INFINITY ? 0.f : __expf(lp[kb] - m);
+    L += w;
+    const float2 v = *reinterpret_cast<const float2*>(opart + ((long long)kb * rows + r) * (H * 64) + h * 64 + 2 * lane);
+    o0 = fmaf(w, v.x, o0);
+    o1 = fmaf(w, v.y, o1);
+  }
+  const float inv = L > 0.f ? 1.f / L : 0.f;
+  *reinterpret_cast<__nv_bfloat162*>(o + r * ldo + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+  if (lane == 0 && lse) lse[li] = L > 0.f ? m + logf(L) : -INFINITY;
+}
+
+__global__ void __launch_bounds__(128) bwd_blk_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                                                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                                                      const __grid_constant__ CUtensorMap to, BlkArgs a) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  // layout (ascending): Pd atom 0 | dS atom 0 | dS atom 1 | Q | K | dO | V (= Pd atom 1 once dP has retired)
+  uint8_t* sPd0 = smem;
+  uint8_t* sdS = smem + TILE;
+  uint8_t* sQ = smem + 3 * TILE;
+  uint8_t* sK = smem + 4 * TILE;
+  uint8_t* sDO = smem + 5 * TILE;
+  uint8_t* sV = smem + 6 * TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BlkMap bm(a, blockIdx.x);
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bars[0]), 1);
+    mbar_init(smem_u32(&bars[1]), 1);
+    mbar_init(smem_u32(&bars[2]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm = *tmem_slot;
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    const uint32_t bar = smem_u32(&bars[0]);
+    mbar_expect_tx(bar, 5 * TILE);
+    issue_blk_loads(&tq, smem_u32(sQ), bar, bm.b, bm.h, a.Lq, bm.qb);
+    issue_blk_loads(&tk, smem_u32(sK), bar, bm.b, bm.h, a.Lk, bm.kb);
+    issue_blk_loads(&tv, smem_u32(sV), bar, bm.b, bm.h, a.Lk, bm.kb);
+    issue_blk_loads(&tdo, smem_u32(sDO), bar, bm.b, bm.h, a.Lq, bm.qb);
+    issue_blk_loads(&to, smem_u32(sdS), bar, bm.b, bm.h, a.Lq, bm.qb);  // O parks in dS atom 0 until D_i is formed
+    mbar_wait(bar, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // S = Q K^T -> cols [0,128)
+      tc_mma_bf16(tm, desc_kmajor(smem_u32(sQ) + k * 32), desc_kmajor(smem_u32(sK) + k * 32), idesc(128, false, false), k > 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // dP = dO V^T -> cols [128,256)
+      tc_mma_bf16(tm + 128, desc_kmajor(smem_u32(sDO) + k * 32), desc_kmajor(smem_u32(sV) + k * 32), idesc(128, false, false), k > 0);
+    tc_commit(smem_u32(&bars[1]));
+  }
+  const int row = warp * 32 + lane;
+  const int i = bm.qb * 128 + row;   // global query index of this row (dQ, softmax)
+  const int jk = bm.kb * 128 + row;  // global key index of this row (dK, dV)
+  const int k0 = bm.kb * 128;
+  const bool qvalid = i < a.Lq;
+  const unsigned char* km = a.kmask ? a.kmask + (long long)bm.b * a.Lk : nullptr;
+  float Di = 0.f, lse2 = 0.f;
+  if (qvalid) lse2 = a.lse[((long long)bm.b * a.H + bm.h) * a.Lq + i] * LOG2E;
+  if (lane == 0) mbar_wait(smem_u32(&bars[0]), 0);
+  __syncwarp();
+  {
+    const uint8_t* orow = sdS + row * 128;
+    const uint8_t* drow = sDO + row * 128;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int sw = (u ^ (row & 7)) << 4;
+      const uint4 x = *reinterpret_cast<const uint4*>(orow + sw), y = *reinterpret_cast<const uint4*>(drow + sw);
+      const __nv_bfloat162* xb = reinterpret_cast<const __nv_bfloat162*>(&x);
+      const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float2 xf = __bfloat1622float2(xb[w]), yf = __bfloat1622float2(yb[w]);
+        Di += xf.x * yf.x + xf.y * yf.y;
+      }
+    }
+    if (!qvalid) Di = 0.f;
+  }
+  const float sl2 = a.scale * LOG2E;
+  const bool drop = a.p_drop > 0.f;
+  const uint32_t thr = drop ? drop_threshold(a.p_drop) : 0u;
+  const float inv_keep = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint32_t dkey = drop_key(a.seed, a.site);
+  const unsigned long long ebase = (((unsigned long long)bm.b * a.H + bm.h) * a.Lq + i) * (unsigned long long)((a.Lk + 1) & ~1) + k0;
+  const uint32_t ebase32 = (uint32_t)ebase;
+  const uint32_t t_row = tm + ((uint32_t)(warp * 32) << 16);
+  uint32_t vbits[4];
+  key_valid_bits_blk(vbits, km, a.Lk, a.causal, i, k0, lane);
+  // a fully masked row has lse = -inf: exp2(s - (-inf)) would be inf; its probabilities are all zero
+  const bool row_live = qvalid && lse2 > -INFINITY;
+
+  if (lane == 0) mbar_wait(smem_u32(&bars[1]), 0);
+  __syncwarp();
+  tc_fence_after();
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    float s[32], dp[32];
+    tmem_ld32f(t_row + ch * 32, s);
+    tmem_ld32f(t_row + 128 + ch * 32, dp);
+    const uint32_t vb = row_live ? vbits[ch] : 0u;
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      const float p0 = (vb >> c) & 1u ? ex2_approx(s[c] * sl2 - lse2) : 0.f;
+      const float p1 = (vb >> (c + 1)) & 1u ? ex2_approx(s[c + 1] * sl2 - lse2) : 0.f;
+      float kk0 = 1.f, kk1 = 1.f;
+      if (drop) {
+        const uint32_t r = drop_pair(dkey, (ebase32 + (uint32_t)(ch * 32 + c)) >> 1);
+        kk0 = (r & 0xFFFFu) >= thr ? inv_keep : 0.f;
+        kk1 = (r >> 16) >= thr ? inv_keep : 0.f;
+      }
+      s[c] = p0 * kk0;                        // P_drop
+      s[c + 1] = p1 * kk1;
+      dp[c] = p0 * (dp[c] * kk0 - Di);        // dS
+      dp[c + 1] = p1 * (dp[c + 1] * kk1 - Di);
+    }
+    const int kcol = ch * 32;
+    uint8_t* pa = (kcol >> 6) ? sV : sPd0;
+    uint8_t* da = sdS + (kcol >> 6) * TILE;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) {
+      uint4 u, w;
+      u.x = pack2(s[c], s[c + 1]); u.y = pack2(s[c + 2], s[c + 3]);
+      u.z = pack2(s[c + 4], s[c + 5]); u.w = pack2(s[c + 6], s[c + 7]);
+      w.x = pack2(dp[c], dp[c + 1]); w.y = pack2(dp[c + 2], dp[c + 3]);
+      w.z = pack2(dp[c + 4], dp[c + 5]); w.w = pack2(dp[c + 6], dp[c + 7]);
+      st_chunk(pa, row, (kcol & 63) + c, u);
+      st_chunk(da, row, (kcol & 63) + c, w);
+    }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    tc_fence_after();
+    const uint32_t pd_stride = smem_u32(sV) - smem_u32(sPd0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // dV[keys x 64] = Pd^T dO     -> cols [0,64)
+      tc_mma_bf16(tm, desc_mnmajor(smem_u32(sPd0) + k * 2048, pd_stride), desc_mnmajor(smem_u32(sDO) + k * 2048, TILE),
+                  idesc(64, true, true), k > 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // dK[keys x 64] = dS^T Q      -> cols [64,128)
+      tc_mma_bf16(tm + 64, desc_mnmajor(smem_u32(sdS) + k * 2048, TILE), desc_mnmajor(smem_u32(sQ) + k * 2048, TILE),
+                  idesc(64, true, true), k > 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)  // dQ[q x 64] = dS K           -> cols [128,192)
+      tc_mma_bf16(tm + 128, desc_kmajor(smem_u32(sdS) + (k >> 2) * TILE + (k & 3) * 32),
+                  desc_mnmajor(smem_u32(sK) + k * 2048, TILE), idesc(64, false, true), k > 0);
+    tc_commit(smem_u32(&bars[2]));
+  }
+  if (lane == 0) mbar_wait(smem_u32(&bars[2]), 0);
+  __syncwarp();
+  tc_fence_after();
+  {
+    const bool kvalid = jk < a.Lk;
+    const int W = a.H * 64;
+    float* dqrow = a.dqpart + ((long long)bm.kb * a.B * a.Lq + (long long)bm.b * a.Lq + i) * W + bm.h * 64;
+    float* dkrow = a.dkpart + ((long long)bm.qb * a.B * a.Lk + (long long)bm.b * a.Lk + jk) * W + bm.h * 64;
+    float* dvrow = a.dvpart + ((long long)bm.qb * a.B * a.Lk + (long long)bm.b * a.Lk + jk) * W + bm.h * 64;
+    const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int part = 0; part < 6; ++part) {  // dV lo/hi, dK lo/hi, dQ lo/hi
+      float v[32];
+      tmem_ld32f(tl + part * 32, v);
+      const int which = part >> 1, half = part & 1;
+      const bool wr = which == 2 ? qvalid : kvalid;
+      const float sc = which == 0 ? 1.f : a.scale;
+      float* dst = (which == 0 ? dvrow : which == 1 ? dkrow : dqrow) + half * 32;
+      if (wr) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c] * sc, v[c + 1] * sc, v[c + 2] * sc, v[c + 3] * sc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(256) : "memory");
+  }
+}
+
+// out[r, c] (bf16, pitch ld) = sum_p part[p][r][c]  for the three gradients (dQ over key blocks, dK / dV over query blocks)
+__global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict__ dqp, const float* __restrict__ dkp,
+                                                        const float* __restrict__ dvp, bf16* dq, long long lddq, bf16* dk,
+                                                        long long lddk, bf16* dv, long long lddv, long long rows_q,
+                                                        long long rows_k, int W, int nkb, int nqb) {
+  pdl_trigger();
+  const long long per_q = rows_q * (W / 4), per_k = rows_k * (W / 4);
+  const long long total = per_q + 2 * per_k;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const float* src;
+    bf16* dst;
+    long long ld, rows, e = idx;
+    int np;
+    if (e < per_q) { src = dqp; dst = dq; ld = lddq; rows = rows_q; np = nkb; }
+    else if (e < per_q + per_k) { e -= per_q; src = dkp; dst = dk; ld = lddk; rows = rows_k; np = nqb; }
+    else { e -= per_q + per_k; src = dvp; dst = dv; ld = lddv; rows = rows_k; np = nqb; }
+    const long long r = e / (W / 4);
+    const int c = (int)(e % (W / 4)) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < np; ++p) {
+      const float4 v = *reinterpret_cast<const float4*>(src + ((long long)p * rows + r) * W + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    uint2 u;
+    u.x = pack2(s.x, s.y);
+    u.y = pack2(s.z, s.w);
+    *reinterpret_cast<uint2*>(dst + r * ld + c) = u;
+  }
+}
+
 static int map64(CUtensorMap* m, const void* p, int H, long long rows, long long ld) {
   return make_map(m, p, (unsigned long long)H * 64, (unsigned long long)rows, (unsigned long long)ld, 64, 64);
 }
@@ -1113,6 +1551,67 @@ extern "C" int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long
     if (!set) { cudaFuncSetAttribute(bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
     if (launch_pdl(bwd_kernel<1>, dim3(a.nprob), dim3(128), smem, stream, tq, tk, tv, tdo, to, a) != cudaSuccess) return MMA_ERR_LAUNCH;
   }
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+// Blocked tcgen05 attention for sequences longer than one 128-row tile (Lq, Lk <= 512; bf16, head dim 64).
+// ws_o: fp32 [nkb][B*Lq][H*64], ws_lse: fp32 [nkb][B*H*Lq] with nkb = ceil(Lk / 128) (caller-owned workspaces).
+extern "C" int mma_attn_fwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                const unsigned char* kmask, void* o, long long ldo, float* lse, float* ws_o, float* ws_lse,
+                                int B, int H, int Lq, int Lk, int causal, float scale, float p_drop, unsigned long long seed,
+                                unsigned int site, cudaStream_t stream) {
+  using namespace at5;
+  if (B <= 0 || Lq <= 0 || Lk <= 0) return MMA_OK;
+  if (Lq > 512 || Lk > 512 || ((ldq | ldk | ldv | ldo) & 7) || !ws_o || !ws_lse) return MMA_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = map64(&tq, q, H, (long long)B * Lq, ldq))) return rc;
+  if ((rc = map64(&tk, k, H, (long long)B * Lk, ldk))) return rc;
+  if ((rc = map64(&tv, v, H, (long long)B * Lk, ldv))) return rc;
+  BlkArgs a{};
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nqb = (Lq + 127) / 128; a.nkb = (Lk + 127) / 128;
+  a.scale = scale; a.p_drop = p_drop; a.seed = seed; a.site = site; a.kmask = kmask; a.opart = ws_o; a.lsepart = ws_lse;
+  const int smem = 3 * TILE + 64;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(fwd_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+  const long long nprob = (long long)B * H * a.nqb * a.nkb;
+  if (launch_pdl(fwd_blk_kernel, dim3((unsigned)nprob), dim3(128), smem, stream, tq, tk, tv, a) != cudaSuccess) return MMA_ERR_LAUNCH;
+  const long long warps = (long long)B * Lq * H;
+  merge_fwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(ws_o, ws_lse, (bf16*)o, ldo, lse, B, H, Lq, a.nkb);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+// ws_dq: fp32 [nkb][B*Lq][H*64]; ws_dk, ws_dv: fp32 [nqb][B*Lk][H*64]
+extern "C" int mma_attn_bwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                                const unsigned char* kmask, const void* o, long long ldo, const float* lse, const void* dout,
+                                long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
+                                float* ws_dq, float* ws_dk, float* ws_dv, int B, int H, int Lq, int Lk, int causal,
+                                float scale, float p_drop, unsigned long long seed, unsigned int site, cudaStream_t stream) {
+  using namespace at5;
+  if (B <= 0 || Lq <= 0 || Lk <= 0) return MMA_OK;
+  if (Lq > 512 || Lk > 512 || ((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 7) || !ws_dq || !ws_dk || !ws_dv)
+    return MMA_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv, tdo, to;
+  int rc;
+  if ((rc = map64(&tq, q, H, (long long)B * Lq, ldq))) return rc;
+  if ((rc = map64(&tk, k, H, (long long)B * Lk, ldk))) return rc;
+  if ((rc = map64(&tv, v, H, (long long)B * Lk, ldv))) return rc;
+  if ((rc = map64(&tdo, dout, H, (long long)B * Lq, lddo))) return rc;
+  if ((rc = map64(&to, o, H, (long long)B * Lq, ldo))) return rc;
+  BlkArgs a{};
+  a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nqb = (Lq + 127) / 128; a.nkb = (Lk + 127) / 128;
+  a.scale = scale; a.p_drop = p_drop; a.seed = seed; a.site = site; a.kmask = kmask; a.lse = lse;
+  a.dqpart = ws_dq; a.dkpart = ws_dk; a.dvpart = ws_dv;
+  const int smem = 7 * TILE + 64;
+  static bool set = false;
+  if (!set) { cudaFuncSetAttribute(bwd_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
+  const long long nprob = (long long)B * H * a.nqb * a.nkb;
+  if (launch_pdl(bwd_blk_kernel, dim3((unsigned)nprob), dim3(128), smem, stream, tq, tk, tv, tdo, to, a) != cudaSuccess)
+    return MMA_ERR_LAUNCH;
+  merge_bwd_kernel<<<148 * 8, 256, 0, stream>>>(ws_dq, ws_dk, ws_dv, (bf16*)dq, lddq, (bf16*)dk, lddk, (bf16*)dv, lddv,
+                                                (long long)B * Lq, (long long)B * Lk, H * 64, a.nkb, a.nqb);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

@@ -47,6 +47,20 @@ __device__ __forceinline__ float ld_sys_f(const float* addr) {
   return v;
 }
 
+// NVLS (NVSwitch multicast objects): one load returns the SUM over all ranks' copies of the address, reduced inside the
+// switch; one store is replicated by the switch into every rank's copy
+__device__ __forceinline__ float4 multimem_ld_reduce_add_f4(const float* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_b128(void* mc_addr, uint4 u) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               ::"l"(mc_addr), "f"(__uint_as_float(u.x)), "f"(__uint_as_float(u.y)), "f"(__uint_as_float(u.z)),
+                 "f"(__uint_as_float(u.w)) : "memory");
+}
+
 // flags: per rank an int[MAX_WORLD] array in symmetric memory; flags_r[s] = last epoch rank s has reached
 __global__ void barrier_kernel(Peers flags, int* epoch_ctr, int world, int rank) {
   __shared__ int e;
@@ -68,19 +82,24 @@ __global__ void barrier_kernel(Peers flags, int* epoch_ctr, int world, int rank)
 }
 
 // g_rank[lo:hi) = sum_p g_p[lo:hi);  partial[block] = sum of squares of the block's part
-__global__ void __launch_bounds__(256) reduce_shard_kernel(Peers g, int world, int rank, long long lo, long long hi,
-                                                           float* __restrict__ partial) {
+__global__ void __launch_bounds__(256) reduce_shard_kernel(Peers g, const float* mc_g, int world, int rank, long long lo,
+                                                           long long hi, float* __restrict__ partial) {
   __shared__ float red[8];
   float ss = 0.f;
   float* mine = reinterpret_cast<float*>(g.p[rank]);
   const long long n4 = (hi - lo) >> 2;  // shard bounds are multiples of 128 elements
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const long long e = lo + (i << 2);
-    float4 s = *reinterpret_cast<const float4*>(mine + e);
-    for (int p = 0; p < world; ++p) {
-      if (p == rank) continue;
-      const float4 v = ld_sys_f4(reinterpret_cast<const float*>(g.p[p]) + e);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    float4 s;
+    if (mc_g) {
+      s = multimem_ld_reduce_add_f4(mc_g + e);  // in-switch sum over every rank's copy (this rank's included)
+    } else {
+      s = *reinterpret_cast<const float4*>(mine + e);
+      for (int p = 0; p < world; ++p) {
+        if (p == rank) continue;
+        const float4 v = ld_sys_f4(reinterpret_cast<const float*>(g.p[p]) + e);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
     }
     *reinterpret_cast<float4*>(mine + e) = s;
     ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
@@ -109,7 +128,7 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restric
 
 // hyper: as adam_kernel (trainops.cu); hyper[8] = 1 / (world * accumulation) scales the SUMMED gradient
 __global__ void __launch_bounds__(256) adam_shard_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                         float* __restrict__ v, Peers pb, Peers sumsq, int world, int rank,
+                                                         float* __restrict__ v, Peers pb, void* mc_pb, Peers sumsq, int world, int rank,
                                                          long long n, long long lo, long long hi,
                                                          const float* __restrict__ hyper, int decoupled) {
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
@@ -160,7 +179,11 @@ __global__ void __launch_bounds__(256) adam_shard_kernel(float* __restrict__ p, 
     __nv_bfloat162 h2 = __floats2bfloat162_rn(pv[4], pv[5]), h3 = __floats2bfloat162_rn(pv[6], pv[7]);
     u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
     u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-    for (int q = 0; q < world; ++q) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(pb.p[q]) + e) = u;
+    if (mc_pb) {
+      multimem_st_b128(reinterpret_cast<bf16*>(mc_pb) + e, u);  // replicated into every rank's mirror by the switch
+    } else {
+      for (int q = 0; q < world; ++q) *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(pb.p[q]) + e) = u;
+    }
     // consumed: the next step accumulates into a clean gradient buffer
     *reinterpret_cast<float4*>(g + e) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(g + e + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -196,15 +219,17 @@ extern "C" int mma_p2p_barrier(const void* const* peer_flags, int* epoch_ctr, in
 }
 
 // g_rank[lo:hi) = sum over the peers' g[lo:hi); sumsq_out[0] = sum of squares of the result.  peer_g: HOST array of the
-// `world` device pointers of the ranks' flat fp32 gradient buffers; lo, hi multiples of 4; workspace >= 1024 floats.
-extern "C" int mma_p2p_reduce_shard(const void* const* peer_g, int world, int rank, long long lo, long long hi,
-                                    float* workspace, float* sumsq_out, cudaStream_t stream) {
+// `world` device pointers of the ranks' flat fp32 gradient buffers; mc_g: NVLS multicast address of the same buffer (the
+// sum is then formed inside the NVSwitch by multimem.ld_reduce) or NULL (explicit P2P loads); lo, hi multiples of 4;
+// workspace >= 1024 floats.
+extern "C" int mma_p2p_reduce_shard(const void* const* peer_g, const void* mc_g, int world, int rank, long long lo,
+                                    long long hi, float* workspace, float* sumsq_out, cudaStream_t stream) {
   Peers G;
   if (int rc = fill(G, peer_g, world)) return rc;
   if (rank < 0 || rank >= world || lo < 0 || hi < lo || ((lo | hi) & 3) || !workspace || !sumsq_out) return MMA_ERR_ARG;
   long long want = ((hi - lo) / 4 + 255) / 256;
   const int blocks = (int)(want < 1 ? 1 : (want > 1024 ? 1024 : want));
-  reduce_shard_kernel<<<blocks, 256, 0, stream>>>(G, world, rank, lo, hi, workspace);
+  reduce_shard_kernel<<<blocks, 256, 0, stream>>>(G, reinterpret_cast<const float*>(mc_g), world, rank, lo, hi, workspace);
   MMA_CHECK_LAUNCH();
   p2p::sumsq_final_kernel<<<1, 256, 0, stream>>>(workspace, blocks, sumsq_out);
   MMA_CHECK_LAUNCH();
@@ -212,10 +237,11 @@ extern "C" int mma_p2p_reduce_shard(const void* const* peer_g, int world, int ra
 }
 
 // Adam / AdamW on the shard [lo, hi) of this rank's master weights with the clipped, world-averaged gradient; the new
-// weights are written as bf16 into every peer's mirror (peer_pb: HOST array of `world` device pointers); this rank's
+// weights are written as bf16 into every peer's mirror (peer_pb: HOST array of `world` device pointers; mc_pb: NVLS
+// multicast address of the mirror - one multimem.st replicated by the switch - or NULL: one P2P store per peer); this rank's
 // whole gradient buffer [0, n) is zeroed.  peer_sumsq: HOST array of the ranks' sumsq slots (mma_p2p_reduce_shard).
 // lo, hi multiples of 8, n multiple of 4.  hyper as mma_adam_step.
-extern "C" int mma_p2p_adam_shard(float* p, float* g, float* m, float* v, const void* const* peer_pb,
+extern "C" int mma_p2p_adam_shard(float* p, float* g, float* m, float* v, const void* const* peer_pb, void* mc_pb,
                                   const void* const* peer_sumsq, int world, int rank, long long n, long long lo,
                                   long long hi, const float* hyper, int decoupled, cudaStream_t stream) {
   Peers PB, SS;
@@ -225,7 +251,7 @@ extern "C" int mma_p2p_adam_shard(float* p, float* g, float* m, float* v, const 
     return MMA_ERR_ARG;
   long long want = (n / 4 + 255) / 256;
   const int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
-  adam_shard_kernel<<<blocks, 256, 0, stream>>>(p, g, m, v, PB, SS, world, rank, n, lo, hi, hyper, decoupled);
+  adam_shard_kernel<<<blocks, 256, 0, stream>>>(p, g, m, v, PB, mc_pb, SS, world, rank, n, lo, hi, hyper, decoupled);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

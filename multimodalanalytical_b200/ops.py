@@ -372,6 +372,18 @@ def cast_bf16_f32(src, dst):
     _count()
 
 
+_ATT_WS = {}
+
+
+def _att_ws(device, name, shape):
+    """fp32 workspace of the blocked attention kernels, one per (device, role, shape)."""
+    key = (str(device), name, tuple(shape))
+    t = _ATT_WS.get(key)
+    if t is None:
+        t = _ATT_WS[key] = torch.empty(shape, dtype=torch.float32, device=device)
+    return t
+
+
 def _attn_tc_ok(dh, *ts):
     return dh == 64 and all(t.dtype == torch.bfloat16 and t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in ts)
 
@@ -386,6 +398,18 @@ def attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop
             o.stride(0), _p(lse), B, H, Lq, Lk, int(causal), dh ** -0.5, float(p_drop), int(seed), int(site),
             _stream()), "mma_attn_fwd_t5")
         _count()
+        return
+    if _attn_tc_ok(dh, q, k, v, o) and Lq <= 512 and Lk <= 512 and ATTN_IMPL == "tcgen05" and lse is not None:
+        # 128 < L <= 512: blocked tcgen05 kernels (128 x 128 tile problems + merge); workspaces are cached per shape so
+        # that captured CUDA graphs keep stable addresses
+        nkb = (Lk + 127) // 128
+        ws_o = _att_ws(q.device, "fwd_o", (nkb, B * Lq, H * dh))
+        ws_l = _att_ws(q.device, "fwd_lse", (nkb, B * H * Lq))
+        check(_lib.load().mma_attn_fwd_t5b(
+            q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+            o.stride(0), lse.data_ptr(), ws_o.data_ptr(), ws_l.data_ptr(), B, H, Lq, Lk, int(causal), dh ** -0.5,
+            float(p_drop), int(seed), int(site), _stream()), "mma_attn_fwd_t5b")
+        _count(2)
         return
     if _attn_tc_ok(dh, q, k, v, o):
         check(_lib.load().mma_attn_fwd_tc(
@@ -411,6 +435,18 @@ def attn_bwd(q, k, v, o, lse, dout, dq, dk, dv, B, H, Lq, Lk, dh, kmask=None, ca
             dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Lq, Lk, int(causal), dh ** -0.5, float(p_drop), int(seed),
             int(site), _stream()), "mma_attn_bwd_t5")
         _count()
+        return
+    if _attn_tc_ok(dh, q, k, v, o, dout, dq, dk, dv) and Lq <= 512 and Lk <= 512 and ATTN_IMPL == "tcgen05":
+        nqb, nkb = (Lq + 127) // 128, (Lk + 127) // 128
+        ws_dq = _att_ws(q.device, "bwd_dq", (nkb, B * Lq, H * dh))
+        ws_dk = _att_ws(q.device, "bwd_dk", (nqb, B * Lk, H * dh))
+        ws_dv = _att_ws(q.device, "bwd_dv", (nqb, B * Lk, H * dh))
+        check(_lib.load().mma_attn_bwd_t5b(
+            q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
+            o.stride(0), lse.data_ptr(), dout.data_ptr(), dout.stride(0), dq.data_ptr(), dq.stride(0), dk.data_ptr(),
+            dk.stride(0), dv.data_ptr(), dv.stride(0), ws_dq.data_ptr(), ws_dk.data_ptr(), ws_dv.data_ptr(), B, H, Lq, Lk,
+            int(causal), dh ** -0.5, float(p_drop), int(seed), int(site), _stream()), "mma_attn_bwd_t5b")
+        _count(2)
         return
     if _attn_tc_ok(dh, q, k, v, o, dout, dq, dk, dv):
         if dsum is None:
@@ -473,16 +509,16 @@ def p2p_barrier(peer_flags, epoch_ctr, world, rank):
     _count()
 
 
-def p2p_reduce_shard(peer_g, world, rank, lo, hi, workspace, sumsq_out):
-    check(_lib.load().mma_p2p_reduce_shard(_ptr_array(peer_g), world, rank, lo, hi, workspace.data_ptr(),
+def p2p_reduce_shard(peer_g, world, rank, lo, hi, workspace, sumsq_out, mc_g=0):
+    check(_lib.load().mma_p2p_reduce_shard(_ptr_array(peer_g), int(mc_g) or None, world, rank, lo, hi, workspace.data_ptr(),
                                            sumsq_out.data_ptr(), _stream()), "mma_p2p_reduce_shard")
     _count(2)
 
 
-def p2p_adam_shard(p, g, m, v, peer_pb, peer_sumsq, world, rank, lo, hi, hyper, decoupled=True):
+def p2p_adam_shard(p, g, m, v, peer_pb, peer_sumsq, world, rank, lo, hi, hyper, decoupled=True, mc_pb=0):
     check(_lib.load().mma_p2p_adam_shard(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr_array(peer_pb),
-                                         _ptr_array(peer_sumsq), world, rank, p.numel(), lo, hi, hyper.data_ptr(),
-                                         int(decoupled), _stream()), "mma_p2p_adam_shard")
+                                         int(mc_pb) or None, _ptr_array(peer_sumsq), world, rank, p.numel(), lo, hi,
+                                         hyper.data_ptr(), int(decoupled), _stream()), "mma_p2p_adam_shard")
     _count()
 
 

@@ -109,8 +109,14 @@ class PeerShardedStep:
         name = pg.group_name
         self._remote = []  # keeps the peers' mapped views alive
 
+        self.mc = {}  # NVLS multicast address of a symmetric tensor (0: not available)
+        use_mc = os.environ.get("MMA_DDP_MULTICAST", "1") != "0"
+
         def peers(t):
             hdl = symm.rendezvous(t, name)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if use_mc else 0
+            # same offset inside the multicast mapping as inside this rank's own allocation
+            self.mc[t.data_ptr()] = mc + (t.data_ptr() - int(hdl.buffer_ptrs[self.rank])) if mc else 0
             out = []
             for r in range(self.world):
                 if r == self.rank:
@@ -148,10 +154,11 @@ class PeerShardedStep:
 
     def step(self, store, hyper, decoupled: bool):
         self.barrier()
-        ops.p2p_reduce_shard(self.peer_g, self.world, self.rank, self.lo, self.hi, self.ws, self.sumsq)
+        ops.p2p_reduce_shard(self.peer_g, self.world, self.rank, self.lo, self.hi, self.ws, self.sumsq,
+                             mc_g=self.mc.get(self.g.data_ptr(), 0))
         self.barrier()
         ops.p2p_adam_shard(store.p, store.g, store.m, store.v, self.peer_pb, self.peer_sumsq, self.world, self.rank,
-                           self.lo, self.hi, hyper, decoupled=decoupled)
+                           self.lo, self.hi, hyper, decoupled=decoupled, mc_pb=self.mc.get(self.pb.data_ptr(), 0))
         self.barrier()
 
 

@@ -554,15 +554,19 @@ def test_tc_attention_dropout_forward_backward_use_one_mask():
         assert rel(got.view(B, L, H, dh).permute(0, 2, 1, 3).float(), want) < 3e-2
 
 
-@pytest.mark.parametrize("B,H,Lq,Lk,causal", [(2, 8, 199, 199, False), (2, 8, 96, 199, False), (3, 8, 100, 100, True)])
-def test_tc_attention_multi_tile(B, H, Lq, Lk, causal):
-    """sequences longer than one 64-row tile (C4 multimodal shapes) on the tensor-core path."""
+@pytest.mark.parametrize("impl", ["tcgen05", "mma"])
+@pytest.mark.parametrize("B,H,Lq,Lk,causal", [(2, 8, 199, 199, False), (2, 8, 96, 199, False), (3, 8, 100, 100, True),
+                                              (2, 8, 295, 295, False), (1, 8, 200, 200, True), (1, 4, 129, 512, False)])
+def test_tc_attention_multi_tile(B, H, Lq, Lk, causal, impl, monkeypatch):
+    """sequences longer than one tile (C4 multimodal shapes): blocked tcgen05 kernels (128 x 128 tile problems + merge)
+    and the streaming mma.sync kernels, forward and backward against torch."""
+    monkeypatch.setattr(ops, "ATTN_IMPL", impl)
     dh, dt = 64, torch.bfloat16
     d = H * dh
     q, k, v = _rand(B, Lq, d, dtype=dt, seed=1), _rand(B, Lk, d, dtype=dt, seed=2), _rand(B, Lk, d, dtype=dt, seed=3)
     kmask = torch.ones(B, Lk, dtype=torch.uint8, device=DEV)
     kmask[0, 70:90] = 0
-    kmask[1, Lk - 5:] = 0
+    kmask[B - 1, Lk - 5:] = 0
     o = torch.empty(B * Lq, d, device=DEV, dtype=dt)
     lse = torch.empty(B * H * Lq, device=DEV)
     ops.attn_fwd(q.view(-1, d), k.view(-1, d), v.view(-1, d), o, lse, B, H, Lq, Lk, dh, kmask=kmask, causal=causal)
@@ -577,6 +581,28 @@ def test_tc_attention_multi_tile(B, H, Lq, Lk, causal):
     assert rel(dq.view_as(q).float(), qr.grad) < 3e-2
     assert rel(dk.view_as(k).float(), kr.grad) < 3e-2
     assert rel(dv.view_as(v).float(), vr.grad) < 3e-2
+
+
+def test_blocked_tcgen05_attention_dropout_equals_streaming_kernel(monkeypatch):
+    """Same dropout stream (global (i, j) indexing) in the blocked tcgen05 kernels and the streaming mma.sync kernels:
+    outputs and gradients of the two implementations agree with dropout on, forward and backward use one mask."""
+    B, H, Lq, Lk, dh, dt, p = 2, 8, 199, 199, 64, torch.bfloat16, 0.2
+    d = H * dh
+    q, k, v = (_rand(B * L, d, dtype=dt, seed=sd) for L, sd in ((Lq, 1), (Lk, 2), (Lk, 3)))
+    do = _rand(B * Lq, d, dtype=dt, seed=4)
+    kmask = torch.ones(B, Lk, dtype=torch.uint8, device=DEV)
+    kmask[1, 150:] = 0
+    res = {}
+    for impl in ("tcgen05", "mma"):
+        monkeypatch.setattr(ops, "ATTN_IMPL", impl)
+        o = torch.empty(B * Lq, d, device=DEV, dtype=dt)
+        lse = torch.empty(B * H * Lq, device=DEV)
+        ops.attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=kmask, p_drop=p, seed=5, site=3)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ops.attn_bwd(q, k, v, o, lse, do, dq, dk, dv, B, H, Lq, Lk, dh, kmask=kmask, p_drop=p, seed=5, site=3)
+        res[impl] = (o.float(), lse.clone(), dq.float(), dk.float(), dv.float())
+    for a, b in zip(res["tcgen05"], res["mma"]):
+        assert rel(a, b) < 2e-2
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "mma"])
