@@ -205,16 +205,16 @@ int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long long ldk, 
 
 /* blocked tcgen05 / TMEM variants for 128 < L <= 512 (the multimodal encoder, S ~ 200-300): the score matrix is cut
  * into 128 x 128 single-shot tile problems; forward merges the key blocks' (O, log-sum-exp), backward sums per-block fp32
- * partial gradients (deterministic, no atomics).  Caller-owned fp32 workspaces with nqb = ceil(Lq/128), nkb = ceil(Lk/128):
- * ws_o [nkb][B*Lq][H*64], ws_lse [nkb][B*H*Lq]; ws_dq [nkb][B*Lq][H*64], ws_dk / ws_dv [nqb][B*Lk][H*64].            */
+ * partial gradients (deterministic, no atomics).  Caller-owned workspaces with nqb = ceil(Lq/128), nkb = ceil(Lk/128):
+ * ws_o bf16 [nkb][B*Lq][H*64], ws_lse fp32 [nkb][B*H*Lq]; ws_dq bf16 [nkb][B*Lq][H*64], ws_dk / ws_dv bf16 [nqb][B*Lk][H*64]. */
 int mma_attn_fwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                     const unsigned char* kmask, void* o, long long ldo, float* lse, float* ws_o, float* ws_lse, int B,
+                     const unsigned char* kmask, void* o, long long ldo, float* lse, void* ws_o, float* ws_lse, int B,
                      int H, int Lq, int Lk, int causal, float scale, float p_drop, unsigned long long seed,
                      unsigned int site, cudaStream_t stream);
 int mma_attn_bwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                      const unsigned char* kmask, const void* o, long long ldo, const float* lse, const void* dout,
                      long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
-                     float* ws_dq, float* ws_dk, float* ws_dv, int B, int H, int Lq, int Lk, int causal, float scale,
+                     void* ws_dq, void* ws_dk, void* ws_dv, int B, int H, int Lq, int Lk, int causal, float scale,
                      float p_drop, unsigned long long seed, unsigned int site, cudaStream_t stream);
 
 /* ---- loss (nn.CrossEntropyLoss, custom_modeling.py:490-491; ignore_index -100 set at wrapper.py:389) --------- */

@@ -997,7 +997,7 @@ bwd_pipe_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 //   forward   block (qb, kb) -> O_kb = softmax_block(S) V_kb (normalised inside the block, fp32) and the block's
 //             log-sum-exp; merge_fwd combines the key blocks: lse = log sum_kb exp(lse_kb), O = sum_kb exp(lse_kb - lse) O_kb
 //   backward  with the MERGED lse and D_i = rowsum(dO o O) every block is independent: P = exp(S - lse), dS = P o (dP - D);
-//             block (qb, kb) contributes dQ_qb += dS K_kb, dK_kb += dS^T Q_qb, dV_kb += P^T dO_qb - written as fp32
+//             block (qb, kb) contributes dQ_qb += dS K_kb, dK_kb += dS^T Q_qb, dV_kb += P^T dO_qb - written as bf16
 //             partials indexed by the OTHER block coordinate and summed by merge_bwd (no atomics: deterministic).
 // Masks (key padding, causal) and the dropout stream use GLOBAL (i, j), so results equal the single-tile / streaming
 // kernels' for the same seed.  The elementwise softmax / dropout work per score - not the MMA - bounds attention at
@@ -1010,12 +1010,12 @@ struct BlkArgs {
   unsigned long long seed;
   unsigned int site;
   const unsigned char* kmask;
-  float* opart;     // fwd out: [nkb][B*Lq][H*64]
+  bf16* opart;      // fwd out: [nkb][B*Lq][H*64]  (partials travel as bf16: half the bytes, merged in fp32)
   float* lsepart;   // fwd out: [nkb][B*H*Lq]
   const float* lse; // bwd in: merged [B*H*Lq]
-  float* dqpart;    // bwd out: [nkb][B*Lq][H*64]
-  float* dkpart;    // bwd out: [nqb][B*Lk][H*64]
-  float* dvpart;    // bwd out: [nqb][B*Lk][H*64]
+  bf16* dqpart;     // bwd out: [nkb][B*Lq][H*64]
+  bf16* dkpart;     // bwd out: [nqb][B*Lk][H*64]
+  bf16* dvpart;     // bwd out: [nqb][B*Lk][H*64]
 };
 
 struct BlkMap {
@@ -1166,15 +1166,19 @@ __global__ void __launch_bounds__(128) fwd_blk_kernel(const __grid_constant__ CU
     const float inv = l > 0.f ? 1.f / l : 0.f;
     const bool wr = i < a.Lq;
     const long long part = (long long)bm.kb * a.B * a.Lq;
-    float* orow = a.opart + (part + (long long)bm.b * a.Lq + i) * (a.H * 64) + bm.h * 64;
+    bf16* orow = a.opart + (part + (long long)bm.b * a.Lq + i) * (a.H * 64) + bm.h * 64;
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
       float v[32];
       tmem_ld32f(tm + ((uint32_t)(warp * 32) << 16) + ch * 32, v);
       if (wr) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4)
-          *reinterpret_cast<float4*>(orow + ch * 32 + c) = make_float4(v[c] * inv, v[c + 1] * inv, v[c + 2] * inv, v[c + 3] * inv);
+        for (int c = 0; c < 32; c += 8) {
+          uint4 u;
+          u.x = pack2(v[c] * inv, v[c + 1] * inv); u.y = pack2(v[c + 2] * inv, v[c + 3] * inv);
+          u.z = pack2(v[c + 4] * inv, v[c + 5] * inv); u.w = pack2(v[c + 6] * inv, v[c + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + ch * 32 + c) = u;
+        }
       }
     }
     if (wr)
@@ -1189,34 +1193,47 @@ __global__ void __launch_bounds__(128) fwd_blk_kernel(const __grid_constant__ CU
   }
 }
 
-// one warp per (row, head): O = sum_kb w_kb O_kb, lse = m + log sum_kb exp(lse_kb - m)
-__global__ void __launch_bounds__(256) merge_fwd_kernel(const float* __restrict__ opart, const float* __restrict__ lsepart, bf16* o,
+// one thread per (row, head, 8 columns): O = sum_kb w_kb O_kb, lse = m + log sum_kb exp(lse_kb - m)
+__global__ void __launch_bounds__(256) merge_fwd_kernel(const bf16* __restrict__ opart, const float* __restrict__ lsepart, bf16* o,
                                                         long long ldo, float* __restrict__ lse, int B, int H, int Lq, int nkb) {
   pdl_trigger();
-  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
   const long long rows = (long long)B * Lq;
-  if (gw >= rows * H) return;
-  const long long r = gw / H;
-  const int h = (int)(gw % H);
-  const int b = (int)(r / Lq), i = (int)(r % Lq);
-  const long long li = ((long long)b * H + h) * Lq + i;
-  float lp[4], m = -INFINITY;
-  for (int kb = 0; kb < nkb; ++kb) {
-    lp[kb] = lsepart[(long long)kb * B * H * Lq + li];
-    m = fmaxf(m, lp[kb]);
+  const long long total = rows * H * 8;
+  const int W = H * 64;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx & 7);
+    const long long rh = idx >> 3;
+    const long long r = rh / H;
+    const int h = (int)(rh % H);
+    const int b = (int)(r / Lq), i = (int)(r % Lq);
+    const long long li = ((long long)b * H + h) * Lq + i;
+    float lp[4], m = -INFINITY;
+    for (int kb = 0; kb < nkb; ++kb) {
+      lp[kb] = lsepart[(long long)kb * B * H * Lq + li];
+      m = fmaxf(m, lp[kb]);
+    }
+    float L = 0.f, acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const float w = lp[kb] == -INFINITY ? 0.f : __expf(lp[kb] - m);
+      L += w;
+      const uint4 raw = *reinterpret_cast<const uint4*>(opart + ((long long)kb * rows + r) * W + h * 64 + c8 * 8);
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        const float2 f = __bfloat1622float2(hp[q2]);
+        acc[2 * q2] = fmaf(w, f.x, acc[2 * q2]);
+        acc[2 * q2 + 1] = fmaf(w, f.y, acc[2 * q2 + 1]);
+      }
+    }
+    const float inv = L > 0.f ? 1.f / L : 0.f;
+    uint4 u;
+    u.x = pack2(acc[0] * inv, acc[1] * inv); u.y = pack2(acc[2] * inv, acc[3] * inv);
+    u.z = pack2(acc[4] * inv, acc[5] * inv); u.w = pack2(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(o + r * ldo + h * 64 + c8 * 8) = u;
+    if (c8 == 0 && lse) lse[li] = L > 0.f ? m + logf(L) : -INFINITY;
   }
-  float L = 0.f, o0 = 0.f, o1 = 0.f;
-  for (int kb = 0; kb < nkb; ++kb) {
-    const float w = lp[kb] == -INFINITY ? 0.f : __expf(lp[kb] - m);
-    L += w;
-    const float2 v = *reinterpret_cast<const float2*>(opart + ((long long)kb * rows + r) * (H * 64) + h * 64 + 2 * lane);
-    o0 = fmaf(w, v.x, o0);
-    o1 = fmaf(w, v.y, o1);
-  }
-  const float inv = L > 0.f ? 1.f / L : 0.f;
-  *reinterpret_cast<__nv_bfloat162*>(o + r * ldo + h * 64 + 2 * lane) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-  if (lane == 0 && lse) lse[li] = L > 0.f ? m + logf(L) : -INFINITY;
 }
 
 __global__ void __launch_bounds__(128) bwd_blk_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
@@ -1372,9 +1389,9 @@ __global__ void __launch_bounds__(128) bwd_blk_kernel(const __grid_constant__ CU
   {
     const bool kvalid = jk < a.Lk;
     const int W = a.H * 64;
-    float* dqrow = a.dqpart + ((long long)bm.kb * a.B * a.Lq + (long long)bm.b * a.Lq + i) * W + bm.h * 64;
-    float* dkrow = a.dkpart + ((long long)bm.qb * a.B * a.Lk + (long long)bm.b * a.Lk + jk) * W + bm.h * 64;
-    float* dvrow = a.dvpart + ((long long)bm.qb * a.B * a.Lk + (long long)bm.b * a.Lk + jk) * W + bm.h * 64;
+    bf16* dqrow = a.dqpart + ((long long)bm.kb * a.B * a.Lq + (long long)bm.b * a.Lq + i) * W + bm.h * 64;
+    bf16* dkrow = a.dkpart + ((long long)bm.qb * a.B * a.Lk + (long long)bm.b * a.Lk + jk) * W + bm.h * 64;
+    bf16* dvrow = a.dvpart + ((long long)bm.qb * a.B * a.Lk + (long long)bm.b * a.Lk + jk) * W + bm.h * 64;
     const uint32_t tl = tm + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int part = 0; part < 6; ++part) {  // dV lo/hi, dK lo/hi, dQ lo/hi
@@ -1383,10 +1400,15 @@ __global__ void __launch_bounds__(128) bwd_blk_kernel(const __grid_constant__ CU
       const int which = part >> 1, half = part & 1;
       const bool wr = which == 2 ? qvalid : kvalid;
       const float sc = which == 0 ? 1.f : a.scale;
-      float* dst = (which == 0 ? dvrow : which == 1 ? dkrow : dqrow) + half * 32;
+      bf16* dst = (which == 0 ? dvrow : which == 1 ? dkrow : dqrow) + half * 32;
       if (wr) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c] * sc, v[c + 1] * sc, v[c + 2] * sc, v[c + 3] * sc);
+        for (int c = 0; c < 32; c += 8) {
+          uint4 u;
+          u.x = pack2(v[c] * sc, v[c + 1] * sc); u.y = pack2(v[c + 2] * sc, v[c + 3] * sc);
+          u.z = pack2(v[c + 4] * sc, v[c + 5] * sc); u.w = pack2(v[c + 6] * sc, v[c + 7] * sc);
+          *reinterpret_cast<uint4*>(dst + c) = u;
+        }
       }
     }
   }
@@ -1399,32 +1421,39 @@ __global__ void __launch_bounds__(128) bwd_blk_kernel(const __grid_constant__ CU
 }
 
 // out[r, c] (bf16, pitch ld) = sum_p part[p][r][c]  for the three gradients (dQ over key blocks, dK / dV over query blocks)
-__global__ void __launch_bounds__(256) merge_bwd_kernel(const float* __restrict__ dqp, const float* __restrict__ dkp,
-                                                        const float* __restrict__ dvp, bf16* dq, long long lddq, bf16* dk,
+__global__ void __launch_bounds__(256) merge_bwd_kernel(const bf16* __restrict__ dqp, const bf16* __restrict__ dkp,
+                                                        const bf16* __restrict__ dvp, bf16* dq, long long lddq, bf16* dk,
                                                         long long lddk, bf16* dv, long long lddv, long long rows_q,
                                                         long long rows_k, int W, int nkb, int nqb) {
   pdl_trigger();
-  const long long per_q = rows_q * (W / 4), per_k = rows_k * (W / 4);
+  const long long per_q = rows_q * (W / 8), per_k = rows_k * (W / 8);
   const long long total = per_q + 2 * per_k;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const float* src;
+    const bf16* src;
     bf16* dst;
     long long ld, rows, e = idx;
     int np;
     if (e < per_q) { src = dqp; dst = dq; ld = lddq; rows = rows_q; np = nkb; }
     else if (e < per_q + per_k) { e -= per_q; src = dkp; dst = dk; ld = lddk; rows = rows_k; np = nqb; }
     else { e -= per_q + per_k; src = dvp; dst = dv; ld = lddv; rows = rows_k; np = nqb; }
-    const long long r = e / (W / 4);
-    const int c = (int)(e % (W / 4)) * 4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long r = e / (W / 8);
+    const int c = (int)(e % (W / 8)) * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     for (int p = 0; p < np; ++p) {
-      const float4 v = *reinterpret_cast<const float4*>(src + ((long long)p * rows + r) * W + c);
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      const uint4 raw = *reinterpret_cast<const uint4*>(src + ((long long)p * rows + r) * W + c);
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        const float2 f = __bfloat1622float2(hp[q2]);
+        acc[2 * q2] += f.x;
+        acc[2 * q2 + 1] += f.y;
+      }
     }
-    uint2 u;
-    u.x = pack2(s.x, s.y);
-    u.y = pack2(s.z, s.w);
-    *reinterpret_cast<uint2*>(dst + r * ld + c) = u;
+    uint4 u;
+    u.x = pack2(acc[0], acc[1]); u.y = pack2(acc[2], acc[3]); u.z = pack2(acc[4], acc[5]); u.w = pack2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dst + r * ld + c) = u;
   }
 }
 
@@ -1556,9 +1585,9 @@ extern "C" int mma_attn_bwd_t5(const void* q, long long ldq, const void* k, long
 }
 
 // Blocked tcgen05 attention for sequences longer than one 128-row tile (Lq, Lk <= 512; bf16, head dim 64).
-// ws_o: fp32 [nkb][B*Lq][H*64], ws_lse: fp32 [nkb][B*H*Lq] with nkb = ceil(Lk / 128) (caller-owned workspaces).
+// ws_o: bf16 [nkb][B*Lq][H*64], ws_lse: fp32 [nkb][B*H*Lq] with nkb = ceil(Lk / 128) (caller-owned workspaces).
 extern "C" int mma_attn_fwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
-                                const unsigned char* kmask, void* o, long long ldo, float* lse, float* ws_o, float* ws_lse,
+                                const unsigned char* kmask, void* o, long long ldo, float* lse, void* ws_o, float* ws_lse,
                                 int B, int H, int Lq, int Lk, int causal, float scale, float p_drop, unsigned long long seed,
                                 unsigned int site, cudaStream_t stream) {
   using namespace at5;
@@ -1571,23 +1600,22 @@ extern "C" int mma_attn_fwd_t5b(const void* q, long long ldq, const void* k, lon
   if ((rc = map64(&tv, v, H, (long long)B * Lk, ldv))) return rc;
   BlkArgs a{};
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nqb = (Lq + 127) / 128; a.nkb = (Lk + 127) / 128;
-  a.scale = scale; a.p_drop = p_drop; a.seed = seed; a.site = site; a.kmask = kmask; a.opart = ws_o; a.lsepart = ws_lse;
+  a.scale = scale; a.p_drop = p_drop; a.seed = seed; a.site = site; a.kmask = kmask; a.opart = (bf16*)ws_o; a.lsepart = ws_lse;
   const int smem = 3 * TILE + 64;
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(fwd_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
   const long long nprob = (long long)B * H * a.nqb * a.nkb;
   if (launch_pdl(fwd_blk_kernel, dim3((unsigned)nprob), dim3(128), smem, stream, tq, tk, tv, a) != cudaSuccess) return MMA_ERR_LAUNCH;
-  const long long warps = (long long)B * Lq * H;
-  merge_fwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, stream>>>(ws_o, ws_lse, (bf16*)o, ldo, lse, B, H, Lq, a.nkb);
+  merge_fwd_kernel<<<148 * 8, 256, 0, stream>>>((const bf16*)ws_o, ws_lse, (bf16*)o, ldo, lse, B, H, Lq, a.nkb);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }
 
-// ws_dq: fp32 [nkb][B*Lq][H*64]; ws_dk, ws_dv: fp32 [nqb][B*Lk][H*64]
+// ws_dq: bf16 [nkb][B*Lq][H*64]; ws_dk, ws_dv: bf16 [nqb][B*Lk][H*64]
 extern "C" int mma_attn_bwd_t5b(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
                                 const unsigned char* kmask, const void* o, long long ldo, const float* lse, const void* dout,
                                 long long lddo, void* dq, long long lddq, void* dk, long long lddk, void* dv, long long lddv,
-                                float* ws_dq, float* ws_dk, float* ws_dv, int B, int H, int Lq, int Lk, int causal,
+                                void* ws_dq, void* ws_dk, void* ws_dv, int B, int H, int Lq, int Lk, int causal,
                                 float scale, float p_drop, unsigned long long seed, unsigned int site, cudaStream_t stream) {
   using namespace at5;
   if (B <= 0 || Lq <= 0 || Lk <= 0) return MMA_OK;
@@ -1603,14 +1631,14 @@ extern "C" int mma_attn_bwd_t5b(const void* q, long long ldq, const void* k, lon
   BlkArgs a{};
   a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.causal = causal; a.nqb = (Lq + 127) / 128; a.nkb = (Lk + 127) / 128;
   a.scale = scale; a.p_drop = p_drop; a.seed = seed; a.site = site; a.kmask = kmask; a.lse = lse;
-  a.dqpart = ws_dq; a.dkpart = ws_dk; a.dvpart = ws_dv;
+  a.dqpart = (bf16*)ws_dq; a.dkpart = (bf16*)ws_dk; a.dvpart = (bf16*)ws_dv;
   const int smem = 7 * TILE + 64;
   static bool set = false;
   if (!set) { cudaFuncSetAttribute(bwd_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); set = true; }
   const long long nprob = (long long)B * H * a.nqb * a.nkb;
   if (launch_pdl(bwd_blk_kernel, dim3((unsigned)nprob), dim3(128), smem, stream, tq, tk, tv, tdo, to, a) != cudaSuccess)
     return MMA_ERR_LAUNCH;
-  merge_bwd_kernel<<<148 * 8, 256, 0, stream>>>(ws_dq, ws_dk, ws_dv, (bf16*)dq, lddq, (bf16*)dk, lddk, (bf16*)dv, lddv,
+  merge_bwd_kernel<<<148 * 8, 256, 0, stream>>>((const bf16*)ws_dq, (const bf16*)ws_dk, (const bf16*)ws_dv, (bf16*)dq, lddq, (bf16*)dk, lddk, (bf16*)dv, lddv,
                                                 (long long)B * Lq, (long long)B * Lk, H * 64, a.nkb, a.nqb);
   MMA_CHECK_LAUNCH();
   return MMA_OK;

@@ -375,12 +375,12 @@ def cast_bf16_f32(src, dst):
 _ATT_WS = {}
 
 
-def _att_ws(device, name, shape):
-    """fp32 workspace of the blocked attention kernels, one per (device, role, shape)."""
+def _att_ws(device, name, shape, dtype=torch.bfloat16):
+    """workspace of the blocked attention kernels (bf16 partials, fp32 log-sum-exp), one per (device, role, shape)."""
     key = (str(device), name, tuple(shape))
     t = _ATT_WS.get(key)
     if t is None:
-        t = _ATT_WS[key] = torch.empty(shape, dtype=torch.float32, device=device)
+        t = _ATT_WS[key] = torch.empty(shape, dtype=dtype, device=device)
     return t
 
 
@@ -404,7 +404,7 @@ def attn_fwd(q, k, v, o, lse, B, H, Lq, Lk, dh, kmask=None, causal=False, p_drop
         # that captured CUDA graphs keep stable addresses
         nkb = (Lk + 127) // 128
         ws_o = _att_ws(q.device, "fwd_o", (nkb, B * Lq, H * dh))
-        ws_l = _att_ws(q.device, "fwd_lse", (nkb, B * H * Lq))
+        ws_l = _att_ws(q.device, "fwd_lse", (nkb, B * H * Lq), torch.float32)
         check(_lib.load().mma_attn_fwd_t5b(
             q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), _p(kmask), o.data_ptr(),
             o.stride(0), lse.data_ptr(), ws_o.data_ptr(), ws_l.data_ptr(), B, H, Lq, Lk, int(causal), dh ** -0.5,
