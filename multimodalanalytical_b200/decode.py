@@ -29,6 +29,13 @@ from .model import Engine
 FUSE_DECODE_LN = int(os.environ.get("MMA_DECODE_FUSE_LN", "0"))
 
 
+# finished-spectrum compaction inside a decode batch (MMA_DECODE_COMPACT=0 disables it); batches below COMPACT_MIN_B
+# spectra are latency-bound and not worth a re-capture
+COMPACT = os.environ.get("MMA_DECODE_COMPACT", "1") != "0"
+COMPACT_MIN_B = int(os.environ.get("MMA_DECODE_COMPACT_MIN_B", "16"))
+COMPACT_LIVE_FRAC = 0.5  # compact when at most this fraction of the batch is still searching
+
+
 class BeamState:
     """Device-resident search state for B spectra x K beams (K == 1: greedy)."""
 
@@ -218,6 +225,15 @@ class Generator:
 
         steps = 0
         max_steps = L - 1
+        # finished-spectrum compaction: a spectrum whose search is over (beam: its finished pool can no longer improve,
+        # greedy: it emitted <eos>) is frozen by the step kernels, but its K rows still ride through every product of the
+        # step.  When at most half of the batch is still searching, the live spectra (state, K/V caches, cross K/V) are
+        # gathered into a batch of half the size (shapes stay powers-of-two fractions of B, so the captured step graphs
+        # are reused across calls) and the results of the retired ones are parked.  Output is unchanged: every spectrum's
+        # state is independent of its neighbours.
+        compact = COMPACT and extra_bias is None
+        orig = torch.arange(B, device=eng.dev)  # original index of each spectrum of the current (compacted) batch
+        parked = None                            # (seq [B, K, L] int32, score [B, K], len [B, K]) of retired spectra
         while steps < max_steps:
             n = min(check_every, max_steps - steps)
             for _ in range(n):
@@ -226,13 +242,116 @@ class Generator:
                 else:
                     self._step(st, ctx, extra_bias)
             steps += n
+            live = st.unfinished if K == 1 else st.improvable
+            live_host = live.cpu()
             if K == 1:
-                if not bool(st.unfinished.any().item()):
+                if not bool(live_host.any()):
                     break
             else:
-                if not (bool(st.improvable.any().item()) and not bool(st.all_hit.all().item())):
+                if not (bool(live_host.any()) and not bool(st.all_hit.all().item())):
                     break
-        return self._collect(st, return_scores)
+            n_live = int(live_host.sum())
+            if compact and st.B >= COMPACT_MIN_B and n_live < st.B and n_live <= COMPACT_LIVE_FRAC * st.B and steps < max_steps:
+                if parked is None:
+                    parked = self._park_init(B, K, L)
+                st, ctx, graph, orig = self._compact(st, ctx, live_host, orig, parked, use_graph, S)
+        if parked is None:
+            return self._collect(st, return_scores)
+        self._park(st, torch.arange(st.B, device=eng.dev), orig, parked)
+        return self._collect_parked(parked, K, return_scores)
+
+    # ------------------------------------------------------------------------------------ compaction
+    def _park_init(self, B, K, L):
+        cfg, dev = self.eng.cfg, self.eng.dev
+        fill = cfg.pad_token_id if (K == 1 or cfg.pad_token_id) else cfg.eos_token_id
+        return dict(seq=torch.full((B, K, L), fill, dtype=torch.int32, device=dev),
+                    score=torch.full((B, K), -1.0e9, dtype=torch.float32, device=dev),
+                    len=torch.zeros(B, K, dtype=torch.int32, device=dev))
+
+    def _park(self, st: BeamState, idx, orig, parked):
+        """Copy the final hypotheses of the spectra `idx` (indices into the current batch) to their original slots."""
+        if idx.numel() == 0:
+            return
+        cur = int(st.cur_len.item())
+        dst = orig[idx]
+        if st.K == 1:
+            parked["seq"][dst, 0] = st.run_seq[idx]
+            parked["len"][dst, 0] = cur
+        else:
+            parked["seq"][dst] = st.fin_seq[cur & 1][idx]
+            parked["score"][dst] = st.fin_score[idx]
+            parked["len"][dst] = st.fin_len[idx]
+
+    def _compact(self, st: BeamState, ctx, live_host, orig, parked, use_graph, S):
+        eng, cfg = self.eng, self.eng.cfg
+        K, L, d, T = st.K, st.L, cfg.d_model, self.eng.adt
+        dev = eng.dev
+        B_old = st.B
+        n_live = max(int(live_host.sum()), 1)
+        B_new = max(B_old // 2, 1)
+        while B_new // 2 >= n_live:
+            B_new //= 2
+        B_new = max(B_new, n_live)
+        live_idx = live_host.nonzero().flatten()
+        dead_idx = (live_host == 0).nonzero().flatten()
+        self._park(st, dead_idx.to(dev), orig, parked)
+        # the new batch: every live spectrum + retired ones as filler (frozen, their results are already parked)
+        keep = torch.cat([live_idx, dead_idx[: B_new - live_idx.numel()]]).to(dev)
+        new = self._states.get((B_new, K, L))
+        if new is None:
+            new = self._states[(B_new, K, L)] = BeamState(B_new, K, L, cfg.pad_token_id, cfg.bos_token_id,
+                                                          cfg.eos_token_id, dev)
+        R_new = B_new * K
+        nctx = dict(kvmem=eng.buf("g.kvmem", (cfg.decoder_layers, B_new * S, 2 * d), T),
+                    kc=eng.buf("g.kc", (cfg.decoder_layers, R_new, L, d), T),
+                    vc=eng.buf("g.vc", (cfg.decoder_layers, R_new, L, d), T), pos=ctx["pos"],
+                    enc_mask=eng.buf("g.enc_mask", (B_new, S), torch.uint8), S=S)
+        graph = None
+        if use_graph:  # capture (warm-up + reset) BEFORE the state moves in
+            graph = self._capture((B_new, K, L, S, 0), new, lambda: self._step(new, nctx, None))
+        rows = (keep[:, None] * K + torch.arange(K, device=dev)[None, :]).reshape(-1)  # old row of every new row
+        cur = int(st.cur_len.item())
+        new.cur_len.copy_(st.cur_len)
+        new.next_tok.copy_(st.next_tok[rows])
+        if K == 1:
+            new.run_seq.copy_(st.run_seq[keep])
+            new.unfinished.copy_(st.unfinished[keep])
+            new.parent_row.copy_(torch.arange(R_new, dtype=torch.int32, device=dev))
+        else:
+            shift = ((torch.arange(B_new, device=dev) - keep) * K).to(torch.int32)  # new row = old row + shift
+            shift_rows = shift.repeat_interleave(K)
+            new.run_seq.copy_(st.run_seq[:, keep])
+            new.fin_seq.copy_(st.fin_seq[:, keep])
+            for name in ("run_score", "fin_score", "fin_flag", "fin_len", "improvable", "all_hit"):
+                getattr(new, name).copy_(getattr(st, name)[keep])
+            new.parent_row.copy_(st.parent_row[rows] + shift_rows)
+            new.anc.copy_(st.anc[:, rows] + shift_rows[None, :, None])
+        nctx["enc_mask"].copy_(ctx["enc_mask"][keep])
+        nctx["kvmem"].view(cfg.decoder_layers, B_new, S, 2 * d).copy_(
+            ctx["kvmem"].view(cfg.decoder_layers, B_old, S, 2 * d)[:, keep])
+        # only the positions written so far carry information
+        nctx["kc"][:, :, :cur].copy_(ctx["kc"][:, rows, :cur])
+        nctx["vc"][:, :, :cur].copy_(ctx["vc"][:, rows, :cur])
+        self.compactions = getattr(self, "compactions", 0) + 1
+        return new, nctx, graph, orig[keep]
+
+    def _collect_parked(self, parked, K, return_scores):
+        seq = parked["seq"].to(torch.int64)
+        B, _, L = seq.shape
+        cfg = self.eng.cfg
+        if K == 1:
+            s = seq[:, 0]
+            is_eos = s == cfg.eos_token_id
+            has = is_eos.any(dim=1)
+            cur = parked["len"][:, 0].to(torch.int64)
+            first = torch.where(has, is_eos.float().argmax(dim=1), cur - 1)
+            out_len = int(first.max().item()) + 1
+            return s[:, :out_len].contiguous()
+        out_len = 1 + int(parked["len"].max().item())
+        out = seq.reshape(B * K, L)[:, :out_len].contiguous()
+        if return_scores:
+            return out, parked["score"].reshape(B * K).clone()
+        return out
 
     def _capture(self, gkey, st: BeamState, fn):
         graph = self._graphs.get(gkey)

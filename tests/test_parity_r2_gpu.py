@@ -217,3 +217,31 @@ def test_lightning_hook_path_three_optimizer_steps_match_oracle_fp32():
         n += w.numel()
     assert moved > 0.5 * n, "the optimiser did not move the weights"
     assert bad < 2e-3 * n, f"{bad} of {n} elements stepped differently"
+
+
+@pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned", "align_conv"])
+def test_finished_spectrum_compaction_keeps_reference_sequences(name, monkeypatch):
+    """Spectra whose search is over are gathered out of the decode batch (state, K/V caches, cross K/V move to a batch
+    of half the size); the returned hypotheses must stay token-identical to the reference's golden sequences (fp32),
+    greedy and beam, and equal to the un-compacted run in bf16."""
+    from multimodalanalytical_b200 import decode
+    fx = load_case(name)
+    m = build(fx, "fp32")
+    m.eval()
+    monkeypatch.setattr(decode, "COMPACT_MIN_B", 2)
+    monkeypatch.setattr(decode, "COMPACT_LIVE_FRAC", 0.99)  # retire every finished spectrum at the next check
+    m.generator.compactions = 0
+    for key, want in fx["ref"].items():
+        if not key.startswith("gen_beam"):
+            continue
+        k = int(key[len("gen_beam"):])
+        got = m.generate(fx["batch"], n_beams=k, check_every=2).cpu()
+        assert got.shape == want.shape and torch.equal(got, want), key
+    assert m.generator.compactions > 0, "the fixture never triggered a compaction"
+    m16 = build(fx, "bf16")
+    m16.eval()
+    k = max(int(key[len("gen_beam"):]) for key in fx["ref"] if key.startswith("gen_beam"))
+    a, sa = m16.generate(fx["batch"], n_beams=k, check_every=2, return_scores=True)
+    monkeypatch.setattr(decode, "COMPACT", False)
+    b, sb = m16.generate(fx["batch"], n_beams=k, check_every=2, return_scores=True)
+    assert torch.equal(a, b) and torch.equal(sa, sb)
