@@ -139,7 +139,7 @@ glu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
         const int n0 = (tile % tiles_n) * GLU_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          MBAR_WAIT_LONG(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + B_BYTES));
           const uint32_t fb = mapa(fb_local, 0);
@@ -162,7 +162,7 @@ glu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < total; tile += npairs) {
-        mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+        MBAR_WAIT_LONG(smem_u32(&tempty[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -357,7 +357,7 @@ dglu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
         const int nb0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          MBAR_WAIT_LONG(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + B_BYTES));
           const uint32_t fb = mapa(fb_local, 0);
@@ -381,7 +381,7 @@ dglu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < total; tile += npairs) {
-        mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+        MBAR_WAIT_LONG(smem_u32(&tempty[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {

@@ -151,7 +151,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int m0 = (tile / tiles_n) * (2 * BM) + (int)rank * BM;
         const int nb0 = (tile % tiles_n) * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          MBAR_WAIT_LONG(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + B_BYTES));  // both CTAs' bytes land on this barrier
           const uint32_t fb = mapa(fb_local, 0);
@@ -186,7 +186,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = pair; tile < total; tile += npairs) {
-        mbar_wait(smem_u32(&tempty[acc]), acc_phase ^ 1);
+        MBAR_WAIT_LONG(smem_u32(&tempty[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb && !(dbg & 2); ++kb) {
@@ -535,7 +535,7 @@ gemm2_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = pair; tile < total; tile += npairs) {
         const int m0 = tile * (2 * BM) + (int)rank * BM;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          MBAR_WAIT_LONG(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + LNB_BYTES));
           const uint32_t fb = mapa(fb_local, 0);
@@ -557,7 +557,7 @@ gemm2_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0, tphase = 0;
       for (int tile = pair; tile < total; tile += npairs) {
-        mbar_wait(smem_u32(tempty), tphase ^ 1);
+        MBAR_WAIT_LONG(smem_u32(tempty), tphase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(smem_u32(&full[stage]), phase);
@@ -857,7 +857,7 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
         const Wg2Problem& P = grp.p[g];
         const int ma = m0 + (int)rank * BM, nb = n0 + (int)rank * (BN / 2);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+          MBAR_WAIT_LONG(smem_u32(&empty[stage]), phase ^ 1);
           const uint32_t fb_local = smem_u32(&full[stage]);
           if (rank == 0) mbar_expect_tx(fb_local, 2 * (A_BYTES + B_BYTES));
           const uint32_t fb = mapa(fb_local, 0);
@@ -884,7 +884,7 @@ wgrad2_group_kernel(const __grid_constant__ Wg2Group grp) {
         locate(item, g, m0, n0, kb0, kb1);
         const Wg2Problem& P = grp.p[g];
         const bool with_bias = n0 == 0 && P.dbias != nullptr;
-        mbar_wait(smem_u32(tempty), tphase ^ 1);
+        MBAR_WAIT_LONG(smem_u32(tempty), tphase ^ 1);
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(smem_u32(&full[stage]), phase);
