@@ -156,6 +156,8 @@ class Generator:
             kv = ctx["kvmem"][i]
             # the K beams of a spectrum attend over the same memory: one (spectrum, head) problem with K queries on
             # the tensor-core forward-attention kernel (K/V are read once per spectrum, not once per beam)
+            # (a per-row SIMT kernel in the shape of decode_self_attn2 was measured here: 1.11 vs 0.96 ms / step at 2560
+            # rows - every beam's CTA re-reads its spectrum's K / V from L2, 10x the tile kernel's traffic)
             ops.attn_fwd(q, kv[:, :d], kv[:, d:], att, None, st.B, H, K, ctx["S"], dh, kmask=ctx["enc_mask"])
             resid_ln(att, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", d, xa, xb,
                      p + "norm3.weight", p + "norm3.bias")

@@ -40,7 +40,7 @@ def _teacher_forced_fp32_logits(m32, batch, seqs, K):
         return m32.forward(tb).logits.float().cpu()
 
 
-@pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned"])
+@pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned", "c5_d512", "c5_d512_k30"])
 def test_bf16_decode_is_epsilon_optimal_under_fp32_scoring(name):
     """bf16 decode kernels (decode self-attention over the K/V cache, the bf16 GEMMs, tcgen05 cross-attention over the beams
     of a spectrum) judged by the fp32 engine, which is token-identical to the reference (test_model_gpu.py).  Sequences
@@ -48,12 +48,26 @@ def test_bf16_decode_is_epsilon_optimal_under_fp32_scoring(name):
     bf16 decoded (teacher forcing): every greedy choice must be within the bf16 logit tolerance of the fp32 arg-max, every
     beam hypothesis' kernel-reported score must equal its fp32 length-normalised log-probability, and the best bf16
     hypothesis must score (in fp32) within tolerance of the best fp32 hypothesis."""
-    fx = load_case(name)
-    K = 10 if name == "c1_ir_tiny" else 4
+    if name.startswith("c5_d512"):
+        # custom_model.yaml width (d 512, 8 heads of 64, 6 + 6 layers): the head-dim-64 decode kernels of the bench
+        # (decode_self_attn2 / decode_cross_attn2: one CTA per (row, 4 heads)), 10 and 30 beams
+        from tests.test_configs_gpu import make_case
+        fx = make_case("c5", 6)
+        K = 30 if name.endswith("k30") else 10
+    else:
+        fx = load_case(name)
+        K = 10 if name == "c1_ir_tiny" else 4
     eos = 3
     m32, m16 = build(fx, "fp32"), build(fx, "bf16")
     m32.eval()
     m16.eval()
+    if name.startswith("c5_d512"):
+        # sharpen the random-init head a little and let hypotheses finish (as tests/golden/make_golden.py does)
+        for m in (m32, m16):
+            m.store.P("hf_model.token_ff.weight").mul_(6.0)
+            m.store.P("hf_model.token_ff.bias")[eos] += 2.0
+            m.store.bf16_dirty = True
+            m.generation_config["max_length"] = 48
     # ---- greedy
     g16 = m16.generate(fx["batch"], n_beams=1).cpu()
     lg = _teacher_forced_fp32_logits(m32, fx["batch"], g16, 1)
