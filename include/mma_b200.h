@@ -248,9 +248,11 @@ int mma_p2p_adam_shard(float* p, float* g, float* m, float* v, const void* const
 /* ---- KV-cached decoding (replaces transformers generate(use_cache=False), wrapper.py:443-451) ---------------- */
 int mma_decode_embed(const int* tok, const float* table, const float* gamma, const float* beta, float eps,
                      const float* pos, const int* cur_len, float* out, int rows, int d, cudaStream_t stream);
+/* K/V cache layout [R][Lmax][H*dh]; anc [2][R][Lmax] ancestor rows (buffer cur_len & 1 is live); beams: rows
+ * [s*beams, (s+1)*beams) belong to one spectrum (>= 4: they may be grouped in one CTA so that shared ancestors hit in L1) */
 int mma_decode_self_attn(const void* q, long long ldq, const void* knew, const void* vnew, long long ldkv,
                          void* kcache, void* vcache, const int* anc, const int* cur_len, void* o, long long ldo, int R,
-                         int H, int dh, int Lmax, float scale, int type, cudaStream_t stream);
+                         int H, int dh, int Lmax, float scale, int type, int beams, cudaStream_t stream);
 int mma_decode_cross_attn(const void* q, long long ldq, const void* kmem, const void* vmem, long long ldm,
                           const unsigned char* kmask, const int* cur_len, void* o, long long ldo, int R, int H, int dh,
                           int S, int beams, float scale, int type, cudaStream_t stream);

@@ -149,7 +149,7 @@ _SIGS = {
     "mma_p2p_reduce_shard": [_vp, _vp, _i, _i, _ll, _ll, _vp, _vp, _vp],
     "mma_p2p_adam_shard": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp, _i, _vp],
     "mma_decode_embed": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp],
-    "mma_decode_self_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _vp],
+    "mma_decode_self_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _i, _vp],
     "mma_decode_cross_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp],
     "mma_beam_step": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                       _vp, _vp],

@@ -148,7 +148,7 @@ class Generator:
             ops.gemm(h, eng.W(p + "self_attn.in_proj_weight"), R, 3 * d, d,
                      ops.make_epi(EPI_STORE, qkv, bias=eng.P(p + "self_attn.in_proj_bias")))
             ops.decode_self_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx["kc"][i], ctx["vc"][i], st.anc,
-                                 st.cur_len, att, R, H, dh, L)
+                                 st.cur_len, att, R, H, dh, L, beams=K)
             resid_ln(att, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", d, x, xa,
                      p + "norm2.weight", p + "norm2.bias")
             ops.gemm(h, eng.W(p + "multihead_attn.in_proj_weight")[:d], R, d, d,

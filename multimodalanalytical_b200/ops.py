@@ -536,12 +536,12 @@ def decode_embed(tok, table, gamma, beta, pos, cur_len, out, eps=1e-5):
     _count()
 
 
-def decode_self_attn(q, knew, vnew, kcache, vcache, anc, cur_len, o, R, H, dh, Lmax):
+def decode_self_attn(q, knew, vnew, kcache, vcache, anc, cur_len, o, R, H, dh, Lmax, beams=1):
     _need_cuda(q, knew, vnew, kcache, vcache, o)
     check(_lib.load().mma_decode_self_attn(
         q.data_ptr(), q.stride(0), knew.data_ptr(), vnew.data_ptr(), knew.stride(0), kcache.data_ptr(),
         vcache.data_ptr(), _p(anc), cur_len.data_ptr(), o.data_ptr(), o.stride(0), R, H, dh, Lmax, dh ** -0.5, _ty(q),
-        _stream()), "mma_decode_self_attn")
+        int(beams), _stream()), "mma_decode_self_attn")
     _count()
 
 
