@@ -265,7 +265,7 @@ class Engine:
         """xo = x + drop(a W^T + b).  `nxt` = (gamma, beta, h buffer) of the LayerNorm that consumes xo next: when the
         fused CTA-pair kernel applies (d_model 512, bf16), h = LN(xo) comes out of the same launch.  Returns h or None."""
         epi = ops.make_epi(EPI_RESID, xo, bias=self.P(bname), resid=x, p_drop=p, seed=self.seed_arg, site=site_r)
-        if nxt is not None and self.precision == "bf16" and ops.FUSE_LN:
+        if nxt is not None and self.precision == "bf16" and ops.fuse_ln_wanted(M, k_in):
             gam, bet, hbuf = nxt
             if ops.gemm_resid_ln(a, self.W(wname), M, n_out, k_in, epi, gam, bet, hbuf):
                 return hbuf

@@ -157,7 +157,19 @@ def ffn_dglu(dy, W2, M, N, K, z1, z2, dz1, dz2, p_drop=0.0, seed=0, site=0, drop
 # timing, scripts/ln_fuse_bench.py): 26.9 vs 33.1 us for the decoder out-projection, but 43.2 vs 28.5 us for the
 # encoder FFN-2 - a CTA pair owns 256 rows x all 512 columns, so M = 9216 fills only 36 of the 74 pairs - and the
 # training step as a whole is 2.5 % slower with it.  Off by default; it pays from M ~ 32k rows upwards.
-FUSE_LN = os.environ.get("MMA_FUSE_LN", "0") != "0"
+# 0 off (default), 1 always, 2 only where the 256-row tiles fill the CTA pairs (K <= d), 3 the same for any K.  Round 2, C2
+# step on one box: 6.80 / 6.85 / 6.81 ms for modes 0 / 2 / 3 - the selective modes do not pay either.
+FUSE_LN = int(os.environ.get("MMA_FUSE_LN", "0"))
+
+
+def fuse_ln_wanted(M, K):
+    """Should the residual product [M, 512] x K be fused with the LayerNorm that follows it?  The fused kernel gives a CTA
+    pair 256 rows x all 512 columns: it pays when ceil(M / 256) tiles fill the 74 pairs of a wave to >= 85 %."""
+    if FUSE_LN in (0, 1):
+        return bool(FUSE_LN)
+    tiles = (M + 255) // 256
+    fill = tiles / (-(-tiles // 74) * 74)
+    return fill >= 0.85 and (FUSE_LN == 3 or K <= 512)
 
 
 def gemm_resid_ln(A, W, M, N, K, epi, gamma, beta, h, eps=1e-5):
