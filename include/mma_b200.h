@@ -256,6 +256,59 @@ int mma_decode_self_attn(const void* q, long long ldq, const void* knew, const v
 int mma_decode_cross_attn(const void* q, long long ldq, const void* kmem, const void* vmem, long long ldm,
                           const unsigned char* kmask, const int* cur_len, void* o, long long ldo, int R, int H, int dh,
                           int S, int beams, float scale, int type, cudaStream_t stream);
+/* Small-batch decode product (R <= 64 rows: a few spectra x beams): out[R,N] = epilogue(LN?(x)[R,K] w[N,K]^T + bias) in
+ * one launch on mma.sync with the weight tile as the 16-row operand (every weight element read once), LayerNorm of the fp32
+ * residual stream as prologue, bias / GELU / gate / residual as epilogue.  Replaces nn.LayerNorm + nn.Linear (+ gelu, gate,
+ * residual) of a decoder layer (custom_modeling.py:155-199) when the tcgen05 tiles would be > 90 % padding.
+ * x: fp32 (x_f32 = 1; LayerNorm when gamma != NULL) or bf16; kind 0 store, 1 GELU, 2 out = resid + result, 3 gated
+ * (gelu(x w^T + bias) * (x w2^T + bias2)).  K % 256 == 0; -3 otherwise / for R > 64.                               */
+int mma_small_linear(const void* x, int x_f32, long long ldx, const float* gamma, const float* beta, float eps,
+                     const void* w, const void* w2, long long ldw, const float* bias, const float* bias2,
+                     const float* resid, long long ldr, void* out, int out_f32, long long ldo, int R, int N, int K,
+                     int kind, cudaStream_t stream);
+/* The WHOLE decoder step of a few spectra (logits of every row) in ONE launch: token embedding, every decoder layer
+ * (LayerNorm + QKV, KV-cached self-attention, out-projection + residual, LayerNorm + cross-query, cross-attention,
+ * out-projection + residual, LayerNorm + FFN-1 (+ gate), FFN-2 + residual), final LayerNorm + LM head.  A thread-block
+ * cluster of `cluster_size` CTAs (8 or 16) owns `rows_per_cluster` consecutive rows (a multiple of `beams`, <= 16)
+ * and separates dependent phases with barrier.cluster, activations travel between the CTAs' shared memories
+ * (st.shared::cluster); clusters are independent.  Replaces the ~50 launches per step of
+ * the cached decode of HFWrapper.generate (wrapper.py:409-453 -> custom_modeling.py:155-199,418-486) when rows are few.
+ * bf16 weights [out, in] contiguous, fp32 biases / norms / residual stream; d = 512, f = 2048, head dim 64
+ * (MMA_ERR_UNSUPPORTED otherwise).  Same buffers and semantics as the per-op entry points above.                  */
+#define MMA_DECODE_MAX_LAYERS 12
+typedef struct MmaDecodeLayer {
+  const void *w_qkv, *w_so, *w_cq, *w_co, *w_f1, *w_fg, *w_f2;        /* bf16: self in_proj [3d,d], self out [d,d], cross
+                                                                         q [d,d], cross out [d,d], linear1 [f,d], gate
+                                                                         [f,d] (NULL when ungated), linear2 [d,f] */
+  const float *b_qkv, *b_so, *b_cq, *b_co, *b_f1, *b_fg, *b_f2;
+  const float *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;                     /* norm1 / norm2 / norm3 weight, bias */
+  void *kc, *vc;                                                      /* bf16 self K / V cache [R][Lmax][d] */
+  const void* kvmem;                                                  /* bf16 cross K | V [B * S][2 d] */
+} MmaDecodeLayer;
+typedef struct MmaDecodeStep {
+  MmaDecodeLayer layer[MMA_DECODE_MAX_LAYERS];
+  const int* tok;          /* [R] token fed to this step */
+  const float* emb;        /* [V, d] target embedding table */
+  const float *emb_g, *emb_b; /* per-modality LayerNorm of the embedding (NULL: none) */
+  const float* pos;        /* [Lmax, d] positional rows */
+  const int* cur_len;      /* device scalar: tokens so far (position of this step = cur_len - 1) */
+  const float *fin_g, *fin_b; /* decoder.norm */
+  const void* w_lm;        /* bf16 [V, d] */
+  const float* b_lm;
+  float *x, *xa, *xb;      /* unused (workspaces of the per-op path; kept so both paths fill one struct) */
+  void *qkv, *att, *q, *a; /* unused */
+  float* logits;           /* fp32 [R, ldv] */
+  const int* anc;          /* [2][R][Lmax] ancestor rows (NULL: identity, greedy) */
+  const unsigned char* enc_mask; /* [B][S], 1 = real memory position */
+  unsigned long long* dbg_times; /* NULL, or [64] device words: %globaltimer of cluster 0 at every phase boundary */
+  long long ldv;
+  int layers, R, rows_per_cluster, beams, d, f, H, Lmax, S, V, gated;
+  float eps, scale;
+} MmaDecodeStep;
+int mma_decode_step(const void* args /* const MmaDecodeStep* (host memory) */, int cluster_size, cudaStream_t stream);
+/* NOT a status: the number of clusters of `cluster_size` CTAs of the step kernel that can be resident at once on the current
+ * device (0: that cluster size cannot be scheduled).  More clusters than that run in waves.                        */
+int mma_decode_step_max_clusters(int cluster_size);
 /* one beam-search step for B spectra x K beams (transformers GenerationMixin._beam_search semantics) */
 int mma_beam_step(const float* logits, long long ldl, const float* extra_bias, int B, int K, int V, int L, int pad_id,
                   int eos_id, const int* cur_len, int* run_seq, int* fin_seq, float* run_score, float* fin_score,

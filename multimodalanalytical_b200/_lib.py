@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libmma_b200.so")
-SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_glu2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "ddp_p2p.cu", "decode.cu", "align.cu", "collate.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_tc2.cu", "gemm_glu2.cu", "gemm_simt.cu", "rowops.cu", "attention.cu", "attention_mma.cu", "attention_tc5.cu", "trainops.cu", "ddp_p2p.cu", "decode.cu", "decode_small.cu", "decode_step.cu", "align.cu", "collate.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550"]
 
@@ -35,6 +35,27 @@ class Epi(C.Structure):
         ("p_drop", C.c_float), ("alpha", C.c_float), ("seed", C.c_ulonglong), ("site", C.c_uint),
         ("accumulate", C.c_int), ("drop_ld", C.c_longlong),
     ]
+
+
+DECODE_MAX_LAYERS = 12
+
+
+class DecodeLayer(C.Structure):
+    """Mirror of `MmaDecodeLayer` (include/mma_b200.h, csrc/decode_step.cu)."""
+
+    _fields_ = [(n, C.c_void_p) for n in (
+        "w_qkv", "w_so", "w_cq", "w_co", "w_f1", "w_fg", "w_f2", "b_qkv", "b_so", "b_cq", "b_co", "b_f1", "b_fg", "b_f2",
+        "n1g", "n1b", "n2g", "n2b", "n3g", "n3b", "kc", "vc", "kvmem")]
+
+
+class DecodeStep(C.Structure):
+    """Mirror of `MmaDecodeStep`."""
+
+    _fields_ = [("layer", DecodeLayer * DECODE_MAX_LAYERS)] + [(n, C.c_void_p) for n in (
+        "tok", "emb", "emb_g", "emb_b", "pos", "cur_len", "fin_g", "fin_b", "w_lm", "b_lm", "x", "xa", "xb", "qkv", "att",
+        "q", "a", "logits", "anc", "enc_mask", "dbg_times")] + [("ldv", C.c_longlong)] + [(n, C.c_int) for n in (
+            "layers", "R", "rows_per_cluster", "beams", "d", "f", "H", "Lmax", "S", "V", "gated")] + [
+                ("eps", C.c_float), ("scale", C.c_float)]
 
 
 def _nvcc():
@@ -149,6 +170,9 @@ _SIGS = {
     "mma_p2p_reduce_shard": [_vp, _vp, _i, _i, _ll, _ll, _vp, _vp, _vp],
     "mma_p2p_adam_shard": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp, _i, _vp],
     "mma_decode_embed": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp],
+    "mma_small_linear": [_vp, _i, _ll, _vp, _vp, _f, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _i, _ll, _i, _i, _i, _i, _vp],
+    "mma_decode_step": [_vp, _i, _vp],
+    "mma_decode_step_max_clusters": [_i],
     "mma_decode_self_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _f, _i, _i, _vp],
     "mma_decode_cross_attn": [_vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _i, _i, _i, _i, _i, _f, _i, _vp],
     "mma_beam_step": [_vp, _ll, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -583,7 +583,6 @@ __global__ void __launch_bounds__(128) decode_self_attn2_kernel(AttnArgs a) {
   const int r = blockIdx.x;
   const int col = blockIdx.y * (4 * DH) + lane * 8;  // this lane's 8 columns: head = col / 64
   const int t = *a.cur_len - 1;
-  const int nkeys = t + 1;
   const bf16* kc = reinterpret_cast<const bf16*>(a.kc) + col;
   const bf16* vc = reinterpret_cast<const bf16*>(a.vc) + col;
   const bf16* knew = reinterpret_cast<const bf16*>(a.knew) + (long long)r * a.ldkv + col;

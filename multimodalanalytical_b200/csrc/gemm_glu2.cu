@@ -200,6 +200,8 @@ glu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     dc.thr = dc.on ? drop_threshold(ga.p_drop) : 0u;
     dc.inv_keep = dc.on ? 1.0f / (1.0f - ga.p_drop) : 1.0f;
     dc.key = dc.on ? drop_key(ga.seed, ga.site) : 0u;
+    DropCtx dch = dc;  // keep-scales carrying the 1/2 of gelu_tanh_scaled
+    if (MMA_GELU_TANH) dch.inv_keep *= 0.5f;
 
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -238,9 +240,10 @@ glu_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (dc.on) {
           float ds[16];
-          drop_scales16(dc, (uint32_t)((unsigned long long)row * (unsigned long long)ga.drop_ld + (unsigned long long)col), ds);
+          drop_scales16(dch, (uint32_t)((unsigned long long)row * (unsigned long long)ga.drop_ld + (unsigned long long)col), ds);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) av[j] = gelu_t<true>(z1[j]) * z2[j] * ds[j];
+          for (int j = 0; j < 16; ++j)
+            av[j] = MMA_GELU_TANH ? gelu_tanh_scaled(z1[j], ds[j]) * z2[j] : gelu_t<true>(z1[j]) * z2[j] * ds[j];
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) av[j] = gelu_t<true>(z1[j]) * z2[j];

@@ -41,28 +41,39 @@ __device__ __forceinline__ void chunk_math(const Epi& ep, const DropCtx& dc, lon
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] += bv[j];
   }
+  // keep-scales; for the GELU kinds the 1/2 of Phi = (1 + erf) / 2 rides along (gelu_tanh_scaled)
+  constexpr bool HALF = MMA_GELU_TANH && (KIND == EPI_GELU || KIND == EPI_DGELU);
+  const float sc = HALF ? 0.5f * dc.inv_keep : dc.inv_keep;
   float ds[16];
   if (dc.on) {
     const uint32_t e0 = (uint32_t)((unsigned long long)row * (unsigned long long)ep.drop_ld + (unsigned long long)col);
     if ((e0 & 1u) == 0) {
+      const uint32_t thr_hi = dc.thr << 16;  // (r >> 16) >= thr  <=>  r >= thr << 16 (thr <= 65535)
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
         const uint32_t r = drop_pair(dc.key, (e0 + j) >> 1);
-        ds[j] = (r & 0xFFFFu) >= dc.thr ? dc.inv_keep : 0.f;
-        ds[j + 1] = (r >> 16) >= dc.thr ? dc.inv_keep : 0.f;
+        ds[j] = (r & 0xFFFFu) >= dc.thr ? sc : 0.f;
+        ds[j + 1] = r >= thr_hi ? sc : 0.f;
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) ds[j] = drop_scale1(dc.key, e0 + j, dc.thr, dc.inv_keep);
+      for (int j = 0; j < 16; ++j) ds[j] = drop_scale1(dc.key, e0 + j, dc.thr, sc);
     }
+  } else if (HALF) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ds[j] = 0.5f;
   }
   if (KIND == EPI_GELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       o2[j] = v[j];
-      float y = gelu_t<true>(v[j]);
-      if (dc.on) y *= ds[j];
-      v[j] = y;
+      if (MMA_GELU_TANH) {
+        v[j] = gelu_tanh_scaled(v[j], ds[j]);
+      } else {
+        float y = gelu_t<true>(v[j]);
+        if (dc.on) y *= ds[j];
+        v[j] = y;
+      }
     }
   } else if (KIND == EPI_RESID) {
 #pragma unroll
@@ -70,9 +81,13 @@ __device__ __forceinline__ void chunk_math(const Epi& ep, const DropCtx& dc, lon
   } else if (KIND == EPI_DGELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float y = v[j] * dgelu_t<true>(in[j]);
-      if (dc.on) y *= ds[j];
-      v[j] = y;
+      if (MMA_GELU_TANH) {
+        v[j] *= dgelu_tanh_scaled(in[j], ds[j]);
+      } else {
+        float y = v[j] * dgelu_t<true>(in[j]);
+        if (dc.on) y *= ds[j];
+        v[j] = y;
+      }
     }
   }
 }
@@ -274,12 +289,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int r0 = rows_of(tile);
       const int c0 = cols_of(tile);
       const long long row = (long long)r0 + lane;
-      // this warp's 64 bias values, two per lane (read back with shuffles)
-      float b_lo = 0.f, b_hi = 0.f;
-      if (has_bias) {
-        if (c0 + lane < N) b_lo = ep.bias[c0 + lane];
-        if (c0 + 32 + lane < N) b_hi = ep.bias[c0 + 32 + lane];
-      }
+      // bias: four warp-uniform 16-byte loads per 16-column chunk (L1 broadcast; the shuffles this replaces were one
+      // MIO instruction per element in an issue-bound loop); index clamped for tiles past N (those columns are clipped
+      // by the TMA store).  The host checks bias % 16 B == 0 and N % 4 == 0.
+      const float4* bias4 = reinterpret_cast<const float4*>(ep.bias);
+      const int last4 = (N >> 2) - 1;
       mbar_wait(smem_u32(&tfull[acc]), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + s * 64);
@@ -297,6 +311,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(ibar0 + (uint32_t)k1 * 8u, (ph >> k1) & 1u);
           ph ^= 1u << k1;
         }
+        float v[16], o2[16], in[16], bv[16];
+        if (has_bias) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 f = __ldg(bias4 + min(((c0 + c * 16) >> 2) + k, last4));
+            bv[4 * k] = f.x; bv[4 * k + 1] = f.y; bv[4 * k + 2] = f.z; bv[4 * k + 3] = f.w;
+          }
+        }
         tmem_wait_ld();
         if (c + 1 < 4) {
           tmem_ld16_nowait(t_row + (uint32_t)((c + 1) * 16), raw[(c + 1) & 1]);
@@ -306,7 +328,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_leader0 + (uint32_t)acc * 8u);
         }
-        float v[16], o2[16], in[16], bv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(raw[c & 1][j]);
         uint8_t* x1 = myb + k1 * BOX_BYTES;
@@ -333,10 +354,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) in[j] = 0.f;
-        }
-        if (has_bias) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) bv[j] = __shfl_sync(0xffffffffu, c < 2 ? b_lo : b_hi, (16 * (c & 1) + j) & 31);
         }
         chunk_math<KIND>(ep, dc, row, c0 + c * 16, v, o2, in, bv, has_bias);
         if (first) {
@@ -1007,6 +1024,7 @@ extern "C" int mma_gemm2_eligible(int a_mn, int b_mn, int M, int N, int K, const
     return 0;
   }
   if (N < 256 || M < 512) return 0;
+  if (ep->bias && ((reinterpret_cast<uintptr_t>(ep->bias) & 15) || (N & 3))) return 0;  // vector bias loads
   static int min_tiles = -1;
   if (min_tiles < 0) {
     const char* e = getenv("MMA_GEMM2_MIN_TILES");

@@ -36,6 +36,17 @@ COMPACT_MIN_B = int(os.environ.get("MMA_DECODE_COMPACT_MIN_B", "16"))
 COMPACT_LIVE_FRAC = 0.5  # compact when at most this fraction of the batch is still searching
 
 
+SMALL_DECODE = os.environ.get("MMA_DECODE_SMALL", "1") != "0"  # <= 64 rows: fused LayerNorm + product launches (decode_small.cu)
+
+
+# few spectra (every cluster resident at once, <= 16 rows per cluster): the whole step as ONE cluster-synchronised launch
+# (decode_step.cu); MMA_DECODE_PERSIST=0 keeps the per-op launches
+PERSIST_DECODE = os.environ.get("MMA_DECODE_PERSIST", "1") != "0"
+PERSIST_CLUSTER = int(os.environ.get("MMA_DECODE_PERSIST_CLUSTER", "16"))
+PERSIST_MAX_CLUSTERS = int(os.environ.get("MMA_DECODE_PERSIST_MAX_CLUSTERS", "0"))  # 0: what the device can hold at once
+PERSIST_MIN_ROWS = int(os.environ.get("MMA_DECODE_PERSIST_MIN_ROWS", "12"))  # 0: no lower bound (tests force the path)
+
+
 class BeamState:
     """Device-resident search state for B spectra x K beams (K == 1: greedy)."""
 
@@ -108,7 +119,160 @@ class Generator:
             ops.beam_step(scores, V, st, extra_bias, prenorm=prenorm, guide=guide)
         ops.advance(st.cur_len)
 
+    def _forward_logits_small(self, st: BeamState, ctx: Dict[str, Any]):
+        """The decoder step for <= 64 rows (a few spectra x beams), bf16: every LayerNorm + product (+ GELU / gate /
+        residual) is ONE `mma_small_linear` launch (52 launches per step instead of 74, none of them a tcgen05 tile that
+        is > 90 % padding).  Same math as `_forward_logits`."""
+        eng, cfg = self.eng, self.eng.cfg
+        d, H = cfg.d_model, cfg.decoder_attention_heads
+        dh = d // H
+        R, K, L = st.B * st.K, st.K, st.L
+        T, f, e, tm = eng.adt, cfg.decoder_ffn_dim, eng.ps.EMB, cfg.target_modality
+        gam = bet = None
+        if cfg.multimodal_norm:
+            gam, bet = eng.P(f"{e}embedding_norm_dict.{tm}.weight"), eng.P(f"{e}embedding_norm_dict.{tm}.bias")
+        x = eng.buf("g.x", (R, d), torch.float32)
+        ops.decode_embed(st.next_tok, eng.P(f"{e}embedding_layer_dict.{tm}.weight"), gam, bet, ctx["pos"], st.cur_len, x)
+        qkv = eng.buf("g.qkv", (R, 3 * d), T)
+        att = eng.buf("g.att", (R, d), T)
+        q = eng.buf("g.q", (R, d), T)
+        a = eng.buf("g.a", (R, f), T)
+        xa = eng.buf("g.xa", (R, d), torch.float32)
+        xb = eng.buf("g.xb", (R, d), torch.float32)
+        P, W = eng.P, eng.W
+
+        def lin(xin, wname, bname, out, n_out, k_in, kind="store", norm=None, resid=None, rows=None, w2=None, b2=None):
+            w = W(wname) if rows is None else W(wname)[rows]
+            b = P(bname) if rows is None else P(bname)[rows]
+            ok = ops.small_linear(xin, w, out, R, n_out, k_in, kind=kind, bias=b,
+                                  gamma=P(norm + "weight") if norm else None, beta=P(norm + "bias") if norm else None,
+                                  w2=W(w2) if w2 else None, bias2=P(b2) if b2 else None, resid=resid)
+            assert ok, "small_linear declined a shape the caller checked"
+
+        for i in range(cfg.decoder_layers):
+            p = f"hf_model.decoder.layers.{i}."
+            lin(x, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", qkv, 3 * d, d, norm=p + "norm1.")
+            ops.decode_self_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx["kc"][i], ctx["vc"][i], st.anc,
+                                 st.cur_len, att, R, H, dh, L, beams=K)
+            lin(att, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", xa, d, d, kind="resid", resid=x)
+            lin(xa, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", q, d, d, norm=p + "norm2.",
+                rows=slice(0, d))
+            kv = ctx["kvmem"][i]
+            ops.attn_fwd(q, kv[:, :d], kv[:, d:], att, None, st.B, H, K, ctx["S"], dh, kmask=ctx["enc_mask"])
+            lin(att, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", xb, d, d, kind="resid",
+                resid=xa)
+            if cfg.gated_linear:
+                lin(xb, p + "linear1.weight", p + "linear1.bias", a, f, d, kind="glu", norm=p + "norm3.",
+                    w2=p + "gate.weight", b2=p + "gate.bias")
+            else:
+                lin(xb, p + "linear1.weight", p + "linear1.bias", a, f, d, kind="gelu", norm=p + "norm3.")
+            lin(a, p + "linear2.weight", p + "linear2.bias", x, d, f, kind="resid", resid=xb)
+        logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
+        lin(x, "hf_model.token_ff.weight", "hf_model.token_ff.bias", logits, cfg.vocab_size, d,
+            norm="hf_model.decoder.norm.")
+        return logits
+
+    def _persist_plan(self, st: BeamState):
+        """(rows per cluster, clusters) of the one-launch step, or None outside its envelope: bf16, d 512 / ffn 2048 /
+        8 heads of 64, <= 16 beams, and few enough spectra that every cluster is resident at once."""
+        cfg, eng = self.eng.cfg, self.eng
+        if not (PERSIST_DECODE and eng.precision == "bf16" and cfg.d_model == 512 and cfg.decoder_ffn_dim == 2048
+                and cfg.decoder_attention_heads == 8 and st.K <= 16 and cfg.decoder_layers <= 12):
+            return None
+        global PERSIST_MAX_CLUSTERS
+        if PERSIST_MAX_CLUSTERS <= 0:
+            PERSIST_MAX_CLUSTERS = max(ops.decode_step_max_clusters(PERSIST_CLUSTER), 1)
+        per = max(1, min(16 // st.K, -(-st.B // PERSIST_MAX_CLUSTERS)))  # spectra per cluster
+        clusters = -(-st.B // per)
+        if clusters > PERSIST_MAX_CLUSTERS:
+            return None
+        # measured on B200 (C5 model, ms per step, one-launch vs per-op): beam-10 x 1 / 2 / 4 / 7 spectra 0.345 / 0.34 / 0.33 /
+        # 0.34 vs 0.344 / 0.39 / 0.50 / 0.53; greedy x 1 / 7 / 16 spectra 0.31 / 0.25 / 0.27 vs 0.25 / 0.24 / 0.29: a lone
+        # cluster streams the step's weights through one GPC and only ties with the per-op launches, which use every SM
+        if PERSIST_MIN_ROWS > 0 and (st.B * st.K < PERSIST_MIN_ROWS or clusters < 2 and st.K > 1):
+            return None
+        return per * st.K, clusters
+
+    def _forward_logits_persist(self, st: BeamState, ctx: Dict[str, Any], plan):
+        """One `mma_decode_step` launch; same buffers, same math as `_forward_logits_small`."""
+        from ._lib import DecodeStep
+        eng, cfg = self.eng, self.eng.cfg
+        d, H, f = cfg.d_model, cfg.decoder_attention_heads, cfg.decoder_ffn_dim
+        R, K, L = st.B * st.K, st.K, st.L
+        T, e, tm = eng.adt, eng.ps.EMB, cfg.target_modality
+        logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
+        key = ("persist", R, K, L, ctx["S"], ctx["kc"].data_ptr(), ctx["kvmem"].data_ptr(), st.next_tok.data_ptr())
+        args = self._persist_args.get(key) if hasattr(self, "_persist_args") else None
+        if args is None:
+            if not hasattr(self, "_persist_args"):
+                self._persist_args = {}
+                eng.on_release.append(self._persist_args.clear)
+            P, W = eng.P, eng.W
+            a = DecodeStep()
+
+            def w(name, rows=None):
+                t = W(name) if rows is None else W(name)[rows]
+                assert t.dtype == torch.bfloat16 and t.stride(1) == 1 and t.stride(0) == t.shape[1], name
+                return t.data_ptr()
+
+            def p_(name, rows=None):
+                t = P(name) if rows is None else P(name)[rows]
+                assert t.dtype == torch.float32 and t.is_contiguous(), name
+                return t.data_ptr()
+
+            for i in range(cfg.decoder_layers):
+                p = f"hf_model.decoder.layers.{i}."
+                ly = a.layer[i]
+                ly.w_qkv, ly.b_qkv = w(p + "self_attn.in_proj_weight"), p_(p + "self_attn.in_proj_bias")
+                ly.w_so, ly.b_so = w(p + "self_attn.out_proj.weight"), p_(p + "self_attn.out_proj.bias")
+                ly.w_cq = w(p + "multihead_attn.in_proj_weight", slice(0, d))
+                ly.b_cq = p_(p + "multihead_attn.in_proj_bias", slice(0, d))
+                ly.w_co, ly.b_co = w(p + "multihead_attn.out_proj.weight"), p_(p + "multihead_attn.out_proj.bias")
+                ly.w_f1, ly.b_f1 = w(p + "linear1.weight"), p_(p + "linear1.bias")
+                if cfg.gated_linear:
+                    ly.w_fg, ly.b_fg = w(p + "gate.weight"), p_(p + "gate.bias")
+                ly.w_f2, ly.b_f2 = w(p + "linear2.weight"), p_(p + "linear2.bias")
+                for j in (1, 2, 3):
+                    setattr(ly, f"n{j}g", p_(p + f"norm{j}.weight"))
+                    setattr(ly, f"n{j}b", p_(p + f"norm{j}.bias"))
+                ly.kc, ly.vc, ly.kvmem = ctx["kc"][i].data_ptr(), ctx["vc"][i].data_ptr(), ctx["kvmem"][i].data_ptr()
+            a.tok, a.emb = st.next_tok.data_ptr(), p_(f"{e}embedding_layer_dict.{tm}.weight")
+            if cfg.multimodal_norm:
+                a.emb_g, a.emb_b = p_(f"{e}embedding_norm_dict.{tm}.weight"), p_(f"{e}embedding_norm_dict.{tm}.bias")
+            a.pos, a.cur_len = ctx["pos"].data_ptr(), st.cur_len.data_ptr()
+            a.fin_g, a.fin_b = p_("hf_model.decoder.norm.weight"), p_("hf_model.decoder.norm.bias")
+            a.w_lm, a.b_lm = w("hf_model.token_ff.weight"), p_("hf_model.token_ff.bias")
+            for name, shape, dt in (("x", (R, d), torch.float32), ("xa", (R, d), torch.float32),
+                                    ("xb", (R, d), torch.float32), ("qkv", (R, 3 * d), T), ("att", (R, d), T),
+                                    ("q", (R, d), T), ("a", (R, f), T)):
+                setattr(a, name, eng.buf("g." + name, shape, dt).data_ptr())
+            a.logits = logits.data_ptr()
+            a.anc = st.anc.data_ptr() if st.anc is not None else None
+            a.enc_mask = ctx["enc_mask"].data_ptr()
+            if os.environ.get("MMA_DECODE_PERSIST_DBG"):  # per-phase %globaltimer stamps of cluster 0 (scripts/decode_step_phases.py)
+                self.dbg_times = torch.zeros(64, dtype=torch.int64, device=eng.dev)
+                a.dbg_times = self.dbg_times.data_ptr()
+            a.ldv = eng.ldv
+            a.layers, a.R, a.rows_per_cluster, a.beams = cfg.decoder_layers, R, plan[0], K
+            a.d, a.f, a.H, a.Lmax, a.S, a.V, a.gated = d, f, H, L, ctx["S"], cfg.vocab_size, int(bool(cfg.gated_linear))
+            a.eps, a.scale = 1e-5, (d // H) ** -0.5
+            assert ctx["pos"].dtype == torch.float32 and ctx["pos"].stride(0) == d
+            args = self._persist_args[key] = a
+        ok = ops.decode_step(args, PERSIST_CLUSTER)
+        assert ok, "mma_decode_step declined a shape the caller checked"
+        return logits
+
+    def _small_ok(self, R):
+        cfg = self.eng.cfg
+        return (SMALL_DECODE and self.eng.precision == "bf16" and R <= 64 and cfg.d_model % 256 == 0
+                and cfg.decoder_ffn_dim % 256 == 0 and (cfg.d_model // cfg.decoder_attention_heads) == 64)
+
     def _forward_logits(self, st: BeamState, ctx: Dict[str, Any]):
+        plan = self._persist_plan(st)
+        if plan is not None:
+            return self._forward_logits_persist(st, ctx, plan)
+        if self._small_ok(st.B * st.K):
+            return self._forward_logits_small(st, ctx)
         eng, cfg = self.eng, self.eng.cfg
         d, H = cfg.d_model, cfg.decoder_attention_heads
         dh = d // H

@@ -540,6 +540,42 @@ def add_u64(t, inc=1):
     _count()
 
 
+SMALL_KINDS = {"store": 0, "gelu": 1, "resid": 2, "glu": 3}
+
+
+def small_linear(x, w, out, R, N, K, kind="store", bias=None, gamma=None, beta=None, w2=None, bias2=None, resid=None,
+                 eps=1e-5):
+    """out[R, N] = epilogue(LN?(x)[R, K] w^T + bias) for R <= 64 rows in ONE launch (decode of a few spectra).
+    Returns False (nothing launched) outside the kernel's envelope."""
+    _need_cuda(x, w, out)
+    rc = _lib.load().mma_small_linear(
+        x.data_ptr(), _ty(x), x.stride(0), _p(gamma), _p(beta), float(eps), w.data_ptr(), _p(w2), w.stride(0), _p(bias),
+        _p(bias2), _p(resid), resid.stride(0) if resid is not None else 0, out.data_ptr(), _ty(out), out.stride(0), R, N, K,
+        SMALL_KINDS[kind], _stream())
+    if rc == -3:
+        return False
+    check(rc, "mma_small_linear")
+    _count()
+    return True
+
+
+def decode_step(args, cluster_size):
+    """The whole decoder step (logits of every row) in one launch; `args` is a filled `_lib.DecodeStep`.
+    Returns False (nothing launched) outside the kernel's envelope."""
+    import ctypes
+    rc = _lib.load().mma_decode_step(ctypes.addressof(args), int(cluster_size), _stream())
+    if rc == -3:
+        return False
+    check(rc, "mma_decode_step")
+    _count()
+    return True
+
+
+def decode_step_max_clusters(cluster_size):
+    """Resident clusters of the one-launch decode step on this device (0: the cluster size cannot be scheduled)."""
+    return int(_lib.load().mma_decode_step_max_clusters(int(cluster_size)))
+
+
 def decode_embed(tok, table, gamma, beta, pos, cur_len, out, eps=1e-5):
     _need_cuda(tok, table, out)
     check(_lib.load().mma_decode_embed(tok.data_ptr(), table.data_ptr(), _p(gamma), _p(beta), eps, pos.data_ptr(),

@@ -60,6 +60,30 @@ int main(void) {
     assert got == want
 
 
+def test_decode_step_struct_layout_matches_c():
+    prog = r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "mma_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(MmaDecodeLayer), sizeof(MmaDecodeStep), offsetof(MmaDecodeStep, tok),
+         offsetof(MmaDecodeStep, logits), offsetof(MmaDecodeStep, ldv), offsetof(MmaDecodeStep, gated),
+         offsetof(MmaDecodeStep, scale));
+  return 0;
+}'''
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.c")
+        open(c, "w").write(prog)
+        exe = os.path.join(td, "t")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include", c, "-o", exe],
+                       check=True)
+        got = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    L, S = _lib.DecodeLayer, _lib.DecodeStep
+    want = [ctypes.sizeof(L), ctypes.sizeof(S), S.tok.offset, S.logits.offset, S.ldv.offset, S.gated.offset, S.scale.offset]
+    assert got == want
+    assert ctypes.sizeof(S) < 4096  # passed by value as a kernel parameter
+
+
 def test_epilogue_enum_matches_header():
     src = open(HEADER).read()
     for name in ("EPI_STORE", "EPI_GELU", "EPI_RESID", "EPI_DGELU", "EPI_GLU_MUL", "EPI_DGLU", "EPI_ACCUM", "EPI_RELU",

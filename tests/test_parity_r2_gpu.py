@@ -259,3 +259,63 @@ def test_finished_spectrum_compaction_keeps_reference_sequences(name, monkeypatc
     monkeypatch.setattr(decode, "COMPACT", False)
     b, sb = m16.generate(fx["batch"], n_beams=k, check_every=2, return_scores=True)
     assert torch.equal(a, b) and torch.equal(sa, sb)
+
+
+@pytest.mark.parametrize("case,B,K", [("c5", 1, 10), ("c5", 3, 10), ("c5", 2, 16), ("c5", 5, 1), ("c5", 20, 1), ("c2", 2, 4)])
+def test_one_launch_decode_step_matches_per_op_step(case, B, K, monkeypatch):
+    """`mma_decode_step` (decode_step.cu: the whole decoder step as one cluster-synchronised launch) against the per-op
+    launches of the same step (LayerNorm + product kernels, decode self-attention, tcgen05 cross-attention), on the SAME
+    search state at EVERY step of a decode: logits within the bf16 tolerance of two differently-ordered bf16 evaluations,
+    and the sequences the one-launch path produces are those of the per-op path wherever no near-tie decided."""
+    from multimodalanalytical_b200 import decode as dec
+    from tests.test_configs_gpu import make_case
+    if case == "c5":
+        fx = make_case("c5", B)  # learned pos-enc + GLU, d 512, 6 + 6 layers
+    else:
+        import bench
+        c = dict(bench.C2)
+        fx = None
+    if fx is not None:
+        m = build(fx, "bf16")
+        batch = fx["batch"]
+    else:
+        m = HFWrapper(data_config=bench.data_config(c), target_tokenizer=bench.Tok(c["V"]), num_steps=10, precision="bf16",
+                      seed=3, **bench.model_kwargs(c))  # sin/cos pos-enc, no gate, per-modality embedding norm
+        batch = bench.map_batch(bench.synth_batch(c, B, 5), lambda x: x.cuda())
+    m.eval()
+    m.store.P("hf_model.token_ff.weight").mul_(6.0)
+    m.store.bf16_dirty = True
+    m.generation_config["max_length"] = 40
+    V = m.engine.cfg.vocab_size
+    orig = dec.Generator._forward_logits
+    worst, steps = [0.0], [0]
+    monkeypatch.setattr(dec, "PERSIST_MIN_ROWS", 0)  # every shape of the envelope, also those the per-op path wins
+
+    def both(self, st, ctx):
+        assert self._persist_plan(st) is not None, "the one-launch step declined a shape inside its envelope"
+        monkeypatch.setattr(dec, "PERSIST_DECODE", False)
+        ref = orig(self, st, ctx)[:, :V].clone()
+        monkeypatch.setattr(dec, "PERSIST_DECODE", True)
+        out = orig(self, st, ctx)
+        worst[0] = max(worst[0], rel_err(out[:, :V], ref))
+        steps[0] += 1
+        return out
+
+    monkeypatch.setattr(dec.Generator, "_forward_logits", both)
+    s_both = m.generate(batch, n_beams=K, use_graph=False).cpu()
+    monkeypatch.setattr(dec.Generator, "_forward_logits", orig)
+    assert steps[0] >= 8 and worst[0] < 2e-2, f"logits of the one-launch step differ from the per-op step by {worst[0]:.4f}"
+    # graph-replayed, each path on its own
+    monkeypatch.setattr(dec, "PERSIST_DECODE", True)
+    m.generator._graphs.clear()
+    s1 = m.generate(batch, n_beams=K).cpu()
+    monkeypatch.setattr(dec, "PERSIST_DECODE", False)
+    m.generator._graphs.clear()
+    s0 = m.generate(batch, n_beams=K).cpu()
+    assert torch.equal(s1, s_both), "graph replay of the one-launch step changed the result"
+    same = sum(tuple(a) == tuple(b) for a, b in zip(s0.tolist(), s1.tolist())) if s0.shape == s1.shape else 0
+    print(f"{case} B={B} K={K}: worst relative logit difference {worst[0]:.5f} over {steps[0]} steps; "
+          f"{same}/{s1.shape[0]} sequences identical to the per-op path")
+    # low-ranked hypotheses of a wide beam flip on near-ties; the best hypothesis of a spectrum should not
+    same_best = sum(tuple(a) == tuple(b) for a, b in zip(s0[::K].tolist(), s1[::K].tolist())) if s0.shape == s1.shape else 0
+    assert same_best >= (B + 1) // 2, f"best hypothesis identical for only {same_best} of {B} spectra"
