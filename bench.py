@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 SEED = 3247
 PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-SWEEP_B, SWEEP_K = "1,8,32,128,256,512,1024", "10,30"
+SWEEP_B, SWEEP_K = "1,4,8,32,128,256,512,1024", "10,30"
 C2 = dict(B=256, S_formula=15, P=21, ps=75, T=64, V=200, d=512, layers=6, heads=8, ffn=2048)
 
 
@@ -657,8 +657,11 @@ def bench_decode_sweep(world, rank, dist, batches, beams):
         for B in batches:
             batch = map_batch(synth_batch(c, B, SEED + 13 + 100 * rank), lambda x: x.cuda())
             t, steps = time_generate(model, batch, K, 2, dist)
+            st = model.generator._states.get((B, K, model.generation_config["max_length"]))
+            plan = model.generator._persist_plan(st) if st is not None else None
             rows.append({"batch_per_gpu": B, "beams": K, "molecules_per_s": world * B / t, "ms_per_step": t * 1e3 / steps,
-                         "steps": steps, "roofline_frac": decode_floor_s(B, K, steps, S, V, True) / t})
+                         "steps": steps, "roofline_frac": decode_floor_s(B, K, steps, S, V, True) / t,
+                         "step": "one launch (%d clusters x 16 CTAs)" % plan[1] if plan else "per-op launches"})
             model.engine.release_buffers()  # K/V caches of B x K rows are shape-keyed workspaces: 48 GB at 1024 x 30
     del model
     torch.cuda.empty_cache()

@@ -146,6 +146,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 struct Ctx {
   uint8_t* smem;
   int crank, csize, r0, Rc, NT, warp, lane, t;
+  unsigned long long* fine; int* fn;  // DSTEP_FINE: fine-grained stamps
   int anc0[2];  // cache rows holding positions lane, lane + 32 of this CTA's first row (the same table for every layer)
 };
 
@@ -243,6 +244,11 @@ __device__ __forceinline__ void ln_stage(const Ctx& c, int slot, float eps) {
 }
 
 enum { O_QKV = 0, O_Q = 1, O_X = 2, O_ACT1 = 3, O_LOGITS = 4 };
+#ifdef DSTEP_FINE
+#define FINE(c) do { if ((c).fine && threadIdx.x == 0 && blockIdx.x == 0 && *(c).fn < 100) (c).fine[(*(c).fn)++] = gtime(); } while (0)
+#else
+#define FINE(c) do {} while (0)
+#endif
 
 // the product a phase hands its weight registers to: loaded right after the last MMAs of the current phase
 struct Next {
@@ -307,6 +313,7 @@ __device__ __forceinline__ void lin_rounds(WR<TB, NIT, GLU>& w, const Ctx& c, co
         }
       }
     }
+    FINE(c);  // after mma + partial sums
     float bs[TB], bs2[GLU ? TB : 1];
 #pragma unroll
     for (int b = 0; b < TB; ++b) {
@@ -316,7 +323,9 @@ __device__ __forceinline__ void lin_rounds(WR<TB, NIT, GLU>& w, const Ctx& c, co
     // the weight registers are free: the next round's (or the next phase's) loads fly during reduction + epilogue
     if (rd + 1 < ROUNDS) w_load<TB, NIT, GLU>(w, c, wt, wt2, bias, bias2, ldw, N, tile0 + CS * TB);
     else if (NEXT) w_load<TB2, NIT2, GLU2>(nw, c, nx.wt, nx.wt2, nx.bias, nx.bias2, nx.ldw, nx.N, c.crank);
+    FINE(c);  // after issuing the next loads
     __syncthreads();
+    FINE(c);  // after sync
     const int n = threadIdx.x >> 4, f = threadIdx.x & 15;  // this thread finishes element (row n, column f) of every tile
     if (n < c.Rc) {
 #pragma unroll
@@ -353,6 +362,7 @@ __device__ __forceinline__ void lin_rounds(WR<TB, NIT, GLU>& w, const Ctx& c, co
       }
     }
     __syncthreads();  // `red` is rewritten by the next round / phase
+    FINE(c);  // after epilogue
     if (OUT == O_X || OUT == O_ACT1) {
       // the round's [rows x 16-column] blocks go to the 15 peers as 16-byte stores (element-wise remote stores were the
       // single largest cost of a phase: one cluster-network transaction per 2 / 4 bytes)
@@ -374,6 +384,7 @@ __device__ __forceinline__ void lin_rounds(WR<TB, NIT, GLU>& w, const Ctx& c, co
         st_cluster_v4(mapa(sbase + off, rk), val);
       }
     }
+    FINE(c);  // after broadcast
   }
 }
 
@@ -516,6 +527,9 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_kernel(const __grid_co
 #pragma unroll
     for (int i = 0; i < 2; ++i) c.anc0[i] = (anc && c.lane + 32 * i < c.t) ? anc[c.lane + 32 * i] : r;
   }
+  int fcount = 0;
+  c.fine = nullptr;
+  c.fn = &fcount;
   int ts = 0;
   const bool stamp = a.dbg_times != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 #define DSTEP_STAMP() do { if (stamp) a.dbg_times[ts++] = gtime(); } while (0)
@@ -585,40 +599,43 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_kernel(const __grid_co
   for (int li = 0; li < a.layers; ++li) {
     const Layer& L = a.layer[li];
     const bool last = li + 1 == a.layers;
+#ifdef DSTEP_FINE
+    c.fine = (li == 2 && a.dbg_times) ? a.dbg_times + 64 : nullptr;
+#endif
     WR<2, 2, false> w_o;  // N = 512 products: 32 tiles, 2 per CTA
     // ---- h = LN1(x); q, k, v = h Wqkv^T + b  ->  the attention CTAs' slots
-    ln_stage(c, 0, a.eps);
+    ln_stage(c, 0, a.eps); FINE(c);
     ln_fetch(c, 1, L.n2g, L.n2b);
     ln_fetch(c, 2, L.n3g, L.n3b);
     lin_rounds<6, 2, false, O_QKV, false, 1, true>(w_qkv, c, a, L.w_qkv, nullptr, L.b_qkv, nullptr, D, 3 * D, ACT0, P_D,
                                                    w_o, Next{L.w_so, nullptr, L.b_so, nullptr, D, D});
-    c_arrive();
+    FINE(c); c_arrive(); FINE(c);
     att_stage<false>(c, a, L, 0, 0);  // the cache rows of the history do not depend on this step's q / k / v
     // slot 0 is free again: the next layer's norm1 (decoder.norm after the last layer) arrives a whole layer early
     ln_fetch(c, 0, last ? a.fin_g : a.layer[li + 1].n1g, last ? a.fin_b : a.layer[li + 1].n1b);
-    c_wait();
+    c_wait(); FINE(c);
     DSTEP_STAMP();
     att_compute<false>(c, a, L);
-    c_arrive();
-    c_wait();
+    FINE(c); c_arrive(); FINE(c);
+    c_wait(); FINE(c);
     DSTEP_STAMP();
     // ---- x += att Wo^T + b
     lin_rounds<2, 2, false, O_X, false, 1, true>(w_o, c, a, L.w_so, nullptr, L.b_so, nullptr, D, D, ATT, P_D, w_o,
                                                  Next{L.w_cq, nullptr, L.b_cq, nullptr, D, D});
-    c_arrive();
-    c_wait();
+    FINE(c); c_arrive(); FINE(c);
+    c_wait(); FINE(c);
     DSTEP_STAMP();
     // ---- q = LN2(x) Wq^T + b  ->  slots
-    ln_stage(c, 1, a.eps);
+    ln_stage(c, 1, a.eps); FINE(c);
     lin_rounds<2, 2, false, O_Q, false, 1, true>(w_o, c, a, L.w_cq, nullptr, L.b_cq, nullptr, D, D, ACT0, P_D, w_o,
                                                  Next{L.w_co, nullptr, L.b_co, nullptr, D, D});
-    c_arrive();
+    FINE(c); c_arrive(); FINE(c);
     att_stage<true>(c, a, L, 0, 0);
-    c_wait();
+    c_wait(); FINE(c);
     DSTEP_STAMP();
     att_compute<true>(c, a, L);
-    c_arrive();
-    c_wait();
+    FINE(c); c_arrive(); FINE(c);
+    c_wait(); FINE(c);
     DSTEP_STAMP();
     // ---- x += att Wo^T + b ;  a = gelu(LN3(x) W1^T + b1) [* (LN3(x) Wg^T + bg)] ;  x += a W2^T + b2
     WR<2, 8, false> w_f2;
@@ -626,40 +643,40 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_kernel(const __grid_co
       WR<4, 2, true> w_f1;
       lin_rounds<2, 2, false, O_X, false, 1, true>(w_o, c, a, L.w_co, nullptr, L.b_co, nullptr, D, D, ATT, P_D, w_f1,
                                                    Next{L.w_f1, L.w_fg, L.b_f1, L.b_fg, D, F});
-      c_arrive();
-      c_wait();
+      FINE(c); c_arrive(); FINE(c);
+      c_wait(); FINE(c);
       DSTEP_STAMP();
-      ln_stage(c, 2, a.eps);
+      ln_stage(c, 2, a.eps); FINE(c);
       lin_rounds<4, 2, true, O_ACT1, false, 2, true>(w_f1, c, a, L.w_f1, L.w_fg, L.b_f1, L.b_fg, D, F, ACT0, P_D, w_f2,
                                                      Next{L.w_f2, nullptr, L.b_f2, nullptr, F, D});
     } else {
       WR<8, 2, false> w_f1;
       lin_rounds<2, 2, false, O_X, false, 1, true>(w_o, c, a, L.w_co, nullptr, L.b_co, nullptr, D, D, ATT, P_D, w_f1,
                                                    Next{L.w_f1, nullptr, L.b_f1, nullptr, D, F});
-      c_arrive();
-      c_wait();
+      FINE(c); c_arrive(); FINE(c);
+      c_wait(); FINE(c);
       DSTEP_STAMP();
-      ln_stage(c, 2, a.eps);
+      ln_stage(c, 2, a.eps); FINE(c);
       lin_rounds<8, 2, false, O_ACT1, true, 1, true>(w_f1, c, a, L.w_f1, nullptr, L.b_f1, nullptr, D, F, ACT0, P_D, w_f2,
                                                      Next{L.w_f2, nullptr, L.b_f2, nullptr, F, D});
     }
-    c_arrive();
-    c_wait();
+    FINE(c); c_arrive(); FINE(c);
+    c_wait(); FINE(c);
     DSTEP_STAMP();
     // (after the last layer the QKV registers are fetched once more for nothing: an unconditional load keeps them from
     // being live across the whole layer body)
     const Layer& Nx = a.layer[last ? 0 : li + 1];
     lin_rounds<2, 8, false, O_X, false, 1, true>(w_f2, c, a, L.w_f2, nullptr, L.b_f2, nullptr, F, D, ACT1, P_F, w_qkv,
                                                  Next{Nx.w_qkv, nullptr, Nx.b_qkv, nullptr, D, 3 * D});
-    c_arrive();
-    c_wait();
+    FINE(c); c_arrive(); FINE(c);
+    c_wait(); FINE(c);
     DSTEP_STAMP();
   }
   // ---- logits = LN(x) Wlm^T + b  (global: the selection kernel reads them).  After the last barrier above no CTA writes
   // into a peer's shared memory any more, so CTAs may finish independently.
   WR<2, 2, false> w_lm;
   w_load<2, 2, false>(w_lm, c, a.w_lm, nullptr, a.b_lm, nullptr, D, a.V, c.crank);
-  ln_stage(c, 0, a.eps);
+  ln_stage(c, 0, a.eps); FINE(c);
   lin_rounds<2, 2, false, O_LOGITS, false, 1, false>(w_lm, c, a, a.w_lm, nullptr, a.b_lm, nullptr, D, a.V, ACT0, P_D, w_lm, none);
   DSTEP_STAMP();
 #undef DSTEP_STAMP

@@ -250,7 +250,7 @@ class Generator:
             a.anc = st.anc.data_ptr() if st.anc is not None else None
             a.enc_mask = ctx["enc_mask"].data_ptr()
             if os.environ.get("MMA_DECODE_PERSIST_DBG"):  # per-phase %globaltimer stamps of cluster 0 (scripts/decode_step_phases.py)
-                self.dbg_times = torch.zeros(64, dtype=torch.int64, device=eng.dev)
+                self.dbg_times = torch.zeros(192, dtype=torch.int64, device=eng.dev)
                 a.dbg_times = self.dbg_times.data_ptr()
             a.ldv = eng.ldv
             a.layers, a.R, a.rows_per_cluster, a.beams = cfg.decoder_layers, R, plan[0], K
