@@ -23,7 +23,7 @@
 //              of a CTA split the reduction; mma.sync.m16n8k16 with the WEIGHT tile as the 16-row operand and the rows as
 //              the 8-column operand (every weight element is read once per cluster); LayerNorm is the prologue (every CTA
 //              normalises its copy of the residual stream), bias / GELU / gate / residual the epilogue.
-//   attention  row n lives on CTA n % size, head h on warp h: the K / V rows of up to 64 positions (ancestor-indexed cache
+//   attention  (row, head) item i lives on warp i / 16 of CTA i % 16: the K / V rows of up to 64 positions (ancestor-indexed cache
 //              rows for self-attention, the spectrum's memory for cross-attention) are pulled into shared memory with
 //              cp.async BEFORE the barrier that delivers q (they do not depend on it); scores lane = position, weighted sum
 //              lane = 2 head dims, online softmax across chunks of 64 positions.
@@ -45,9 +45,9 @@ constexpr int P_D = D + 32, P_F = F + 32;  // bf16 pitches of the staged operand
 constexpr int OFF_X = 0;                             // fp32 [16][512]   residual stream (replicated in every CTA)
 constexpr int OFF_ATT = OFF_X + MAXR * D * 4;        // bf16 [16][544]   attention output (replicated)
 constexpr int OFF_ACT0 = OFF_ATT + MAXR * P_D * 2;   // bf16 [16][544]   LayerNorm output (local)
-constexpr int OFF_SLOT = OFF_ACT0 + MAXR * P_D * 2;  // [2 slots][8 heads]{q fp32[64], k bf16[64], v bf16[64]}  this CTA's rows
+constexpr int OFF_SLOT = OFF_ACT0 + MAXR * P_D * 2;  // [8 warps]{q fp32[64], k bf16[64], v bf16[64]}  this CTA's (row, head) items
 constexpr int SLOT_BYTES = 512;
-constexpr int OFF_ACT1 = OFF_SLOT + 2 * H * SLOT_BYTES;  // bf16 [16][2080]  FFN activation (replicated)
+constexpr int OFF_ACT1 = OFF_SLOT + WARPS * SLOT_BYTES;  // bf16 [16][2080]  FFN activation (replicated)
 constexpr int OFF_RED = OFF_ACT1 + MAXR * P_F * 2;       // fp32 [8 tiles][8 warps][16][16] partial sums
 constexpr int RED_BYTES = 8 * WARPS * MAXR * 16 * 4;
 constexpr int OFF_STG = OFF_ACT1;  // attention staging aliases ACT1 + RED (both dead during an attention phase)
@@ -146,8 +146,9 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 struct Ctx {
   uint8_t* smem;
   int crank, csize, r0, Rc, NT, warp, lane, t;
+  int an, ah;  // this warp's attention item: row an of the cluster (-1: none), head ah
   unsigned long long* fine; int* fn;  // DSTEP_FINE: fine-grained stamps
-  int anc0[2];  // cache rows holding positions lane, lane + 32 of this CTA's first row (the same table for every layer)
+  int anc0[2];  // cache rows holding positions lane, lane + 32 of this warp's row (the same table for every layer)
 };
 
 // ---- weights of one round of a product, in registers --------------------------------------------------------------
@@ -349,10 +350,12 @@ __device__ __forceinline__ void lin_rounds(WR<TB, NIT, GLU>& w, const Ctx& c, co
           } else if (OUT == O_ACT1) {
             reinterpret_cast<bf16*>(c.smem + OFF_ACT1)[n * P_F + col] = __float2bfloat16_rn(v);
           } else if (OUT == O_QKV || OUT == O_Q) {
-            // row n is attended on CTA n % size, slot n / size; head h on warp h
+            // item (row n, head h) = n * 8 + h is attended by warp item / 16 of CTA item % 16: the (row, head) pairs of
+            // the cluster are spread over ALL its SMs (with 10 beams: 5 warps on each of 16 SMs, not 8 warps on 10)
             const int which = OUT == O_Q ? 0 : col >> 9, cc = col & (D - 1), h = cc >> 6, e = cc & 63;
-            const uint32_t slot = (uint32_t)(OFF_SLOT + ((n / CS) * H + h) * SLOT_BYTES);
-            const uint32_t dst = mapa(sbase + slot, (uint32_t)(n % CS));
+            const int item = n * H + h;
+            const uint32_t slot = (uint32_t)(OFF_SLOT + (item / CS) * SLOT_BYTES);
+            const uint32_t dst = mapa(sbase + slot, (uint32_t)(item % CS));
             if (which == 0) st_cluster_f32(dst + (uint32_t)(e * 4), v * a.scale);
             else st_cluster_b16(dst + 256u + (uint32_t)((which - 1) * 128 + e * 2), __bfloat16_as_ushort(__float2bfloat16_rn(v)));
           } else {
@@ -389,13 +392,12 @@ __device__ __forceinline__ void lin_rounds(WR<TB, NIT, GLU>& w, const Ctx& c, co
 }
 
 // ---- attention ---------------------------------------------------------------------------------------------------
-// Row n = slot * size + rank of the cluster lives on this CTA, head h on warp h.  att_stage: issue the cp.async of one
-// chunk of K / V rows (self: cache rows of positions < t through the ancestor table; cross: memory rows) - no wait.
+// One (row, head) item per warp (Ctx::an / ah).  att_stage: issue the cp.async of one chunk of K / V rows (self: cache rows
+// of positions < t through the ancestor table; cross: memory rows) - no wait.
 template <bool CROSS>
-__device__ __forceinline__ void att_stage(const Ctx& c, const Args& a, const Layer& L, int slot, int c0) {
-  const int n = slot * CS + c.crank;
-  if (n >= c.Rc) return;
-  const int r = c.r0 + n, h = c.warp;
+__device__ __forceinline__ void att_stage(const Ctx& c, const Args& a, const Layer& L, int c0) {
+  if (c.an < 0) return;
+  const int r = c.r0 + c.an, h = c.ah;
   const int nkeys = CROSS ? a.S : c.t;  // self: position t itself arrives through the slot
   uint8_t* Ks = c.smem + OFF_STG + c.warp * STG_WARP;
   uint8_t* Vs = Ks + ATT_CHUNK * KS_PITCH;
@@ -409,7 +411,7 @@ __device__ __forceinline__ void att_stage(const Ctx& c, const Args& a, const Lay
         ksrc = L.kvmem + ((long long)(r / a.beams) * a.S + j) * (2 * D) + h * DH;
         vsrc = ksrc + D;
       } else {
-        const int src = (slot == 0 && c0 == 0) ? c.anc0[i] : (anc ? anc[j] : r);
+        const int src = c0 == 0 ? c.anc0[i] : (anc ? anc[j] : r);
         const long long off = ((long long)src * a.Lmax + j) * D + h * DH;
         ksrc = L.kc + off;
         vsrc = L.vc + off;
@@ -424,88 +426,86 @@ __device__ __forceinline__ void att_stage(const Ctx& c, const Args& a, const Lay
   }
 }
 
-// chunk 0 of slot 0 is already in flight (att_stage before the barrier)
+// chunk 0 is already in flight (att_stage before the barrier)
 template <bool CROSS>
 __device__ __forceinline__ void att_compute(const Ctx& c, const Args& a, const Layer& L) {
-  const int lane = c.lane, h = c.warp;
+  if (c.an < 0) return;
+  const int lane = c.lane, h = c.ah, n = c.an;
   uint8_t* Ks = c.smem + OFF_STG + c.warp * STG_WARP;
   uint8_t* Vs = Ks + ATT_CHUNK * KS_PITCH;
   float* ps = reinterpret_cast<float*>(Vs + ATT_CHUNK * 128);
   const uint32_t sbase = smem_addr(c.smem);
   const int nkeys = CROSS ? a.S : c.t + 1;
-  for (int slot = 0; slot * CS + c.crank < c.Rc; ++slot) {
-    const int n = slot * CS + c.crank;
-    const int r = c.r0 + n;
-    const uint8_t* sl = c.smem + OFF_SLOT + (slot * H + h) * SLOT_BYTES;
-    const float* qs = reinterpret_cast<const float*>(sl);
-    const unsigned char* km = (CROSS && a.enc_mask) ? a.enc_mask + (long long)(r / a.beams) * a.S : nullptr;
-    if (!CROSS && lane < 16) {  // append this step's K / V to the cache: later steps (and this row's descendants) read them
+  const int r = c.r0 + n;
+  const uint8_t* sl = c.smem + OFF_SLOT + c.warp * SLOT_BYTES;
+  const float* qs = reinterpret_cast<const float*>(sl);
+  const unsigned char* km = (CROSS && a.enc_mask) ? a.enc_mask + (long long)(r / a.beams) * a.S : nullptr;
+  if (!CROSS && lane < 16) {  // append this step's K / V to the cache: later steps (and this row's descendants) read them
+    const uint4 u = *reinterpret_cast<const uint4*>(sl + 256 + (lane >> 3) * 128 + (lane & 7) * 16);
+    bf16* dst = (lane < 8 ? L.kc : L.vc) + ((long long)r * a.Lmax + c.t) * D + h * DH + (lane & 7) * 8;
+    *reinterpret_cast<uint4*>(dst) = u;
+  }
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int c0 = 0; c0 < nkeys; c0 += ATT_CHUNK) {
+    const int nn = min(ATT_CHUNK, nkeys - c0);
+    if (c0 > 0) att_stage<CROSS>(c, a, L, c0);
+    if (!CROSS && c.t >= c0 && c.t < c0 + ATT_CHUNK && lane < 16) {  // position t: from the slot
       const uint4 u = *reinterpret_cast<const uint4*>(sl + 256 + (lane >> 3) * 128 + (lane & 7) * 16);
-      bf16* dst = (lane < 8 ? L.kc : L.vc) + ((long long)r * a.Lmax + c.t) * D + h * DH + (lane & 7) * 8;
+      uint8_t* dst = lane < 8 ? Ks + (c.t - c0) * KS_PITCH + lane * 16 : Vs + (c.t - c0) * 128 + (lane & 7) * 16;
       *reinterpret_cast<uint4*>(dst) = u;
     }
-    float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
-    for (int c0 = 0; c0 < nkeys; c0 += ATT_CHUNK) {
-      const int nn = min(ATT_CHUNK, nkeys - c0);
-      if (slot > 0 || c0 > 0) att_stage<CROSS>(c, a, L, slot, c0);
-      if (!CROSS && c.t >= c0 && c.t < c0 + ATT_CHUNK && lane < 16) {  // position t: from the slot
-        const uint4 u = *reinterpret_cast<const uint4*>(sl + 256 + (lane >> 3) * 128 + (lane & 7) * 16);
-        uint8_t* dst = lane < 8 ? Ks + (c.t - c0) * KS_PITCH + lane * 16 : Vs + (c.t - c0) * 128 + (lane & 7) * 16;
-        *reinterpret_cast<uint4*>(dst) = u;
-      }
-      cp_async_wait_all();
-      __syncwarp();
-      float s[2];
+    cp_async_wait_all();
+    __syncwarp();
+    float s[2];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int p = lane + 32 * i, j = c0 + p;
-        const bool valid = p < nn && (!km || km[j]);
-        float acc = 0.f;
-        if (valid) {
-          const uint8_t* kr = Ks + p * KS_PITCH;
+    for (int i = 0; i < 2; ++i) {
+      const int p = lane + 32 * i, j = c0 + p;
+      const bool valid = p < nn && (!km || km[j]);
+      float acc = 0.f;
+      if (valid) {
+        const uint8_t* kr = Ks + p * KS_PITCH;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint4 u = *reinterpret_cast<const uint4*>(kr + 16 * k);
-            const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * k), qb = *reinterpret_cast<const float4*>(qs + 8 * k + 4);
-            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
-            const float2 f0 = __bfloat1622float2(hh[0]), f1 = __bfloat1622float2(hh[1]);
-            const float2 f2 = __bfloat1622float2(hh[2]), f3 = __bfloat1622float2(hh[3]);
-            acc = fmaf(qa.x, f0.x, acc); acc = fmaf(qa.y, f0.y, acc); acc = fmaf(qa.z, f1.x, acc); acc = fmaf(qa.w, f1.y, acc);
-            acc = fmaf(qb.x, f2.x, acc); acc = fmaf(qb.y, f2.y, acc); acc = fmaf(qb.z, f3.x, acc); acc = fmaf(qb.w, f3.y, acc);
-          }
+        for (int k = 0; k < 8; ++k) {
+          const uint4 u = *reinterpret_cast<const uint4*>(kr + 16 * k);
+          const float4 qa = *reinterpret_cast<const float4*>(qs + 8 * k), qb = *reinterpret_cast<const float4*>(qs + 8 * k + 4);
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+          const float2 f0 = __bfloat1622float2(hh[0]), f1 = __bfloat1622float2(hh[1]);
+          const float2 f2 = __bfloat1622float2(hh[2]), f3 = __bfloat1622float2(hh[3]);
+          acc = fmaf(qa.x, f0.x, acc); acc = fmaf(qa.y, f0.y, acc); acc = fmaf(qa.z, f1.x, acc); acc = fmaf(qa.w, f1.y, acc);
+          acc = fmaf(qb.x, f2.x, acc); acc = fmaf(qb.y, f2.y, acc); acc = fmaf(qb.z, f3.x, acc); acc = fmaf(qb.w, f3.y, acc);
         }
-        s[i] = valid ? acc : -INFINITY;
       }
-      const float mc = warp_max(fmaxf(s[0], s[1]));
-      const float mn = fmaxf(m, mc);
-      float p0 = 0.f, p1 = 0.f, corr = 1.f;
-      if (mn != -INFINITY) {
-        p0 = s[0] == -INFINITY ? 0.f : __expf(s[0] - mn);
-        p1 = s[1] == -INFINITY ? 0.f : __expf(s[1] - mn);
-        corr = m == -INFINITY ? 0.f : __expf(m - mn);
-      }
-      l = l * corr + warp_sum(p0 + p1);
-      m = mn;
-      ps[lane] = p0;
-      ps[lane + 32] = p1;
-      __syncwarp();
-      o0 *= corr;
-      o1 *= corr;
-#pragma unroll 8
-      for (int p = 0; p < nn; ++p) {
-        const float pv = ps[p];
-        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vs + p * 128 + 4 * lane));
-        o0 = fmaf(pv, f.x, o0);
-        o1 = fmaf(pv, f.y, o1);
-      }
-      __syncwarp();  // the staging buffers are refilled by the next chunk / slot
+      s[i] = valid ? acc : -INFINITY;
     }
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat162 o = __floats2bfloat162_rn(o0 * inv, o1 * inv);
-    const uint32_t off = (uint32_t)(OFF_ATT + (n * P_D + h * DH + 2 * lane) * 2);
-    const uint32_t ov = *reinterpret_cast<uint32_t*>(&o);
-    for (int rk = 0; rk < CS; ++rk) st_cluster_b32(mapa(sbase + off, rk), ov);
+    const float mc = warp_max(fmaxf(s[0], s[1]));
+    const float mn = fmaxf(m, mc);
+    float p0 = 0.f, p1 = 0.f, corr = 1.f;
+    if (mn != -INFINITY) {
+      p0 = s[0] == -INFINITY ? 0.f : __expf(s[0] - mn);
+      p1 = s[1] == -INFINITY ? 0.f : __expf(s[1] - mn);
+      corr = m == -INFINITY ? 0.f : __expf(m - mn);
+    }
+    l = l * corr + warp_sum(p0 + p1);
+    m = mn;
+    ps[lane] = p0;
+    ps[lane + 32] = p1;
+    __syncwarp();
+    o0 *= corr;
+    o1 *= corr;
+#pragma unroll 8
+    for (int p = 0; p < nn; ++p) {
+      const float pv = ps[p];
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vs + p * 128 + 4 * lane));
+      o0 = fmaf(pv, f.x, o0);
+      o1 = fmaf(pv, f.y, o1);
+    }
+    __syncwarp();  // the staging buffers are refilled by the next chunk
   }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  __nv_bfloat162 o = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+  const uint32_t off = (uint32_t)(OFF_ATT + (n * P_D + h * DH + 2 * lane) * 2);
+  const uint32_t ov = *reinterpret_cast<uint32_t*>(&o);
+  for (int rk = 0; rk < CS; ++rk) st_cluster_b32(mapa(sbase + off, rk), ov);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) decode_step_kernel(const __grid_constant__ Args a) {
@@ -522,8 +522,11 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_kernel(const __grid_co
   if (c.Rc <= 0 || c.csize != CS) return;  // the whole cluster leaves together
   c.t = *a.cur_len - 1;
   {
-    const int r = c.r0 + c.crank;  // slot 0 row of this CTA
-    const int* anc = (a.anc && c.crank < c.Rc) ? a.anc + ((long long)((c.t + 1) & 1) * a.R + r) * a.Lmax : nullptr;
+    const int item = c.warp * CS + c.crank;
+    c.an = item < c.Rc * H ? item / H : -1;
+    c.ah = item % H;
+    const int r = c.r0 + max(c.an, 0);
+    const int* anc = (a.anc && c.an >= 0) ? a.anc + ((long long)((c.t + 1) & 1) * a.R + r) * a.Lmax : nullptr;
 #pragma unroll
     for (int i = 0; i < 2; ++i) c.anc0[i] = (anc && c.lane + 32 * i < c.t) ? anc[c.lane + 32 * i] : r;
   }
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_kernel(const __grid_co
     lin_rounds<6, 2, false, O_QKV, false, 1, true>(w_qkv, c, a, L.w_qkv, nullptr, L.b_qkv, nullptr, D, 3 * D, ACT0, P_D,
                                                    w_o, Next{L.w_so, nullptr, L.b_so, nullptr, D, D});
     FINE(c); c_arrive(); FINE(c);
-    att_stage<false>(c, a, L, 0, 0);  // the cache rows of the history do not depend on this step's q / k / v
+    att_stage<false>(c, a, L, 0);  // the cache rows of the history do not depend on this step's q / k / v
     // slot 0 is free again: the next layer's norm1 (decoder.norm after the last layer) arrives a whole layer early
     ln_fetch(c, 0, last ? a.fin_g : a.layer[li + 1].n1g, last ? a.fin_b : a.layer[li + 1].n1b);
     c_wait(); FINE(c);
@@ -630,7 +633,7 @@ __global__ void __launch_bounds__(THREADS, 1) decode_step_kernel(const __grid_co
     lin_rounds<2, 2, false, O_Q, false, 1, true>(w_o, c, a, L.w_cq, nullptr, L.b_cq, nullptr, D, D, ACT0, P_D, w_o,
                                                  Next{L.w_co, nullptr, L.b_co, nullptr, D, D});
     FINE(c); c_arrive(); FINE(c);
-    att_stage<true>(c, a, L, 0, 0);
+    att_stage<true>(c, a, L, 0);
     c_wait(); FINE(c);
     DSTEP_STAMP();
     att_compute<true>(c, a, L);

@@ -44,7 +44,7 @@ SMALL_DECODE = os.environ.get("MMA_DECODE_SMALL", "1") != "0"  # <= 64 rows: fus
 PERSIST_DECODE = os.environ.get("MMA_DECODE_PERSIST", "1") != "0"
 PERSIST_CLUSTER = int(os.environ.get("MMA_DECODE_PERSIST_CLUSTER", "16"))
 PERSIST_MAX_CLUSTERS = int(os.environ.get("MMA_DECODE_PERSIST_MAX_CLUSTERS", "0"))  # 0: what the device can hold at once
-PERSIST_MIN_ROWS = int(os.environ.get("MMA_DECODE_PERSIST_MIN_ROWS", "12"))  # 0: no lower bound (tests force the path)
+PERSIST_MIN_ROWS = int(os.environ.get("MMA_DECODE_PERSIST_MIN_ROWS", "0"))  # 0: no lower bound (tests force the path)
 
 
 class BeamState:
@@ -186,10 +186,10 @@ class Generator:
         clusters = -(-st.B // per)
         if clusters > PERSIST_MAX_CLUSTERS:
             return None
-        # measured on B200 (C5 model, ms per step, one-launch vs per-op): beam-10 x 1 / 2 / 4 / 7 spectra 0.345 / 0.34 / 0.33 /
-        # 0.34 vs 0.344 / 0.39 / 0.50 / 0.53; greedy x 1 / 7 / 16 spectra 0.31 / 0.25 / 0.27 vs 0.25 / 0.24 / 0.29: a lone
-        # cluster streams the step's weights through one GPC and only ties with the per-op launches, which use every SM
-        if PERSIST_MIN_ROWS > 0 and (st.B * st.K < PERSIST_MIN_ROWS or clusters < 2 and st.K > 1):
+        # measured on B200 (C5 model, ms per step, one-launch vs per-op launches): beam-10 x 1 / 2 / 4 / 7 spectra
+        # 0.327 / 0.327 / 0.333 / 0.332 vs 0.344 / 0.388 / 0.497 / 0.532; greedy x 1 / 7 / 16 spectra 0.212 / 0.219 / 0.236 vs
+        # 0.250 / 0.240 / 0.290
+        if st.B * st.K < PERSIST_MIN_ROWS:
             return None
         return per * st.K, clusters
 
