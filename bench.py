@@ -452,7 +452,7 @@ def run_ours(args):
             cv, cs = cpu_train_baseline(c, cb, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": cv, "unit": "spectra/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"3 timed train steps of batch {cb} (C2 shapes, fp32, oracle port of the "
-                                              "reference algorithm; /root/reference does not travel to the GPU box)"}
+                                              "reference algorithm; the reference tree does not travel to the GPU box)"}
             if dec is not None:
                 # the reference's decode: transformers generate(num_beams=10, use_cache=False) = the oracle's cache-less
                 # beam search (wrapper.py:443-451), all 127 steps, on a bounded sample of 2 spectra
