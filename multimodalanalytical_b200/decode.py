@@ -180,8 +180,11 @@ class Generator:
                 and cfg.decoder_attention_heads == 8 and st.K <= 16 and cfg.decoder_layers <= 12):
             return None
         global PERSIST_MAX_CLUSTERS
-        if PERSIST_MAX_CLUSTERS <= 0:
-            PERSIST_MAX_CLUSTERS = max(ops.decode_step_max_clusters(PERSIST_CLUSTER), 1)
+        if PERSIST_MAX_CLUSTERS == 0:
+            # -1: the device cannot hold a 16-CTA cluster of this kernel (a partitioned GPU): per-op launches only
+            PERSIST_MAX_CLUSTERS = ops.decode_step_max_clusters(PERSIST_CLUSTER) or -1
+        if PERSIST_MAX_CLUSTERS < 0:
+            return None
         per = max(1, min(16 // st.K, -(-st.B // PERSIST_MAX_CLUSTERS)))  # spectra per cluster
         clusters = -(-st.B // per)
         if clusters > PERSIST_MAX_CLUSTERS:
