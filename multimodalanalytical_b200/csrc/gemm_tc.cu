@@ -37,6 +37,32 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory"); }
+
+// LayerNorm fused behind the residual epilogue (LNF variant of gemm_tc_kernel, N = 512 = four 128-column tiles of a 4-CTA
+// cluster): the rows' statistics meet in every CTA's shared memory through st.shared::cluster
+struct LnArgs {
+  const float* gamma;
+  const float* beta;
+  float eps;
+  bf16* h;
+  long long ldh;
+};
+constexpr int LNF_N = 512, LNF_CS = 4, LNF_PARTS = LNF_CS * 4;  // 16 partial statistics per row (32 columns each)
+constexpr uint32_t LNF_EXTRA_SMEM = 2 * 128 * 4 + BM * LNF_PARTS * 8;
+__device__ __forceinline__ uint32_t cl_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cl_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t local_addr, uint32_t rank, float a, float b) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(r), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -184,10 +210,10 @@ struct Cfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // power of two for BN in {64,128,256}
 };
 
-template <int BN, bool A_MN, bool B_MN, int KIND>
+template <int BN, bool A_MN, bool B_MN, int KIND, bool LNF = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-               int splits_dbg, Epi ep) {
+               int splits_dbg, Epi ep, LnArgs ln) {
   pdl_trigger();
   // diagnostics (MMA_GEMM_DBG, scripts/gemm_bench.py): bit0 epilogue skips its global loads / stores, bit1 no TMA
   // loads and no MMAs (epilogue alone), bit2 TMA loads but no MMAs.  Zero in production.
@@ -207,6 +233,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* sBias = reinterpret_cast<float*>(bars) + 64;  // [BN], 256 bytes past the barrier block start
   uint8_t* sStage = reinterpret_cast<uint8_t*>(sBias + BN);  // [NUM_EPI_WARPS][32 rows][128 B]
+  float* sGam = sBias + BN;                                  // LNF: gamma / beta of this tile's 128 columns,
+  float* sBet = sGam + BN;
+  float2* sStats = reinterpret_cast<float2*>(sBet + BN);     //      [BM rows][16 partial (mean, M2)]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -278,6 +307,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if constexpr (LNF) {  // every thread of the cluster meets at the statistics exchange
+      __syncwarp();
+      cl_sync_all();
+    }
   } else if (warp == 1) {
     if (lane == 0) {
       // ================= MMA issuer (single thread) =================
@@ -319,6 +352,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if constexpr (LNF) {
+      __syncwarp();
+      cl_sync_all();
+    }
   } else {
     // ================= epilogue warps (TMEM -> registers -> global) =================
     const int q = warp & 3;           // a warp may only touch TMEM lanes [32*(warp%4), +32)
@@ -334,6 +371,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < M && !(dbg & 1);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * COLS);
       const int col0 = n0 + half * COLS;
+      if constexpr (LNF) {
+        // out = resid + acc + bias (fp32, stored) and h = LayerNorm(out) (bf16): one tile per CTA, the four CTAs of the
+        // cluster hold the four 128-column tiles of the same 128 rows.  Each thread keeps its 32 columns of its row in
+        // registers, publishes (mean, M2) of them to all four CTAs, and after the cluster barrier merges the row's 16
+        // partials (Chan's formula: equal counts) - one exchange, no cancellation.
+        static_assert(!LNF || (BN == 128 && KIND == EPI_RESID), "LNF: 128-column tiles, residual epilogue");
+        epi_bar_sync();
+        const int et = threadIdx.x - 64;
+        if (et < BN) {
+          sBias[et] = ep.bias ? ep.bias[n0 + et] : 0.f;
+          sGam[et] = ln.gamma[n0 + et];
+          sBet[et] = ln.beta[n0 + et];
+        }
+        EpiIn<16, KIND> in[2];
+        epi_prefetch<16, KIND>(ep, row, col0, N, row_ok, in[0]);
+        epi_prefetch<16, KIND>(ep, row, col0 + 16, N, row_ok, in[1]);
+        epi_bar_sync();
+        if (lane == 0) mbar_wait(smem_u32(&tfull[acc]), acc_phase);
+        __syncwarp();
+        tc_fence_after();
+        float xv[2][16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld16(t_row + (uint32_t)(c * 16), xv[c]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xv[c][j] = in[c].a[j] + xv[c][j] + sBias[half * COLS + c * 16 + j];
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(ep.out) + row * ep.ldo + col0 + c * 16;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<float4*>(o + 4 * k) = make_float4(xv[c][4 * k], xv[c][4 * k + 1], xv[c][4 * k + 2], xv[c][4 * k + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty[acc]));
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum += xv[c][j];
+        const float m_i = sum * (1.0f / 32.0f);
+        float m2_i = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) m2_i = fmaf(xv[c][j] - m_i, xv[c][j] - m_i, m2_i);
+        const int rloc = q * 32 + lane;
+        const uint32_t slot = smem_u32(&sStats[rloc * LNF_PARTS + (int)cl_ctarank() * 4 + half]);
+#pragma unroll
+        for (uint32_t rk = 0; rk < (uint32_t)LNF_CS; ++rk) st_cluster_f32x2(slot, rk, m_i, m2_i);
+        __syncwarp();
+        cl_sync_all();
+        float mean = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNF_PARTS; ++i) mean += sStats[rloc * LNF_PARTS + i].x;
+        mean *= 1.0f / LNF_PARTS;
+        float m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LNF_PARTS; ++i) {
+          const float2 pt = sStats[rloc * LNF_PARTS + i];
+          m2 += pt.y + 32.0f * (pt.x - mean) * (pt.x - mean);
+        }
+        const float rstd = rsqrtf(m2 * (1.0f / LNF_N) + ln.eps);
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int cc = half * COLS + c * 16 + 2 * j;
+              const float y0 = (xv[c][2 * j] - mean) * rstd * sGam[cc] + sBet[cc];
+              const float y1 = (xv[c][2 * j + 1] - mean) * rstd * sGam[cc + 1] + sBet[cc + 1];
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(y0, y1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&p2);
+            }
+            bf16* hp = ln.h + row * ln.ldh + col0 + c * 16;
+            *reinterpret_cast<uint4*>(hp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4*>(hp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
       if (KIND >= 0) {
         // software-pipelined epilogue: bias staged in smem and the first chunk's side inputs fetched while the MMAs
         // of this tile are still running; chunk c+1's TMEM read and global loads overlap chunk c's math and stores
@@ -445,8 +569,54 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, 
     const char* e = getenv("MMA_GEMM_DBG");
     dbg = e ? atoi(e) : 0;
   }
-  if (launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, tmA, tmB, M, N, K, splits | (dbg << 16), ep) != cudaSuccess)
+  if (launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), C::SMEM, stream, tmA, tmB, M, N, K, splits | (dbg << 16), ep, LnArgs{}) != cudaSuccess)
     return MMA_ERR_LAUNCH;
+  return MMA_OK;
+}
+
+// out = resid + A W^T + bias (fp32) and h = LayerNorm(out) (bf16) for N = 512 and a few thousand rows: one 128 x 128 tile
+// per CTA, clusters of four CTAs along N (every tile of the launch resident or in later waves - clusters are independent).
+// The decode step's three residual products per layer at 640 ... 4736 rows, where the CTA-pair fused kernel
+// (gemm2_ln_kernel: 256 rows x all 512 columns per pair) leaves most of the machine idle.
+int gemm_resid_ln_c4(const void* A, long long lda, const void* W, long long ldw, int M, int K, const Epi& ep,
+                     const float* gamma, const float* beta, float eps, void* h, long long ldh, cudaStream_t stream) {
+  using C = Cfg<128>;
+  constexpr uint32_t SMEM = C::SMEM + LNF_EXTRA_SMEM;
+  static_assert(SMEM <= 232448, "shared memory budget");
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, A, (unsigned long long)K, (unsigned long long)M, lda, BK, BM);
+  if (rc) return rc;
+  if ((rc = make_map(&tmB, W, (unsigned long long)K, (unsigned long long)LNF_N, ldw, BK, 128))) return rc;
+  auto kern = gemm_tc_kernel<128, false, false, EPI_RESID, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return MMA_ERR_LAUNCH;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(((M + BM - 1) / BM) * LNF_CS));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = LNF_CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // prologue overlaps the previous kernel's tail
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  static int pdl = -1;
+  if (pdl < 0) {
+    const char* e = getenv("MMA_RESID_LN_C4_PDL");
+    pdl = e ? atoi(e) : 1;
+  }
+  cfg.numAttrs = pdl ? 2 : 1;
+  LnArgs ln{gamma, beta, eps, reinterpret_cast<bf16*>(h), ldh};
+  if (cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, LNF_N, K, 1, ep, ln) != cudaSuccess) {
+    cudaGetLastError();
+    return MMA_ERR_LAUNCH;
+  }
   return MMA_OK;
 }
 

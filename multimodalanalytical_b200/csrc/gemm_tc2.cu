@@ -1202,6 +1202,11 @@ extern "C" int mma_wgrad2_group(int count, const void* const* dy, const long lon
 // x_new = resid + drop(A W^T + bias)  (fp32, ep->out)  and  h = LayerNorm(x_new) gamma + beta  (bf16), d_model = 512.
 // ep: kind EPI_RESID with fp32 out / resid; everything else as in mma_gemm_bf16.  Returns MMA_ERR_UNSUPPORTED for
 // shapes / layouts outside that envelope (the caller then runs the product and the LayerNorm separately).
+namespace tc {
+int gemm_resid_ln_c4(const void* A, long long lda, const void* W, long long ldw, int M, int K, const Epi& ep,
+                     const float* gamma, const float* beta, float eps, void* h, long long ldh, cudaStream_t stream);
+}
+
 extern "C" int mma_gemm2_resid_ln(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                                   const Epi* ep, const float* gamma, const float* beta, float eps, void* h,
                                   long long ldh, cudaStream_t stream) {
@@ -1213,6 +1218,16 @@ extern "C" int mma_gemm2_resid_ln(const void* A, long long lda, const void* W, l
   if (N != LN_N || ep->kind != EPI_RESID || !ep->out_f32 || !ep->resid_f32 || !ok16(ep->out, ep->ldo, 4) ||
       !ok16(ep->resid, ep->ldr, 4) || !ok16(h, ldh, 2) || (ep->p_drop > 0.f && (ep->drop_ld & 1)))
     return MMA_ERR_UNSUPPORTED;
+  // a few thousand rows without dropout (the decode step): 128 x 128 tiles in clusters of four along N (gemm_tc.cu) fill
+  // the machine where 256-row pairs that own all 512 columns do not
+  static int c4_max = -1;
+  if (c4_max < 0) {
+    const char* e = getenv("MMA_RESID_LN_C4_MAX_ROWS");
+    c4_max = e ? atoi(e) : 4736;  // 37 row tiles x 4 = 148 CTAs: one wave
+  }
+  if (M <= c4_max && ep->p_drop <= 0.f && (lda & 7) == 0 && (ldw & 7) == 0 && (K & 7) == 0 &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0)
+    return tc::gemm_resid_ln_c4(A, lda, W, ldw, M, K, *ep, gamma, beta, eps, h, ldh, stream);
   static int swz = -1;
   if (swz < 0) {
     const char* e = getenv("MMA_GEMM2_SWZ");

@@ -23,9 +23,11 @@ from .model import Engine
 
 
 # Residual products of the decode step fused with the LayerNorm that follows them (mma_gemm2_resid_ln): opt-in
-# (MMA_DECODE_FUSE_LN=1 every residual product, 2 only the K = d_model ones).  Measured on B200 at 2560 rows (256 spectra x
-# 10 beams): 1.75 ms / step fused against 1.58 ms with separate launches - a CTA pair owns 256 rows x all 512 columns, so
-# only 10 pairs work.
+# (MMA_DECODE_FUSE_LN=1 every residual product, 2 only the K = d_model ones, 3 only up to 4736 rows, where the 4-CTA-cluster
+# kernel applies).  Measured on B200, beam-10, ms / step fused vs separate launches: CTA-pair kernel at 2560 rows 1.75 vs
+# 1.58 (a pair owns 256 rows x all 512 columns, so only 10 pairs work); 4-CTA-cluster kernel (128 x 128 tiles, row
+# statistics exchanged through distributed shared memory) 1.003 vs 0.953 at 2560 rows, 0.654 vs 0.590 at 320 rows - the
+# cluster barrier in the middle of the epilogue and the row-per-thread stores of h cost more than the ~3 us LayerNorm launch.
 FUSE_DECODE_LN = int(os.environ.get("MMA_DECODE_FUSE_LN", "0"))
 
 
@@ -303,7 +305,8 @@ class Generator:
             """out = resid + a_in W^T + b and h = LayerNorm(out) with the NEXT sub-layer's norm: one CTA-pair launch when
             the fused kernel applies (bf16, d_model 512, >= 256 rows), else the product followed by the LayerNorm."""
             epi = ops.make_epi(EPI_RESID, out, bias=eng.P(bname), resid=resid)
-            if not (bf and (FUSE_DECODE_LN == 1 or (FUSE_DECODE_LN == 2 and k_in <= d)) and
+            if not (bf and (FUSE_DECODE_LN == 1 or (FUSE_DECODE_LN == 2 and k_in <= d) or
+                            (FUSE_DECODE_LN == 3 and R <= 4736)) and
                     ops.gemm_resid_ln(a_in, eng.W(wname), R, d, k_in, epi, eng.P(gname), eng.P(bename), h)):
                 ops.gemm(a_in, eng.W(wname), R, d, k_in, epi)
                 ops.ln_fwd(out, eng.P(gname), eng.P(bename), h)

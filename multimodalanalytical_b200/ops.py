@@ -173,12 +173,15 @@ def fuse_ln_wanted(M, K):
 
 
 def gemm_resid_ln(A, W, M, N, K, epi, gamma, beta, h, eps=1e-5):
-    """epi.out = epi.resid + drop(A W^T + bias) and h = LayerNorm(epi.out) * gamma + beta in ONE launch (CTA-pair
-    tcgen05 kernel, N == 512).  Returns False (nothing launched) when the shape / layout is outside the fused
-    kernel's envelope - the caller then runs `gemm` and `ln_fwd`."""
+    """epi.out = epi.resid + drop(A W^T + bias) and h = LayerNorm(epi.out) * gamma + beta in ONE launch (N == 512: up to
+    4736 rows without dropout 128 x 128 tiles in 4-CTA clusters that exchange the row statistics through distributed
+    shared memory, else the CTA-pair kernel).  Returns False (nothing launched) when the shape / layout is outside the
+    fused kernels' envelope - the caller then runs `gemm` and `ln_fwd`."""
     _need_cuda(A, W, h)
-    if not (N == 512 and M >= 512 and epi.kind == EPI_RESID and epi.out_f32 and epi.resid_f32
+    if not (N == 512 and M >= 65 and epi.kind == EPI_RESID and epi.out_f32 and epi.resid_f32
             and h.dtype == torch.bfloat16 and _tc_ok(A, False, M, K) and _tc_ok(W, False, N, K)):
+        return False
+    if epi.p_drop > 0 and M < 512:
         return False
     if epi.p_drop > 0 and epi.drop_ld == 0:
         epi.drop_ld = N
