@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
         best = other > best ? other : best;
       }
       if (lane == 0) {
-        s_wkeys[warp * 2 * MAXK + sel] = best;
+        s_wkeys[warp * keep + sel] = best;  // dense [nwarp][keep]: the merge below indexes it flat
         if (best) cand[(int)(0xffffffffu - (uint32_t)(best & 0xffffffffull))] = 0u;
       }
       __syncwarp();
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
       unsigned long long best = 0ull;
       int where = -1;
       for (int i = lane; i < n; i += 32) {
-        const unsigned long long key = s_wkeys[(i / keep) * 2 * MAXK + (i % keep)];
+        const unsigned long long key = s_wkeys[i];
         if (key > best) { best = key; where = i; }
       }
 #pragma unroll
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
         if (best) {
           c_idx[sel] = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
           c_score[sel] = ord2f((uint32_t)(best >> 32));
-          s_wkeys[(where / keep) * 2 * MAXK + (where % keep)] = 0ull;
+          s_wkeys[where] = 0ull;
         } else {  // fewer than 2K candidates (K*V < 2K): pad with -inf on slot 0
           c_idx[sel] = 0;
           c_score[sel] = -INFINITY;
@@ -443,13 +443,15 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
   __syncthreads();
   // 5. parallel state rewrite (ping-pong buffers)
   const long long seq_stride = (long long)a.B * K * L;
-  const int* rs_old = a.run_seq + rd * seq_stride + (long long)b * K * L;
-  int* rs_new = a.run_seq + wr * seq_stride + (long long)b * K * L;
-  const int* fs_old = a.fin_seq + rd * seq_stride + (long long)b * K * L;
-  int* fs_new = a.fin_seq + wr * seq_stride + (long long)b * K * L;
+  // (ping-pong halves never alias: __restrict__ lets the loads of several iterations be in flight together)
+  const int* __restrict__ rs_old = a.run_seq + rd * seq_stride + (long long)b * K * L;
+  int* __restrict__ rs_new = a.run_seq + wr * seq_stride + (long long)b * K * L;
+  const int* __restrict__ fs_old = a.fin_seq + rd * seq_stride + (long long)b * K * L;
+  int* __restrict__ fs_new = a.fin_seq + wr * seq_stride + (long long)b * K * L;
   const long long anc_stride = (long long)a.B * K * L;
-  const int* an_old = a.anc + rd * anc_stride + (long long)b * K * L;
-  int* an_new = a.anc + wr * anc_stride + (long long)b * K * L;
+  const int* __restrict__ an_old = a.anc + rd * anc_stride + (long long)b * K * L;
+  int* __restrict__ an_new = a.anc + wr * anc_stride + (long long)b * K * L;
+#pragma unroll 4
   for (int i = threadIdx.x; i < K * L; i += blockDim.x) {
     const int k = i / L, p = i % L;
     {  // running beams
