@@ -314,15 +314,27 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
     cand[i] = f2ord(lp + a.run_score[b * K + k]);
   }
   __syncthreads();
-  // 3. top-2K, descending, ties -> lowest flat index.  Two levels without block-wide syncs per pick: every warp
-  //    extracts the top-2K of its own slice of the K*V candidates (shuffle arg-max, owner warp marks "taken"), then
-  //    warp 0 extracts the top-2K of the nwarp*2K survivors.
+  // 3. top-2K, descending, ties -> lowest flat index (keys (score, ~index) are unique).  Two levels without block-wide
+  //    syncs per pick: every warp extracts the top-2K of its own slice of the K*V candidates, then warp 0 extracts the
+  //    top-2K of the nwarp*2K survivors.  A lane keeps the best key of ITS strided elements in a register; a pick is a
+  //    shuffle arg-max over the 32 lane heads, and only the winning lane re-scans its own elements for its next head
+  //    (measured at 1 spectrum x 10 beams, V = 120: 12.6 + 8.1 us for the two levels when every pick re-scanned the whole
+  //    slice from shared memory and wrote the "taken" marker through lane 0; 7.8 + 7.6 us with lane heads and a 64-bit
+  //    shuffle ladder).
   const int keep = 2 * K;
   const int KV = K * V;
+  // warp-wide maximum of a 64-bit key with two REDUX instructions (high words, then low words among the lanes that hold
+  // the maximal high word) instead of a 5-step shuffle ladder of 64-bit values
+  auto wmax64 = [](unsigned long long v) {
+    const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | (unsigned long long)ml;
+  };
   {
     const int per_warp = (KV + nwarp - 1) / nwarp;
     const int lo = warp * per_warp, hi = min(KV, lo + per_warp);
-    for (int sel = 0; sel < keep; ++sel) {
+    auto head = [&]() {  // best remaining key among this lane's elements lo + lane, lo + lane + 32, ...
       unsigned long long best = 0ull;
       for (int i = lo + lane; i < hi; i += 32) {
         const uint32_t o = cand[i];
@@ -331,45 +343,47 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
           best = key > best ? key : best;
         }
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
-        best = other > best ? other : best;
+      return best;
+    };
+    unsigned long long mine = head();
+    for (int sel = 0; sel < keep; ++sel) {
+      const unsigned long long best = wmax64(mine);
+      if (lane == 0) s_wkeys[warp * keep + sel] = best;  // dense [nwarp][keep]: the merge below indexes it flat
+      if (best && mine == best) {  // the owner retires the element (only this lane ever touches it) and finds its next head
+        cand[(int)(0xffffffffu - (uint32_t)(best & 0xffffffffull))] = 0u;
+        mine = head();
       }
-      if (lane == 0) {
-        s_wkeys[warp * keep + sel] = best;  // dense [nwarp][keep]: the merge below indexes it flat
-        if (best) cand[(int)(0xffffffffu - (uint32_t)(best & 0xffffffffull))] = 0u;
-      }
-      __syncwarp();
     }
   }
   __syncthreads();
   if (warp == 0) {
     const int n = nwarp * keep;
-    for (int sel = 0; sel < keep; ++sel) {
+    auto head = [&](int& where) {
       unsigned long long best = 0ull;
-      int where = -1;
+      where = -1;
       for (int i = lane; i < n; i += 32) {
         const unsigned long long key = s_wkeys[i];
         if (key > best) { best = key; where = i; }
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, off);
-        const int ow = __shfl_xor_sync(0xffffffffu, where, off);
-        if (other > best) { best = other; where = ow; }
-      }
+      return best;
+    };
+    int where;
+    unsigned long long mine = head(where);
+    for (int sel = 0; sel < keep; ++sel) {
+      const unsigned long long best = wmax64(mine);
       if (lane == 0) {
         if (best) {
           c_idx[sel] = (int)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
           c_score[sel] = ord2f((uint32_t)(best >> 32));
-          s_wkeys[where] = 0ull;
         } else {  // fewer than 2K candidates (K*V < 2K): pad with -inf on slot 0
           c_idx[sel] = 0;
           c_score[sel] = -INFINITY;
         }
       }
-      __syncwarp();
+      if (best && mine == best) {
+        s_wkeys[where] = 0ull;
+        mine = head(where);
+      }
     }
   }
   __syncthreads();
