@@ -465,9 +465,13 @@ __global__ void __launch_bounds__(256) beam_step_kernel(BeamArgs a) {
   const long long anc_stride = (long long)a.B * K * L;
   const int* __restrict__ an_old = a.anc + rd * anc_stride + (long long)b * K * L;
   int* __restrict__ an_new = a.anc + wr * anc_stride + (long long)b * K * L;
+  // only positions 0 .. cur carry information: beyond them both halves still hold the fill value they were initialised
+  // with (sequences) or stale entries that are rewritten before they are read (ancestors)
+  const int Lc = min(L, cur + 1);
 #pragma unroll 4
-  for (int i = threadIdx.x; i < K * L; i += blockDim.x) {
-    const int k = i / L, p = i % L;
+  for (int j = threadIdx.x; j < K * Lc; j += blockDim.x) {
+    const int k = j / Lc, p = j - k * Lc;
+    const int i = k * L + p;
     {  // running beams
       const int c = n_run_src[k];
       const int beam = c_idx[c] / V, tok = c_idx[c] % V;
