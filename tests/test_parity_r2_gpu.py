@@ -309,6 +309,10 @@ def test_one_launch_decode_step_matches_per_op_step(case, B, K, monkeypatch):
     monkeypatch.setattr(dec, "PERSIST_DECODE", True)
     m.generator._graphs.clear()
     s1 = m.generate(batch, n_beams=K).cpu()
+    # the processed-scores loop (generic logits processors: decoder forward graph-replayed, selection on processed scores)
+    # runs the same one-launch forward: an identity processor must not change anything
+    s_proc = m.generate(batch, n_beams=K, logits_processor=[lambda ids, scores: scores]).cpu()
+    assert torch.equal(s_proc, s1), "identity processor changed the one-launch result"
     monkeypatch.setattr(dec, "PERSIST_DECODE", False)
     m.generator._graphs.clear()
     s0 = m.generate(batch, n_beams=K).cpu()
