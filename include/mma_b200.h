@@ -256,12 +256,12 @@ int mma_decode_self_attn(const void* q, long long ldq, const void* knew, const v
 int mma_decode_cross_attn(const void* q, long long ldq, const void* kmem, const void* vmem, long long ldm,
                           const unsigned char* kmask, const int* cur_len, void* o, long long ldo, int R, int H, int dh,
                           int S, int beams, float scale, int type, cudaStream_t stream);
-/* Small-batch decode product (R <= 64 rows: a few spectra x beams): out[R,N] = epilogue(LN?(x)[R,K] w[N,K]^T + bias) in
+/* Small-batch decode product (R <= 512 rows in blocks of <= 64: a few spectra x beams): out[R,N] = epilogue(LN?(x)[R,K] w[N,K]^T + bias) in
  * one launch on mma.sync with the weight tile as the 16-row operand (every weight element read once), LayerNorm of the fp32
  * residual stream as prologue, bias / GELU / gate / residual as epilogue.  Replaces nn.LayerNorm + nn.Linear (+ gelu, gate,
  * residual) of a decoder layer (custom_modeling.py:155-199) when the tcgen05 tiles would be > 90 % padding.
  * x: fp32 (x_f32 = 1; LayerNorm when gamma != NULL) or bf16; kind 0 store, 1 GELU, 2 out = resid + result, 3 gated
- * (gelu(x w^T + bias) * (x w2^T + bias2)).  K % 256 == 0; -3 otherwise / for R > 64.                               */
+ * (gelu(x w^T + bias) * (x w2^T + bias2)).  K % 256 == 0; -3 otherwise / for R > 512.                              */
 int mma_small_linear(const void* x, int x_f32, long long ldx, const float* gamma, const float* beta, float eps,
                      const void* w, const void* w2, long long ldw, const float* bias, const float* bias2,
                      const float* resid, long long ldr, void* out, int out_f32, long long ldo, int R, int N, int K,

@@ -1,5 +1,5 @@
-// Small-batch decode products: Y[R, N] = epilogue( LN?(X)[R, K] W[N, K]^T + b ) for R <= 64 rows (a handful of spectra x
-// beams).  At that size the step is ~70 strictly dependent launches whose cost is latency, not math: the tcgen05 kernels pay
+// Small-batch decode products: Y[R, N] = epilogue( LN?(X)[R, K] W[N, K]^T + b ) for a handful of spectra x beams: blocks of
+// <= 64 rows (grid.y walks up to 8 such blocks; the weights of the second and later blocks come out of L2).  At that size the step is ~70 strictly dependent launches whose cost is latency, not math: the tcgen05 kernels pay
 // TMEM allocation, tensor-map fetch, a TMA pipeline fill and a row-per-thread epilogue for a 128-row tile that is 92 %
 // padding, and every LayerNorm is a launch of its own.  Here one CTA owns 16 output features, its 8 warps split the
 // reduction, and the product runs on mma.sync.m16n8k16 with the WEIGHT tile as the 16-row A operand and the (few) rows
@@ -13,6 +13,7 @@ namespace dsm {
 
 constexpr int MAXR = 64;
 constexpr int NT_MAX = MAXR / 8;
+constexpr int MAXBLK = 8;  // row blocks per launch
 enum { K_STORE = 0, K_GELU = 1, K_RESID = 2, K_GLU = 3 };
 
 struct LinArgs {
@@ -24,6 +25,7 @@ struct LinArgs {
   void* out; int out_f32; long long ldo;
   int R, N, K, kind;
   int ftiles;  // 16-feature tiles per CTA: more rows -> more tiles per CTA, so the per-CTA LayerNorm prologue is amortised
+  int rblk;    // rows per row block (blockIdx.y), a multiple of 8, <= MAXR
 };
 
 __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -40,7 +42,9 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinArgs a) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int R = a.R, K = a.K;
+  const int r0 = blockIdx.y * a.rblk;          // this CTA's row block
+  const int R = min(a.rblk, a.R - r0), K = a.K;
+  if (R <= 0) return;  // uniform over the CTA (cannot happen with the host's even split)
   const int NT = (R + 7) >> 3;
   const int pitch = K + 32;  // bf16 elements per staged row: rows 64 bytes apart in bank space -> conflict-free 16-byte reads
   bf16* xs = reinterpret_cast<bf16*>(smem);                                   // [NT * 8][pitch] when staged
@@ -56,7 +60,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinArgs a) {
         for (int c = lane * 8; c < K; c += 256) *reinterpret_cast<uint4*>(dst + c) = make_uint4(0u, 0u, 0u, 0u);
         continue;
       }
-      const float* src = X + (long long)r * a.ldx;
+      const float* src = X + (long long)(r0 + r) * a.ldx;
       // one pass over global memory: the row lives in registers (K <= 1024: 8 float4 per lane)
       float4 v[8];
       float s = 0.f;
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinArgs a) {
   const int kbeg = warp * ks;
   const int rows8 = NT * 8;
   const int set_stride = rows8 * 16;
-  const bf16* xg = staged ? nullptr : reinterpret_cast<const bf16*>(a.x);
+  const bf16* xg = staged ? nullptr : reinterpret_cast<const bf16*>(a.x) + (long long)r0 * a.ldx;
   for (int ft = 0; ft < a.ftiles; ++ft) {
   const int f0 = (blockIdx.x * a.ftiles + ft) * 16;
   if (f0 >= a.N) break;  // uniform over the CTA
@@ -183,10 +187,10 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinArgs a) {
     } else if (a.kind == K_GELU) {
       v = gelu_t<true>(v);
     } else if (a.kind == K_RESID) {
-      v += a.resid[(long long)n * a.ldr + col];
+      v += a.resid[(long long)(r0 + n) * a.ldr + col];
     }
-    if (a.out_f32) reinterpret_cast<float*>(a.out)[(long long)n * a.ldo + col] = v;
-    else reinterpret_cast<bf16*>(a.out)[(long long)n * a.ldo + col] = __float2bfloat16_rn(v);
+    if (a.out_f32) reinterpret_cast<float*>(a.out)[(long long)(r0 + n) * a.ldo + col] = v;
+    else reinterpret_cast<bf16*>(a.out)[(long long)(r0 + n) * a.ldo + col] = __float2bfloat16_rn(v);
   }
   __syncthreads();  // `red` is rewritten by the next feature tile
   }
@@ -194,28 +198,30 @@ __global__ void __launch_bounds__(256) small_linear_kernel(LinArgs a) {
 
 }  // namespace dsm
 
-// out[R, N] = epilogue( LN?(x)[R, K] w[N, K]^T + bias ) for R <= 64 (the decode step of a few spectra).
+// out[R, N] = epilogue( LN?(x)[R, K] w[N, K]^T + bias ) for R <= 512 (the decode step of a few spectra), in row blocks of <= 64.
 //   x: fp32 [R, K] (x_f32 = 1; LayerNorm(gamma, beta, eps) applied when gamma != NULL) or bf16 [R, K] (x_f32 = 0);
 //   w (and, kind 3, the gate weights w2 with bias2): bf16 [N, K], pitch ldw;  kind: 0 store, 1 exact-erf GELU,
 //   2 out = resid (fp32 [R, N]) + result, 3 gated: gelu(x w^T + bias) * (x w2^T + bias2);  out: fp32 or bf16 [R, N].
-// K must be a multiple of 256 (8 warps x 32-element blocks); returns MMA_ERR_UNSUPPORTED otherwise or when R > 64.
+// K must be a multiple of 256 (8 warps x 32-element blocks); returns MMA_ERR_UNSUPPORTED otherwise or when R > 512.
 extern "C" int mma_small_linear(const void* x, int x_f32, long long ldx, const float* gamma, const float* beta, float eps,
                                 const void* w, const void* w2, long long ldw, const float* bias, const float* bias2,
                                 const float* resid, long long ldr, void* out, int out_f32, long long ldo, int R, int N,
                                 int K, int kind, cudaStream_t stream) {
   using namespace dsm;
   if (R <= 0 || N <= 0 || K <= 0 || !x || !w || !out || kind < 0 || kind > 3) return MMA_ERR_ARG;
-  if (R > MAXR || (K & 255) || (x_f32 && K > 1024) || (ldw & 7) || (reinterpret_cast<uintptr_t>(w) & 15) || (kind == K_GLU && !w2) ||
+  if (R > MAXR * MAXBLK || (K & 255) || (x_f32 && K > 1024) || (ldw & 7) || (reinterpret_cast<uintptr_t>(w) & 15) || (kind == K_GLU && !w2) ||
       (kind == K_RESID && !resid))
     return MMA_ERR_UNSUPPORTED;
   if (x_f32 ? ((ldx & 3) || (reinterpret_cast<uintptr_t>(x) & 15)) : ((ldx & 7) || (reinterpret_cast<uintptr_t>(x) & 15)))
     return MMA_ERR_UNSUPPORTED;
   if (gamma && !x_f32) return MMA_ERR_ARG;
   LinArgs a{x, x_f32, ldx, gamma, beta, eps, reinterpret_cast<const bf16*>(w), reinterpret_cast<const bf16*>(w2), ldw, bias,
-            bias2, resid, ldr, out, out_f32, ldo, R, N, K, kind, 1};
-  const int NT = (R + 7) / 8;
+            bias2, resid, ldr, out, out_f32, ldo, R, N, K, kind, 1, 0};
+  const int nblk = (R + MAXR - 1) / MAXR;
+  a.rblk = (((R + nblk - 1) / nblk) + 7) & ~7;  // even split, whole 8-row MMA tiles
+  const int NT = a.rblk / 8;
   const size_t smem = (x_f32 ? (size_t)NT * 8 * (K + 32) * 2 : 0) + (size_t)8 * (kind == K_GLU ? 2 : 1) * NT * 8 * 16 * 4;
-  const int grid = (N + 16 * a.ftiles - 1) / (16 * a.ftiles);
+  const dim3 grid((N + 16 * a.ftiles - 1) / (16 * a.ftiles), nblk);
   if (kind == K_GLU) {
     static size_t set = 0;
     if (smem > set) {

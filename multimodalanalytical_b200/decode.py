@@ -38,7 +38,8 @@ COMPACT_MIN_B = int(os.environ.get("MMA_DECODE_COMPACT_MIN_B", "16"))
 COMPACT_LIVE_FRAC = 0.5  # compact when at most this fraction of the batch is still searching
 
 
-SMALL_DECODE = os.environ.get("MMA_DECODE_SMALL", "1") != "0"  # <= 64 rows: fused LayerNorm + product launches (decode_small.cu)
+SMALL_DECODE = os.environ.get("MMA_DECODE_SMALL", "1") != "0"  # few rows: fused LayerNorm + product launches (decode_small.cu)
+SMALL_MAX_ROWS = int(os.environ.get("MMA_DECODE_SMALL_ROWS", "64"))  # rows (spectra x beams) up to which that path is taken
 
 
 # few spectra (every cluster resident at once, <= 16 rows per cluster): the whole step as ONE cluster-synchronised launch
@@ -269,7 +270,7 @@ class Generator:
 
     def _small_ok(self, R):
         cfg = self.eng.cfg
-        return (SMALL_DECODE and self.eng.precision == "bf16" and R <= 64 and cfg.d_model % 256 == 0
+        return (SMALL_DECODE and self.eng.precision == "bf16" and R <= min(SMALL_MAX_ROWS, 512) and cfg.d_model % 256 == 0
                 and cfg.decoder_ffn_dim % 256 == 0 and (cfg.d_model // cfg.decoder_attention_heads) == 64)
 
     def _forward_logits(self, st: BeamState, ctx: Dict[str, Any]):

@@ -548,7 +548,7 @@ SMALL_KINDS = {"store": 0, "gelu": 1, "resid": 2, "glu": 3}
 
 def small_linear(x, w, out, R, N, K, kind="store", bias=None, gamma=None, beta=None, w2=None, bias2=None, resid=None,
                  eps=1e-5):
-    """out[R, N] = epilogue(LN?(x)[R, K] w^T + bias) for R <= 64 rows in ONE launch (decode of a few spectra).
+    """out[R, N] = epilogue(LN?(x)[R, K] w^T + bias) for R <= 512 rows (blocks of <= 64) in ONE launch (decode of a few spectra).
     Returns False (nothing launched) outside the kernel's envelope."""
     _need_cuda(x, w, out)
     rc = _lib.load().mma_small_linear(

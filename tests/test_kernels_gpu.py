@@ -686,7 +686,7 @@ def test_grouped_wgrad_split_reduction(specs):
         assert rel(it[3], rb) < 3e-5, it[4:]
 
 
-@pytest.mark.parametrize("R", [1, 10, 30, 64])
+@pytest.mark.parametrize("R", [1, 10, 30, 64, 65, 80, 320, 449, 512])
 def test_small_linear_decode_products(R):
     """mma_small_linear (decode_small.cu): LayerNorm prologue + product + bias / GELU / gate / residual epilogue for a
     handful of rows, every kind against torch (bf16 operands, fp32 accumulate)."""
@@ -720,7 +720,7 @@ def test_small_linear_decode_products(R):
     lg = torch.zeros(R, 208, device=DEV)
     assert ops.small_linear(x, Wv, lg, R, V, d, bias=bv, gamma=gamma, beta=beta)
     assert rel(lg[:, :V], hn @ Wv.float().T + bv) < 2e-3 and float(lg[:, V:].abs().max()) == 0.0
-    # outside the envelope: more than 64 rows, K not a multiple of 256
-    big = _rand(65, d)
-    assert not ops.small_linear(big, W, torch.empty(65, 3 * d, device=DEV, dtype=torch.bfloat16), 65, 3 * d, d, bias=b)
+    # outside the envelope: more than 512 rows (8 blocks of 64), K not a multiple of 256
+    big = _rand(513, d)
+    assert not ops.small_linear(big, W, torch.empty(513, 3 * d, device=DEV, dtype=torch.bfloat16), 513, 3 * d, d, bias=b)
     assert not ops.small_linear(_rand(4, 200), _rand(16, 200, dtype=torch.bfloat16), torch.empty(4, 16, device=DEV), 4, 16, 200)
