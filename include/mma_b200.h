@@ -135,6 +135,13 @@ int mma_patchify(const float* raw, long long ld, int offset, float mean, float s
 int mma_patchify_rows(const float* raw, long long ld, const int* rows, int offset, float mean, float std, float* out,
                       unsigned char* pad, const unsigned char* missing, int masking, int B, int P, int ps, int hop,
                       cudaStream_t stream);
+/* PatchPreprocessor(derivative=True) (patches.py:41-46,91-95): out [B, P + Pd, ps] = the P standardised patches followed
+ * by the Pd = n_use / ps patches of torch.gradient over the n_use raw points the preprocessor sees from `offset` on
+ * (central differences, one-sided at both ends; not standardised, never overlapping); pad [B, P + Pd].  rows: NULL or
+ * the dataset rows of the batch.                                                                                   */
+int mma_patchify_deriv(const float* raw, long long ld, const int* rows, int offset, int n_use, float mean, float std,
+                       float* out, unsigned char* pad, const unsigned char* missing, int masking, int B, int P, int Pd,
+                       int ps, int hop, cudaStream_t stream);
 
 /* ---- batch assembly from an HBM-resident pre-tokenised dataset (replaces the host collator,
  * data/datamodules.py:140-351).  Ragged storage: flat values + int64 row offsets [N+1]; rows [B] are

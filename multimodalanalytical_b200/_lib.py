@@ -140,6 +140,7 @@ _SIGS = {
     "mma_cast_bf16_f32": [_vp, _vp, _ll, _vp],
     "mma_patchify": [_vp, _ll, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "mma_patchify_rows": [_vp, _ll, _vp, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "mma_patchify_deriv": [_vp, _ll, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "mma_collate_tokens": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
     "mma_collate_target": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "mma_collate_values": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp],

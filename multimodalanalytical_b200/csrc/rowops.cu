@@ -637,17 +637,33 @@ __global__ void __launch_bounds__(128) patchify_kernel(const float* __restrict__
                                                        float mean, float std, float* __restrict__ out,
                                                        unsigned char* __restrict__ pad,
                                                        const unsigned char* __restrict__ missing, int masking, int P,
-                                                       int ps, int hop, const int* __restrict__ rows) {
+                                                       int ps, int hop, const int* __restrict__ rows, int Ptot, int p0,
+                                                       int deriv, int n_use) {
   pdl_trigger();
   const int b = blockIdx.y, p = blockIdx.x;
   const long long r = rows ? rows[b] : b;  // dataset-resident spectra: batch element b is row rows[b] of `raw`
   const float* src = raw + r * ld + offset + (long long)p * hop;
-  float* dst = out + ((long long)b * P + p) * ps;
+  // this launch fills patches [p0, p0 + P) of a sample's Ptot output patches
+  float* dst = out + ((long long)b * Ptot + p0 + p) * ps;
   float s = 0.f;
-  for (int k = threadIdx.x; k < ps; k += blockDim.x) {
-    const float v = (src[k] - mean) / std;  // exact division: bit-identical to the reference's fp32 arithmetic
-    dst[k] = v;
-    s += v;
+  if (!deriv) {
+    for (int k = threadIdx.x; k < ps; k += blockDim.x) {
+      const float v = (src[k] - mean) / std;  // exact division: bit-identical to the reference's fp32 arithmetic
+      dst[k] = v;
+      s += v;
+    }
+  } else {
+    // torch.gradient of the raw (not standardised) spectrum, patches.py:91-95: central differences inside the n_use
+    // points the preprocessor sees, one-sided at their two ends
+    for (int k = threadIdx.x; k < ps; k += blockDim.x) {
+      const int i = p * hop + k;
+      float v;
+      if (i == 0) v = src[k + 1] - src[k];
+      else if (i == n_use - 1) v = src[k] - src[k - 1];
+      else v = (src[k + 1] - src[k - 1]) * 0.5f;
+      dst[k] = v;
+      s += v;
+    }
   }
   if (pad) {
     __shared__ float red[4];
@@ -656,7 +672,7 @@ __global__ void __launch_bounds__(128) patchify_kernel(const float* __restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
       const float tot = red[0] + red[1] + red[2] + red[3];
-      pad[(long long)b * P + p] = masking ? (tot == 0.f) : (missing ? missing[r] : 0);
+      pad[(long long)b * Ptot + p0 + p] = masking ? (tot == 0.f) : (missing ? missing[r] : 0);
     }
   }
 }
@@ -666,7 +682,7 @@ extern "C" int mma_patchify(const float* raw, long long ld, int offset, float me
                             int hop, cudaStream_t stream) {
   if (B <= 0 || P <= 0 || ps <= 0 || hop <= 0 || std == 0.f) return MMA_ERR_ARG;
   patchify_kernel<<<dim3(P, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, P, ps, hop,
-                                                  nullptr);
+                                                  nullptr, P, 0, 0, 0);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }
@@ -676,7 +692,23 @@ extern "C" int mma_patchify_rows(const float* raw, long long ld, const int* rows
                                  int P, int ps, int hop, cudaStream_t stream) {
   if (B <= 0 || P <= 0 || ps <= 0 || hop <= 0 || std == 0.f || !rows) return MMA_ERR_ARG;
   patchify_kernel<<<dim3(P, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, P, ps, hop,
-                                                  rows);
+                                                  rows, P, 0, 0, 0);
+  MMA_CHECK_LAUNCH();
+  return MMA_OK;
+}
+
+// PatchPreprocessor(derivative=True), patches.py:91-95: out [B, P + Pd, ps] = the P standardised patches (hop as above)
+// followed by the Pd = n_use / ps patches of torch.gradient(raw spectrum) (not standardised, never overlapping); pad
+// [B, P + Pd] by the same rule over all of them.  n_use: the points the preprocessor sees from `offset` on (the whole
+// spectrum, or the 1625 of the interpolation slice) - the one-sided differences sit at its ends.  rows may be NULL.
+extern "C" int mma_patchify_deriv(const float* raw, long long ld, const int* rows, int offset, int n_use, float mean,
+                                  float std, float* out, unsigned char* pad, const unsigned char* missing, int masking,
+                                  int B, int P, int Pd, int ps, int hop, cudaStream_t stream) {
+  if (B <= 0 || P <= 0 || Pd <= 0 || ps <= 0 || hop <= 0 || std == 0.f || n_use < 2 || Pd * ps > n_use) return MMA_ERR_ARG;
+  patchify_kernel<<<dim3(P, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, P, ps, hop,
+                                                  rows, P + Pd, 0, 0, n_use);
+  patchify_kernel<<<dim3(Pd, B), 128, 0, stream>>>(raw, ld, offset, mean, std, out, pad, missing, masking, Pd, ps, ps,
+                                                   rows, P + Pd, P, 1, n_use);
   MMA_CHECK_LAUNCH();
   return MMA_OK;
 }

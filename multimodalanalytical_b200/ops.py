@@ -293,6 +293,27 @@ def patchify(raw, out, mean, std, offset=0, hop=None, pad=None, missing=None, ma
     _count()
 
 
+def patchify_deriv(raw, out, mean, std, n_patches, offset=0, n_use=None, hop=None, pad=None, missing=None, masking=False,
+                   rows=None):
+    """PatchPreprocessor(derivative=True): out fp32 [B, P + Pd, ps] = the P standardised patches, then the Pd = `n_patches`
+    patches of torch.gradient over the `n_use` raw points from `offset` on (patches.py:91-95)."""
+    _need_cuda(raw, out)
+    assert raw.dtype == torch.float32 and raw.stride(1) == 1 and out.dtype == torch.float32 and out.is_contiguous()
+    B, Ptot, ps = out.shape
+    Pd = int(n_patches)
+    P = Ptot - Pd
+    hop = ps if hop is None else hop
+    n_use = raw.shape[1] - offset if n_use is None else int(n_use)
+    assert P > 0 and offset + n_use <= raw.shape[1] and (P - 1) * hop + ps <= n_use and Pd * ps <= n_use
+    if rows is not None:
+        _need_cuda(rows)
+        assert rows.dtype == torch.int32 and rows.numel() == B
+    check(_lib.load().mma_patchify_deriv(raw.data_ptr(), raw.stride(0), _p(rows), int(offset), n_use, float(mean),
+                                         float(std), out.data_ptr(), _p(pad), _p(missing), int(masking), B, P, Pd, ps,
+                                         hop, _stream()), "mma_patchify_deriv")
+    _count(2)
+
+
 def _ragged_ok(flat, offsets, rows):
     _need_cuda(flat, offsets, rows)
     assert offsets.dtype == torch.int64 and rows.dtype == torch.int32 and flat.is_contiguous()

@@ -26,6 +26,9 @@ from . import ops
 from .preprocess import INTERP_OFFSET, INTERP_POINTS
 
 TOKENISED_TYPES = ("multiplets", "carbon", "msms_text")  # datamodules.py:254-259 (padded to the batch's longest row)
+# spectra written out as text: their preprocessors pad every batch to `max_sequence_length` (text_spectrum.py:113-119,
+# 465-471), so these columns have a fixed padded length like the plain text inputs
+SPECTRUM_TEXT_TYPES = ("text_spectrum", "run_length_encoding")  # datamodules.py:277-304, 321-332
 
 
 # ---------------------------------------------------------------------------------------------- host: ragged columns
@@ -117,7 +120,8 @@ def pretokenise(rows, preprocessors: Dict[str, Any], data_config: Dict[str, Any]
     for m in inputs:
         mtype = data_config[m]["type"]
         pre = preprocessors[m]
-        data = _column(rows, m)
+        # a text_spectrum modality reads other columns (its own name need not be one)
+        data = None if mtype == "text_spectrum" else _column(rows, m)
         if mtype == "text":
             toks: List[np.ndarray] = []
             for lo in range(0, n, chunk):
@@ -142,6 +146,31 @@ def pretokenise(rows, preprocessors: Dict[str, Any], data_config: Dict[str, Any]
             if vals:
                 col.values, col.pad_value = Ragged.from_rows(vals, np.float32, width=1), 1.0
             cols[m] = col
+        elif mtype in SPECTRUM_TEXT_TYPES:
+            mc = data_config[m]
+            formulae = None
+            if mtype == "text_spectrum":
+                data = _column(rows, mc["spectra_column"])
+                formulae = None if mc["spectra_only"] else _column(rows, mc["formula_column"])
+            pad_id = int(pre.tokenizer.pad_token_id)
+            toks, vals = [], []
+            for lo in range(0, n, chunk):
+                spectra = np.asarray(data[lo: lo + chunk])  # add_padding_numerical_values reads spectra.shape
+                if mtype == "text_spectrum":
+                    enc = pre(formulae=None if formulae is None else formulae[lo: lo + chunk], spectra=spectra)
+                else:
+                    enc = pre(spectra=spectra)
+                ids = enc["input_ids"].numpy()
+                r, lens, _ = _ragged_from_padded(ids, pad_id, None)
+                toks += [x.astype(np.int32) for x in r]
+                if "numerical_values" in enc:
+                    nv = enc["numerical_values"].numpy()
+                    vals += [nv[i, : lens[i]].astype(np.float32) for i in range(len(r))]
+            width = int(pre.max_sequence_length)
+            col = Column("tokens", pad_len=width, max_len=width, pad_id=pad_id, tokens=Ragged.from_rows(toks, np.int32))
+            if vals:
+                col.values, col.pad_value = Ragged.from_rows(vals, np.float32, width=1), 1.0
+            cols[m] = col
         elif mtype == "msms_number":
             peaks = []
             for lo in range(0, n, chunk):
@@ -151,8 +180,6 @@ def pretokenise(rows, preprocessors: Dict[str, Any], data_config: Dict[str, Any]
                 peaks += [x[i, : lens[i]].astype(np.float32) for i in range(x.shape[0])]
             cols[m] = Column("values", values=Ragged.from_rows(peaks, np.float32, width=2), pad_value=0.0)
         elif mtype == "1D_patches":
-            if getattr(pre, "derivative", False):
-                raise NotImplementedError("derivative patches are not on the accelerated path")
             sizes = [len(s) if s is not None else -1 for s in data]
             width = max(sizes) if max(sizes) != -1 else 500  # patches.py:63-67
             raw = np.zeros((n, width), dtype=np.float32)
@@ -164,7 +191,7 @@ def pretokenise(rows, preprocessors: Dict[str, Any], data_config: Dict[str, Any]
             cols[m] = Column("patches", raw=raw, missing=np.asarray([s == -1 for s in sizes], dtype=np.uint8),
                              patch=dict(patch_size=int(pre.patch_size), mean=float(pre.mean), std=float(pre.std),
                                         interpolation=bool(pre.interpolation), overlap=int(pre.overlap),
-                                        masking=bool(pre.masking)))
+                                        masking=bool(pre.masking), derivative=bool(getattr(pre, "derivative", False))))
         else:
             raise NotImplementedError(f"modality type {mtype} is not on the accelerated path")
     if data_config[tgt]["type"] != "text":
@@ -280,10 +307,15 @@ class DeviceDataset:
                 hop = ps // p["overlap"]
                 n_patches = n_use // ps
                 P = n_patches if p["overlap"] == 1 else (n_patches * ps - ps) // hop + 1
-                out = torch.empty(B, P, ps, dtype=torch.float32, device=dev)
-                pad = torch.empty(B, P, dtype=torch.uint8, device=dev)
-                ops.patchify(d["raw"], out, p["mean"], p["std"], offset=offset, hop=hop, pad=pad, missing=d["missing"],
-                             masking=p["masking"], rows=rows)
+                Pd = n_patches if p.get("derivative") else 0  # patches.py:91-95: gradient patches appended
+                out = torch.empty(B, P + Pd, ps, dtype=torch.float32, device=dev)
+                pad = torch.empty(B, P + Pd, dtype=torch.uint8, device=dev)
+                if Pd:
+                    ops.patchify_deriv(d["raw"], out, p["mean"], p["std"], Pd, offset=offset, n_use=n_use, hop=hop, pad=pad,
+                                       missing=d["missing"], masking=p["masking"], rows=rows)
+                else:
+                    ops.patchify(d["raw"], out, p["mean"], p["std"], offset=offset, hop=hop, pad=pad,
+                                 missing=d["missing"], masking=p["masking"], rows=rows)
                 mask = pad ^ 1  # the kernel writes the reference's pad flag; the engine wants validity
                 enc[name] = out
             masks.append(mask)

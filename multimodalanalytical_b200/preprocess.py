@@ -4,7 +4,7 @@ Same constructor fields and `initialise` statistics as the reference class; `__c
 batch and returns `(patches [B, P, patch_size] fp32, attention_mask [B, P] bool)` - computed by one CUDA kernel on
 the device (standardise + the interpolation, which is a slice because both wavenumber grids share their knots +
 trim + patch), batch-first, so the collator no longer makes a host pass over B x 1791 floats nor a transpose.
-The derivative variant (`derivative=True`) is not on the accelerated path.
+`derivative=True` appends the patches of torch.gradient(raw spectrum) (patches.py:91-95) from the same launch pair.
 """
 from __future__ import annotations
 
@@ -31,6 +31,8 @@ class DevicePatchPreprocessor:
     encoding_type: str = ""
     mean: float = field(init=False, default=0.0)
     std: float = field(init=False, default=1.0)
+    mean_deriv: Optional[float] = field(init=False, default=None)  # computed like the reference's, and like there unused
+    std_deriv: Optional[float] = field(init=False, default=None)
 
     def initialise(self, spectra: Union[np.ndarray, Sequence[Sequence[float]]], modality: Optional[str] = None) -> None:
         """Mean / std over the non-zero points of the sampled spectra (patches.py:37-39).  Accepts the array itself or
@@ -40,12 +42,11 @@ class DevicePatchPreprocessor:
         arr = np.array(spectra)
         self.mean = float(arr[arr != 0].mean())
         self.std = float(arr[arr != 0].std())
-        if self.derivative:
-            raise NotImplementedError("derivative patches are not on the accelerated path")
+        if self.derivative:  # patches.py:41-46 (torch.gradient, unbiased std)
+            g = np.gradient(arr.astype(np.float32), axis=-1)
+            self.mean_deriv, self.std_deriv = float(g.mean()), float(g.std(ddof=1))
 
     def __call__(self, spectra: Union[torch.Tensor, List[Optional[List[float]]]], device="cuda") -> Tuple[torch.Tensor, torch.Tensor]:
-        if self.derivative:
-            raise NotImplementedError("derivative patches are not on the accelerated path")
         missing = None
         if not isinstance(spectra, torch.Tensor):
             sizes = [len(s) if s is not None else -1 for s in spectra]
@@ -62,8 +63,14 @@ class DevicePatchPreprocessor:
         n_patches = n_use // self.patch_size
         hop = self.patch_size // self.overlap
         P = n_patches if self.overlap == 1 else (n_patches * self.patch_size - self.patch_size) // hop + 1
-        out = torch.empty(B, P, self.patch_size, dtype=torch.float32, device=raw.device)
-        pad = torch.empty(B, P, dtype=torch.uint8, device=raw.device)
+        Pd = n_patches if self.derivative else 0
+        out = torch.empty(B, P + Pd, self.patch_size, dtype=torch.float32, device=raw.device)
+        pad = torch.empty(B, P + Pd, dtype=torch.uint8, device=raw.device)
         miss_dev = None if missing is None else missing.to(raw.device, non_blocking=True)
-        ops.patchify(raw, out, self.mean, self.std, offset=offset, hop=hop, pad=pad, missing=miss_dev, masking=self.masking)
+        if self.derivative:
+            ops.patchify_deriv(raw, out, self.mean, self.std, Pd, offset=offset, n_use=n_use, hop=hop, pad=pad,
+                               missing=miss_dev, masking=self.masking)
+        else:
+            ops.patchify(raw, out, self.mean, self.std, offset=offset, hop=hop, pad=pad, missing=miss_dev,
+                         masking=self.masking)
         return out, pad.bool()

@@ -54,11 +54,11 @@ def collate(host, indices):
             if all(s is None for s in spectra):  # the table width stands in for the reference's 500-point default
                 spectra = [[0.0] * col.raw.shape[1] for _ in idx]
                 patches, _ = patch_oracle.patch_preprocess(spectra, p["mean"], p["std"], p["patch_size"], p["masking"],
-                                                           p["interpolation"], p["overlap"])
+                                                           p["interpolation"], p["overlap"], p.get("derivative", False))
                 pad = np.ones(patches.shape[:2], bool) if not p["masking"] else patches.sum(-1) == 0
             else:
                 patches, pad = patch_oracle.patch_preprocess(spectra, p["mean"], p["std"], p["patch_size"], p["masking"],
-                                                             p["interpolation"], p["overlap"])
+                                                             p["interpolation"], p["overlap"], p.get("derivative", False))
             enc[name] = torch.from_numpy(np.transpose(patches, (1, 0, 2)).copy())
         masks.append(pad.T)
     tcol = host.target

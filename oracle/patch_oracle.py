@@ -25,7 +25,16 @@ def interpolate(spectrum):
     return y0 + (y1 - y0) / (x1 - x0) * (new_x - x0)
 
 
-def patch_preprocess(spectra, mean, std, patch_size, masking=False, interpolation=False, overlap=1):
+def gradient(x):
+    """torch.gradient(x, dim=-1)[0] for unit spacing: central differences, one-sided at both ends (patches.py:92)."""
+    g = np.empty_like(x)
+    g[:, 1:-1] = (x[:, 2:] - x[:, :-2]) / np.float32(2)
+    g[:, 0] = x[:, 1] - x[:, 0]
+    g[:, -1] = x[:, -1] - x[:, -2]
+    return g
+
+
+def patch_preprocess(spectra, mean, std, patch_size, masking=False, interpolation=False, overlap=1, derivative=False):
     """-> (patches float32 [B, P, patch_size], attention_mask bool [B, P])."""
     sizes = [len(s) if s is not None else -1 for s in spectra]
     n = max(sizes) if max(sizes) != -1 else 500
@@ -33,6 +42,7 @@ def patch_preprocess(spectra, mean, std, patch_size, masking=False, interpolatio
     if interpolation:
         rows = [interpolate(r) for r in rows]
     x = np.asarray(rows, dtype=np.float32)                      # torch.Tensor(spectra): float32
+    raw = x
     x = (x - np.float32(mean)) / np.float32(std)
     n_patches = x.shape[1] // patch_size
     x = x[:, : n_patches * patch_size]
@@ -42,6 +52,9 @@ def patch_preprocess(spectra, mean, std, patch_size, masking=False, interpolatio
         hop = patch_size // overlap
         count = (x.shape[1] - patch_size) // hop + 1
         p = np.stack([x[:, i * hop: i * hop + patch_size] for i in range(count)], axis=1)
+    if derivative:  # patches.py:91-95: gradient of the raw (not standardised) tensor, never overlapping
+        g = gradient(raw)[:, : n_patches * patch_size].reshape(-1, n_patches, patch_size)
+        p = np.concatenate([p, g], axis=1)
     if masking:
         mask = p.sum(-1) == 0
     else:

@@ -5,6 +5,9 @@ collator `MultiModalDataCollator` (analytical_fm/data/datamodules.py:18-399) and
   c1     the bundled IR parquet (Formula text + IR patches -> Smiles), same pipeline as make_golden.case_c1
   multi  a synthetic multimodal set: Formula text, 13C peak lists (carbon), 1H multiplets as text and as XVal numerical
          encoding, MS/MS peak lists (msms_number), IR with interpolation; some samples lack a modality (None)
+  spectext  spectra written out as text (the legacy ablation inputs): text_spectrum with a formula prefix and integer
+         intensities, text_spectrum with XVal numerical encoding (spectra only), run_length_encoding; plus IR patches
+         with derivative=True (gradient patches appended, patches.py:91-95)
 For each case the fixture holds the reference batches for several index lists and the `HostDataset` that
 `multimodalanalytical_b200.pipeline.pretokenise` extracted from the same preprocessor objects (the reference cannot
 travel to the GPU box); for c1 also the raw rows and the tokenizers' JSON so a CPU test can re-run `pretokenise`.
@@ -131,9 +134,48 @@ def case_multi():
             "max_source_length": dict(col.max_source_length), "max_target_length": int(col.max_target_length)}
 
 
+def case_spectext():
+    rng = np.random.default_rng(5)
+    n = 14
+    rows = {"Formula": [f"C{rng.integers(2, 30)}H{rng.integers(2, 40)}" + ("N2" if i % 3 == 0 else "O") for i in range(n)],
+            "IR": [np.round(rng.random(1791) * (rng.random(1791) > 0.3), 3).astype(np.float32).tolist() for _ in range(n)],
+            "Smiles": ["".join(rng.choice(list("CcNO()=1")) for _ in range(int(rng.integers(3, 30)))) for _ in range(n)]}
+    rows["RLE"] = [np.repeat(rng.random(200), 9)[:1791].astype(np.float32).tolist() for _ in range(n)]  # runs to encode
+    rows["IRd"] = rows["IR"]
+    ds = Dataset.from_dict(rows)
+    cols = {"spectra_column": "IR", "formula_column": "Formula"}
+    dc = {
+        "SpecText": {"type": "text_spectrum", "target": False, "spectra_only": False, **cols,
+                     "preprocessor_arguments": {"spectrum_tokens_x": 40, "spectrum_tokens_y": 20, **cols}},
+        "SpecNum": {"type": "text_spectrum", "target": False, "spectra_only": True, **cols,
+                    "preprocessor_arguments": {"spectrum_tokens_x": 30, "spectrum_to_text_y": "numerical_encoding",
+                                               "spectra_only": True, **cols}},
+        "RLE": {"type": "run_length_encoding", "target": False,
+                "preprocessor_arguments": {"spectrum_tokens_x": 25, "spectrum_tokens_y": 6}},
+        "IRd": {"type": "1D_patches", "target": False,
+                "preprocessor_arguments": {"patch_size": 125, "interpolation": False, "masking": False, "derivative": True}},
+        "Smiles": {"type": "text", "target": True, "preprocessor_arguments": {"tokenizer_regex": "(.)"}},
+    }
+    np.random.seed(9)
+    data_config, pre = data_utils.load_preprocessors(ds, dc)
+    col = datamodules.MultiModalDataCollator(preprocessors=pre, data_config=data_config, model_type="CustomModel",
+                                             dataset={"train": ds}, extra_columns=[None])
+    lists = [list(range(n)), [3, 1, 7], [n - 1], [5, 5, 0, 9, 13, 2]]
+    host = pretokenise(ds, pre, data_config, col.max_source_length, col.max_target_length)
+    return {"data_config": data_config, "batches": reference_batches(col, ds, lists), "host": host,
+            "max_source_length": dict(col.max_source_length), "max_target_length": int(col.max_target_length)}
+
+
+CASES = {"c1": case_c1, "multi": case_multi, "spectext": case_spectext}
+
+
 def main():
-    out = {"c1": case_c1(), "multi": case_multi()}
+    # `python make_collate_golden.py spectext` regenerates only the named cases and keeps the others as committed
     path = os.path.join(HERE, "collate.pt")
+    names = [a for a in sys.argv[1:] if a in CASES]
+    out = torch.load(path, weights_only=False) if names and os.path.exists(path) else {}
+    for name in names or list(CASES):
+        out[name] = CASES[name]()
     torch.save(out, path)
     for name, fx in out.items():
         b = fx["batches"][0]["batch"]

@@ -26,6 +26,11 @@ for name, spectra, kw in (
     ("ir_patch75_overlap3", real[:8], dict(patch_size=75, masking=False, interpolation=False, overlap=3)),
     ("mix1800_interp_patch75_masking", synth1800, dict(patch_size=75, masking=True, interpolation=True)),
     ("with_missing", [real[0], None, real[2]], dict(patch_size=150, masking=False, interpolation=False)),
+    # derivative=True (patches.py:91-95): gradient patches appended; incl. a patch size that divides the spectrum (the
+    # one-sided difference at the last point lands in a patch), interpolation, masking, a missing spectrum
+    ("ir_patch125_derivative", real, dict(patch_size=125, masking=False, interpolation=False, derivative=True)),
+    ("mix1800_patch75_derivative_exact", synth1800, dict(patch_size=75, masking=True, interpolation=False, derivative=True)),
+    ("ir_interp_patch65_derivative", real[:6] + [None], dict(patch_size=65, masking=False, interpolation=True, derivative=True)),
 ):
     pp = PatchPreprocessor(**kw)
     pp.initialise({"m": [s for s in spectra if s is not None]}, "m")
