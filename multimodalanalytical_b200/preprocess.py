@@ -5,6 +5,9 @@ batch and returns `(patches [B, P, patch_size] fp32, attention_mask [B, P] bool)
 the device (standardise + the interpolation, which is a slice because both wavenumber grids share their knots +
 trim + patch), batch-first, so the collator no longer makes a host pass over B x 1791 floats nor a transpose.
 `derivative=True` appends the patches of torch.gradient(raw spectrum) (patches.py:91-95) from the same launch pair.
+With `masking=True` a patch is flagged when its fp32 sum is exactly 0 (patches.py:98-100); a gradient patch telescopes to
+about 0, so for those patches the flag is a function of the summation order and can differ from a torch-CPU run on near-ties
+(as it does between torch's own CPU and CUDA sums).
 """
 from __future__ import annotations
 

@@ -49,7 +49,15 @@ def test_device_patch_preprocessor_matches_reference_golden():
         assert tuple(patches.shape) == tuple(want.shape), c["name"]
         err = (patches.cpu() - want).abs().max() / want.abs().max()
         assert float(err) < 2e-6, (c["name"], float(err))
-        assert torch.equal(mask.cpu(), c["mask"]), c["name"]
+        diff = (mask.cpu() != c["mask"]).nonzero().tolist()
+        if diff:
+            # `masking=True` flags a patch whose fp32 sum is exactly 0 (patches.py:98-100).  A gradient patch telescopes to
+            # ~0, so whether rounding leaves exactly 0 depends on the summation ORDER (torch CPU / torch CUDA / this kernel
+            # all differ): only such near-ties may disagree
+            assert c["kwargs"].get("derivative") and c["kwargs"]["masking"], c["name"]
+            for b, pi in diff:
+                v = want[b, pi].double()
+                assert pi >= want.shape[1] // 2 and abs(float(v.sum())) < 1e-6 * float(v.abs().sum()), (c["name"], b, pi)
 
 
 @pytest.mark.gpu
