@@ -273,7 +273,65 @@ class Generator:
         return (SMALL_DECODE and self.eng.precision == "bf16" and R <= min(SMALL_MAX_ROWS, 512) and cfg.d_model % 256 == 0
                 and cfg.decoder_ffn_dim % 256 == 0 and (cfg.d_model // cfg.decoder_attention_heads) == 64)
 
+    def _forward_logits_post(self, st: BeamState, ctx: Dict[str, Any]):
+        """The decoder step of a `post_layer_normalisation=False` model, LN(x + f(x)) layers (custom_modeling.py:166-176
+        with torch's norm_first=False): per-op launches, each LayerNorm writing the fp32 stream and the next product's
+        operand at once.  No shipped config uses it, so the fused small-row / one-launch steps do not cover it."""
+        eng, cfg = self.eng, self.eng.cfg
+        d, H, f = cfg.d_model, cfg.decoder_attention_heads, cfg.decoder_ffn_dim
+        dh = d // H
+        R, K, L = st.B * st.K, st.K, st.L
+        T, e, tm = eng.adt, eng.ps.EMB, cfg.target_modality
+        gam = bet = None
+        if cfg.multimodal_norm:
+            gam, bet = eng.P(f"{e}embedding_norm_dict.{tm}.weight"), eng.P(f"{e}embedding_norm_dict.{tm}.bias")
+        x = eng.buf("g.x", (R, d), torch.float32)
+        ops.decode_embed(st.next_tok, eng.P(f"{e}embedding_layer_dict.{tm}.weight"), gam, bet, ctx["pos"], st.cur_len, x)
+        bf = eng.precision == "bf16"
+        h = eng.buf("g.h", (R, d), T) if bf else x  # the stream in the activation dtype
+        if bf:
+            ops.cast_f32_bf16(x, h)
+        qkv = eng.buf("g.qkv", (R, 3 * d), T)
+        att = eng.buf("g.att", (R, d), T)
+        q = eng.buf("g.q", (R, d), T)
+        a = eng.buf("g.a", (R, f), T)
+        z = eng.buf("g.z", (R, f), T)
+        xs = eng.buf("g.xa", (R, d), torch.float32)
+        P, W = eng.P, eng.W
+
+        def resid_norm(a_in, wname, bname, k_in, norm):
+            """x, h = LayerNorm(x + a_in W^T + b)"""
+            ops.gemm(a_in, W(wname), R, d, k_in, ops.make_epi(EPI_RESID, xs, bias=P(bname), resid=x))
+            ops.ln_fwd(xs, P(norm + "weight"), P(norm + "bias"), x, y2=h if bf else None)
+
+        for i in range(cfg.decoder_layers):
+            p = f"hf_model.decoder.layers.{i}."
+            ops.gemm(h, W(p + "self_attn.in_proj_weight"), R, 3 * d, d,
+                     ops.make_epi(EPI_STORE, qkv, bias=P(p + "self_attn.in_proj_bias")))
+            ops.decode_self_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx["kc"][i], ctx["vc"][i], st.anc,
+                                 st.cur_len, att, R, H, dh, L, beams=K)
+            resid_norm(att, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", d, p + "norm1.")
+            ops.gemm(h, W(p + "multihead_attn.in_proj_weight")[:d], R, d, d,
+                     ops.make_epi(EPI_STORE, q, bias=P(p + "multihead_attn.in_proj_bias")[:d]))
+            kv = ctx["kvmem"][i]
+            ops.attn_fwd(q, kv[:, :d], kv[:, d:], att, None, st.B, H, K, ctx["S"], dh, kmask=ctx["enc_mask"])
+            resid_norm(att, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", d, p + "norm2.")
+            if not cfg.gated_linear:
+                ops.gemm(h, W(p + "linear1.weight"), R, f, d, ops.make_epi(EPI_GELU, a, bias=P(p + "linear1.bias")))
+            else:
+                ops.gemm(h, W(p + "linear1.weight"), R, f, d, ops.make_epi(EPI_STORE, z, bias=P(p + "linear1.bias")))
+                ops.gemm(h, W(p + "gate.weight"), R, f, d, ops.make_epi(EPI_GLU_MUL, a, bias=P(p + "gate.bias"), aux=z))
+            resid_norm(a, p + "linear2.weight", p + "linear2.bias", f, p + "norm3.")
+        hT = eng.buf("g.hT", (R, d), T)
+        ops.ln_fwd(x, P("hf_model.decoder.norm.weight"), P("hf_model.decoder.norm.bias"), hT)
+        logits = eng.buf("g.logits", (R, eng.ldv), torch.float32)
+        ops.gemm(hT, W("hf_model.token_ff.weight"), R, cfg.vocab_size, d,
+                 ops.make_epi(EPI_STORE, logits, bias=P("hf_model.token_ff.bias")))
+        return logits
+
     def _forward_logits(self, st: BeamState, ctx: Dict[str, Any]):
+        if not self.eng.norm_first:
+            return self._forward_logits_post(st, ctx)
         plan = self._persist_plan(st)
         if plan is not None:
             return self._forward_logits_persist(st, ctx, plan)

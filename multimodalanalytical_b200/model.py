@@ -45,6 +45,9 @@ class Engine:
         self.ldv = (cfg.vocab_size + 7) // 8 * 8
         self._wq: List[Any] = []  # weight / bias gradient products deferred to one grouped launch per layer
         self.group_wgrad = True
+        # custom_modeling.py:129,176 hand `post_layer_normalisation` to torch as norm_first: True (every shipped config) is
+        # x + f(LN(x)); False is LN(x + f(x)) - same kernels, other order (the `xb=` / `_post` paths below)
+        self.norm_first = bool(cfg.post_layer_normalisation)
         # The grouped weight-gradient launch of a layer is off the critical path of backward (nothing but the
         # optimiser reads its output), so it CAN run on a side stream next to the memory-bound LayerNorm / attention
         # kernels of the next layer down (MMA_WGRAD_STREAM=1).  Measured on B200: no gain - the persistent 200 KB CTAs
@@ -276,19 +279,55 @@ class Engine:
         """(gamma, beta, output buffer) for the LayerNorm that opens the block `tag`."""
         return self.P(wname), self.P(bname), self.buf(tag + ".h", (M, self.cfg.d_model), self.adt)
 
+    def _operand_copy(self, x, name):
+        """The fp32 residual stream as a GEMM operand (LN(x + f(x)) layers feed the stream itself to the next block)."""
+        if self.adt == torch.float32:
+            return x
+        xb = self.buf(name, tuple(x.shape), self.adt)
+        ops.cast_f32_bf16(x, xb)
+        return xb
+
+    def _post_norm_fwd(self, tag, xo, wp, M):
+        """LN(x + f(x)) layers: the block's output is LayerNorm(xo) - in fp32 for the residual stream and in the
+        activation dtype as the next block's operand, from one launch."""
+        xn = self.buf(tag + ".xn", (M, self.cfg.d_model), torch.float32)
+        if self.adt == torch.float32:
+            ops.ln_fwd(xo, self.P(wp["n_w"]), self.P(wp["n_b"]), xn)
+            return xn, xn
+        xnb = self.buf(tag + ".xnb", (M, self.cfg.d_model), self.adt)
+        ops.ln_fwd(xo, self.P(wp["n_w"]), self.P(wp["n_b"]), xn, y2=xnb)
+        return xn, xnb
+
+    def _post_norm_bwd(self, tag, kind, dxn, M, wp, p, site_r):
+        """Backward of `_post_norm_fwd`: dxn (fp32, total gradient of the block output) -> ds (fp32 gradient of
+        s = x + drop(f(x)); the sub-layer's input gradient is accumulated into it afterwards, which makes it the total
+        gradient of the block input) and its dropout-masked low-precision copy, the gradient of f's output."""
+        d = self.cfg.d_model
+        ds = self._other_dx(dxn, M)
+        dsb = self.wbuf("bw.dsb." + kind, (M, d), self.adt)
+        ops.ln_bwd(dxn, self.saved[tag]["x"], self.P(wp["n_w"]), dx=ds, dxb=dsb, dgamma=self.G(wp["n_w"]),
+                   dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=site_r)
+        return ds, dsb
+
     # ----------------------------------------------------------------------------- layer forward
-    def _attn_block_fwd(self, tag, x, B, L, heads, wp, kmask, causal, p, site_a, site_r, train, h_pre=None, nxt=None):
+    def _attn_block_fwd(self, tag, x, B, L, heads, wp, kmask, causal, p, site_a, site_r, train, h_pre=None, nxt=None,
+                        xb=None):
         """x -> x + drop(out_proj(attn(LN(x))))  (self-attention).  `h_pre`: LN(x) if the previous block's fused
-        product already made it; `nxt`: the LayerNorm that follows.  Returns (new residual stream, LN of it or None)."""
+        product already made it; `nxt`: the LayerNorm that follows.  Returns (new residual stream, LN of it or None).
+        `xb` (x in the activation dtype) selects the LN(x + f(x)) form: returns (LN(x + drop(out_proj(attn(x)))), its
+        activation-dtype copy)."""
         d = self.cfg.d_model
         M = B * L
         dh = d // heads
         T = self.adt
-        h = self.buf(tag + ".h", (M, d), T)
-        if h_pre is None:
-            ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        if xb is not None:
+            h = xb
         else:
-            assert h_pre.data_ptr() == h.data_ptr()
+            h = self.buf(tag + ".h", (M, d), T)
+            if h_pre is None:
+                ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+            else:
+                assert h_pre.data_ptr() == h.data_ptr()
         qkv = self.buf(tag + ".qkv", (M, 3 * d), T)
         ops.gemm(h, self.W(wp["in_w"]), M, 3 * d, d, ops.make_epi(EPI_STORE, qkv, bias=self.P(wp["in_b"])))
         ctx = self.buf(tag + ".ctx", (M, d), T)
@@ -296,9 +335,11 @@ class Engine:
         ops.attn_fwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], ctx, lse, B, heads, L, L, dh, kmask=kmask,
                      causal=causal, p_drop=p, seed=self.seed_arg, site=site_a)
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
-        h_next = self._resid_gemm(ctx, wp["out_w"], wp["out_b"], M, d, d, xo, x, p, site_r, nxt)
+        h_next = self._resid_gemm(ctx, wp["out_w"], wp["out_b"], M, d, d, xo, x, p, site_r, None if xb is not None else nxt)
         if train:
-            self.saved[tag] = dict(x=x, h=h, qkv=qkv, ctx=ctx, lse=lse)
+            self.saved[tag] = dict(x=xo if xb is not None else x, h=h, qkv=qkv, ctx=ctx, lse=lse)
+        if xb is not None:
+            return self._post_norm_fwd(tag, xo, wp, M)
         return xo, h_next
 
     def _attn_block_bwd(self, tag, dx, dyb, B, L, heads, wp, kmask, causal, p, site_a, prev_site, first=False,
@@ -324,14 +365,17 @@ class Engine:
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
 
-    def _ffn_block_fwd(self, tag, x, M, f, wp, p, site_i, site_r, train, h_pre=None, nxt=None):
+    def _ffn_block_fwd(self, tag, x, M, f, wp, p, site_i, site_r, train, h_pre=None, nxt=None, xb=None):
         d = self.cfg.d_model
         T = self.adt
-        h = self.buf(tag + ".h", (M, d), T)
-        if h_pre is None:
-            ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        if xb is not None:  # LN(x + f(x)) form, see _attn_block_fwd
+            h = xb
         else:
-            assert h_pre.data_ptr() == h.data_ptr()
+            h = self.buf(tag + ".h", (M, d), T)
+            if h_pre is None:
+                ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+            else:
+                assert h_pre.data_ptr() == h.data_ptr()
         a = self.buf(tag + ".a", (M, f), T)
         z = self.buf(tag + ".z", (M, f), T)
         z2 = None
@@ -352,9 +396,11 @@ class Engine:
                          ops.make_epi(EPI_GLU_MUL, a, out2=z2, bias=self.P(wp["bg"]), aux=z, p_drop=p,
                                       seed=self.seed_arg, site=site_i))
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
-        h_next = self._resid_gemm(a, wp["w2"], wp["b2"], M, d, f, xo, x, p, site_r, nxt)
+        h_next = self._resid_gemm(a, wp["w2"], wp["b2"], M, d, f, xo, x, p, site_r, None if xb is not None else nxt)
         if train:
-            self.saved[tag] = dict(x=x, h=h, a=a, z=z, z2=z2)
+            self.saved[tag] = dict(x=xo if xb is not None else x, h=h, a=a, z=z, z2=z2)
+        if xb is not None:
+            return self._post_norm_fwd(tag, xo, wp, M)
         return xo, h_next
 
     def _ffn_block_bwd(self, tag, dx, dyb, M, f, wp, p, site_i, prev_site):
@@ -393,6 +439,71 @@ class Engine:
                    dbeta=self.G(wp["n_b"]), p_drop=p, seed=self.seed_arg, site=prev_site)
         return dx_in, dyb_in
 
+    # ---- LN(x + f(x)) layers: backward.  dxn = total fp32 gradient of the block output; returns that of the block input
+    def _attn_block_bwd_post(self, tag, dxn, B, L, heads, wp, kmask, causal, p, site_a, site_r):
+        d = self.cfg.d_model
+        M = B * L
+        dh = d // heads
+        T = self.adt
+        s = self.saved[tag]
+        ds, dsb = self._post_norm_bwd(tag, "sa", dxn, M, wp, p, site_r)
+        dctx = self.wbuf("bw.dctx", (M, d), T)
+        self._lin_bwd(dsb, s["ctx"], wp["out_w"], wp["out_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dctx))
+        dqkv = self.wbuf("bw.dqkv", (M, 3 * d), T)
+        qkv = s["qkv"]
+        ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], s["ctx"], s["lse"], dctx, dqkv[:, :d],
+                     dqkv[:, d:2 * d], dqkv[:, 2 * d:], B, heads, L, L, dh, kmask=kmask, causal=causal, p_drop=p,
+                     seed=self.seed_arg, site=site_a, dsum=self.buf("bw.dsum", (B * heads * L,), torch.float32))
+        self._lin_bwd(dqkv, s["h"], wp["in_w"], wp["in_b"], M, 3 * d, d,
+                      dx_epi=ops.make_epi(EPI_ACCUM, ds, accumulate=1))
+        return ds
+
+    def _cross_block_bwd_post(self, tag, dxn, mem, dmem, first_mem, B, T_, S, heads, wp, kmask, p, site_a, site_r):
+        d = self.cfg.d_model
+        M, Me = B * T_, B * S
+        dh = d // heads
+        T = self.adt
+        s = self.saved[tag]
+        ds, dsb = self._post_norm_bwd(tag, "ca", dxn, M, wp, p, site_r)
+        dctx = self.wbuf("bw.dctx", (M, d), T)
+        self._lin_bwd(dsb, s["ctx"], wp["out_w"], wp["out_b"], M, d, d, dx_epi=ops.make_epi(EPI_STORE, dctx))
+        dq = self.wbuf("bw.dq", (M, d), T)
+        dkv = self.wbuf("bw.dkv", (Me, 2 * d), T)
+        kv = s["kv"]
+        ops.attn_bwd(s["q"], kv[:, :d], kv[:, d:], s["ctx"], s["lse"], dctx, dq, dkv[:, :d], dkv[:, d:], B, heads, T_,
+                     S, dh, kmask=kmask, causal=False, p_drop=p, seed=self.seed_arg, site=site_a,
+                     dsum=self.buf("bw.dsum", (B * heads * T_,), torch.float32))
+        self._lin_bwd(dq, s["h"], wp["in_w"], wp["in_b"], M, d, d, dx_epi=ops.make_epi(EPI_ACCUM, ds, accumulate=1),
+                      row_slice=slice(0, d))
+        self._lin_bwd(dkv, mem, wp["in_w"], wp["in_b"], Me, 2 * d, d,
+                      dx_epi=ops.make_epi(EPI_ACCUM, dmem, accumulate=0 if first_mem else 1),
+                      row_slice=slice(d, 3 * d))
+        return ds
+
+    def _ffn_block_bwd_post(self, tag, dxn, M, f, wp, p, site_i, site_r):
+        d = self.cfg.d_model
+        T = self.adt
+        s = self.saved[tag]
+        ds, dsb = self._post_norm_bwd(tag, "ff", dxn, M, wp, p, site_r)
+        dz = self.wbuf("bw.dz", (M, f), T)
+        acc = ops.make_epi(EPI_ACCUM, ds, accumulate=1)
+        if not self.cfg.gated_linear:
+            self._lin_bwd(dsb, s["a"], wp["w2"], wp["b2"], M, d, f,
+                          dx_epi=ops.make_epi(EPI_DGELU, dz, aux=s["z"], p_drop=p, seed=self.seed_arg, site=site_i, drop_ld=f))
+            self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=acc)
+            return ds
+        dz2 = self.wbuf("bw.dz2", (M, f), T)
+        if self.precision == "bf16" and ops.ffn_dglu(dsb, self.W(wp["w2"]), M, f, d, s["z"], s["z2"], dz, dz2, p_drop=p,
+                                                     seed=self.seed_arg, site=site_i, drop_ld=f):
+            self._lin_bwd(dsb, s["a"], wp["w2"], wp["b2"], M, d, f)  # weight / bias gradient only
+        else:
+            self._lin_bwd(dsb, s["a"], wp["w2"], wp["b2"], M, d, f,
+                          dx_epi=ops.make_epi(EPI_DGLU, dz, out2=dz2, aux=s["z"], aux2=s["z2"], p_drop=p,
+                                              seed=self.seed_arg, site=site_i, drop_ld=f))
+        self._lin_bwd(dz, s["h"], wp["w1"], wp["b1"], M, f, d, dx_epi=acc)
+        self._lin_bwd(dz2, s["h"], wp["wg"], wp["bg"], M, f, d, dx_epi=ops.make_epi(EPI_ACCUM, ds, accumulate=1))
+        return ds
+
     def _other_dx(self, dx, M):
         a = self.buf(f"bw.dx.{M}.0", (M, self.cfg.d_model), torch.float32)
         if dx is None or dx.data_ptr() != a.data_ptr():
@@ -412,16 +523,20 @@ class Engine:
                     n_w=f"{prefix}{norm}.weight", n_b=f"{prefix}{norm}.bias")
 
     # -------------------------------------------------------------------------------- cross-attn
-    def _cross_block_fwd(self, tag, x, mem, B, T_, S, heads, wp, kmask, p, site_a, site_r, train, h_pre=None, nxt=None):
+    def _cross_block_fwd(self, tag, x, mem, B, T_, S, heads, wp, kmask, p, site_a, site_r, train, h_pre=None, nxt=None,
+                         xb=None):
         d = self.cfg.d_model
         M, Me = B * T_, B * S
         dh = d // heads
         T = self.adt
-        h = self.buf(tag + ".h", (M, d), T)
-        if h_pre is None:
-            ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+        if xb is not None:  # LN(x + f(x)) form, see _attn_block_fwd
+            h = xb
         else:
-            assert h_pre.data_ptr() == h.data_ptr()
+            h = self.buf(tag + ".h", (M, d), T)
+            if h_pre is None:
+                ops.ln_fwd(x, self.P(wp["n_w"]), self.P(wp["n_b"]), h)
+            else:
+                assert h_pre.data_ptr() == h.data_ptr()
         q = self.buf(tag + ".q", (M, d), T)
         Win, bin_ = self.W(wp["in_w"]), self.P(wp["in_b"])
         ops.gemm(h, Win[:d], M, d, d, ops.make_epi(EPI_STORE, q, bias=bin_[:d]))
@@ -432,9 +547,11 @@ class Engine:
         ops.attn_fwd(q, kv[:, :d], kv[:, d:], ctx, lse, B, heads, T_, S, dh, kmask=kmask, causal=False, p_drop=p,
                      seed=self.seed_arg, site=site_a)
         xo = self.buf(tag + ".xo", (M, d), torch.float32)
-        h_next = self._resid_gemm(ctx, wp["out_w"], wp["out_b"], M, d, d, xo, x, p, site_r, nxt)
+        h_next = self._resid_gemm(ctx, wp["out_w"], wp["out_b"], M, d, d, xo, x, p, site_r, None if xb is not None else nxt)
         if train:
-            self.saved[tag] = dict(x=x, h=h, q=q, kv=kv, ctx=ctx, lse=lse)
+            self.saved[tag] = dict(x=xo if xb is not None else x, h=h, q=q, kv=kv, ctx=ctx, lse=lse)
+        if xb is not None:
+            return self._post_norm_fwd(tag, xo, wp, M)
         return xo, h_next
 
     def _cross_block_bwd(self, tag, dx, dyb, mem, dmem, first_mem, B, T_, S, heads, wp, kmask, p, site_a, prev_site):
@@ -473,6 +590,20 @@ class Engine:
         Me = B * S
         mem = self.buf("enc.mem", (Me, cfg.d_model), self.adt)
         h = None  # LN of x for the next block, when the previous block's fused product already produced it
+        if not self.norm_first:
+            xb = self._operand_copy(x, "enc.x0b")
+            for i in range(cfg.encoder_layers):
+                pre = f"hf_model.encoder.layers.{i}."
+                tg = f"enc{i if train else ''}"
+                x, xb = self._attn_block_fwd(tg + ".sa", x, B, S, cfg.encoder_attention_heads,
+                                             self._wp_attn(pre, "self_attn", "norm1"), enc_mask, False, p,
+                                             self._site(False, i, 0), self._site(False, i, 1), train, xb=xb)
+                x, xb = self._ffn_block_fwd(tg + ".ff", x, Me, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"), p,
+                                            self._site(False, i, 2), self._site(False, i, 3), train, xb=xb)
+            ops.ln_fwd(x, self.P("hf_model.encoder.norm.weight"), self.P("hf_model.encoder.norm.bias"), mem)
+            if train:
+                self.saved["enc"] = dict(recs=recs, xL=x, mem=mem, B=B, S=S, mask=enc_mask)
+            return mem
         for i in range(cfg.encoder_layers):
             pre = f"hf_model.encoder.layers.{i}."
             tg = f"enc{i if train else ''}"
@@ -504,6 +635,22 @@ class Engine:
         M = B * T_
         hT = self.buf("dec.hT", (M, cfg.d_model), self.adt)
         h = None
+        if not self.norm_first:
+            xb = self._operand_copy(x, "dec.x0b")
+            for i in range(cfg.decoder_layers):
+                pre = f"hf_model.decoder.layers.{i}."
+                tg = f"dec{i if train else ''}"
+                x, xb = self._attn_block_fwd(tg + ".sa", x, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"), dec_mask,
+                                             True, p, self._site(True, i, 0), self._site(True, i, 1), train, xb=xb)
+                x, xb = self._cross_block_fwd(tg + ".ca", x, mem, B, T_, S, H,
+                                              self._wp_attn(pre, "multihead_attn", "norm2"), enc_mask, p,
+                                              self._site(True, i, 4), self._site(True, i, 5), train, xb=xb)
+                x, xb = self._ffn_block_fwd(tg + ".ff", x, M, cfg.decoder_ffn_dim, self._wp_ffn(pre, "norm3"), p,
+                                            self._site(True, i, 2), self._site(True, i, 3), train, xb=xb)
+            ops.ln_fwd(x, self.P("hf_model.decoder.norm.weight"), self.P("hf_model.decoder.norm.bias"), hT)
+            if train:
+                self.saved["dec"] = dict(recs=recs, xL=x, hT=hT, B=B, T=T_, mask=dec_mask)
+            return hT
         for i in range(cfg.decoder_layers):
             pre = f"hf_model.decoder.layers.{i}."
             tg = f"dec{i if train else ''}"
@@ -664,6 +811,8 @@ class Engine:
         notify(ps.offsets["hf_model.decoder.norm.weight"][0])
 
         dmem = self.buf("bw.dmem", (Me, d), torch.float32)
+        if not self.norm_first:
+            return self._backward_post_layers(dx, dmem, gscale, notify)
         for i in reversed(range(cfg.decoder_layers)):
             self._begin_group(cfg.decoder_layers - i)
             pre = f"hf_model.decoder.layers.{i}."
@@ -701,6 +850,49 @@ class Engine:
             dxe, dybe = self._attn_block_bwd(tg + ".sa", dxe, dybe, B, S, He, self._wp_attn(pre, "self_attn", "norm1"),
                                              enc["mask"], False, p, self._site(False, i, 0), prev_site=prev,
                                              first=(i == 0), out_tag=f"x{i % 2}")
+            self._flush_wgrads()
+            notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
+        self._embed_bwd(dxe, enc["recs"], S, "enc", B)
+        notify(0)
+        self._join_wgrads()
+
+    def _backward_post_layers(self, dx, dmem, gscale, notify):
+        """Layer loops of `backward` for LN(x + f(x)) layers (post_layer_normalisation=False).  dx: fp32 gradient of the
+        last decoder block's output (the input of decoder.norm)."""
+        cfg, ps = self.cfg, self.ps
+        d, p = cfg.d_model, cfg.dropout
+        dec, enc = self.saved["dec"], self.saved["enc"]
+        B, T_, S = dec["B"], dec["T"], enc["S"]
+        M, Me = B * T_, B * S
+        H, He = cfg.decoder_attention_heads, cfg.encoder_attention_heads
+        for i in reversed(range(cfg.decoder_layers)):
+            self._begin_group(cfg.decoder_layers - i)
+            pre = f"hf_model.decoder.layers.{i}."
+            tg = f"dec{i}"
+            dx = self._ffn_block_bwd_post(tg + ".ff", dx, M, cfg.decoder_ffn_dim, self._wp_ffn(pre, "norm3"), p,
+                                          self._site(True, i, 2), self._site(True, i, 3))
+            dx = self._cross_block_bwd_post(tg + ".ca", dx, enc["mem"], dmem, i == cfg.decoder_layers - 1, B, T_, S, H,
+                                            self._wp_attn(pre, "multihead_attn", "norm2"), enc["mask"], p,
+                                            self._site(True, i, 4), self._site(True, i, 5))
+            dx = self._attn_block_bwd_post(tg + ".sa", dx, B, T_, H, self._wp_attn(pre, "self_attn", "norm1"),
+                                           dec["mask"], True, p, self._site(True, i, 0), self._site(True, i, 1))
+            self._flush_wgrads()
+            notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
+        self._embed_bwd(dx, dec["recs"], T_, "dec", B)
+        if "align" in self.saved:
+            self._align_bwd(dmem, gscale)
+        dxe = self._other_dx(None, Me)
+        ops.ln_bwd(dmem, enc["xL"], self.P("hf_model.encoder.norm.weight"), dx=dxe,
+                   dgamma=self.G("hf_model.encoder.norm.weight"), dbeta=self.G("hf_model.encoder.norm.bias"))
+        notify(ps.offsets["hf_model.encoder.norm.weight"][0])
+        for i in reversed(range(cfg.encoder_layers)):
+            self._begin_group(cfg.decoder_layers + cfg.encoder_layers - i)
+            pre = f"hf_model.encoder.layers.{i}."
+            tg = f"enc{i}"
+            dxe = self._ffn_block_bwd_post(tg + ".ff", dxe, Me, cfg.encoder_ffn_dim, self._wp_ffn(pre, "norm2"), p,
+                                           self._site(False, i, 2), self._site(False, i, 3))
+            dxe = self._attn_block_bwd_post(tg + ".sa", dxe, B, S, He, self._wp_attn(pre, "self_attn", "norm1"),
+                                            enc["mask"], False, p, self._site(False, i, 0), self._site(False, i, 1))
             self._flush_wgrads()
             notify(ps.offsets[pre + "self_attn.in_proj_weight"][0])
         self._embed_bwd(dxe, enc["recs"], S, "enc", B)

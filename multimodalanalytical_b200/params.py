@@ -36,6 +36,9 @@ class ModelConfig:
     decoder_ffn_dim: int = 2048
     dropout: float = 0.1
     gated_linear: bool = False
+    # custom_modeling.py:119-129,166-176: handed to torch as `norm_first` - True (every shipped yaml): x + f(LN(x));
+    # False: LN(x + f(x))
+    post_layer_normalisation: bool = True
     positional_encoding_type: str = "sin_cos"
     multimodal_norm: bool = True
     max_position_embeddings: int = 1024

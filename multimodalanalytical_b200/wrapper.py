@@ -124,6 +124,7 @@ def load_custom_model(model_name: str, target_tokenizer, target_modality: str, d
         decoder_ffn_dim=kwargs.get("decoder_ffn_dim", 2048),
         dropout=kwargs.get("dropout", 0.1),
         gated_linear=bool(kwargs.get("gated_linear", False)),
+        post_layer_normalisation=bool(kwargs.get("post_layer_normalisation", True)),
         positional_encoding_type=kwargs.get("positional_encoding_type", "sin_cos"),
         multimodal_norm=bool(multimodal_norm),
         max_position_embeddings=kwargs.get("max_position_embeddings", 1024),
@@ -133,8 +134,6 @@ def load_custom_model(model_name: str, target_tokenizer, target_modality: str, d
         align_config=kwargs.get("align_config"),
         label_smoothing=float(kwargs.get("label_smoothing", 0.0)),
     )
-    if kwargs.get("post_layer_normalisation", True) is not True:
-        raise NotImplementedError("post_layer_normalisation=False (post-LN) is not on the accelerated path")
     if cfg.align_config:
         ac = cfg.align_config = dict(cfg.align_config)
         if ac.get("align_network") not in ("convolutional", "mlp"):

@@ -54,6 +54,7 @@ class OracleConfig:
     encoder_attention_heads: int = 8
     decoder_attention_heads: int = 8
     gated_linear: bool = False
+    post_layer_normalisation: bool = True  # the reference hands this to torch as `norm_first` (custom_modeling.py:129,176)
     positional_encoding_type: str = "sin_cos"
     multimodal_norm: bool = True
     pad_token_id: int = 0
@@ -171,10 +172,16 @@ def _key_pad_mask(valid):  # valid: [B, L] (1 = real token) -> additive [B,1,1,L
 
 
 def encoder_stack(sd, cfg: OracleConfig, x, attention_mask, prefix="hf_model.encoder."):
-    """Pre-LN encoder layers + final LayerNorm (custom_modeling.py:220-243,350-360)."""
+    """Encoder layers + final LayerNorm (custom_modeling.py:220-243,350-360).  `post_layer_normalisation=True` (every
+    shipped config) is torch's norm_first branch, x + f(LN(x)); False is LN(x + f(x))."""
     km = _key_pad_mask(attention_mask)
     for i in range(cfg.encoder_layers):
         p = f"{prefix}layers.{i}."
+        if not cfg.post_layer_normalisation:
+            x = _ln(x + _drop(_mha(x, x, sd, p + "self_attn.", cfg.encoder_attention_heads, km, cfg), cfg),
+                    sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+            x = _ln(x + _drop(_ffn(x, sd, p, cfg.gated_linear, cfg), cfg), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+            continue
         h = _ln(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
         x = x + _drop(_mha(h, h, sd, p + "self_attn.", cfg.encoder_attention_heads, km, cfg), cfg)
         h = _ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])
@@ -192,6 +199,14 @@ def decoder_stack(sd, cfg: OracleConfig, ids, memory, memory_mask, dec_mask=None
     mem_mask = _key_pad_mask(memory_mask)
     for i in range(cfg.decoder_layers):
         p = f"{prefix}layers.{i}."
+        if not cfg.post_layer_normalisation:
+            H = cfg.decoder_attention_heads
+            x = _ln(x + _drop(_mha(x, x, sd, p + "self_attn.", H, self_mask, cfg), cfg),
+                    sd[p + "norm1.weight"], sd[p + "norm1.bias"])
+            x = _ln(x + _drop(_mha(x, memory, sd, p + "multihead_attn.", H, mem_mask, cfg), cfg),
+                    sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+            x = _ln(x + _drop(_ffn(x, sd, p, cfg.gated_linear, cfg), cfg), sd[p + "norm3.weight"], sd[p + "norm3.bias"])
+            continue
         h = _ln(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
         x = x + _drop(_mha(h, h, sd, p + "self_attn.", cfg.decoder_attention_heads, self_mask, cfg), cfg)
         h = _ln(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"])

@@ -220,8 +220,45 @@ def case_align():
     return {"model_kwargs": mk, "data_config": data_config, "state_dict": sd, "batch": batch, "ref": res}
 
 
+def case_postln():
+    """`post_layer_normalisation: False` -> torch's norm_first=False layers, LN(x + f(x)) (custom_modeling.py:119-129,
+    166-176), with the gated FFN; no shipped yaml sets it, the model surface has it."""
+    g = torch.Generator().manual_seed(13)
+    B = 5
+    data_config = {
+        "Formula": {"type": "text", "target": False, "vocab_size": 30, "pad_token_id": 0,
+                    "preprocessor_arguments": {}},
+        "IR": {"type": "1D_patches", "target": False, "preprocessor_arguments": {"patch_size": 20}},
+        "Smiles": {"type": "text", "target": True, "vocab_size": 31, "pad_token_id": 0,
+                   "preprocessor_arguments": {}},
+    }
+    f_ids, f_pad = _tok(B, 8, 30, g, 3)
+    ir = torch.randn(6, B, 20, generator=g)
+    t_ids, t_pad = _tok(B, 17, 31, g, 5)
+    batch = {
+        "encoder_input": {"Formula": f_ids, "IR": ir},
+        "encoder_pad_mask": torch.cat([f_pad, torch.zeros(6, B, dtype=torch.bool)], dim=0),
+        "decoder_input": {"Smiles": t_ids[:-1]},
+        "decoder_pad_mask": t_pad[:-1],
+        "target": t_ids[1:],
+        "target_mask": t_pad[1:],
+    }
+    mk = model_kwargs(d_model=64, num_heads=2, encoder_attention_heads=2, decoder_attention_heads=2,
+                      encoder_layers=2, decoder_layers=2, encoder_ffn_dim=96, decoder_ffn_dim=128,
+                      gated_linear=True, post_layer_normalisation=False, n_beams=3)
+    sd, res = run_reference(data_config, FakeTokenizer(31), mk, batch, beams=(1, 3), seed=37)
+    return {"model_kwargs": mk, "data_config": data_config, "state_dict": sd, "batch": batch, "ref": res}
+
+
+CASES = (("c1_ir_tiny", case_c1), ("mm_gated_learned", case_mm), ("align_conv", case_align), ("post_ln", case_postln))
+
+
 def main():
-    for name, fn in (("c1_ir_tiny", case_c1), ("mm_gated_learned", case_mm), ("align_conv", case_align)):
+    # `python make_golden.py post_ln` rewrites only the named fixtures
+    only = set(sys.argv[1:])
+    for name, fn in CASES:
+        if only and name not in only:
+            continue
         fx = fn()
         path = os.path.join(HERE, f"{name}.pt")
         torch.save(fx, path)

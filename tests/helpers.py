@@ -6,7 +6,7 @@ import torch
 from oracle import spectra_oracle as orc
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality")
+CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality", "post_ln")
 
 
 def load_case(name):
@@ -23,6 +23,7 @@ def oracle_cfg(fx):
         encoder_attention_heads=mk["encoder_attention_heads"],
         decoder_attention_heads=mk["decoder_attention_heads"],
         gated_linear=mk["gated_linear"],
+        post_layer_normalisation=mk.get("post_layer_normalisation", True),
         positional_encoding_type=mk["positional_encoding_type"],
         multimodal_norm=mk["multimodal_norm"],
         align_config=mk.get("align_config"),

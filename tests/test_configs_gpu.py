@@ -114,6 +114,49 @@ def test_named_configs_train_step_matches_oracle(name, B):
     assert not worst_al or worst_al[0][0] < 0.3, worst_al[:5]
 
 
+@pytest.mark.parametrize("gated", [False, True])
+def test_post_layer_normalisation_false_at_model_size(gated):
+    """`post_layer_normalisation: False` = LN(x + f(x)) layers (custom_modeling.py:119-129,166-176) at d 512 / 6 + 6 layers on
+    the tensor-core path: loss, logits and every parameter gradient of a bf16 train step against the oracle (whose post-LN
+    branch is pinned to the unmodified reference by tests/golden/post_ln.pt), and fp32 greedy / beam-4 token identity."""
+    fx = make_case("c3", 256)  # 6144 decoder rows: the residual-stream accumulations run on the CTA-pair kernel
+    fx["model_kwargs"] = dict(fx["model_kwargs"], post_layer_normalisation=False, gated_linear=gated)
+    fx["state_dict"] = orc.init_state_dict(oracle_cfg(fx), vocab=64, enc_ffn=2048, dec_ffn=2048, seed=5)
+    want_out, want_g = oracle_grads(fx)
+    m = build(fx, "bf16")
+    m.train()
+    m.store.g.zero_()
+    out = m.forward(fx["batch"])
+    out.loss.backward()
+    torch.cuda.synchronize()
+    assert rel_err(out.logits.float().cpu(), want_out["logits"].detach()) < 1e-2
+    assert abs(float(out.loss) - float(want_out["loss"])) < 1e-2 * abs(float(want_out["loss"]))
+    worst = sorted(((rel_err(m.store.G(k).cpu(), g), k) for k, g in want_g.items()), reverse=True)
+    assert worst[0][0] < 8e-2, worst[:5]
+    # the fused trainer (graph-captured step) runs the same schedule
+    tr = FusedTrainer(m, clip_grad=1.0)
+    l0 = float(tr.train_step(fx["batch"], 0))
+    for i in range(1, 4):
+        l1 = float(tr.train_step(fx["batch"], i))
+    assert l1 < l0
+    cfg = oracle_cfg(fx)
+    cfg.max_length = 24
+    m32 = build(fx, "fp32")
+    m32.eval()
+    m32.generation_config["max_length"] = 24
+    small = {k: (v[:, :4] if torch.is_tensor(v) else {kk: vv[:, :4] for kk, vv in v.items()}) for k, v in fx["batch"].items()}
+    for k in (1, 4):
+        got = m32.generate(small, n_beams=k).cpu()
+        with torch.no_grad():
+            want = orc.generate(fx["state_dict"], cfg, small, n_beams=k)
+        assert got.shape == want.shape and torch.equal(got, want), k
+    # bf16 decode of the same model runs the per-op post-LN step
+    m.eval()
+    m.generation_config["max_length"] = 24
+    got16 = m.generate(small, n_beams=4).cpu()
+    assert got16.shape[0] == 16 and bool((got16[:, 0] == 2).all())
+
+
 def test_c5_beam10_decode_identical_to_oracle_fp32():
     """IR-of-mixtures model (align weights present, head unused while generating): greedy and beam-10 sequences."""
     fx = make_case("c5", 3)

@@ -53,7 +53,7 @@ def oracle_grads(fx):
     return out, {k: v.grad for k, v in leaves.items() if v.grad is not None}
 
 
-CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality")
+CASES = ("c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality", "post_ln")
 
 
 @pytest.mark.parametrize("name", CASES)
