@@ -78,6 +78,13 @@ def train_case(name):
                     batch=lambda B, seed: synth_batch(c, B, seed),
                     flops=flops_train(S, T, V, d, f, L, L, c["P"] * c["ps"] * d, True),
                     workload="C2 paper variant: learned pos-enc + GLU FFN (replicate_table_2.sh:16-34), S=15+21x75, T=64, V=200")
+    if name in ("c2_postln", "c2_paper_postln"):  # not a BASELINE config: the LN(x + f(x)) layer order (scripts/case_bench.py)
+        S, T, V, B = 36, 64, 200, 256
+        gated = name == "c2_paper_postln"
+        return dict(dc=data_config(c), mk=model_kwargs(c, post_layer_normalisation=False, **(PAPER if gated else {})),
+                    B=B, S=S, T=T, V=V, gated=gated, batch=lambda B, seed: synth_batch(c, B, seed),
+                    flops=flops_train(S, T, V, d, f, L, L, c["P"] * c["ps"] * d, gated),
+                    workload="C2 shapes with post_layer_normalisation=False" + (" (learned + GLU)" if gated else ""))
     if name == "c3":
         S, T, V, B = 14, 24, 64, 128
         dc = {"Formula": _tokcfg(64), "Phosphor_NMR": {"type": "1D_patches", "target": False, "preprocessor_arguments":
