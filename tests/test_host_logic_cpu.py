@@ -22,7 +22,7 @@ def cfg_from(fx):
                        max_position_embeddings=mk["max_position_embeddings"], align_config=mk.get("align_config"))
 
 
-@pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality"])
+@pytest.mark.parametrize("name", ["c1_ir_tiny", "mm_gated_learned", "align_conv", "align_modality", "post_ln"])
 def test_param_store_has_reference_checkpoint_layout(name):
     fx = load_case(name)
     ps = ParamStore(cfg_from(fx), device="cpu")
@@ -38,6 +38,20 @@ def test_param_store_has_reference_checkpoint_layout(name):
     tail = emb[len("hf_model.embedding."):]
     assert sd["hf_model.decoder.embedding." + tail].data_ptr() == sd[emb].data_ptr()
     assert sd["multimodal_embedding." + tail].data_ptr() == sd[emb].data_ptr()
+
+
+def test_post_layer_normalisation_reaches_the_engine():
+    """The model yaml's `post_layer_normalisation` (custom_modeling.py:55,119-129) selects the layer order of the engine
+    (True, the default of every shipped config: x + f(LN(x)); False: LN(x + f(x))) - it is no longer refused."""
+    from multimodalanalytical_b200.wrapper import load_custom_model
+    fx = load_case("post_ln")
+    tok = type("T", (), dict(vocab_size=31, pad_token_id=0, bos_token_id=2, eos_token_id=3))()
+    for flag in (False, True):
+        mk = dict(fx["model_kwargs"], post_layer_normalisation=flag)
+        for k in ("multimodal_norm", "model_name", "model_type"):
+            mk.pop(k, None)
+        m, _ = load_custom_model("facebook/bart-base", tok, "Smiles", fx["data_config"], True, device="cpu", **mk)
+        assert m.config.post_layer_normalisation is flag and m.engine.norm_first is flag
 
 
 def test_flat_layout_is_aligned_and_forward_ordered():
